@@ -1,0 +1,233 @@
+"""Drop-in for the reference's `adversarialAttacks.py` hot path (adversarialAttacks.py:30-198).
+
+Same function names, argument names, defaults, return types, prints, exceptions and
+pickle side effect.  For a `BNN` the per-image loop (adversarialAttacks.py:118-131) becomes
+one batched device pass per gradient evaluation:
+
+  phase 1  sum_s softmax(f_s(x))  over this rank's bank rows  -> allreduce [B,C] -> pbar
+  phase 2  sum_s p_s*(g-<p_s,g>) back-propagated to x, g = softmax(pbar)-e_y -> allreduce [B,D]
+  update   fused sign / step / project / clip kernel
+
+with no host synchronisation between iterations of PGD.  Other network types
+(duck-typed `forward` returning logits) take the reference's generic autograd route.
+"""
+import random
+
+import torch
+import torch.nn.functional as nnf
+
+from . import dist as rdist
+from . import engine as E
+from ._lib import HEAD_GRAD_OF_MEAN, HEAD_LOGITS_CE
+from .model_bnn import BNN
+from .savedir import TESTS
+from .utils import load_from_pickle, save_to_pickle
+
+DEBUG = False
+PGD_ITERS = 40         # hard-coded in the reference (adversarialAttacks.py:89,91)
+EVAL_BATCH = 128       # adversarialAttacks.py:170-171
+
+
+#######################
+# robustness measures #
+#######################
+
+def softmax_difference(original_predictions, adversarial_predictions):
+    """L-inf norm over classes of softmax(orig) - softmax(adv), per point (adversarialAttacks.py:30-51)."""
+    if len(original_predictions) != len(adversarial_predictions):
+        raise ValueError("\nInput arrays should have the same length.")
+    if original_predictions.is_cuda:
+        rob, mm = E.softmax_robustness(original_predictions.float().contiguous(),
+                                       adversarial_predictions.float().contiguous())
+        diff = 1.0 - rob
+        lo, hi = mm.tolist()
+    else:
+        a = nnf.softmax(original_predictions, dim=-1)
+        b = nnf.softmax(adversarial_predictions, dim=-1)
+        diff = (a - b).abs().max(dim=-1)[0]
+        lo, hi = float(diff.min()), float(diff.max())
+    if lo < 0. or hi > 1.:
+        raise ValueError("Softmax difference should be in [0,1]")
+    return diff
+
+
+def softmax_robustness(original_outputs, adversarial_outputs):
+    """1 - softmax_difference, per point (adversarialAttacks.py:53-62)."""
+    if len(original_outputs) != len(adversarial_outputs):
+        raise ValueError("\nInput arrays should have the same length.")
+    if original_outputs.is_cuda:
+        robustness, mm = E.softmax_robustness(original_outputs.float().contiguous(),
+                                              adversarial_outputs.float().contiguous())
+        lo, hi = mm.tolist()
+        if lo < 0. or hi > 1.:
+            raise ValueError("Softmax difference should be in [0,1]")
+    else:
+        d = softmax_difference(original_outputs, adversarial_outputs)
+        robustness = torch.ones_like(d) - d
+    print(f"avg softmax robustness = {robustness.mean().item():.2f}")
+    return robustness
+
+
+#######################
+# adversarial attacks #
+#######################
+
+def _bnn_input_grad(net, x, labels_i32, n_samples, avg_posterior):
+    """d/dx CE(BNN.forward(x), y) summed over the batch, [B, D] on the device (not yet sign()ed)."""
+    eng = net.engine()
+    if avg_posterior and net.inference == "svi":
+        row = net._pin_cap
+        net._scratch_generation += 1
+        eng.reserve(row + 1)
+        eng.upload(net._loc.reshape(1, -1), row)
+        return eng.input_grad_sum(HEAD_LOGITS_CE, x, labels_i32, row, row + 1)
+    n = 10 if n_samples is None else int(n_samples)      # BNN.forward's default n_samples=10 (model_bnn.py:198)
+    rows, _ = net._rows(n, None)
+    pbar = eng.forward_probs_sum(x, rows[0], rows[1])
+    rdist.allreduce_sum_(pbar)
+    pbar *= 1.0 / n
+    g = eng.input_grad_sum(HEAD_GRAD_OF_MEAN, x, labels_i32, rows[0], rows[1], pbar=pbar)
+    rdist.allreduce_sum_(g)
+    return g          # the 1/S factor does not change sign(g)
+
+
+def _generic_input_grad(net, image, label, n_samples, avg_posterior):
+    """The reference's autograd route for non-BNN networks (adversarialAttacks.py:73-79)."""
+    image = image.detach().clone()
+    image.requires_grad = True
+    output = net.forward(inputs=image, n_samples=n_samples, avg_posterior=avg_posterior)
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(output, label)
+    net.zero_grad()
+    loss.backward()
+    return image.grad.data
+
+
+def _prep(net, image, label):
+    eng = net.engine()
+    x = torch.as_tensor(image).detach().to(device=eng.device, dtype=torch.float32).contiguous()
+    y = torch.as_tensor(label).to(device=eng.device).reshape(-1).to(torch.int32).contiguous()
+    return x, y
+
+
+def fgsm_attack(net, image, label, hyperparams=None, n_samples=None, avg_posterior=False):
+    """clamp(x + eps*sign(grad), 0, 1), eps = hyperparams["epsilon"] or 0.3 (adversarialAttacks.py:69-83).
+    `image` is [B, ch, h, w] (the reference passes B=1), `label` [B] class indices."""
+    epsilon = hyperparams["epsilon"] if hyperparams is not None else 0.3
+    if not isinstance(net, BNN):
+        grad = _generic_input_grad(net, image, label, n_samples, avg_posterior)
+        return torch.clamp(image.detach() + epsilon * grad.sign(), 0, 1)
+    x, y = _prep(net, image, label)
+    g = _bnn_input_grad(net, x, y, n_samples, avg_posterior)
+    return net.engine().fgsm_step(x.reshape(-1), g.reshape(-1), float(epsilon)).reshape(x.shape)
+
+
+def pgd_attack(net, image, label, hyperparams=None, n_samples=None, avg_posterior=False, iters=PGD_ITERS):
+    """Projected gradient ascent in the L-inf ball around the original image
+    (adversarialAttacks.py:86-108): (eps, alpha) = (hyperparams eps, 2/image.max()) or (0.5, 2/225),
+    `iters`=40 as hard-coded upstream; alpha is per image."""
+    if not isinstance(net, BNN):
+        if hyperparams is not None:
+            epsilon, alpha = hyperparams["epsilon"], 2 / image.max()
+        else:
+            epsilon, alpha = 0.5, 2 / 225
+        original_image = image.detach().clone()
+        image = original_image.clone()
+        for _ in range(iters):
+            grad = _generic_input_grad(net, image, label, n_samples, avg_posterior)
+            perturbed = image + alpha * grad.sign()
+            eta = torch.clamp(perturbed - original_image, min=-epsilon, max=epsilon)
+            image = torch.clamp(original_image + eta, min=0, max=1).detach()
+        return image
+    x0, y = _prep(net, image, label)
+    B = x0.shape[0]
+    if hyperparams is not None:
+        epsilon = float(hyperparams["epsilon"])
+        alpha = net.engine().pgd_alpha(x0.reshape(B, -1))
+    else:
+        epsilon = 0.5
+        alpha = torch.full((B,), 2 / 225, dtype=torch.float32, device=x0.device)
+    x = x0
+    for _ in range(iters):
+        g = _bnn_input_grad(net, x, y, n_samples, avg_posterior)
+        x = net.engine().pgd_step(x.reshape(B, -1), x0.reshape(B, -1), g.reshape(B, -1), alpha, epsilon).reshape(x0.shape)
+    return x
+
+
+ATTACK_BATCH = 8192     # images per device pass
+
+
+def attack(net, x_test, y_test, dataset_name, device, method, filename, savedir=None,
+           hyperparams=None, n_samples=None, avg_posterior=False):
+    """All test points at once (adversarialAttacks.py:111-143); returns [N, ch, h, w] on the device."""
+    print(f"\nProducing {method} attacks on {dataset_name}:")
+    labels = torch.as_tensor(y_test).argmax(-1)
+    adversarial_attack = []
+    for b0 in range(0, len(x_test), ATTACK_BATCH):
+        image = torch.as_tensor(x_test[b0:b0 + ATTACK_BATCH])
+        label = labels[b0:b0 + ATTACK_BATCH]
+        if not isinstance(net, BNN):
+            image, label = image.to(device), label.to(device)
+        if method == "fgsm":
+            perturbed_image = fgsm_attack(net=net, image=image, label=label, hyperparams=hyperparams,
+                                          n_samples=n_samples, avg_posterior=avg_posterior)
+        elif method == "pgd":
+            perturbed_image = pgd_attack(net=net, image=image, label=label, hyperparams=hyperparams,
+                                         n_samples=n_samples, avg_posterior=avg_posterior)
+        adversarial_attack.append(perturbed_image)
+    adversarial_attack = torch.cat(adversarial_attack)
+
+    path = TESTS + filename + "/" if savedir is None else TESTS + savedir + "/"
+    name = filename + "_" + str(method)
+    # (the reference also writes two PNG grids here through matplotlib, utils.py:276-290: plotting is out of scope)
+    name = name + "_attackSamp=" + str(n_samples) + "_attack.pkl" if n_samples else name + "_attack.pkl"
+    save_to_pickle(data=adversarial_attack, path=path, filename=name)
+    return adversarial_attack
+
+
+def load_attack(method, filename, savedir=None, n_samples=None, rel_path=TESTS):
+    path = TESTS + filename + "/" if savedir is None else TESTS + savedir + "/"
+    name = filename + "_" + str(method)
+    name = name + "_attackSamp=" + str(n_samples) + "_attack.pkl" if n_samples else name + "_attack.pkl"
+    return load_from_pickle(path=path + name)
+
+
+def attack_evaluation(net, x_test, x_attack, y_test, device, n_samples=None, batch_size=EVAL_BATCH):
+    """(original accuracy %, adversarial accuracy %, softmax robustness [N]) (adversarialAttacks.py:151-198)."""
+    print(f"\nEvaluating against the attacks", end="")
+    if n_samples:
+        print(f" with {n_samples} defence samples")
+    random.seed(0)
+    if not isinstance(net, BNN):
+        x_test, x_attack, y_test = x_test.to(device), x_attack.to(device), y_test.to(device)
+        outs, correct = [[], []], [0.0, 0.0]
+        with torch.no_grad():
+            for which, data in enumerate((x_test, x_attack)):
+                for b0 in range(0, len(data), batch_size):
+                    out = net.forward(data[b0:b0 + batch_size], n_samples)
+                    correct[which] += (out.argmax(-1) == y_test[b0:b0 + batch_size].argmax(-1)).sum().item()
+                    outs[which].append(out)
+        original_accuracy = 100 * correct[0] / len(x_test)
+        adversarial_accuracy = 100 * correct[1] / len(x_test)
+        print(f"\ntest accuracy = {original_accuracy}\tadversarial accuracy = {adversarial_accuracy}", end="\t")
+        return original_accuracy, adversarial_accuracy, softmax_robustness(torch.cat(outs[0]), torch.cat(outs[1]))
+
+    net.reseed(0)                                           # pyro.set_rng_seed(0), adversarialAttacks.py:161
+    eng = net.engine()
+    x_test = torch.as_tensor(x_test).to(device=eng.device, dtype=torch.float32)
+    x_attack = torch.as_tensor(x_attack).to(device=eng.device, dtype=torch.float32)
+    labels = torch.as_tensor(y_test).to(eng.device).argmax(-1).to(torch.int32).contiguous()
+    n = 10 if n_samples is None else int(n_samples)
+    counters = torch.zeros((2,), dtype=torch.int64, device=eng.device)
+    outs = [[], []]
+    with torch.no_grad():
+        for which, data in enumerate((x_test, x_attack)):
+            for b0 in range(0, len(data), batch_size):
+                out = net.forward(data[b0:b0 + batch_size], n)
+                eng.count_correct(out, labels[b0:b0 + batch_size], counters[which:which + 1])
+                outs[which].append(out)
+    original_correct, adversarial_correct = (float(v) for v in counters.tolist())
+    original_accuracy = 100 * original_correct / len(x_test)
+    adversarial_accuracy = 100 * adversarial_correct / len(x_test)
+    print(f"\ntest accuracy = {original_accuracy}\tadversarial accuracy = {adversarial_accuracy}", end="\t")
+    softmax_rob = softmax_robustness(torch.cat(outs[0]), torch.cat(outs[1]))
+    return original_accuracy, adversarial_accuracy, softmax_rob

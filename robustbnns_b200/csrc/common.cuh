@@ -1,0 +1,158 @@
+// Shared declarations for librbnn.so (see include/rbnn.h for the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rbnn.h"
+
+namespace rbnn {
+
+constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default (model_nn.py:68-69)
+
+void set_error(const char* fmt, ...);
+
+#define RBNN_CUDA(expr)                                                                 \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      rbnn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define RBNN_CHECK(cond, ...)          \
+  do {                                 \
+    if (!(cond)) {                     \
+      rbnn::set_error(__VA_ARGS__);    \
+      return 1;                        \
+    }                                  \
+  } while (0)
+
+#define RBNN_TRY(expr)        \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+// Offsets (in floats) of each state_dict tensor inside one bank row.
+struct ParamLayout {
+  // fc / fc2: w1 [H,D] b1 [H] (w2 [H,H] b2 [H])? wo [C,H] bo [C]
+  // conv    : cw1 [32,1,5,5] cb1 [32] cw2 [H,32,5,5] cb2 [H] wo [C,49H] bo [C]
+  int64_t w1 = 0, b1 = 0, w2 = 0, b2 = 0, wo = 0, bo = 0;
+  int64_t cw1 = 0, cb1 = 0, cw2 = 0, cb2 = 0;
+  int64_t P = 0;
+};
+
+}  // namespace rbnn
+
+// Derived, kernel-ready copies of the bank for the tcgen05 FC path (tc_fc.cu).
+struct TcBank {
+  int capacity = 0;
+  int mode = -1;            // precision the copies were built for
+  float* w1_hi = nullptr;   // [S, H, D]   K-major B operand of the forward GEMM
+  float* w1_lo = nullptr;
+  float* w1t_hi = nullptr;  // [S, D, H]   K-major B operand of the backward GEMM
+  float* w1t_lo = nullptr;
+  void* w1_bf = nullptr;    // bf16 variants
+  void* w1t_bf = nullptr;
+  uint8_t* dirty = nullptr; // host flags per row (derived copies stale)
+};
+
+struct rbnn_net {
+  int arch = 0, in_ch = 1, in_h = 28, in_w = 28, D = 784, H = 512, C = 10;
+  int device = 0;
+  int prec = RBNN_PREC_FP32;
+  rbnn::ParamLayout L;
+  // bank
+  int capacity = 0;
+  float* bank = nullptr;      // [capacity, P]
+  float* woutp = nullptr;     // conv only: [capacity, C, 49H] output weights permuted to (pos, h) order
+  float* sigma = nullptr;     // [P] scratch: softplus(rho) of the last sample_diag call
+  // workspace arena
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  size_t ws_budget = (size_t)1536 << 20;
+  int64_t launches = 0;
+  int sm_count = 148;
+  TcBank tc;
+  // optional per-kernel-class device timing (bench.py's roofline leg): event pairs on the launch stream
+  int timing = 0;
+  std::vector<cudaEvent_t> ev[3][2];   // [class][begin/end]; class 1 = first-layer forward GEMM, 2 = input-grad GEMM
+};
+
+namespace rbnn {
+
+int ws_reserve(rbnn_net* net, size_t bytes);
+
+struct Arena {
+  char* base;
+  size_t off = 0, cap;
+  Arena(rbnn_net* n) : base(n->ws), cap(n->ws_bytes) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// ---- gemm_simt.cu -----------------------------------------------------------------------
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_LEAKY = 2, EPI_MASK = 3 };
+
+struct GemmArgs {
+  const float* A; int64_t lda, sAz;      // A[z][m][k], k contiguous
+  const float* B; int64_t ldb, sBz;      // NT: B[z][n][k]   NN: B[z][k][n]
+  float* C; int64_t ldc, sCz;            // C[z][m][n]
+  const float* bias; int64_t sbz;        // bias[z][n]             (EPI_BIAS*)
+  const float* mask; int64_t ldm, sMz;   // activation[z][m][n]    (EPI_MASK: acc *= act>0 ? 1 : slope)
+  int M, N, K, Z;
+  int epi;
+  int b_kn;        // 0 = NT, 1 = NN
+  int reduce_z;    // 1: C[m][n] (+)= sum_z ...  (C is a single [M,N] matrix)
+  int accumulate;  // reduce_z only: add to what C already holds
+  int tag;         // timing class (0 = untimed)
+};
+int timing_begin(rbnn_net* net, int cls, cudaStream_t st);
+int timing_end(rbnn_net* net, int cls, cudaStream_t st);
+int gemm_simt(rbnn_net* net, const GemmArgs& a, cudaStream_t st);
+
+// ---- head.cu ----------------------------------------------------------------------------
+int head_probs_accumulate(rbnn_net* net, const float* logits, int Z, int B, int C, float* out_sum,
+                          cudaStream_t st);
+int head_dlogits(rbnn_net* net, int head, const float* logits, const int32_t* labels, const float* pbar,
+                 int Z, int B, int C, float* dlogits, cudaStream_t st);
+
+// ---- sampler.cu -------------------------------------------------------------------------
+int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
+                int64_t stride, int s0, int count, cudaStream_t st);
+int conv_permute_wout(rbnn_net* net, int s0, int count, cudaStream_t st);
+
+// ---- conv.cu ----------------------------------------------------------------------------
+int conv1_pool_fwd(rbnn_net* net, const float* x, const float* bank, int s0, int Z, int B, float* p1,
+                   uint8_t* idx1, cudaStream_t st);
+int im2col_conv2(rbnn_net* net, const float* p1, int ZB, float* col, cudaStream_t st);
+int pool2_fwd(rbnn_net* net, const float* a2, int ZB, int H, float* p2, cudaStream_t st);
+int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, float* dz2, cudaStream_t st);
+int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, float* g1, cudaStream_t st);
+int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,
+                  float* dx_sum, int accumulate, cudaStream_t st);
+
+// ---- attack.cu --------------------------------------------------------------------------
+int scale_inplace(rbnn_net* net, float* p, float scale, int64_t n, cudaStream_t st);
+int add_inplace(rbnn_net* net, float* dst, const float* src, int64_t n, cudaStream_t st);
+
+// ---- tc_fc.cu (tcgen05 FC path) -----------------------------------------------------------
+int tc_supported(const rbnn_net* net);
+int tc_bank_refresh(rbnn_net* net, int s0, int s1, cudaStream_t st);
+int tc_fc_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_t* d_labels, int B, int s0, int s1,
+                         const float* d_pbar, float* d_out_sum, cudaStream_t st);
+int tc_fc_forward_probs_sum(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum,
+                            cudaStream_t st);
+
+}  // namespace rbnn

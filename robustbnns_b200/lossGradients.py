@@ -1,0 +1,101 @@
+"""Drop-in for the reference's `lossGradients.py` hot path (lossGradients.py:20-76).
+
+`loss_gradient` / `loss_gradients` keep the reference's signatures, return types,
+prints and pickle side effect; the per-image x per-sample Python loop
+(lossGradients.py:29-38, :56-60) is replaced by one batched, sample-major
+evaluation on the GPU: sum_s dCE(softmax(softmax(f_s(x))), y)/dx over the bank rows
+of seeds 0..S-1, one allreduce of the [B, D] partial sums across ranks, times 1/S.
+"""
+import numpy as np
+import torch
+
+from . import dist as rdist
+from ._lib import HEAD_MEAN_OF_GRADS
+from .savedir import DATA
+from .utils import load_from_pickle, save_to_pickle
+
+DEBUG = False
+MAX_BATCH = 16384     # inputs per device pass
+
+
+def expected_loss_gradients(net, images, labels, n_samples):
+    """[B, *input_shape] tensor on the device: (1/S) sum_{s<S} dL_s/dx for a batch
+    (`labels` are class indices).  Sample s is seed s (lossGradients.py:33)."""
+    eng = net.engine()
+    images = torch.as_tensor(images).to(device=eng.device, dtype=torch.float32)
+    labels = torch.as_tensor(labels).to(device=eng.device, dtype=torch.int32)
+    outs = []
+    rows, _ = net._rows(n_samples, list(range(n_samples)))
+    for b0 in range(0, images.shape[0], MAX_BATCH):
+        x = images[b0:b0 + MAX_BATCH].contiguous()
+        g = eng.input_grad_sum(HEAD_MEAN_OF_GRADS, x, labels[b0:b0 + MAX_BATCH].contiguous(), rows[0], rows[1])
+        rdist.allreduce_sum_(g)
+        outs.append((g * (1.0 / float(n_samples))).reshape(x.shape))
+    return torch.cat(outs) if len(outs) != 1 else outs[0]
+
+
+def loss_gradient(net, image, label, n_samples=None):
+    """One image [ch,h,w] + one-hot label -> expected loss gradient [ch,h,w] (lossGradients.py:20-50)."""
+    if not n_samples:
+        # the reference's deterministic branch dereferences undefined names (lossGradients.py:43)
+        raise NameError("name 'net_copy' is not defined")
+    image = torch.as_tensor(image).unsqueeze(0)
+    label = torch.as_tensor(label).argmax(-1).unsqueeze(0)
+    return expected_loss_gradients(net, image, label, n_samples)[0]
+
+
+def loss_gradients(net, data_loader, device, filename, savedir, n_samples=None):
+    print(f"\n === Loss gradients on {len(data_loader.dataset)} input images:")
+    images, labels = [], []
+    for x_batch, y_batch in data_loader:
+        images.append(torch.as_tensor(x_batch))
+        labels.append(torch.as_tensor(y_batch).argmax(-1))
+    images, labels = torch.cat(images), torch.cat(labels)
+    if not n_samples:
+        raise NameError("name 'net_copy' is not defined")
+    grads = expected_loss_gradients(net, images, labels, n_samples)
+    print(f"\nmin = {grads.min():.4f} \t max = {grads.max():.4f}")
+    grads = grads.cpu().detach().numpy().squeeze()
+    save_loss_gradients(grads, n_samples, filename, savedir)
+    return grads
+
+
+def save_loss_gradients(loss_gradients, n_samples, filename, savedir, relpath=DATA):
+    save_to_pickle(data=loss_gradients, path=relpath + savedir,
+                   filename=filename + "_samp=" + str(n_samples) + "_lossGrads.pkl")
+
+
+def load_loss_gradients(n_samples, filename, savedir, relpath=DATA):
+    path = relpath + savedir + filename + "_samp=" + str(n_samples) + "_lossGrads.pkl"
+    return load_from_pickle(path=path)
+
+
+def compute_vanishing_norms_idxs(loss_gradients, n_samples_list, norm):
+    """Indices of images whose gradient norm is non-increasing along `n_samples_list`
+    (lossGradients.py:78-127), vectorised; prints the reference's three summary lines."""
+    loss_gradients = np.asarray(loss_gradients)
+    if loss_gradients.shape[1] != len(n_samples_list):
+        raise ValueError("Second dimension should equal the length of `n_samples_list`")
+    flat = loss_gradients.reshape(loss_gradients.shape[0], loss_gradients.shape[1], -1)
+    if norm == "linfty":
+        norms = np.abs(flat).max(-1)
+    elif norm == "l2":
+        norms = np.sqrt((flat.astype(np.float64) ** 2).sum(-1)).astype(flat.dtype)
+    else:
+        raise ValueError("norm must be 'linfty' or 'l2'")
+    nonnull = norms[:, 0] != 0.0
+    # running minimum semantics of the reference: a step counts when it does not exceed the last accepted norm
+    cur = norms[:, 0].copy()
+    count = np.zeros(len(norms), dtype=np.int64)
+    for j in range(norms.shape[1]):
+        ok = norms[:, j] <= cur
+        cur = np.where(ok, norms[:, j], cur)
+        count += ok
+    vanishing = nonnull & (count == norms.shape[1])
+    idxs = [int(i) for i in np.nonzero(vanishing)[0]]
+    n = len(loss_gradients)
+    print(f"vanishing gradients = {vanishing.sum()/n} %")
+    print(f"increasing gradients = {(nonnull & ~vanishing).sum()/n} %")
+    print(f"null gradients = {(~nonnull).sum()/n} %")
+    print("\nvanishing_gradients_idxs = ", idxs)
+    return idxs

@@ -1,0 +1,201 @@
+"""Host-side logic of the drop-in classes, exercised on CPU with the oracle-backed test double
+(tests/helpers.py::OracleEngine) in place of the CUDA engine: sample placement, seeds rules,
+fresh-draw bookkeeping, 2-rank gloo sharding + allreduce, result formats."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import oracle as orc
+from tests.helpers import Case, OracleEngine, rel_err
+
+
+def _bnn(case, inference="svi", n_samples=None):
+    from robustbnns_b200.model_bnn import BNN
+    eng = OracleEngine(case.arch, case.input_shape, case.hidden, case.n_classes, case.dataset)
+    return BNN(case.dataset, case.hidden, "leaky", case.arch, inference, 1, 0.01, n_samples, 5,
+               case.input_shape, case.n_classes, engine=eng)
+
+
+def test_forward_seed_rules_and_explicit_bank():
+    c = Case("svi_fc16_mnist")
+    S = c.bank.shape[0]
+    bnn = _bnn(c)
+    bnn.set_guide(c.t("loc"), c.t("rho"))
+    bnn.set_posterior_samples(c.bank)
+    with pytest.raises(ValueError):
+        bnn.forward(c.x, n_samples=2, seeds=[0, 1, 2])                # model_bnn.py:200-202
+    out = bnn.forward(c.x, n_samples=S, seeds=list(range(S)))
+    assert rel_err(out, c.t("probs_seeded")) < 1e-5
+    out = bnn.forward(c.x, n_samples=2, seeds=[2, 0])                 # arbitrary seeds -> gathered rows
+    ref = orc.bnn_forward(c.net, c.layout, c.bank, c.x, [2, 0])
+    assert rel_err(out, ref) < 1e-6
+    with pytest.raises(IndexError):
+        bnn.forward(c.x, n_samples=S + 1)
+    logits = bnn.forward(c.x, n_samples=S, avg_posterior=True)
+    assert rel_err(logits, c.t("logits_avg")) < 1e-5
+
+
+def test_svi_philox_prefix_and_fresh_draws():
+    c = Case("svi_fc2_32_moons")
+    bnn = _bnn(c)
+    loc, rho = c.t("loc"), c.t("rho")
+    bnn.set_guide(loc, rho)
+    eng = bnn.engine()
+    bnn.forward(c.x, n_samples=3, seeds=[0, 1, 2])
+    bnn.forward(c.x, n_samples=5, seeds=list(range(5)))
+    # seeds 0..4 each generated exactly once, global index == seed, key == rng_seed
+    assert sorted(g for (k, g, _) in eng.sampled) == [0, 1, 2, 3, 4]
+    assert all(k == bnn.rng_seed for (k, _, _) in eng.sampled)
+    assert torch.equal(eng.bank[:5], orc.philox_bank(loc, rho, bnn.rng_seed, range(5)))
+    n0 = len(eng.sampled)
+    a = bnn.forward(c.x, n_samples=4)          # unseeded: fresh draws, different every call
+    b = bnn.forward(c.x, n_samples=4)
+    assert not torch.equal(a, b)
+    fresh = eng.sampled[n0:]
+    assert len(fresh) == 8 and len({g for (_, g, _) in fresh}) == 8
+    assert all(g >= (1 << 31) for (_, g, _) in fresh)
+    bnn.reseed(0)
+    a2 = bnn.forward(c.x, n_samples=4)         # reseed(0) replays the stream (pyro.set_rng_seed(0))
+    assert torch.equal(a, a2)
+
+
+def test_loss_gradients_and_attacks_through_the_drop_in(tmp_path, monkeypatch):
+    from robustbnns_b200 import adversarialAttacks as aa
+    from robustbnns_b200 import lossGradients as lg
+    monkeypatch.chdir(tmp_path)
+    c = Case("hmc_fc2_32_moons")
+    S = c.bank.shape[0]
+    bnn = _bnn(c, "hmc", S)
+    bnn.set_posterior_samples(c.bank)
+    g = torch.stack([lg.loss_gradient(bnn, c.x[i], c.y[i], n_samples=S) for i in range(len(c.x))])
+    assert rel_err(g, c.t("loss_gradient")) < 1e-5
+    loader = torch.utils.data.DataLoader(list(zip(c.x, c.y)), batch_size=4)
+    out = lg.loss_gradients(bnn, loader, "cpu", "f", "f/", n_samples=S)
+    assert isinstance(out, np.ndarray) and out.shape == (len(c.x), 2)             # squeezed (lossGradients.py:66)
+    with open(os.path.join("data", "f", "f_samp=%d_lossGrads.pkl" % S), "rb") as f:
+        assert np.array_equal(pickle.load(f), out)
+    assert np.array_equal(lg.load_loss_gradients(S, "f", "f/"), out)
+    with pytest.raises(NameError):
+        lg.loss_gradient(bnn, c.x[0], c.y[0])                                     # broken upstream branch
+    # autograd through forward: what the reference's fgsm does (adversarialAttacks.py:73-79)
+    x = c.x.clone().requires_grad_(True)
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(bnn.forward(x, n_samples=S), c.labels)
+    loss.backward()
+    ref = orc.attack_gradient(c.net, c.layout, c.bank, c.x, c.labels, range(S))
+    assert rel_err(x.grad, ref) < 1e-5
+
+
+def test_vanishing_norms_matches_reference_loop():
+    from robustbnns_b200.lossGradients import compute_vanishing_norms_idxs
+    rng = np.random.RandomState(0)
+    g = rng.randn(40, 4, 5, 5).astype(np.float32) * np.array([1.0, 0.7, 0.5, 0.3], np.float32)[None, :, None, None]
+    g[3] = 0.0
+    for norm in ("linfty", "l2"):
+        expect = []
+        for i, ig in enumerate(g):                      # restatement of lossGradients.py:90-117
+            nrm = (lambda a: np.max(np.abs(a))) if norm == "linfty" else np.linalg.norm
+            cur = nrm(ig[0])
+            if cur != 0.0:
+                cnt = 0
+                for j in range(4):
+                    new = nrm(ig[j])
+                    if new <= cur:
+                        cur = new
+                        cnt += 1
+                if cnt == 4:
+                    expect.append(i)
+        assert compute_vanishing_norms_idxs(g, [1, 10, 50, 100], norm) == expect
+    with pytest.raises(ValueError):
+        compute_vanishing_norms_idxs(g, [1, 10], "l2")
+
+
+def test_save_load_roundtrip_reference_formats(tmp_path):
+    c = Case("svi_fc16_mnist")
+    bnn = _bnn(c)
+    bnn.set_guide(c.t("loc"), c.t("rho"))
+    bnn.save(rel_path=str(tmp_path) + "/")
+    state = torch.load(os.path.join(tmp_path, bnn.name, bnn.name + "_weights.pt"), weights_only=False)
+    assert set(state.keys()) == {"params", "constraints"}                          # Pyro param-store layout
+    assert "model.1.weight_loc" in state["params"] and "model.3.bias_scale" in state["params"]
+    b2 = _bnn(c)
+    b2.load("cpu", rel_path=str(tmp_path) + "/")
+    assert torch.equal(b2._loc, bnn._loc) and torch.equal(b2._rho, bnn._rho)
+    h = Case("hmc_fc16_fmnist")
+    S = h.bank.shape[0]
+    hb = _bnn(h, "hmc", S)
+    hb.set_posterior_samples(h.bank)
+    hb.save(rel_path=str(tmp_path) + "/")
+    sd = torch.load(os.path.join(tmp_path, hb.name, hb.name + "_weights_1.pt"), weights_only=False)
+    assert list(sd.keys()) == ["model.1.weight", "model.1.bias", "model.3.weight", "model.3.bias"]
+    h2 = _bnn(h, "hmc", S)
+    h2.load("cpu", rel_path=str(tmp_path) + "/")
+    assert torch.equal(h2._bank_host, h.bank)
+    h3 = _bnn(h, "hmc", S + 1)
+    with pytest.raises(AttributeError):
+        h3.load("cpu", rel_path=str(tmp_path) + "/", filename=hb.name + "_weights")
+
+
+def _rank_main(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from robustbnns_b200 import adversarialAttacks as aa
+        from robustbnns_b200 import lossGradients as lg
+        torch.set_num_threads(1)
+        c = Case("hmc_fc16_fmnist")
+        S = c.bank.shape[0]
+        bnn = _bnn(c, "hmc", S)
+        bnn.set_posterior_samples(c.bank)
+        assert bnn.engine().bank.shape[0] >= 1 and bnn._pin_rows == len(range(rank, S, world))
+        probs = bnn.forward(c.x, n_samples=S)
+        grads = lg.expected_loss_gradients(bnn, c.x, c.labels, S)
+        adv = aa.fgsm_attack(bnn, c.x, c.labels, hyperparams={"epsilon": float(c.z["eps"])}, n_samples=S)
+        s = Case("svi_fc2_32_moons")
+        sb = _bnn(s)
+        sb.set_guide(s.t("loc"), s.t("rho"))
+        sp = sb.forward(s.x, n_samples=5, seeds=list(range(5)))
+        fr = sb.forward(s.x, n_samples=3)
+        pgd = aa.pgd_attack(bnn, c.x, c.labels, hyperparams=None, n_samples=S, iters=3)
+        ev = aa.attack_evaluation(bnn, c.x, c.t("fgsm_hyper_adv"), c.y, "cpu", n_samples=S)
+        q.put((rank, probs, grads, adv, sp, fr, pgd, ev[:2], ev[2]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_equals_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    c = Case("hmc_fc16_fmnist")
+    S = c.bank.shape[0]
+    sched = lambda call: range(S)  # noqa: E731
+    pgd_ref = orc.pgd_attack(c.net, c.layout, c.bank, c.x, c.labels, sched, None, iters=3)
+    for (_, probs, grads, adv, sp, fr, pgd, acc, rob) in res:
+        assert rel_err(probs, c.t("probs")) < 1e-5
+        assert rel_err(grads, c.t("loss_gradient")) < 1e-5
+        assert float((adv - c.t("fgsm_hyper_adv")).abs().max()) <= 1e-6
+        assert float((pgd - pgd_ref).abs().max()) <= 1e-6
+        assert list(acc) == c.z["fgsm_hyper_eval"].tolist()
+        assert float((rob - c.t("fgsm_hyper_rob")).abs().max()) <= 1e-6
+    # both ranks hold identical reduced results; SVI seeded/fresh draws do not depend on the sharding
+    assert torch.equal(res[0][4], res[1][4]) and torch.equal(res[0][5], res[1][5])
+    s = Case("svi_fc2_32_moons")
+    sb = _bnn(s)
+    sb.set_guide(s.t("loc"), s.t("rho"))
+    assert rel_err(res[0][4], sb.forward(s.x, n_samples=5, seeds=list(range(5)))) < 1e-6
+    assert rel_err(res[0][5], sb.forward(s.x, n_samples=3)) < 1e-6
