@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's headline configuration.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): MNIST-shaped FC BNN 784-512-10 (LeakyReLU), VI guide with
+random parameters, expected loss gradients of 10 000 synthetic 28x28 inputs over 1 000 posterior
+samples.  One step = one full evaluation = 1e7 (posterior sample x input) gradient units.  The
+1 000 samples are sharded over the N ranks (fixed total work => "strong" scaling) and the [B, D]
+partial sums are all-reduced once per step (NCCL).
+
+Our arm prints one JSON line with: value (units/s, inputs resident in HBM, CUDA-event timed, max
+over ranks), e2e (same metric through the public Python API with pinned HOST buffers: H2D copy of
+the inputs and D2H read of the gradients inside the timed region), roofline (dominant kernel,
+timed with CUDA events on its launch stream inside the timed region), cpu_baseline (the oracle
+running the reference's loop order on the box's host cores, bounded sample), clocks.
+
+The reference arm times the reference's own CPU algorithm (per image -> per sample -> re-draw all
+weights -> batch-1 forward + full backward, lossGradients.py:29-38 + model_bnn.py:121-130) as
+restated in oracle/oracle.py, on the host cores, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ARCH, SHAPE, HIDDEN, NCLS = "fc", (1, 28, 28), 512, 10
+FLOP_PER_UNIT = 1626112            # fwd 813 056 + input-only bwd 813 056
+FLOP_FWD_GEMM = 2 * 784 * 512      # per unit, first-layer forward GEMM
+FLOP_BWD_GEMM = 2 * 512 * 784      # per unit, input-gradient GEMM
+METRIC = "posterior-sample x input loss-gradients per second (MNIST FC BNN 784-512-10)"
+UNIT = "grads/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(int(float(r[0])))
+                mx = max(mx, int(float(r[1])))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_units_per_s(n_img, n_samp, threads=None):
+    """The reference's CPU algorithm (loop order R1, weights re-drawn per unit, full backward)."""
+    import torch
+    from oracle import oracle as orc
+    if threads:
+        torch.set_num_threads(threads)
+    net = orc.build_net(ARCH, SHAPE, HIDDEN, NCLS)
+    layout = orc.param_layout(net)
+    loc, rho = orc.scaled_guide_params(layout, seed=1)
+    x, y = orc.synthetic_inputs(n_img, SHAPE, NCLS, seed=0)
+    t0 = time.perf_counter()
+    orc.loss_gradients_reference_order(net, layout, loc, rho, x, y, n_samp)
+    dt = time.perf_counter() - t0
+    return n_img * n_samp / dt, dt
+
+
+def run_reference(args, rank, world):
+    import torch
+    if rank != 0:
+        return
+    n_img, n_samp = 8, 8
+    for _ in range(args.warmup):
+        reference_units_per_s(2, 2)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_units_per_s(n_img, n_samp)
+    dt = time.perf_counter() - t0
+    value = args.steps * n_img * n_samp / dt
+    sample = "%d inputs x %d posterior samples per step (of 10000 x 1000), reference loop order" % (n_img, n_samp)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, world):
+    return {"workload": "BASELINE configs[1]: expected loss gradients, fc 784-512-10 LeakyReLU, VI guide "
+                        "(loc~N(0,1/fan_in), rho~N(-5,1)), %d synthetic 28x28 inputs x %d posterior samples"
+                        % (args.inputs, args.samples),
+            "inputs": args.inputs, "posterior_samples": args.samples, "precision": args.prec,
+            "parallelism": "posterior samples sharded over %d rank(s), one allreduce of [B,784] fp32 per step" % world,
+            "l2": "per-step working set (%.1f GB of sampled weights per rank) exceeds the 126 MB L2"
+                  % (args.samples / world * 407050 * 4 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--prec", default=os.environ.get("RBNN_BENCH_PREC", "auto"),
+                    choices=["auto", "fp32", "tf32x3", "bf16"])
+    ap.add_argument("--inputs", type=int, default=10000)
+    ap.add_argument("--samples", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from robustbnns_b200 import lossGradients as lg
+    from robustbnns_b200.model_bnn import BNN
+    from robustbnns_b200._lib import HEAD_MEAN_OF_GRADS
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- synthetic problem (no oracle involved on this arm) --------------------------------------
+    import math
+    B, S = args.inputs, args.samples
+    g = torch.Generator().manual_seed(1)
+    bnn = BNN("mnist", HIDDEN, "leaky", ARCH, "svi", 1, 0.01, None, None, SHAPE, NCLS)
+    locs, rhos = [], []
+    fan = 784
+    for key, shp in bnn.basenet.layout:
+        n = 1
+        for v in shp:
+            n *= v
+        if len(shp) > 1:
+            fan = shp[1]
+        locs.append(torch.randn(n, generator=g) / math.sqrt(fan))
+        rhos.append(torch.randn(n, generator=g) - 5.0)
+    bnn.set_guide(torch.cat(locs), torch.cat(rhos))
+    gx = torch.Generator().manual_seed(0)
+    x_host = torch.rand((B, *SHAPE), generator=gx).pin_memory()
+    y_host = torch.randint(0, NCLS, (B,), generator=gx).pin_memory()
+    out_host = torch.empty((B, *SHAPE)).pin_memory()
+    eng = bnn.engine()
+    prec = args.prec
+    if prec == "auto":
+        prec = "fp32"
+        try:
+            eng.set_precision("tf32x3")
+            prec = "tf32x3"
+        except Exception as e:
+            log("tcgen05 engine unavailable, using the CUDA-core engine:", e)
+    eng.set_precision(prec)
+    args.prec = prec
+
+    x_dev = x_host.to(dev)
+    y_dev = y_host.to(dev).to(torch.int32)
+    rows, _ = bnn._rows(S, list(range(S)))            # K-sample: this rank's share of seeds 0..S-1 -> HBM bank
+    torch.cuda.synchronize()
+    local_S = rows[1] - rows[0]
+
+    def step_resident():
+        gsum = eng.input_grad_sum(HEAD_MEAN_OF_GRADS, x_dev, y_dev, rows[0], rows[1])
+        if world > 1:
+            dist.all_reduce(gsum)
+        gsum *= 1.0 / S
+        return gsum
+
+    def step_e2e():
+        gr = lg.expected_loss_gradients(bnn, x_host, y_host, S)     # public API: H2D inside
+        out_host.copy_(gr, non_blocking=True)                        # D2H read of the result
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_clocks=False):
+        barrier()
+        sampler = None
+        if with_clocks and rank == 0:
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            time.sleep(0.3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop() if sampler else None
+        return float(ms.item()), clocks
+
+    for _ in range(args.warmup):
+        step_resident()
+    eng.timing_read(1), eng.timing_read(2)
+    launches0 = eng.launch_count
+    eng.timing_enable(True)
+    ms, clocks = timed(step_resident, args.steps, with_clocks=True)
+    eng.timing_enable(False)
+    launches = eng.launch_count - launches0
+    fwd_ms, fwd_n = eng.timing_read(1)
+    bwd_ms, bwd_n = eng.timing_read(2)
+    units = float(B) * S * args.steps
+    value = units / (ms * 1e-3)
+
+    step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+    e2e_value = units / (e2e_ms * 1e-3)
+
+    pk, pk_kind = peaks()
+    local_units = float(B) * local_S * args.steps
+    if bwd_ms >= fwd_ms:
+        kname, kms, kn, kflop = "input-gradient GEMM (dX += dZ1_s . W1_s over samples)", bwd_ms, bwd_n, FLOP_BWD_GEMM
+    else:
+        kname, kms, kn, kflop = "first-layer forward GEMM (+bias+LeakyReLU)", fwd_ms, fwd_n, FLOP_FWD_GEMM
+    roofline = None
+    if kms > 0:
+        achieved = local_units * kflop / (kms * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(prec)
+        roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": pk_kind + " bf16 sustained",
+                    "launches": int(kn), "avg_launch_ms": kms / max(kn, 1),
+                    "step_share": kms / ms, "other_class_ms": (fwd_ms if bwd_ms >= fwd_ms else bwd_ms),
+                    "whole_step_tflops": value * FLOP_PER_UNIT / world / 1e12}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_img, n_samp = 16, 32
+        v, dt = reference_units_per_s(n_img, n_samp)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d inputs x %d samples of the same workload in the reference's loop order "
+                         "(%.1f s; cost is linear in inputs x samples)" % (n_img, n_samp, dt)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32" if prec != "bf16" else "bf16",
+                "data": "synthetic", "config": config_dict(args, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
+                        "d2h_bytes_per_step": int(out_host.numel() * 4)},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "engine": prec}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -253,6 +253,46 @@ def loss_gradients_r1(net, layout, bank, images, labels_onehot, n_samples) -> np
     return torch.stack(out).cpu().detach().numpy().squeeze()
 
 
+def loss_gradients_reference_order(net: _Net, layout, loc: torch.Tensor, rho: torch.Tensor,
+                                   images: torch.Tensor, labels_onehot: torch.Tensor, n_samples: int):
+    """The reference's full CPU cost model for an SVI BNN, used as the timed CPU baseline:
+    for every image, for every sample i: set_rng_seed(i), the guide's two wasted randn_like per key,
+    a reparameterised draw of ALL weights from (loc, softplus(scale)) that stay attached to the
+    autograd graph (the params require grad in Pyro), deepcopy of the base net by random_module, a
+    batch-1 forward, CE on probabilities and a FULL backward (weight-side gradients included)
+    -- lossGradients.py:29-38,56-60 + model_bnn.py:121-136,222-226."""
+    loc = loc.clone().requires_grad_(True)
+    rho = rho.clone().requires_grad_(True)
+    out = []
+    for n in range(len(images)):
+        image = images[n].unsqueeze(0)
+        label = labels_onehot[n].argmax(-1).unsqueeze(0)
+        grads = []
+        for i in range(n_samples):
+            x_copy = copy.deepcopy(image)
+            x_copy.requires_grad = True
+            torch.manual_seed(i)
+            weights, off = {}, 0
+            for key, shp in layout:
+                torch.randn(shp)
+                torch.randn(shp)
+            net_copy = copy.deepcopy(net)
+            for key, shp in layout:
+                cnt = int(np.prod(shp))
+                mu = loc[off:off + cnt].reshape(shp)
+                sd = softplus(rho[off:off + cnt].reshape(shp))
+                weights[key] = torch.distributions.Normal(mu, sd).rsample()
+                off += cnt
+            output = nnf.softmax(net_logits(net_copy, weights, x_copy), dim=-1)
+            output = torch.stack([output]).mean(0)
+            loss = torch.nn.CrossEntropyLoss()(output, label)
+            loc.grad = rho.grad = None
+            loss.backward()
+            grads.append(copy.deepcopy(x_copy.grad.data[0]))
+        out.append(torch.stack(grads, 0).mean(0))
+    return torch.stack(out)
+
+
 def expected_loss_gradients(net: _Net, layout, bank: torch.Tensor, x: torch.Tensor,
                             labels: torch.Tensor, sample_ids: Sequence[int],
                             dtype=torch.float32) -> torch.Tensor:

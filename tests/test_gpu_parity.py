@@ -1,0 +1,258 @@
+"""Parity of the CUDA path (through the C ABI / the drop-in classes) against the oracle and the
+golden vectors the reference's own code produced.  Needs a B200: run with `-m gpu`.
+
+Tolerances (BASELINE.json north_star): expected gradients / probabilities rel <= 1e-4 in the
+max-norm relative to max|ref| (fp32 oracle, TF32 off; fp64 oracle as tie-breaker); adversarial
+examples equal within 1e-6 except measure-zero sign ties; accuracy counts bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests.helpers import HMC_CASES, SVI_CASES, Case, rel_err
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+def _bnn(case, inference="svi", n_samples=None):
+    from robustbnns_b200.model_bnn import BNN
+    return BNN(case.dataset, case.hidden, "leaky", case.arch, inference, 1, 0.01, n_samples, 5,
+               case.input_shape, case.n_classes)
+
+
+def _mismatch_fraction(a, b, tol=1e-6):
+    return float(((a.cpu() - b.cpu()).abs() > tol).float().mean())
+
+
+# ------------------------------------------------------------------ golden vectors (reference code) ----
+@pytest.mark.parametrize("name", SVI_CASES)
+def test_golden_svi(name, tmp_path, monkeypatch):
+    from robustbnns_b200 import lossGradients as lg
+    monkeypatch.chdir(tmp_path)
+    c = Case(name)
+    S = c.bank.shape[0]
+    bnn = _bnn(c)
+    bnn.set_guide(c.t("loc"), c.t("rho"))
+    bnn.set_posterior_samples(c.bank)          # seed i == row i: the draws the reference made
+    out = bnn.forward(c.x, n_samples=S, seeds=list(range(S)))
+    assert out.is_cuda and out.shape == (len(c.x), c.n_classes)
+    assert rel_err(out.cpu(), c.t("probs_seeded")) < REL
+    assert rel_err(bnn.forward(c.x, n_samples=S, avg_posterior=True).cpu(), c.t("logits_avg")) < REL
+    g = torch.stack([lg.loss_gradient(bnn, c.x[i], c.y[i], n_samples=S) for i in range(len(c.x))])
+    assert rel_err(g.cpu(), c.t("loss_gradient")) < REL
+    loader = torch.utils.data.DataLoader(list(zip(c.x, c.y)), batch_size=2)
+    arr = lg.loss_gradients(bnn, loader, "cuda", "f", "f/", n_samples=S)
+    assert arr.shape == c.z["loss_gradients_np"].shape and rel_err(arr, c.z["loss_gradients_np"]) < REL
+    loader = torch.utils.data.DataLoader(list(zip(c.x, c.y)), batch_size=2)
+    assert bnn.evaluate(loader, "cuda", n_samples=S) == float(c.z["evaluate_acc"])
+    # unseeded SVI attack replayed on the draws the reference consumed, image by image
+    from robustbnns_b200 import adversarialAttacks as aa
+    fresh = c.t("fresh_bank")
+    hyper = {"epsilon": float(c.z["fgsm_fresh_eps"])}
+    advs = []
+    for i in range(len(c.x)):
+        bnn.set_posterior_samples(fresh[i * S:(i + 1) * S])
+        advs.append(aa.fgsm_attack(bnn, c.x[i:i + 1], c.labels[i:i + 1], hyperparams=hyper, n_samples=S))
+    assert _mismatch_fraction(torch.cat(advs), c.t("fgsm_fresh")) <= 1e-3
+
+
+@pytest.mark.parametrize("name", HMC_CASES)
+def test_golden_hmc_attacks_and_evaluation(name, tmp_path, monkeypatch):
+    from robustbnns_b200 import adversarialAttacks as aa
+    from robustbnns_b200 import lossGradients as lg
+    monkeypatch.chdir(tmp_path)
+    c = Case(name)
+    S = c.bank.shape[0]
+    bnn = _bnn(c, "hmc", S)
+    bnn.set_posterior_samples(c.bank)
+    assert rel_err(bnn.forward(c.x, n_samples=S).cpu(), c.t("probs")) < REL
+    g = lg.expected_loss_gradients(bnn, c.x, c.labels, S)
+    assert rel_err(g.cpu(), c.t("loss_gradient")) < REL
+    hyper = {"epsilon": float(c.z["eps"])}
+    for method in ("fgsm", "pgd"):
+        for hname, h in (("hyper", hyper), ("default", None)):
+            adv = aa.attack(net=bnn, x_test=c.x, y_test=c.y, dataset_name=c.dataset, device="cuda",
+                            method=method, filename="a", savedir="a", hyperparams=h, n_samples=S)
+            ref = c.t(f"{method}_{hname}_adv")
+            assert adv.is_cuda and adv.shape == ref.shape
+            assert _mismatch_fraction(adv, ref) <= 2e-3, (method, hname)
+            o, a, rob = aa.attack_evaluation(net=bnn, x_test=c.x, x_attack=ref, y_test=c.y, device="cuda",
+                                             n_samples=S)
+            assert [o, a] == c.z[f"{method}_{hname}_eval"].tolist()          # counts bit-exact
+            assert float((rob.cpu() - c.t(f"{method}_{hname}_rob")).abs().max()) <= 1e-6
+            loaded = aa.load_attack(method, "a", savedir="a", n_samples=S)
+            assert torch.equal(loaded.cpu(), adv.cpu())
+
+
+# ------------------------------------------------------------------ oracle at larger sizes -------------
+def _problem(arch, input_shape, hidden, n_classes, B, S, dataset="mnist", seed=5):
+    net = orc.build_net(arch, input_shape, hidden, n_classes, dataset_name=dataset)
+    layout = orc.param_layout(net)
+    loc, rho = orc.scaled_guide_params(layout, seed=seed, rho_mean=-4.0)
+    g = torch.Generator().manual_seed(seed + 1)
+    bank = loc + orc.softplus(rho) * torch.randn((S, loc.numel()), generator=g)
+    x, y = orc.synthetic_inputs(B, input_shape, n_classes, seed=seed + 2)
+    return net, layout, loc, rho, bank, x, y.argmax(-1)
+
+
+CONFIGS = [
+    ("fc", (1, 28, 28), 512, 10, 200, 6, "mnist"),        # headline architecture
+    ("fc", (1, 28, 28), 64, 10, 7, 10, "mnist"),          # ragged batch
+    ("fc2", (1, 28, 28), 128, 10, 130, 5, "mnist"),
+    ("fc2", (1, 2, 1), 128, 2, 100, 100, "half_moons"),   # BASELINE config 1: 100 points x 100 samples
+    ("fc2", (1, 2, 1), 512, 2, 100, 20, "half_moons"),
+    ("conv", (1, 28, 28), 32, 10, 9, 3, "mnist"),
+    ("conv", (1, 28, 28), 512, 10, 4, 2, "mnist"),        # the real model_idx=0 width
+]
+
+
+@pytest.mark.parametrize("arch,shape,hidden,C,B,S,ds", CONFIGS)
+def test_engine_vs_oracle(arch, shape, hidden, C, B, S, ds):
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    net, layout, loc, rho, bank, x, labels = _problem(arch, shape, hidden, C, B, S, ds)
+    eng = Net(arch, shape, hidden, C)
+    assert eng.P == bank.shape[1]
+    eng.upload(bank, 0)
+    assert torch.equal(eng.download(0, S), bank)
+    probs = eng.forward_probs_sum(x, 0, S).cpu() / S
+    ref_p = orc.bnn_forward(net, layout, bank, x, range(S)).detach()
+    assert rel_err(probs, ref_p) < REL
+    assert rel_err(eng.forward_logits(x, 1).cpu(), orc.bnn_forward_avg_posterior(net, layout, bank[1], x).detach()) < REL
+    g = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S).cpu().reshape(x.shape) / S
+    ref64 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    ref32 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S))
+    assert min(rel_err(g, ref64), rel_err(g, ref32)) < REL
+    pbar = eng.forward_probs_sum(x, 0, S) / S
+    ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
+    ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    assert rel_err(ga, ra) < REL
+    gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, 2, 3).cpu().reshape(x.shape)
+    rl = orc.attack_gradient_avg_posterior(net, layout, bank[2], x, labels, dtype=torch.float64)
+    assert rel_err(gl, rl) < REL
+    # split over row ranges == whole (what sample sharding relies on); empty range == zeros
+    ga_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S // 2)
+    gb_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, S // 2, S)
+    assert rel_err((ga_ + gb_).cpu().reshape(x.shape) / S, g) < 1e-5
+    assert float(eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 1, 1).abs().max()) == 0.0
+    # rows of the batch are independent: a sub-batch reproduces the same rows (the split of the
+    # sample loop over CTAs depends on the batch size, so only up to fp32 summation order)
+    gs = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x[:3], labels[:3], 0, S).cpu().reshape(x[:3].shape) / S
+    assert rel_err(gs, g[:3]) < 1e-5
+    eng.close()
+
+
+def test_autograd_through_forward_matches_attack_gradient():
+    from robustbnns_b200.model_bnn import BNN
+    net, layout, loc, rho, bank, x, labels = _problem("fc", (1, 28, 28), 64, 10, 12, 4)
+    bnn = BNN("mnist", 64, "leaky", "fc", "hmc", None, None, 4, 5, (1, 28, 28), 10)
+    bnn.set_posterior_samples(bank)
+    xg = x.cuda().requires_grad_(True)
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(bnn.forward(xg, n_samples=4), labels.cuda())
+    loss.backward()
+    ref = orc.attack_gradient(net, layout, bank, x, labels, range(4), dtype=torch.float64)
+    assert rel_err(xg.grad.cpu(), ref) < REL
+
+
+# ------------------------------------------------------------------ sampler -----------------------------
+def test_philox_sampler_matches_restatement_and_moments():
+    from robustbnns_b200.engine import Net
+    net = orc.build_net("fc", (1, 28, 28), 64, 10)
+    layout = orc.param_layout(net)
+    loc, rho = orc.scaled_guide_params(layout, seed=3, rho_mean=-2.0)
+    rho[:50] = torch.linspace(15.0, 30.0, 50)              # crosses the softplus threshold (rho > 20)
+    eng = Net("fc", (1, 28, 28), 64, 10)
+    seed = 0x1234567812345678
+    eng.sample_diag(loc, rho, seed, 5, 0, 3)                # global indices 5,6,7
+    eng.sample_diag(loc, rho, seed, 100, 3, 4, stride=8)    # 100,108,116,124 (rank-strided)
+    got = eng.download(0, 7)
+    ref = orc.philox_bank(loc, rho, seed, [5, 6, 7, 100, 108, 116, 124])
+    sd = orc.softplus(rho)
+    assert float(((got - ref).abs() / sd).max()) < 2e-5      # same Philox bits; libm-level differences only
+    # statistical check against the guide's moments N(loc, softplus(rho)^2), independent across samples
+    S = 256
+    eng.sample_diag(loc, rho, 7, 0, 0, S)
+    z = (eng.download(0, S) - loc) / sd
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    assert float(z.mean(0).abs().max()) < 6.0 / np.sqrt(S)
+    corr = float((z[0::2] * z[1::2]).mean())
+    assert abs(corr) < 5e-3
+    from scipy import stats
+    assert stats.kstest(z[:, ::97].reshape(-1).numpy(), "norm").pvalue > 1e-3
+    eng.close()
+
+
+# ------------------------------------------------------------------ stateless kernels -------------------
+def test_attack_and_evaluation_kernels_edge_cases():
+    from robustbnns_b200 import engine as E
+    from robustbnns_b200 import adversarialAttacks as aa
+    g = torch.Generator().manual_seed(0)
+    for B, D in ((1, 784), (5, 2), (33, 784), (7, 13)):
+        x = torch.rand((B, D), generator=g).cuda()
+        x0 = torch.rand((B, D), generator=g).cuda()
+        gr = torch.randn((B, D), generator=g).cuda()
+        gr[0, :D // 2] = 0.0                                 # sign(0) = 0
+        ref = torch.clamp(x + 0.3 * gr.sign(), 0, 1)
+        assert torch.equal(E.fgsm_step(x.reshape(-1), gr.reshape(-1), 0.3).reshape(B, D), ref)
+        alpha = E.pgd_alpha(x)
+        assert torch.equal(alpha, 2 / x.max(dim=1)[0])
+        eta = torch.clamp(x + alpha[:, None] * gr.sign() - x0, min=-0.1, max=0.1)
+        assert torch.equal(E.pgd_step(x, x0, gr, alpha, 0.1), torch.clamp(x0 + eta, 0, 1))
+    # all-zero image: alpha = inf, inf*0 = NaN exactly as upstream
+    z = torch.zeros((1, 16)).cuda()
+    a = E.pgd_alpha(z)
+    assert torch.isinf(a).all()
+    out = E.pgd_step(z, z, torch.zeros_like(z), a, 0.3)
+    assert torch.isnan(out).all()
+    for N, C in ((0, 10), (1, 2), (129, 10), (1000, 10), (77, 32)):
+        o0 = torch.randn((N, C), generator=g).cuda()
+        o1 = torch.randn((N, C), generator=g).cuda()
+        lab = torch.randint(0, C, (N,), generator=g).cuda()
+        if N:
+            o0[0] = 0.5                                      # ties: first maximum wins, like torch.argmax
+        cnt = torch.zeros((1,), dtype=torch.int64).cuda()
+        E.count_correct(o0, lab.to(torch.int32), cnt)
+        assert int(cnt.item()) == int((o0.argmax(-1) == lab).sum().item())
+        if N:
+            rob = aa.softmax_robustness(o0, o1)
+            assert float((rob.cpu() - orc.softmax_robustness(o0.cpu(), o1.cpu())).abs().max()) <= 1e-6
+            d = aa.softmax_difference(o0, o1)
+            assert float((d.cpu() - orc.softmax_difference(o0.cpu(), o1.cpu())).abs().max()) <= 1e-6
+    with pytest.raises(ValueError):
+        aa.softmax_difference(torch.rand(4, 10).cuda(), torch.rand(3, 10).cuda())
+
+
+# ------------------------------------------------------------------ BASELINE-size properties ------------
+def test_full_size_properties_fc_headline():
+    """cfg2 shape (10 000 MNIST-shaped inputs, fc 784-512-10) with a few samples: size-independent
+    properties the oracle cannot check in seconds."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    B, S = 10000, 6
+    net, layout, loc, rho, bank, x, labels = _problem("fc", (1, 28, 28), 512, 10, B, S)
+    eng = Net("fc", (1, 28, 28), 512, 10)
+    eng.upload(bank, 0)
+    xd, ld = x.cuda(), labels.cuda().to(torch.int32)
+    full = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, 0, S)
+    # (1) linearity over the sample range
+    parts = sum(eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, s, s + 1) for s in range(S))
+    assert rel_err(parts.cpu(), full.cpu()) < 1e-5
+    # (2) permuting the batch permutes the rows
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+    gp = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd[perm].contiguous(), ld[perm].contiguous(), 0, S)
+    assert torch.equal(gp, full[perm])
+    # (3) a random subset of rows agrees with the oracle
+    idx = torch.randperm(B, generator=torch.Generator().manual_seed(2))[:64]
+    ref = orc.expected_loss_gradients(net, layout, bank, x[idx], labels[idx], range(S), dtype=torch.float64)
+    assert rel_err(full.cpu()[idx].reshape(ref.shape) / S, ref) < REL
+    # (4) probabilities: rows sum to one
+    p = eng.forward_probs_sum(xd, 0, S) / S
+    assert float((p.sum(-1) - 1).abs().max()) < 1e-5
+    # (5) host-buffer entry point == device entry point
+    out = eng.loss_gradients_host(x.reshape(B, -1), labels, 0, S, S)
+    assert rel_err(out, full.cpu() / S) < 1e-6
+    eng.close()
