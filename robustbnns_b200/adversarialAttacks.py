@@ -146,7 +146,13 @@ def pgd_attack(net, image, label, hyperparams=None, n_samples=None, avg_posterio
     else:
         epsilon = 0.5
         alpha = torch.full((B,), 2 / 225, dtype=torch.float32, device=x0.device)
-    x = x0
+    return _pgd_loop(net, x0, x0, y, alpha, epsilon, n_samples, avg_posterior, iters)
+
+
+def _pgd_loop(net, x, x0, y, alpha, epsilon, n_samples, avg_posterior, iters):
+    """`iters` PGD updates of `x` inside the eps-ball around `x0` (adversarialAttacks.py:95-105); all
+    launches are enqueued back to back, nothing is read back between iterations."""
+    B = x0.shape[0]
     for _ in range(iters):
         g = _bnn_input_grad(net, x, y, n_samples, avg_posterior)
         x = net.engine().pgd_step(x.reshape(B, -1), x0.reshape(B, -1), g.reshape(B, -1), alpha, epsilon).reshape(x0.shape)

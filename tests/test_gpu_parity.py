@@ -79,13 +79,35 @@ def test_golden_hmc_attacks_and_evaluation(name, tmp_path, monkeypatch):
                             method=method, filename="a", savedir="a", hyperparams=h, n_samples=S)
             ref = c.t(f"{method}_{hname}_adv")
             assert adv.is_cuda and adv.shape == ref.shape
-            assert _mismatch_fraction(adv, ref) <= 2e-3, (method, hname)
+            if (method, hname) == ("pgd", "default"):
+                # 40 small steps (alpha = 2/225) are chaotic in floating point: the oracle's own fp32 and
+                # fp64 trajectories end up differing on most pixels of the conv case.  Parity is therefore
+                # checked step by step along the reference trajectory (below); the end point is only
+                # required to stay inside the eps-ball.
+                assert float((adv.cpu() - c.x).abs().max()) <= 0.5 + 1e-6
+            else:
+                assert _mismatch_fraction(adv, ref) <= 2e-3, (method, hname)
             o, a, rob = aa.attack_evaluation(net=bnn, x_test=c.x, x_attack=ref, y_test=c.y, device="cuda",
                                              n_samples=S)
             assert [o, a] == c.z[f"{method}_{hname}_eval"].tolist()          # counts bit-exact
             assert float((rob.cpu() - c.t(f"{method}_{hname}_rob")).abs().max()) <= 1e-6
             loaded = aa.load_attack(method, "a", savedir="a", n_samples=S)
             assert torch.equal(loaded.cpu(), adv.cpu())
+    # default PGD, teacher-forced: from every image x_t of the oracle's fp32 trajectory one CUDA step must
+    # land on the oracle's x_{t+1} (up to measure-zero sign ties).
+    sched = lambda call: range(S)  # noqa: E731
+    traj = [c.x.clone()]
+    for t in range(40):
+        g = orc.attack_gradient(c.net, c.layout, c.bank, traj[-1], c.labels, sched(t))
+        traj.append(orc.pgd_step(traj[-1], c.x, g, 2 / 225, 0.5).detach())
+    # (tests/test_oracle_golden.py pins this trajectory's end point to the reference's own output)
+    x0, y = aa._prep(bnn, c.x, c.labels)
+    alpha = torch.full((len(c.x),), 2 / 225, dtype=torch.float32, device=x0.device)
+    worst = 0.0
+    for t in range(40):
+        nxt = aa._pgd_loop(bnn, traj[t].cuda(), x0, y, alpha, 0.5, S, False, 1)
+        worst = max(worst, _mismatch_fraction(nxt, traj[t + 1]))
+    assert worst <= 2e-3, worst
 
 
 # ------------------------------------------------------------------ oracle at larger sizes -------------
@@ -131,8 +153,8 @@ def test_engine_vs_oracle(arch, shape, hidden, C, B, S, ds):
     ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
     ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
     assert rel_err(ga, ra) < REL
-    gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, 2, 3).cpu().reshape(x.shape)
-    rl = orc.attack_gradient_avg_posterior(net, layout, bank[2], x, labels, dtype=torch.float64)
+    gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, S - 1, S).cpu().reshape(x.shape)
+    rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
     assert rel_err(gl, rl) < REL
     # split over row ranges == whole (what sample sharding relies on); empty range == zeros
     ga_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S // 2)
@@ -254,5 +276,5 @@ def test_full_size_properties_fc_headline():
     assert float((p.sum(-1) - 1).abs().max()) < 1e-5
     # (5) host-buffer entry point == device entry point
     out = eng.loss_gradients_host(x.reshape(B, -1), labels, 0, S, S)
-    assert rel_err(out, full.cpu() / S) < 1e-6
+    assert rel_err(out, full.cpu().reshape(B, -1) / S) < 1e-6
     eng.close()
