@@ -1,0 +1,68 @@
+// tcgen05 grouped GEMM for sm_100a: the tensor-core engine behind RBNN_PREC_TF32X3 / RBNN_PREC_BF16.
+//
+//   per posterior sample z:   C_z[M,N] = epi( A_z[M,K] . B_z[N,K]^T )            (reduce_z = 0)
+//   over a range of samples:  C  [M,N] = sum_z A_z[M,K] . B_z[N,K]^T            (reduce_z = 1)
+//
+// It stands in for nn.Linear forward (model_nn.py:80,89) and autograd's input gradient of nn.Linear
+// for every posterior sample at once; the sum over samples (lossGradients.py:40) is a concatenated-K
+// accumulation in TMEM.  Both operands are K-major; operand tiles are TMA-staged into 128B-swizzled
+// shared memory, the accumulator lives in TMEM (double buffered, 2 x 256 columns), one thread issues
+// tcgen05.mma, four epilogue warps drain TMEM with tcgen05.ld and apply bias / LeakyReLU / mask.
+//
+// Precision modes
+//   TF32X3 : every fp32 operand is pre-split into hi = rn_tf32(x) and lo = x - hi (both fp32 arrays);
+//            D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi with kind::tf32 => fp32-class accuracy (~2^-21).
+//   BF16   : single kind::f16 pass on bf16 operands (throughput mode, not parity grade).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace rbnn {
+namespace tc {
+
+constexpr int kBM = 128;            // tile rows = TMEM lanes
+constexpr int kBNMax = 256;         // tile columns (UMMA N) upper bound; runtime BN is a multiple of 16
+constexpr int kThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kTmemCols = 512;      // 2 accumulator stages x 256 fp32 columns
+
+enum { EPI_NONE = 0, EPI_BIAS_LEAKY = 1, EPI_MASK = 2, EPI_BIAS = 3 };
+enum { MODE_TF32X3 = 0, MODE_BF16 = 1 };
+
+// One GEMM operand: [Z][rows][K] with K contiguous.  `lo` is the tf32 residual array (TF32X3 only).
+struct Operand {
+  const void* hi = nullptr;
+  const void* lo = nullptr;
+  int64_t rows = 0;      // M for A, N for B
+  int64_t ld = 0;        // elements between consecutive rows (>= K, multiple of 16 bytes)
+  int64_t zstride = 0;   // elements between consecutive z (0 = shared by all z)
+};
+
+struct GemmDesc {
+  int mode = MODE_TF32X3;
+  int M = 0, N = 0, K = 0, Z = 1;
+  int BN = 256;          // tile width
+  Operand A, B;
+  int reduce_z = 0;      // 1: sum over z; the z range is cut into `slots` contiguous pieces -> out[slot]
+  int slots = 1;
+  int epi = EPI_NONE;
+  const float* bias = nullptr; int64_t bias_zstride = 0;                 // bias[z][n]
+  const float* act = nullptr; int64_t act_zstride = 0; int64_t act_ld = 0; // EPI_MASK: acc *= act>0 ? 1 : slope
+  // outputs, [z or slot][m][n] with leading dimension out_ld (elements) and z stride out_zstride:
+  float* out = nullptr;       // fp32 result (or tf32 hi part when out_lo != nullptr)
+  float* out_lo = nullptr;    // optional: tf32 residual -> the result is written pre-split for the next GEMM
+  void* out_bf = nullptr;     // optional: bf16 copy of the result
+  int64_t out_ld = 0, out_zstride = 0;
+  int sm_count = 148;
+};
+
+// Enqueues the GEMM on `st`.  Returns 0 on success; on failure fills *err.
+int gemm(const GemmDesc& d, cudaStream_t st, std::string* err);
+
+// Dynamic shared memory the kernel asks for (same for both modes).
+size_t smem_bytes();
+
+}  // namespace tc
+}  // namespace rbnn

@@ -1,0 +1,203 @@
+// Stand-alone bring-up / timing harness for the tcgen05 GEMM (tc_gemm.cu).  Not part of librbnn.so.
+//   build/tc_gemm_test            correctness on small ragged shapes vs a double-precision host reference
+//   build/tc_gemm_test bench      + timing of the headline shapes (10 000 x 784 x 512 per posterior sample)
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include <cuda_bf16.h>
+
+#include "tc_gemm.cuh"
+
+using namespace rbnn::tc;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);  \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+__host__ __device__ inline uint32_t hash32(uint64_t i, uint32_t seed) {
+  uint64_t x = i * 0x9E3779B97F4A7C15ull + seed;
+  x ^= x >> 31; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 29; x *= 0x94D049BB133111EBull; x ^= x >> 32;
+  return (uint32_t)x;
+}
+__host__ __device__ inline float val(uint64_t i, uint32_t seed, float scale) {
+  return ((float)(hash32(i, seed) & 0xFFFFFF) * (1.0f / 16777216.0f) - 0.5f) * scale;
+}
+__host__ __device__ inline float tf32_rn(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & ~0x1FFFu;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+__global__ void fill_kernel(float* hi, float* lo, __nv_bfloat16* bf, int64_t n, uint32_t seed, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = val(i, seed, scale);
+    uint32_t u = __float_as_uint(v);
+    u = (u + 0x1000u) & ~0x1FFFu;
+    const float h = __uint_as_float(u);
+    hi[i] = h;
+    lo[i] = v - h;
+    if (bf) bf[i] = __float2bfloat16(v);
+  }
+}
+
+struct Dev {
+  float *hi = nullptr, *lo = nullptr;
+  __nv_bfloat16* bf = nullptr;
+  int64_t n = 0;
+  uint32_t seed;
+  float scale;
+  void init(int64_t n_, uint32_t seed_, float scale_, bool want_bf) {
+    n = n_; seed = seed_; scale = scale_;
+    CK(cudaMalloc(&hi, n * 4));
+    CK(cudaMalloc(&lo, n * 4));
+    if (want_bf) CK(cudaMalloc(&bf, n * 2));
+    fill_kernel<<<1184, 256>>>(hi, lo, bf, n, seed, scale);
+    CK(cudaGetLastError());
+  }
+  float at(int64_t i) const { return val(i, seed, scale); }
+  void free_() { cudaFree(hi); cudaFree(lo); cudaFree(bf); }
+};
+
+struct Case {
+  const char* name;
+  int mode, M, N, K, Z, BN, reduce, slots, a_per_z, epi, split_out;
+};
+
+static float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+// returns max |err| / max |ref| over the checked entries
+static double run_case(const Case& c, bool full_check, int timing_iters, double* ms_out) {
+  const bool bf = c.mode == MODE_BF16;
+  Dev A, B, bias, act;
+  const int64_t a_z = c.a_per_z ? c.Z : 1;
+  A.init(a_z * c.M * c.K, 11, 2.0f, bf);
+  B.init((int64_t)c.Z * c.N * c.K, 22, 0.2f, bf);
+  bias.init((int64_t)c.Z * c.N, 33, 1.0f, false);
+  const int out_z = c.reduce ? c.slots : c.Z;
+  act.init((int64_t)out_z * c.M * c.N, 44, 1.0f, false);
+  float *out = nullptr, *out_lo = nullptr;
+  const int64_t on = (int64_t)out_z * c.M * c.N;
+  CK(cudaMalloc(&out, on * 4));
+  CK(cudaMemset(out, 0xFF, on * 4));
+  if (c.split_out) { CK(cudaMalloc(&out_lo, on * 4)); CK(cudaMemset(out_lo, 0xFF, on * 4)); }
+
+  GemmDesc d;
+  d.mode = c.mode; d.M = c.M; d.N = c.N; d.K = c.K; d.Z = c.Z; d.BN = c.BN;
+  d.A.hi = bf ? (void*)A.bf : (void*)A.hi; d.A.lo = A.lo; d.A.rows = c.M; d.A.ld = c.K;
+  d.A.zstride = c.a_per_z ? (int64_t)c.M * c.K : 0;
+  d.B.hi = bf ? (void*)B.bf : (void*)B.hi; d.B.lo = B.lo; d.B.rows = c.N; d.B.ld = c.K; d.B.zstride = (int64_t)c.N * c.K;
+  d.reduce_z = c.reduce; d.slots = c.slots; d.epi = c.epi;
+  d.bias = bias.hi; d.bias_zstride = c.N;     // bias.hi holds tf32-rounded values; reference uses the same
+  d.act = act.hi; d.act_zstride = (int64_t)c.M * c.N; d.act_ld = c.N;
+  d.out = out; d.out_lo = out_lo; d.out_ld = c.N; d.out_zstride = (int64_t)c.M * c.N;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  d.sm_count = prop.multiProcessorCount;
+  std::string err;
+  if (gemm(d, 0, &err)) { printf("%s: gemm failed: %s\n", c.name, err.c_str()); exit(3); }
+  CK(cudaDeviceSynchronize());
+
+  if (timing_iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < timing_iters; ++i) gemm(d, 0, &err);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / timing_iters;
+  }
+
+  std::vector<float> h(on), hl;
+  CK(cudaMemcpy(h.data(), out, on * 4, cudaMemcpyDeviceToHost));
+  if (c.split_out) { hl.resize(on); CK(cudaMemcpy(hl.data(), out_lo, on * 4, cudaMemcpyDeviceToHost)); }
+  std::vector<float> hb((int64_t)c.Z * c.N), hact;
+  CK(cudaMemcpy(hb.data(), bias.hi, hb.size() * 4, cudaMemcpyDeviceToHost));
+  if (c.epi == EPI_MASK) { hact.resize(on); CK(cudaMemcpy(hact.data(), act.hi, on * 4, cudaMemcpyDeviceToHost)); }
+
+  double max_err = 0, max_ref = 0;
+  const int64_t nchk = full_check ? on : 4096;
+  for (int64_t q = 0; q < nchk; ++q) {
+    const int64_t idx = full_check ? q : (int64_t)(hash32(q, 777) % (uint64_t)on);
+    const int zz = (int)(idx / ((int64_t)c.M * c.N));
+    const int m = (int)((idx / c.N) % c.M), n = (int)(idx % c.N);
+    const int z0 = c.reduce ? (int)((long long)zz * c.Z / c.slots) : zz;
+    const int z1 = c.reduce ? (int)((long long)(zz + 1) * c.Z / c.slots) : zz + 1;
+    double acc = 0;
+    for (int z = z0; z < z1; ++z) {
+      const int64_t ao = (c.a_per_z ? (int64_t)z * c.M * c.K : 0) + (int64_t)m * c.K;
+      const int64_t bo = ((int64_t)z * c.N + n) * c.K;
+      for (int k = 0; k < c.K; ++k) {
+        float a = A.at(ao + k), b = B.at(bo + k);
+        if (bf) { a = bf16_round(a); b = bf16_round(b); }
+        acc += (double)a * (double)b;
+      }
+    }
+    if (c.epi == EPI_BIAS_LEAKY || c.epi == EPI_BIAS) acc += hb[(int64_t)zz * c.N + n];
+    if (c.epi == EPI_BIAS_LEAKY) acc = acc > 0 ? acc : acc * 0.01;
+    if (c.epi == EPI_MASK) acc = hact[idx] > 0.f ? acc : acc * 0.01;
+    double got = h[idx];
+    if (c.split_out) got += hl[idx];
+    max_err = fmax(max_err, fabs(got - acc));
+    max_ref = fmax(max_ref, fabs(acc));
+  }
+  A.free_(); B.free_(); bias.free_(); act.free_();
+  cudaFree(out); cudaFree(out_lo);
+  return max_err / fmax(max_ref, 1e-30);
+}
+
+int main(int argc, char** argv) {
+  const bool bench = argc > 1 && !strcmp(argv[1], "bench");
+  int fails = 0;
+  const Case small[] = {
+      {"tf32x3 fwd ragged M, K tail, bias+leaky", MODE_TF32X3, 300, 512, 784, 3, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+      {"tf32x3 bwd reduce_z, BN=208, N tail", MODE_TF32X3, 300, 784, 512, 5, 208, 1, 2, 1, EPI_NONE, 0},
+      {"tf32x3 mask epilogue, split output", MODE_TF32X3, 200, 512, 512, 2, 256, 0, 1, 1, EPI_MASK, 1},
+      {"tf32x3 tiny M=7, H=64", MODE_TF32X3, 7, 64, 784, 4, 64, 0, 1, 0, EPI_BIAS, 0},
+      {"tf32x3 one tile, many z (phase wrap)", MODE_TF32X3, 128, 256, 64, 9, 256, 1, 1, 1, EPI_NONE, 0},
+      {"bf16 fwd", MODE_BF16, 300, 512, 784, 3, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+      {"bf16 bwd reduce_z", MODE_BF16, 300, 784, 512, 5, 208, 1, 2, 1, EPI_NONE, 0},
+  };
+  for (const Case& c : small) {
+    double ms = 0;
+    const double e = run_case(c, true, 0, &ms);
+    const double tol = c.mode == MODE_BF16 ? 2e-5 : 2e-6;   // bf16 reference uses the same rounded operands
+    printf("%-45s rel err %.3e  %s\n", c.name, e, e < tol ? "ok" : "FAIL");
+    if (!(e < tol)) fails++;
+  }
+  if (bench) {
+    const Case big[] = {
+        {"tf32x3 fwd 10000x512x784 Z=148 BN=256", MODE_TF32X3, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+        {"tf32x3 fwd 10000x512x784 Z=148 BN=128", MODE_TF32X3, 10000, 512, 784, 148, 128, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+        {"tf32x3 bwd 10000x784x512 Z=148 BN=208 s37", MODE_TF32X3, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
+        {"tf32x3 bwd 10000x784x512 Z=148 BN=256 s37", MODE_TF32X3, 10000, 784, 512, 148, 256, 1, 37, 1, EPI_NONE, 0},
+        {"tf32x3 bwd 10000x784x512 Z=148 BN=112 s21", MODE_TF32X3, 10000, 784, 512, 148, 112, 1, 21, 1, EPI_NONE, 0},
+        {"bf16 fwd 10000x512x784 Z=148 BN=256", MODE_BF16, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+        {"bf16 bwd 10000x784x512 Z=148 BN=208 s37", MODE_BF16, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
+    };
+    for (const Case& c : big) {
+      double ms = 0;
+      const double e = run_case(c, false, 3, &ms);
+      const double flop = 2.0 * c.M * c.N * (double)c.K * c.Z;
+      printf("%-45s rel err %.3e  %.3f ms  %.1f TFLOP/s (algorithmic, 1 pass)\n", c.name, e, ms, flop / ms * 1e-9);
+      const double tol = c.mode == MODE_BF16 ? 2e-5 : 2e-6;
+      if (!(e < tol)) fails++;
+    }
+  }
+  printf(fails ? "FAILED (%d)\n" : "ALL OK\n", fails);
+  return fails ? 1 : 0;
+}
