@@ -369,7 +369,10 @@ int rbnn_net_create(rbnn_net** out, int arch, int in_ch, int in_h, int in_w, int
   n->D = in_ch * in_h * in_w; n->H = hidden; n->C = n_classes; n->device = device;
   build_layout(n);
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) n->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    n->sm_count = prop.multiProcessorCount;
+    n->cc_major = prop.major;
+  }
   *out = n;
   return 0;
 }
@@ -379,9 +382,7 @@ int rbnn_net_destroy(rbnn_net* n) {
   DeviceGuard dg(n->device);
   cudaDeviceSynchronize();
   cudaFree(n->bank); cudaFree(n->woutp); cudaFree(n->sigma); cudaFree(n->ws);
-  cudaFree(n->tc.w1_hi); cudaFree(n->tc.w1_lo); cudaFree(n->tc.w1t_hi); cudaFree(n->tc.w1t_lo);
-  cudaFree(n->tc.w1_bf); cudaFree(n->tc.w1t_bf);
-  delete[] n->tc.dirty;
+  tc_bank_free(n);
   delete n;
   return 0;
 }
@@ -392,8 +393,7 @@ int rbnn_net_set_precision(rbnn_net* n, int prec) {
   RBNN_CHECK(n != nullptr, "null net handle");
   RBNN_CHECK(prec == RBNN_PREC_FP32 || prec == RBNN_PREC_TF32X3 || prec == RBNN_PREC_BF16, "unknown precision %d", prec);
   if (prec != RBNN_PREC_FP32)
-    RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%4==0 and H%%64==0 on sm_100 only");
-  if (prec != n->prec && n->tc.dirty) std::fill(n->tc.dirty, n->tc.dirty + n->tc.capacity, (uint8_t)1);
+    RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%8==0 and H>=32 on sm_100 only");
   n->prec = prec;
   return 0;
 }
@@ -506,8 +506,7 @@ int rbnn_forward_probs_sum(rbnn_net* n, const float* d_x, int B, int s0, int s1,
   cudaStream_t st = (cudaStream_t)stream;
   RBNN_CUDA(cudaMemsetAsync(d_out_sum, 0, (size_t)B * n->C * sizeof(float), st));
   if (s1 == s0) return 0;
-  if (n->prec != RBNN_PREC_FP32 && n->arch == RBNN_ARCH_FC)
-    return tc_fc_forward_probs_sum(n, d_x, B, s0, s1, d_out_sum, st);
+  if (n->prec != RBNN_PREC_FP32) return tc_fc_forward(n, d_x, B, s0, s1, d_out_sum, nullptr, st);
   const int bc = batch_chunk(n, B, false);
   for (int b0 = 0; b0 < B; b0 += bc) {
     const int nb = std::min(bc, B - b0);
@@ -524,6 +523,7 @@ int rbnn_forward_logits(rbnn_net* n, const float* d_x, int B, int s, float* d_ou
   if (B <= 0) return 0;
   DeviceGuard dg(n->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n->prec != RBNN_PREC_FP32) return tc_fc_forward(n, d_x, B, s, s + 1, nullptr, d_out, st);
   const int bc = batch_chunk(n, B, false);
   for (int b0 = 0; b0 < B; b0 += bc) {
     const int nb = std::min(bc, B - b0);
@@ -549,8 +549,7 @@ int rbnn_input_grad_sum(rbnn_net* n, int head, const float* d_x, const int32_t* 
     RBNN_CUDA(cudaMemsetAsync(d_out_sum, 0, (size_t)B * n->D * sizeof(float), st));
     return 0;
   }
-  if (n->prec != RBNN_PREC_FP32 && n->arch == RBNN_ARCH_FC)
-    return tc_fc_input_grad_sum(n, head, d_x, d_labels, B, s0, s1, d_pbar, d_out_sum, st);
+  if (n->prec != RBNN_PREC_FP32) return tc_fc_input_grad_sum(n, head, d_x, d_labels, B, s0, s1, d_pbar, d_out_sum, st);
   const int bc = batch_chunk(n, B, true);
   for (int b0 = 0; b0 < B; b0 += bc) {
     const int nb = std::min(bc, B - b0);

@@ -48,16 +48,21 @@ struct ParamLayout {
 
 }  // namespace rbnn
 
-// Derived, kernel-ready copies of the bank for the tcgen05 FC path (tc_fc.cu).
+// Derived, kernel-ready copies of one weight matrix of the bank for the tcgen05 path (tc_fc.cu):
+// K-major operands for the forward GEMM ([S, R, C]) and, transposed, for the backward GEMM ([S, C, R]).
+struct TcMat {
+  int64_t off = 0;          // offset of the [R, C] matrix inside a bank row
+  int R = 0, C = 0;
+  float *hi = nullptr, *lo = nullptr;      // tf32 split:  w = hi + lo, hi = rn_tf32(w)
+  float *thi = nullptr, *tlo = nullptr;    // the same, transposed
+  void *bf = nullptr, *tbf = nullptr;      // bf16 variants
+};
+
 struct TcBank {
   int capacity = 0;
   int mode = -1;            // precision the copies were built for
-  float* w1_hi = nullptr;   // [S, H, D]   K-major B operand of the forward GEMM
-  float* w1_lo = nullptr;
-  float* w1t_hi = nullptr;  // [S, D, H]   K-major B operand of the backward GEMM
-  float* w1t_lo = nullptr;
-  void* w1_bf = nullptr;    // bf16 variants
-  void* w1t_bf = nullptr;
+  int nmat = 0;
+  TcMat mat[2];
   uint8_t* dirty = nullptr; // host flags per row (derived copies stale)
 };
 
@@ -74,9 +79,10 @@ struct rbnn_net {
   // workspace arena
   char* ws = nullptr;
   size_t ws_bytes = 0;
-  size_t ws_budget = (size_t)1536 << 20;
+  size_t ws_budget = (size_t)12 << 30;   // upper bound of the activation workspace (HBM is 180 GB)
   int64_t launches = 0;
   int sm_count = 148;
+  int cc_major = 0;           // compute capability major of `device` (10 = Blackwell: tcgen05 engine usable)
   TcBank tc;
   // optional per-kernel-class device timing (bench.py's roofline leg): event pairs on the launch stream
   int timing = 0;
@@ -149,10 +155,11 @@ int add_inplace(rbnn_net* net, float* dst, const float* src, int64_t n, cudaStre
 
 // ---- tc_fc.cu (tcgen05 FC path) -----------------------------------------------------------
 int tc_supported(const rbnn_net* net);
-int tc_bank_refresh(rbnn_net* net, int s0, int s1, cudaStream_t st);
+void tc_bank_free(rbnn_net* net);
 int tc_fc_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_t* d_labels, int B, int s0, int s1,
                          const float* d_pbar, float* d_out_sum, cudaStream_t st);
-int tc_fc_forward_probs_sum(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum,
-                            cudaStream_t st);
+// out_sum != nullptr: out_sum[B,C] += sum_s softmax(logits_s); out_logits != nullptr (one row): logits of row s0
+int tc_fc_forward(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum, float* d_out_logits,
+                  cudaStream_t st);
 
 }  // namespace rbnn

@@ -9,6 +9,9 @@
 //
 // With q = softmax(p) (the "double softmax"), g = q - e_y and p = softmax(z):
 //   dL/dz = p * (g - <p, g>)          (softmax Jacobian applied to g)
+// evaluated in exactly this form -- the one torch's softmax backward uses (grad - sum(grad*out)) * out -- so that
+// the fp32 rounding behaviour of saturated rows follows the reference's (a cancellation-free rewrite is more
+// accurate but moves the sign of near-zero gradients away from the reference's golden vectors).
 #include "common.cuh"
 
 namespace rbnn {

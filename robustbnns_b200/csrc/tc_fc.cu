@@ -1,8 +1,708 @@
-// placeholder (replaced by the tcgen05 FC engine)
+// The tcgen05 engine for the fully connected nets (arch fc / fc2, model_nn.py:77-91): per chunk of
+// posterior samples
+//   forward   H1_z = leaky(X . W1_z^T + b1_z) [, H2_z = leaky(H1_z . W2_z^T + b2_z)]       tc::gemm, per-z
+//   head      logits_z = H_z . Wo_z^T + bo_z -> softmax -> loss head -> dlogits            fc_head_kernel
+//             dH_z = (dlogits_z . Wo_z) (.) leaky'(H_z)           (written pre-split for the next GEMM)
+//   backward  [dH1_z = (dH2_z . W2_z) (.) leaky'(H1_z)]                                    tc::gemm, per-z
+//             dX += sum_z dH1_z . W1_z             (K-concatenated over the samples, in TMEM) tc::gemm, reduce_z
+// which is lossGradients.py:29-40 / adversarialAttacks.py:74-78 for all inputs and samples at once,
+// input gradients only (no weight gradients).  Operands of the tensor-core GEMMs are kept K-major:
+// the bank's weight matrices are re-laid once per refresh as [S,R,C] and transposed [S,C,R] copies,
+// split into tf32 hi/lo pairs (RBNN_PREC_TF32X3) or rounded to bf16 (RBNN_PREC_BF16).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+#include "tc_gemm.cuh"
+
 namespace rbnn {
-int tc_supported(const rbnn_net*) { return 0; }
-int tc_bank_refresh(rbnn_net*, int, int, cudaStream_t) { set_error("tcgen05 engine not built"); return 1; }
-int tc_fc_input_grad_sum(rbnn_net*, int, const float*, const int32_t*, int, int, int, const float*, float*, cudaStream_t) { set_error("tcgen05 engine not built"); return 1; }
-int tc_fc_forward_probs_sum(rbnn_net*, const float*, int, int, int, float*, cudaStream_t) { set_error("tcgen05 engine not built"); return 1; }
+
+namespace {
+
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
 }
+
+// ---- operand preparation --------------------------------------------------------------------------
+// x[n] -> hi/lo (tf32 split) or bf16
+__global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                             __nv_bfloat16* __restrict__ bf, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    if (bf) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&a);
+      pk.y = *reinterpret_cast<const uint32_t*>(&b);
+      reinterpret_cast<uint2*>(bf)[i] = pk;
+    } else {
+      float4 h, l;
+      h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+      l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+      reinterpret_cast<float4*>(hi)[i] = h;
+      reinterpret_cast<float4*>(lo)[i] = l;
+    }
+  }
+}
+
+// bank row s, matrix [R, C] at `off`  ->  [s][R][C] and transposed [s][C][R] copies (32x32 smem tiles)
+// grid: (C/32 ceil, R/32 ceil, count), block (32, 8)
+__global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0,
+                                float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ thi,
+                                float* __restrict__ tlo, __nv_bfloat16* __restrict__ bf,
+                                __nv_bfloat16* __restrict__ tbf) {
+  __shared__ float tile[32][33];
+  const int s = s0 + blockIdx.z;
+  const float* __restrict__ src = bank + (int64_t)s * P + off;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = blockIdx.y * 32 + i;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = __ldg(src + (int64_t)r * C + c);
+      const int64_t o = ((int64_t)s * R + r) * C + c;
+      if (bf) {
+        bf[o] = __float2bfloat16(v);
+      } else {
+        const float h = tf32_rn(v);
+        hi[o] = h;
+        lo[o] = v - h;
+      }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c2 = blockIdx.x * 32 + i;
+    if (r2 < R && c2 < C) {
+      const float v = tile[threadIdx.x][i];
+      const int64_t o = ((int64_t)s * C + c2) * R + r2;
+      if (tbf) {
+        tbf[o] = __float2bfloat16(v);
+      } else {
+        const float h = tf32_rn(v);
+        thi[o] = h;
+        tlo[o] = v - h;
+      }
+    }
+  }
+}
+
+// ---- head -------------------------------------------------------------------------------------------
+constexpr int kHeadWarps = 8;
+constexpr int kHeadRowsPerWarp = 8;
+constexpr int kMaxC = 32;
+
+template <int C_MAX>
+__device__ __forceinline__ void softmax_c(float (&v)[C_MAX], int C) {
+  float mx = v[0];
+#pragma unroll
+  for (int c = 1; c < C_MAX; ++c)
+    if (c < C) mx = fmaxf(mx, v[c]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < C_MAX; ++c)
+    if (c < C) { v[c] = expf(v[c] - mx); sum += v[c]; }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int c = 0; c < C_MAX; ++c)
+    if (c < C) v[c] *= inv;
+}
+
+// One warp per (sample z, input b) row of the top hidden activations.
+//   GRAD = false : logits[z][b][:] = H . Wo_z^T + bo_z
+//   GRAD = true  : additionally the loss head (same algebra as head.cu::dlogits_kernel) and
+//                  dH[z][b][j] = leaky'(H[z][b][j]) * sum_c dlogits_c Wo_z[c][j], written as tf32 hi/lo or bf16.
+// grid: (ceil(B / 64), Z); block 256; dynamic smem: (C*H + C) floats (Wo_z, bo_z of this block's sample)
+template <int C_MAX, bool GRAD>
+__global__ void __launch_bounds__(kHeadWarps * 32)
+fc_head_kernel(int head, const float* __restrict__ Hact, const float* __restrict__ bank, int64_t P, int64_t wo_off,
+               int64_t bo_off, int z_row0, const int32_t* __restrict__ labels, const float* __restrict__ pbar,
+               int B, int H, int C, float* __restrict__ logits_out, float* __restrict__ dh_hi,
+               float* __restrict__ dh_lo, __nv_bfloat16* __restrict__ dh_bf) {
+  extern __shared__ float sm[];
+  float* wo = sm;               // [C][H]
+  float* bo = sm + C * H;       // [C]
+  const int z = blockIdx.y;
+  const float* __restrict__ row_w = bank + (int64_t)(z_row0 + z) * P;
+  for (int i = threadIdx.x; i < C * H; i += blockDim.x) wo[i] = __ldg(row_w + wo_off + i);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) bo[i] = __ldg(row_w + bo_off + i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b_begin = (blockIdx.x * kHeadWarps + warp) * kHeadRowsPerWarp;
+  for (int b = b_begin; b < min(b_begin + kHeadRowsPerWarp, B); ++b) {
+    const int64_t row = (int64_t)z * B + b;
+    const float* __restrict__ h = Hact + row * H;
+    float acc[C_MAX];
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c) acc[c] = 0.f;
+    for (int j = lane * 4; j < H; j += 128) {
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + j));
+#pragma unroll
+      for (int c = 0; c < C_MAX; ++c)
+        if (c < C) {
+          const float4 w = *reinterpret_cast<const float4*>(wo + c * H + j);
+          acc[c] = fmaf(hv.x, w.x, acc[c]);
+          acc[c] = fmaf(hv.y, w.y, acc[c]);
+          acc[c] = fmaf(hv.z, w.z, acc[c]);
+          acc[c] = fmaf(hv.w, w.w, acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c)
+      if (c < C) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        acc[c] += bo[c];
+      }
+    if (!GRAD) {
+      if (lane < C) {
+        float v = 0.f;
+#pragma unroll
+        for (int c = 0; c < C_MAX; ++c)
+          if (c == lane) v = acc[c];
+        logits_out[row * C + lane] = v;
+      }
+      continue;
+    }
+    // ---- loss head: dlogits = softmax-Jacobian applied to g (see head.cu) ----
+    const int y = labels[b];
+    float g[C_MAX];
+    softmax_c<C_MAX>(acc, C);                 // acc = p = softmax(z)
+    if (head == RBNN_HEAD_LOGITS_CE) {
+#pragma unroll
+      for (int c = 0; c < C_MAX; ++c) acc[c] = acc[c] - (c == y ? 1.f : 0.f);
+    } else {
+      if (head == RBNN_HEAD_MEAN_OF_GRADS) {
+#pragma unroll
+        for (int c = 0; c < C_MAX; ++c) g[c] = acc[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < C_MAX; ++c) g[c] = (c < C) ? __ldg(pbar + (int64_t)b * C + c) : 0.f;
+      }
+      if (head != RBNN_HEAD_UPSTREAM) {
+        softmax_c<C_MAX>(g, C);
+#pragma unroll
+        for (int c = 0; c < C_MAX; ++c) g[c] -= (c == y ? 1.f : 0.f);
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C_MAX; ++c)
+        if (c < C) dot = fmaf(acc[c], g[c], dot);
+#pragma unroll
+      for (int c = 0; c < C_MAX; ++c) acc[c] = acc[c] * (g[c] - dot);
+    }
+    // ---- dH = (dlogits . Wo) (.) leaky'(H) ----
+    for (int j = lane * 4; j < H; j += 128) {
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + j));
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < C_MAX; ++c)
+        if (c < C) {
+          const float4 w = *reinterpret_cast<const float4*>(wo + c * H + j);
+          d[0] = fmaf(acc[c], w.x, d[0]);
+          d[1] = fmaf(acc[c], w.y, d[1]);
+          d[2] = fmaf(acc[c], w.z, d[2]);
+          d[3] = fmaf(acc[c], w.w, d[3]);
+        }
+      d[0] = hv.x > 0.f ? d[0] : d[0] * kLeakySlope;
+      d[1] = hv.y > 0.f ? d[1] : d[1] * kLeakySlope;
+      d[2] = hv.z > 0.f ? d[2] : d[2] * kLeakySlope;
+      d[3] = hv.w > 0.f ? d[3] : d[3] * kLeakySlope;
+      if (dh_bf) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(d[0], d[1]), bb = __floats2bfloat162_rn(d[2], d[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&a);
+        pk.y = *reinterpret_cast<const uint32_t*>(&bb);
+        *reinterpret_cast<uint2*>(dh_bf + row * H + j) = pk;
+      } else {
+        float4 hi4, lo4;
+        hi4.x = tf32_rn(d[0]); hi4.y = tf32_rn(d[1]); hi4.z = tf32_rn(d[2]); hi4.w = tf32_rn(d[3]);
+        lo4.x = d[0] - hi4.x; lo4.y = d[1] - hi4.y; lo4.z = d[2] - hi4.z; lo4.w = d[3] - hi4.w;
+        *reinterpret_cast<float4*>(dh_hi + row * H + j) = hi4;
+        *reinterpret_cast<float4*>(dh_lo + row * H + j) = lo4;
+      }
+    }
+  }
+}
+
+// Guard-band refinement of a forward GEMM output (TF32X3 mode).  LeakyReLU makes the input gradient
+// discontinuous in the pre-activations: a hidden unit whose pre-activation is within the tensor-core
+// rounding error of zero may come out with the wrong sign and change its row of the gradient by O(1/H).
+// Every unit with |pre-activation| < eps * (row max) is therefore recomputed exactly (fp64 accumulation of
+// the fp32 products, CUDA cores) and rewritten in place.  About 1e-3 of the units qualify.
+// One warp per (sample z, input b) row; H_hi (+ H_lo when the output is stored tf32-split) hold leaky(pre).
+__global__ void __launch_bounds__(256)
+refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, int H, const float* __restrict__ a_hi,
+              const float* __restrict__ a_lo, int64_t a_zstride, int K, const float* __restrict__ bank, int64_t P,
+              int64_t w_off, int64_t b_off, int z_row0, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < (int64_t)Z * B; row += nwarps) {
+    const int z = (int)(row / B), b = (int)(row % B);
+    float* hh = Hhi + row * H;
+    float* hl = Hlo ? Hlo + row * H : nullptr;
+    float m = 0.f;
+    for (int j = lane * 4; j < H; j += 128) {
+      float4 v = *reinterpret_cast<const float4*>(hh + j);
+      if (hl) {
+        const float4 l = *reinterpret_cast<const float4*>(hl + j);
+        v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+      }
+      m = fmaxf(m, fmaxf(fmaxf(v.x > 0.f ? v.x : -100.f * v.x, v.y > 0.f ? v.y : -100.f * v.y),
+                         fmaxf(v.z > 0.f ? v.z : -100.f * v.z, v.w > 0.f ? v.w : -100.f * v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float guard = eps * m;
+    const float* __restrict__ ah = a_hi + (int64_t)z * a_zstride + (int64_t)b * K;
+    const float* __restrict__ al = a_lo ? a_lo + (int64_t)z * a_zstride + (int64_t)b * K : nullptr;
+    const float* __restrict__ wrow = bank + (int64_t)(z_row0 + z) * P;
+    for (int j0 = 0; j0 < H; j0 += 128) {
+      const int j = j0 + lane * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      unsigned flags = 0u;
+      if (j < H) {
+        float4 t = *reinterpret_cast<const float4*>(hh + j);
+        if (hl) {
+          const float4 l = *reinterpret_cast<const float4*>(hl + j);
+          t.x += l.x; t.y += l.y; t.z += l.z; t.w += l.w;
+        }
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pre = v[e] > 0.f ? v[e] : -100.f * v[e];
+          if (pre < guard) flags |= 1u << e;
+        }
+      }
+      unsigned any = __ballot_sync(0xffffffffu, flags != 0u);
+      bool changed = false;
+      while (any) {
+        const int src = __ffs(any) - 1;
+        const unsigned f = __shfl_sync(0xffffffffu, flags, src);
+        const int e = __ffs(f) - 1;
+        const int jj = j0 + src * 4 + e;
+        const float* __restrict__ w = wrow + w_off + (int64_t)jj * K;
+        double s = 0.0;
+        for (int d = lane; d < K; d += 32) {
+          float a = ah[d];
+          if (al) a += al[d];
+          s = fma((double)a, (double)__ldg(w + d), s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s += (double)__ldg(wrow + b_off + jj);
+        float val = (float)s;
+        val = val > 0.f ? val : val * kLeakySlope;
+        if (lane == src) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q == e) v[q] = val;
+          flags &= ~(1u << e);
+          changed = true;
+        }
+        any = __ballot_sync(0xffffffffu, flags != 0u);
+      }
+      if (changed) {
+        if (hl) {
+          float4 h4, l4;
+          h4.x = tf32_rn(v[0]); h4.y = tf32_rn(v[1]); h4.z = tf32_rn(v[2]); h4.w = tf32_rn(v[3]);
+          l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
+          *reinterpret_cast<float4*>(hh + j) = h4;
+          *reinterpret_cast<float4*>(hl + j) = l4;
+        } else {
+          *reinterpret_cast<float4*>(hh + j) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+  }
+}
+
+// out[i] = (accumulate ? out[i] : 0) + sum_p partial[p][i]  (fixed order => deterministic)
+__global__ void reduce_slots_kernel(const float* __restrict__ partial, int nparts, int64_t n4,
+                                    float* __restrict__ out, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = accumulate ? reinterpret_cast<const float4*>(out)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = 0; p < nparts; ++p) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial) + (int64_t)p * n4 + i);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = s;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+int tc_supported(const rbnn_net* n) {
+  if (n->arch != RBNN_ARCH_FC && n->arch != RBNN_ARCH_FC2) return 0;
+  if ((n->D & 7) || n->H < 32 || n->C > kMaxC) return 0;
+  return n->cc_major == 10;
+}
+
+void tc_bank_free(rbnn_net* n) {
+  for (int i = 0; i < 2; ++i) {
+    TcMat& m = n->tc.mat[i];
+    cudaFree(m.hi); cudaFree(m.lo); cudaFree(m.thi); cudaFree(m.tlo); cudaFree(m.bf); cudaFree(m.tbf);
+    m = TcMat();
+  }
+  delete[] n->tc.dirty;
+  n->tc.dirty = nullptr;
+  n->tc.capacity = 0;
+  n->tc.mode = -1;
+}
+
+// Bring the derived copies of bank rows [s0, s1) up to date (all rows after a capacity / precision change).
+static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
+  TcBank& tc = n->tc;
+  const bool bf = n->prec == RBNN_PREC_BF16;
+  if (tc.capacity < n->capacity || tc.mode != n->prec) {
+    RBNN_CUDA(cudaDeviceSynchronize());
+    tc_bank_free(n);
+    tc.nmat = n->arch == RBNN_ARCH_FC2 ? 2 : 1;
+    tc.mat[0].off = n->L.w1; tc.mat[0].R = n->H; tc.mat[0].C = n->D;
+    if (tc.nmat == 2) { tc.mat[1].off = n->L.w2; tc.mat[1].R = n->H; tc.mat[1].C = n->H; }
+    for (int i = 0; i < tc.nmat; ++i) {
+      TcMat& m = tc.mat[i];
+      const size_t elems = (size_t)n->capacity * m.R * m.C;
+      if (bf) {
+        RBNN_CUDA(cudaMalloc(&m.bf, elems * 2));
+        RBNN_CUDA(cudaMalloc(&m.tbf, elems * 2));
+      } else {
+        RBNN_CUDA(cudaMalloc(&m.hi, elems * 4));
+        RBNN_CUDA(cudaMalloc(&m.lo, elems * 4));
+        RBNN_CUDA(cudaMalloc(&m.thi, elems * 4));
+        RBNN_CUDA(cudaMalloc(&m.tlo, elems * 4));
+      }
+    }
+    tc.dirty = new uint8_t[n->capacity];
+    std::fill(tc.dirty, tc.dirty + n->capacity, (uint8_t)1);
+    tc.capacity = n->capacity;
+    tc.mode = n->prec;
+  }
+  int s = s0;
+  while (s < s1) {
+    if (!tc.dirty[s]) { ++s; continue; }
+    int e = s;
+    while (e < s1 && tc.dirty[e]) ++e;
+    for (int i = 0; i < tc.nmat; ++i) {
+      TcMat& m = tc.mat[i];
+      dim3 grid((m.C + 31) / 32, (m.R + 31) / 32, e - s);
+      relayout_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, s, m.hi, m.lo, m.thi, m.tlo,
+                                                    reinterpret_cast<__nv_bfloat16*>(m.bf),
+                                                    reinterpret_cast<__nv_bfloat16*>(m.tbf));
+      n->launches++;
+      RBNN_CUDA(cudaGetLastError());
+    }
+    std::fill(tc.dirty + s, tc.dirty + e, (uint8_t)0);
+    s = e;
+  }
+  return 0;
+}
+
+static int run_gemm(rbnn_net* n, tc::GemmDesc& d, int tag, cudaStream_t st) {
+  d.mode = n->prec == RBNN_PREC_BF16 ? tc::MODE_BF16 : tc::MODE_TF32X3;
+  d.sm_count = n->sm_count;
+  std::string err;
+  if (tag) RBNN_TRY(timing_begin(n, tag, st));
+  if (tc::gemm(d, st, &err)) {
+    set_error("%s", err.c_str());
+    return 1;
+  }
+  n->launches++;
+  if (tag) RBNN_TRY(timing_end(n, tag, st));
+  return 0;
+}
+
+static int pick_bn(int N) {
+  // widest tile that wastes the least of the last column block (784 -> 4 x 208, 512 -> 2 x 256)
+  int best = 16;
+  double best_eff = 0.0;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    const int tiles = (N + bn - 1) / bn;
+    const double eff = (double)N / ((double)tiles * bn) * (bn >= 128 ? 1.0 : 0.5 + bn / 256.0);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = bn; }
+  }
+  return best;
+}
+
+namespace {
+struct FcWs {
+  // per call
+  float *x_hi = nullptr, *x_lo = nullptr;
+  __nv_bfloat16* x_bf = nullptr;
+  // per chunk of Z samples ([Z, B, H] each)
+  float *h1 = nullptr, *h1_lo = nullptr, *h2 = nullptr;       // tf32x3/fc2: h1 holds the hi part (sign == sign of H1)
+  __nv_bfloat16 *h1_bf = nullptr;
+  float *dtop_hi = nullptr, *dtop_lo = nullptr, *d1_hi = nullptr, *d1_lo = nullptr;
+  __nv_bfloat16 *dtop_bf = nullptr, *d1_bf = nullptr;
+  float *logits = nullptr, *partial = nullptr;
+};
+}  // namespace
+
+static size_t fc_per_z_bytes(const rbnn_net* n, int B, bool grad) {
+  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
+  const size_t bh = pad256((size_t)B * n->H * 4), bh2 = pad256((size_t)B * n->H * 2);
+  size_t per = bh;                                   // h1 (fp32 or hi)
+  if (two) per += (bf ? bh2 : bh) + bh;              // h1 lo / bf16 + h2
+  if (grad) {
+    per += bf ? bh2 : 2 * bh;                        // dtop
+    if (two) per += bf ? bh2 : 2 * bh;               // d1
+  } else {
+    per += pad256((size_t)B * n->C * 4);             // logits
+  }
+  return per;
+}
+
+// forward GEMMs of one chunk; returns the top hidden activations (fp32) in *top
+constexpr float kGuardEps = 1.0f / 4096.0f;   // ~50x the measured TF32x3 error bound (5e-6 of the output max)
+
+static int refine(rbnn_net* n, float* h_hi, float* h_lo, int Z, int B, const float* a_hi, const float* a_lo,
+                  int64_t a_zstride, int K, int64_t w_off, int64_t b_off, int z0, cudaStream_t st) {
+  const int64_t rows = (int64_t)Z * B;
+  const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)n->sm_count * 8);
+  refine_kernel<<<blocks, 256, 0, st>>>(h_hi, h_lo, Z, B, n->H, a_hi, a_lo, a_zstride, K, n->bank, n->L.P, w_off,
+                                        b_off, z0, kGuardEps);
+  n->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B, int z0, int Z, const float** top,
+                               cudaStream_t st) {
+  const int H = n->H, D = n->D;
+  const int64_t P = n->L.P;
+  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
+  const TcMat& m1 = n->tc.mat[0];
+  tc::GemmDesc g;
+  g.M = B; g.N = H; g.K = D; g.Z = Z; g.BN = pick_bn(H);
+  g.A.hi = bf ? (const void*)w.x_bf : (const void*)w.x_hi; g.A.lo = w.x_lo; g.A.rows = B; g.A.ld = D; g.A.zstride = 0;
+  if (bf) g.B.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * D;
+  else { g.B.hi = m1.hi + (int64_t)z0 * H * D; g.B.lo = m1.lo + (int64_t)z0 * H * D; }
+  g.B.rows = H; g.B.ld = D; g.B.zstride = (int64_t)H * D;
+  g.epi = tc::EPI_BIAS_LEAKY;
+  g.bias = n->bank + (int64_t)z0 * P + n->L.b1; g.bias_zstride = P;
+  g.out = w.h1; g.out_ld = H; g.out_zstride = (int64_t)B * H;
+  if (two) {
+    if (bf) g.out_bf = w.h1_bf; else g.out_lo = w.h1_lo;
+  }
+  RBNN_TRY(run_gemm(n, g, 1, st));
+  if (!bf) RBNN_TRY(refine(n, w.h1, two ? w.h1_lo : nullptr, Z, B, x, nullptr, 0, D, n->L.w1, n->L.b1, z0, st));
+  *top = w.h1;
+  if (two) {
+    const TcMat& m2 = n->tc.mat[1];
+    tc::GemmDesc q;
+    q.M = B; q.N = H; q.K = H; q.Z = Z; q.BN = pick_bn(H);
+    q.A.hi = bf ? (const void*)w.h1_bf : (const void*)w.h1; q.A.lo = w.h1_lo; q.A.rows = B; q.A.ld = H;
+    q.A.zstride = (int64_t)B * H;
+    if (bf) q.B.hi = reinterpret_cast<const __nv_bfloat16*>(m2.bf) + (int64_t)z0 * H * H;
+    else { q.B.hi = m2.hi + (int64_t)z0 * H * H; q.B.lo = m2.lo + (int64_t)z0 * H * H; }
+    q.B.rows = H; q.B.ld = H; q.B.zstride = (int64_t)H * H;
+    q.epi = tc::EPI_BIAS_LEAKY;
+    q.bias = n->bank + (int64_t)z0 * P + n->L.b2; q.bias_zstride = P;
+    q.out = w.h2; q.out_ld = H; q.out_zstride = (int64_t)B * H;
+    RBNN_TRY(run_gemm(n, q, 0, st));
+    if (!bf) RBNN_TRY(refine(n, w.h2, nullptr, Z, B, w.h1, w.h1_lo, (int64_t)B * H, H, n->L.w2, n->L.b2, z0, st));
+    *top = w.h2;
+  }
+  return 0;
+}
+
+static int launch_head(rbnn_net* n, bool grad, int head, const float* top, int z0, int Z, const int32_t* labels,
+                       const float* pbar, int B, float* logits, float* dh_hi, float* dh_lo, __nv_bfloat16* dh_bf,
+                       cudaStream_t st) {
+  const int H = n->H, C = n->C;
+  const size_t smem = (size_t)(C * H + C) * sizeof(float);
+  dim3 grid((B + kHeadWarps * kHeadRowsPerWarp - 1) / (kHeadWarps * kHeadRowsPerWarp), Z);
+#define RBNN_HEAD_LAUNCH(CM, G)                                                                                   \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      RBNN_CUDA(cudaFuncSetAttribute(fc_head_kernel<CM, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    fc_head_kernel<CM, G><<<grid, kHeadWarps * 32, smem, st>>>(head, top, n->bank, n->L.P, n->L.wo, n->L.bo, z0,   \
+                                                                labels, pbar, B, H, C, logits, dh_hi, dh_lo, dh_bf); \
+  } while (0)
+  RBNN_CHECK(smem <= 200 * 1024, "tcgen05 engine: n_classes * hidden too large for the head kernel");
+  if (C <= 16) {
+    if (grad) RBNN_HEAD_LAUNCH(16, true); else RBNN_HEAD_LAUNCH(16, false);
+  } else {
+    if (grad) RBNN_HEAD_LAUNCH(32, true); else RBNN_HEAD_LAUNCH(32, false);
+  }
+#undef RBNN_HEAD_LAUNCH
+  n->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, cudaStream_t st) {
+  const int64_t n4 = count / 4;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
+  split_kernel<<<blocks, 256, 0, st>>>(x, w.x_hi, w.x_lo, w.x_bf, n4);
+  n->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// rows of the batch per pass such that at least one sample fits the workspace budget
+static int tc_batch_rows(const rbnn_net* n, int B, bool grad) {
+  const size_t per_row = fc_per_z_bytes(n, 1024, grad) / 1024 + (size_t)n->D * 12 + 64;
+  const size_t rows = std::max<size_t>(128, (n->ws_budget / 2) / per_row);
+  return (int)std::min<size_t>(rows, (size_t)B);
+}
+
+static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1,
+                        const float* pbar, float* out_sum, cudaStream_t st) {
+  const int H = n->H, D = n->D;
+  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
+  const int S = s1 - s0;
+  const size_t per = fc_per_z_bytes(n, B, true);
+  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : 2 * pad256((size_t)B * D * 4);
+  const size_t out_bytes = pad256((size_t)B * D * 4);
+  // samples per chunk: as many as the budget allows; the backward reduce cuts a chunk into `slots`
+  // K-concatenated ranges of ~4 samples (bounds the tensor-core accumulation chain, fills the SMs)
+  size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
+  int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / (per + out_bytes / 4 + 1), (size_t)S));
+  const int bn_b = pick_bn(D);
+  const int tiles_mn = ((B + tc::kBM - 1) / tc::kBM) * ((D + bn_b - 1) / bn_b);
+  auto slots_for = [&](int Z) {
+    int best = 1;
+    double best_score = -1.0;
+    for (int s = 1; s <= std::min(Z, 64); ++s) {
+      const int tiles = tiles_mn * s;
+      const int waves = (tiles + n->sm_count - 1) / n->sm_count;
+      double score = (double)tiles / ((double)waves * n->sm_count);          // SM fill
+      if ((Z + s - 1) / s > 4) score -= 0.02 * ((Z + s - 1) / s - 4);        // prefer chains of <= 4 samples
+      if (score > best_score + 1e-9) { best_score = score; best = s; }
+    }
+    return best;
+  };
+  int slots = slots_for(zc);
+  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots));
+  Arena ar(n);
+  FcWs w;
+  if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
+  else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
+  const size_t zbh = (size_t)zc * B * H;
+  w.h1 = ar.take<float>(zbh);
+  if (two) {
+    if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
+    w.h2 = ar.take<float>(zbh);
+  }
+  if (bf) w.dtop_bf = ar.take<__nv_bfloat16>(zbh);
+  else { w.dtop_hi = ar.take<float>(zbh); w.dtop_lo = ar.take<float>(zbh); }
+  if (two) {
+    if (bf) w.d1_bf = ar.take<__nv_bfloat16>(zbh);
+    else { w.d1_hi = ar.take<float>(zbh); w.d1_lo = ar.take<float>(zbh); }
+  }
+  w.partial = ar.take<float>((size_t)slots * B * D);
+  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, st));
+
+  bool first = true;
+  for (int z0 = s0; z0 < s1; z0 += zc) {
+    const int Z = std::min(zc, s1 - z0);
+    const int sl = Z == zc ? slots : std::min(slots, slots_for(Z));
+    const float* top = nullptr;
+    RBNN_TRY(fc_forward_chunk_tc(n, w, x, B, z0, Z, &top, st));
+    RBNN_TRY(launch_head(n, true, head, top, z0, Z, labels, pbar, B, nullptr, w.dtop_hi, w.dtop_lo, w.dtop_bf, st));
+    const void* dfirst_hi = bf ? (const void*)w.dtop_bf : (const void*)w.dtop_hi;
+    const void* dfirst_lo = w.dtop_lo;
+    if (two) {
+      // dH1 = (dH2 . W2) (.) leaky'(H1): per-z GEMM with K = H over the transposed copy of W2
+      const TcMat& m2 = n->tc.mat[1];
+      tc::GemmDesc q;
+      q.M = B; q.N = H; q.K = H; q.Z = Z; q.BN = pick_bn(H);
+      q.A.hi = dfirst_hi; q.A.lo = dfirst_lo; q.A.rows = B; q.A.ld = H; q.A.zstride = (int64_t)B * H;
+      if (bf) q.B.hi = reinterpret_cast<const __nv_bfloat16*>(m2.tbf) + (int64_t)z0 * H * H;
+      else { q.B.hi = m2.thi + (int64_t)z0 * H * H; q.B.lo = m2.tlo + (int64_t)z0 * H * H; }
+      q.B.rows = H; q.B.ld = H; q.B.zstride = (int64_t)H * H;
+      q.epi = tc::EPI_MASK;
+      q.act = w.h1; q.act_zstride = (int64_t)B * H; q.act_ld = H;
+      if (bf) q.out_bf = w.d1_bf; else { q.out = w.d1_hi; q.out_lo = w.d1_lo; }
+      q.out_ld = H; q.out_zstride = (int64_t)B * H;
+      RBNN_TRY(run_gemm(n, q, 0, st));
+      dfirst_hi = bf ? (const void*)w.d1_bf : (const void*)w.d1_hi;
+      dfirst_lo = w.d1_lo;
+    }
+    // dX partial sums: K-concatenated over the samples of each slot
+    const TcMat& m1 = n->tc.mat[0];
+    tc::GemmDesc r;
+    r.M = B; r.N = D; r.K = H; r.Z = Z; r.BN = bn_b;
+    r.A.hi = dfirst_hi; r.A.lo = dfirst_lo; r.A.rows = B; r.A.ld = H; r.A.zstride = (int64_t)B * H;
+    if (bf) r.B.hi = reinterpret_cast<const __nv_bfloat16*>(m1.tbf) + (int64_t)z0 * D * H;
+    else { r.B.hi = m1.thi + (int64_t)z0 * D * H; r.B.lo = m1.tlo + (int64_t)z0 * D * H; }
+    r.B.rows = D; r.B.ld = H; r.B.zstride = (int64_t)D * H;
+    r.reduce_z = 1; r.slots = sl;
+    r.out = w.partial; r.out_ld = D; r.out_zstride = (int64_t)B * D;
+    RBNN_TRY(run_gemm(n, r, 2, st));
+    const int64_t n4 = (int64_t)B * D / 4;
+    reduce_slots_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(w.partial, sl, n4, out_sum, first ? 0 : 1);
+    n->launches++;
+    RBNN_CUDA(cudaGetLastError());
+    first = false;
+  }
+  return 0;
+}
+
+int tc_fc_input_grad_sum(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1,
+                         const float* pbar, float* out_sum, cudaStream_t st) {
+  RBNN_CHECK(tc_supported(n), "tcgen05 engine does not cover this network");
+  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
+  const int bc = tc_batch_rows(n, B, true);
+  for (int b0 = 0; b0 < B; b0 += bc) {
+    const int nb = std::min(bc, B - b0);
+    RBNN_TRY(tc_grad_pass(n, head, x + (int64_t)b0 * n->D, labels + b0, nb, s0, s1,
+                          pbar ? pbar + (int64_t)b0 * n->C : nullptr, out_sum + (int64_t)b0 * n->D, st));
+  }
+  return 0;
+}
+
+static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, float* out_logits,
+                           cudaStream_t st) {
+  const int H = n->H, D = n->D, C = n->C;
+  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
+  const int S = s1 - s0;
+  const size_t per = fc_per_z_bytes(n, B, false);
+  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : 2 * pad256((size_t)B * D * 4);
+  size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
+  const int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / per, (size_t)S));
+  RBNN_TRY(ws_reserve(n, x_bytes + per * zc));
+  Arena ar(n);
+  FcWs w;
+  if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
+  else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
+  const size_t zbh = (size_t)zc * B * H;
+  w.h1 = ar.take<float>(zbh);
+  if (two) {
+    if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
+    w.h2 = ar.take<float>(zbh);
+  }
+  w.logits = ar.take<float>((size_t)zc * B * C);
+  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, st));
+  for (int z0 = s0; z0 < s1; z0 += zc) {
+    const int Z = std::min(zc, s1 - z0);
+    const float* top = nullptr;
+    RBNN_TRY(fc_forward_chunk_tc(n, w, x, B, z0, Z, &top, st));
+    float* lg = out_logits ? out_logits : w.logits;
+    RBNN_TRY(launch_head(n, false, 0, top, z0, Z, nullptr, nullptr, B, lg, nullptr, nullptr, nullptr, st));
+    if (out_sum) RBNN_TRY(head_probs_accumulate(n, lg, Z, B, C, out_sum, st));
+  }
+  return 0;
+}
+
+int tc_fc_forward(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, float* out_logits,
+                  cudaStream_t st) {
+  RBNN_CHECK(tc_supported(n), "tcgen05 engine does not cover this network");
+  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
+  const int bc = tc_batch_rows(n, B, false);
+  for (int b0 = 0; b0 < B; b0 += bc) {
+    const int nb = std::min(bc, B - b0);
+    RBNN_TRY(tc_forward_pass(n, x + (int64_t)b0 * n->D, nb, s0, s1, out_sum ? out_sum + (int64_t)b0 * n->C : nullptr,
+                             out_logits ? out_logits + (int64_t)b0 * n->C : nullptr, st));
+  }
+  return 0;
+}
+
+}  // namespace rbnn

@@ -284,8 +284,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                         __uint_as_float(r[j + 3])};
           if (p.epi == EPI_BIAS_LEAKY || p.epi == EPI_BIAS) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
-            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+            // scalar loads: bank rows are P floats apart, so bias_z is only 4-byte aligned
+            v[0] += __ldg(bias + n); v[1] += __ldg(bias + n + 1); v[2] += __ldg(bias + n + 2); v[3] += __ldg(bias + n + 3);
             if (p.epi == EPI_BIAS_LEAKY) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * kSlope;

@@ -93,21 +93,31 @@ def test_golden_hmc_attacks_and_evaluation(name, tmp_path, monkeypatch):
             assert float((rob.cpu() - c.t(f"{method}_{hname}_rob")).abs().max()) <= 1e-6
             loaded = aa.load_attack(method, "a", savedir="a", n_samples=S)
             assert torch.equal(loaded.cpu(), adv.cpu())
-    # default PGD, teacher-forced: from every image x_t of the oracle's fp32 trajectory one CUDA step must
-    # land on the oracle's x_{t+1} (up to measure-zero sign ties).
+    # default PGD, teacher-forced: at images x_t of the oracle's fp32 trajectory (a) the attack gradient must
+    # match the fp64 oracle to the north-star tolerance and (b) one CUDA step must land on the oracle's
+    # x_{t+1} wherever the sign of the gradient is numerically determined (|g| above the gradient tolerance,
+    # 1e-4 max|g|; below that fp32 rounding decides the sign in the reference itself -- late PGD states
+    # saturate the softmax and the softmax backward cancels catastrophically).
+    from robustbnns_b200 import _lib
     sched = lambda call: range(S)  # noqa: E731
     traj = [c.x.clone()]
     for t in range(40):
         g = orc.attack_gradient(c.net, c.layout, c.bank, traj[-1], c.labels, sched(t))
         traj.append(orc.pgd_step(traj[-1], c.x, g, 2 / 225, 0.5).detach())
-    # (tests/test_oracle_golden.py pins this trajectory's end point to the reference's own output)
     x0, y = aa._prep(bnn, c.x, c.labels)
     alpha = torch.full((len(c.x),), 2 / 225, dtype=torch.float32, device=x0.device)
-    worst = 0.0
-    for t in range(40):
-        nxt = aa._pgd_loop(bnn, traj[t].cuda(), x0, y, alpha, 0.5, S, False, 1)
-        worst = max(worst, _mismatch_fraction(nxt, traj[t + 1]))
-    assert worst <= 2e-3, worst
+    eng = bnn.engine()
+    for t in (0, 1, 2, 3, 5, 8, 13, 21, 30, 39):
+        g64 = orc.attack_gradient(c.net, c.layout, c.bank, traj[t], c.labels, sched(t), dtype=torch.float64)
+        xt = traj[t].cuda()
+        pbar = eng.forward_probs_sum(xt, 0, S) / S
+        g = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, xt, y, 0, S, pbar=pbar).cpu().reshape(g64.shape) / S
+        assert rel_err(g, g64) < REL, (t, rel_err(g, g64))
+        nxt = aa._pgd_loop(bnn, xt, x0, y, alpha, 0.5, S, False, 1).cpu()
+        ref_nxt = orc.pgd_step(traj[t].double(), c.x.double(), g64, 2 / 225, 0.5)
+        determined = g64.abs() > REL * g64.abs().max()
+        bad = ((nxt.double() - ref_nxt).abs() > 1e-6) & determined
+        assert float(bad.float().sum() / determined.float().sum().clamp_min(1)) <= 2e-3, t
 
 
 # ------------------------------------------------------------------ oracle at larger sizes -------------
@@ -165,6 +175,75 @@ def test_engine_vs_oracle(arch, shape, hidden, C, B, S, ds):
     # sample loop over CTAs depends on the batch size, so only up to fp32 summation order)
     gs = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x[:3], labels[:3], 0, S).cpu().reshape(x[:3].shape) / S
     assert rel_err(gs, g[:3]) < 1e-5
+    eng.close()
+
+
+TC_CONFIGS = [
+    ("fc", (1, 28, 28), 512, 10, 300, 9),       # headline architecture; ragged M tile; 9 samples -> several slots
+    ("fc", (1, 28, 28), 64, 10, 7, 10),         # tiny batch, narrow hidden layer
+    ("fc", (1, 28, 28), 32, 10, 130, 3),
+    ("fc2", (1, 28, 28), 128, 10, 130, 5),
+    ("fc2", (1, 28, 28), 512, 10, 257, 6),
+]
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32x3", REL), ("bf16", 1.0)])
+@pytest.mark.parametrize("arch,shape,hidden,C,B,S", TC_CONFIGS)
+def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol):
+    """The tensor-core engine (tcgen05 / TMA / TMEM) against the fp64 oracle: TF32x3 is parity grade
+    (rel <= 1e-4, the north-star tolerance); single-pass BF16 is the throughput mode and is only held
+    to a loose bound (its measured deviation is reported by bench.py)."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    net, layout, loc, rho, bank, x, labels = _problem(arch, shape, hidden, C, B, S)
+    eng = Net(arch, shape, hidden, C)
+    eng.set_precision(prec)
+    assert eng.precision == prec
+    eng.upload(bank, 0)
+    probs = eng.forward_probs_sum(x, 0, S).cpu() / S
+    ref_p = orc.bnn_forward(net, layout, bank, x, range(S)).detach()
+    assert rel_err(probs, ref_p) < tol
+    assert rel_err(eng.forward_logits(x, 1).cpu(),
+                   orc.bnn_forward_avg_posterior(net, layout, bank[1], x).detach()) < max(tol, 1e-4) * (1 if prec == "tf32x3" else 0.25)
+    g = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S).cpu().reshape(x.shape) / S
+    ref64 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    e_mean = rel_err(g, ref64)
+    pbar = eng.forward_probs_sum(x, 0, S) / S
+    ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
+    ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    e_att = rel_err(ga, ra)
+    gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, S - 1, S).cpu().reshape(x.shape)
+    rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
+    e_log = rel_err(gl, rl)
+    cos = float(torch.nn.functional.cosine_similarity(g.double().flatten(), ref64.flatten(), dim=0))
+    print(f"tcgen05 {prec} {arch}-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} "
+          f"logits-CE {e_log:.2e} cosine {cos:.6f}")
+    assert cos > 0.98
+    if arch == "fc2" and prec == "tf32x3":
+        # Two hidden layers: the second layer's LeakyReLU masks are evaluated on first-layer activations that
+        # carry the tensor-core accumulation rounding (~5e-6 of the layer max, vs ~1e-7 for fp32 FFMA).  A
+        # second-layer unit within ~1e-5 of zero (probability ~1e-5 per unit) can therefore still come out on
+        # the other side than in fp64, which moves ONE (sample, input) row by O(1/hidden).  Held to: all but
+        # 2 % of the rows within the north-star tolerance, every row within 10 %.
+        def bad_rows(a, ref):
+            d = (a.double() - ref).abs().flatten(1).max(dim=1)[0] / ref.abs().max()
+            return float((d > tol).float().mean())
+        assert bad_rows(g, ref64) <= 0.02 and bad_rows(ga, ra) <= 0.02 and bad_rows(gl, rl) <= 0.02
+        assert max(e_mean, e_att, e_log) < 0.1
+    else:
+        assert max(e_mean, e_att, e_log) < tol
+    # the split of the sample range over calls (what sample sharding relies on) and a re-upload of one row
+    ga_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S // 2)
+    gb_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, S // 2, S)
+    assert rel_err((ga_ + gb_).cpu().reshape(x.shape) / S, g) < max(1e-5, tol * 0.1)
+    eng.upload(bank[0:1], 1)                       # row 1 <- row 0: derived tensor-core copies must follow
+    g11 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 1, 2).cpu()
+    g00 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, 1).cpu()
+    assert torch.equal(g11, g00)
+    # switching back to the CUDA-core engine on the same handle
+    eng.set_precision("fp32")
+    g32 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, 1).cpu()
+    assert rel_err(g32, g00) < tol
     eng.close()
 
 
