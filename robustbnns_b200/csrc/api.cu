@@ -1,6 +1,7 @@
 // C ABI of librbnn.so (include/rbnn.h): handle management, the posterior-sample bank, and the
 // per-architecture orchestration of the forward / input-gradient passes over bank rows.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -368,6 +369,7 @@ int rbnn_net_create(rbnn_net** out, int arch, int in_ch, int in_h, int in_w, int
   n->arch = arch; n->in_ch = in_ch; n->in_h = in_h; n->in_w = in_w;
   n->D = in_ch * in_h * in_w; n->H = hidden; n->C = n_classes; n->device = device;
   build_layout(n);
+  if (const char* e = getenv("RBNN_TC_UNFUSED")) n->tc_unfused = atoi(e);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
     n->sm_count = prop.multiProcessorCount;

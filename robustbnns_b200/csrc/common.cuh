@@ -63,6 +63,7 @@ struct TcBank {
   int mode = -1;            // precision the copies were built for
   int nmat = 0;
   TcMat mat[2];
+  float* wnorm = nullptr;   // [capacity] max_j ||W1_s[j,:]||_2 (guard band of the fused forward kernel)
   uint8_t* dirty = nullptr; // host flags per row (derived copies stale)
 };
 
@@ -84,6 +85,7 @@ struct rbnn_net {
   int sm_count = 148;
   int cc_major = 0;           // compute capability major of `device` (10 = Blackwell: tcgen05 engine usable)
   TcBank tc;
+  int tc_unfused = 0;         // 1: arch fc takes the unfused GEMM -> head route (RBNN_TC_UNFUSED=1; A/B testing)
   // optional per-kernel-class device timing (bench.py's roofline leg): event pairs on the launch stream
   int timing = 0;
   std::vector<cudaEvent_t> ev[3][2];   // [class][begin/end]; class 1 = first-layer forward GEMM, 2 = input-grad GEMM

@@ -322,6 +322,42 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
   }
 }
 
+// xnorm[b] = ||x_b||_2 : one warp per input row
+__global__ void xnorm_kernel(const float* __restrict__ x, int B, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (b >= B) return;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) { const float v = __ldg(x + (int64_t)b * D + d); s = fmaf(v, v, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[b] = sqrtf(s);
+}
+
+// wnorm[s] = max_j ||W_s[j, :]||_2 over the R rows of the [R, C] matrix at `off` of bank row s; one block per s
+__global__ void __launch_bounds__(256)
+wnorm_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0, float* __restrict__ out) {
+  __shared__ float red[8];
+  const int s = s0 + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float best = 0.f;
+  for (int r = warp; r < R; r += 8) {
+    const float* __restrict__ w = bank + (int64_t)s * P + off + (int64_t)r * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = __ldg(w + c); acc = fmaf(v, v, acc); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    best = fmaxf(best, acc);
+  }
+  if (lane == 0) red[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, red[i]);
+    out[s] = sqrtf(m);
+  }
+}
+
 // out[i] = (accumulate ? out[i] : 0) + sum_p partial[p][i]  (fixed order => deterministic)
 __global__ void reduce_slots_kernel(const float* __restrict__ partial, int nparts, int64_t n4,
                                     float* __restrict__ out, int accumulate) {
@@ -350,6 +386,8 @@ void tc_bank_free(rbnn_net* n) {
     cudaFree(m.hi); cudaFree(m.lo); cudaFree(m.thi); cudaFree(m.tlo); cudaFree(m.bf); cudaFree(m.tbf);
     m = TcMat();
   }
+  cudaFree(n->tc.wnorm);
+  n->tc.wnorm = nullptr;
   delete[] n->tc.dirty;
   n->tc.dirty = nullptr;
   n->tc.capacity = 0;
@@ -379,6 +417,7 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
         RBNN_CUDA(cudaMalloc(&m.tlo, elems * 4));
       }
     }
+    RBNN_CUDA(cudaMalloc(&tc.wnorm, (size_t)n->capacity * sizeof(float)));
     tc.dirty = new uint8_t[n->capacity];
     std::fill(tc.dirty, tc.dirty + n->capacity, (uint8_t)1);
     tc.capacity = n->capacity;
@@ -398,6 +437,9 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }
+    wnorm_kernel<<<e - s, 256, 0, st>>>(n->bank, n->L.P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C, s, tc.wnorm);
+    n->launches++;
+    RBNN_CUDA(cudaGetLastError());
     std::fill(tc.dirty + s, tc.dirty + e, (uint8_t)0);
     s = e;
   }
@@ -440,13 +482,23 @@ struct FcWs {
   __nv_bfloat16 *h1_bf = nullptr;
   float *dtop_hi = nullptr, *dtop_lo = nullptr, *d1_hi = nullptr, *d1_lo = nullptr;
   __nv_bfloat16 *dtop_bf = nullptr, *d1_bf = nullptr;
-  float *logits = nullptr, *partial = nullptr;
+  float *logits = nullptr, *partial = nullptr, *xnorm = nullptr;
+  unsigned long long* worklist = nullptr;
 };
 }  // namespace
+
+// arch fc with a hidden layer the fused forward+head kernel covers: H never goes to HBM
+static bool use_fused(const rbnn_net* n) {
+  return n->arch == RBNN_ARCH_FC && n->L.w1 == 0 && tc::fused_supported(n->H, n->C) && !n->tc_unfused;
+}
 
 static size_t fc_per_z_bytes(const rbnn_net* n, int B, bool grad) {
   const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
   const size_t bh = pad256((size_t)B * n->H * 4), bh2 = pad256((size_t)B * n->H * 2);
+  if (use_fused(n)) {
+    if (!grad) return pad256((size_t)B * n->C * 4);
+    return (bf ? bh2 : 2 * bh) + pad256(tc::fused_worklist_slots(B, 1) * 8);
+  }
   size_t per = bh;                                   // h1 (fp32 or hi)
   if (two) per += (bf ? bh2 : bh) + bh;              // h1 lo / bf16 + h2
   if (grad) {
@@ -459,6 +511,7 @@ static size_t fc_per_z_bytes(const rbnn_net* n, int B, bool grad) {
 }
 
 // forward GEMMs of one chunk; returns the top hidden activations (fp32) in *top
+constexpr float kGuardEpsFused = 1.0f / 16384.0f;   // x ||x_b|| max_j ||w_zj||: above the worst-case tensor-core error
 constexpr float kGuardEps = 1.0f / 4096.0f;   // ~50x the measured TF32x3 error bound (5e-6 of the output max)
 
 static int refine(rbnn_net* n, float* h_hi, float* h_lo, int Z, int B, const float* a_hi, const float* a_lo,
@@ -508,6 +561,38 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
     RBNN_TRY(run_gemm(n, q, 0, st));
     if (!bf) RBNN_TRY(refine(n, w.h2, nullptr, Z, B, w.h1, w.h1_lo, (int64_t)B * H, H, n->L.w2, n->L.b2, z0, st));
     *top = w.h2;
+  }
+  return 0;
+}
+
+// fused forward + head of one chunk (arch fc): dH (head >= 0) or logits (head < 0) straight from TMEM
+static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, const int32_t* labels, const float* pbar,
+                       int B, int z0, int Z, float* logits, cudaStream_t st) {
+  const int H = n->H, D = n->D;
+  const bool bf = n->prec == RBNN_PREC_BF16;
+  const TcMat& m1 = n->tc.mat[0];
+  tc::FusedDesc f;
+  f.mode = bf ? tc::MODE_BF16 : tc::MODE_TF32X3;
+  f.B = B; f.D = D; f.H = H; f.C = n->C; f.Z = Z;
+  f.X.hi = bf ? (const void*)w.x_bf : (const void*)w.x_hi; f.X.lo = w.x_lo; f.X.rows = B; f.X.ld = D;
+  if (bf) f.W1.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * D;
+  else { f.W1.hi = m1.hi + (int64_t)z0 * H * D; f.W1.lo = m1.lo + (int64_t)z0 * H * D; }
+  f.W1.rows = H; f.W1.ld = D; f.W1.zstride = (int64_t)H * D;
+  f.head = head;
+  f.bank = n->bank; f.P = n->L.P; f.b1_off = n->L.b1; f.wo_off = n->L.wo; f.bo_off = n->L.bo; f.z_row0 = z0;
+  f.labels = labels; f.pbar = pbar;
+  f.x = x; f.xnorm = w.xnorm; f.wnorm = n->tc.wnorm; f.eps = kGuardEpsFused;
+  f.dh_hi = w.dtop_hi; f.dh_lo = w.dtop_lo; f.dh_bf = w.dtop_bf; f.logits = logits;
+  f.worklist = w.worklist;
+  f.sm_count = n->sm_count;
+  std::string err;
+  if (head >= 0) RBNN_TRY(timing_begin(n, 1, st));
+  if (tc::fused_forward_head(f, st, &err)) { set_error("%s", err.c_str()); return 1; }
+  n->launches++;
+  if (head >= 0) RBNN_TRY(timing_end(n, 1, st));
+  if (head >= 0 && !bf) {
+    if (tc::fused_fixup(f, st, &err)) { set_error("%s", err.c_str()); return 1; }
+    n->launches++;
   }
   return 0;
 }
@@ -580,13 +665,14 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     return best;
   };
   int slots = slots_for(zc);
-  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots));
+  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots + pad256((size_t)B * 4) + 4096));
   Arena ar(n);
   FcWs w;
   if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
   else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
   const size_t zbh = (size_t)zc * B * H;
-  w.h1 = ar.take<float>(zbh);
+  const bool fused = use_fused(n);
+  if (!fused) w.h1 = ar.take<float>(zbh);
   if (two) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
     w.h2 = ar.take<float>(zbh);
@@ -597,16 +683,27 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     if (bf) w.d1_bf = ar.take<__nv_bfloat16>(zbh);
     else { w.d1_hi = ar.take<float>(zbh); w.d1_lo = ar.take<float>(zbh); }
   }
+  if (fused && !bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc));
+  w.xnorm = ar.take<float>((size_t)B);
   w.partial = ar.take<float>((size_t)slots * B * D);
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, st));
+  if (fused && !bf) {
+    xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
+    n->launches++;
+    RBNN_CUDA(cudaGetLastError());
+  }
 
   bool first = true;
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
     const int sl = Z == zc ? slots : std::min(slots, slots_for(Z));
-    const float* top = nullptr;
-    RBNN_TRY(fc_forward_chunk_tc(n, w, x, B, z0, Z, &top, st));
-    RBNN_TRY(launch_head(n, true, head, top, z0, Z, labels, pbar, B, nullptr, w.dtop_hi, w.dtop_lo, w.dtop_bf, st));
+    if (fused) {
+      RBNN_TRY(fused_chunk(n, w, head, x, labels, pbar, B, z0, Z, nullptr, st));
+    } else {
+      const float* top = nullptr;
+      RBNN_TRY(fc_forward_chunk_tc(n, w, x, B, z0, Z, &top, st));
+      RBNN_TRY(launch_head(n, true, head, top, z0, Z, labels, pbar, B, nullptr, w.dtop_hi, w.dtop_lo, w.dtop_bf, st));
+    }
     const void* dfirst_hi = bf ? (const void*)w.dtop_bf : (const void*)w.dtop_hi;
     const void* dfirst_lo = w.dtop_lo;
     if (two) {
@@ -674,7 +771,8 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
   else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
   const size_t zbh = (size_t)zc * B * H;
-  w.h1 = ar.take<float>(zbh);
+  const bool fused = use_fused(n);
+  if (!fused) w.h1 = ar.take<float>(zbh);
   if (two) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
     w.h2 = ar.take<float>(zbh);
@@ -683,10 +781,14 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, st));
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
-    const float* top = nullptr;
-    RBNN_TRY(fc_forward_chunk_tc(n, w, x, B, z0, Z, &top, st));
     float* lg = out_logits ? out_logits : w.logits;
-    RBNN_TRY(launch_head(n, false, 0, top, z0, Z, nullptr, nullptr, B, lg, nullptr, nullptr, nullptr, st));
+    if (fused) {
+      RBNN_TRY(fused_chunk(n, w, -1, x, nullptr, nullptr, B, z0, Z, lg, st));
+    } else {
+      const float* top = nullptr;
+      RBNN_TRY(fc_forward_chunk_tc(n, w, x, B, z0, Z, &top, st));
+      RBNN_TRY(launch_head(n, false, 0, top, z0, Z, nullptr, nullptr, B, lg, nullptr, nullptr, nullptr, st));
+    }
     if (out_sum) RBNN_TRY(head_probs_accumulate(n, lg, Z, B, C, out_sum, st));
   }
   return 0;

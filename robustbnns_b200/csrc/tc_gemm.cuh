@@ -44,6 +44,8 @@ struct GemmDesc {
   int mode = MODE_TF32X3;
   int M = 0, N = 0, K = 0, Z = 1;
   int BN = 256;          // tile width
+  int kblock_bytes = 128; // bytes of K per pipeline stage row: 128 (default) or 64 (twice the stages, measured slower)
+  int pair = 0;          // 1: CTA pairs (tcgen05 cta_group::2, 256-row tiles; measured +5% only); 0: one CTA per 128-row tile
   Operand A, B;
   int reduce_z = 0;      // 1: sum over z; the z range is cut into `slots` contiguous pieces -> out[slot]
   int slots = 1;
@@ -56,10 +58,48 @@ struct GemmDesc {
   void* out_bf = nullptr;     // optional: bf16 copy of the result
   int64_t out_ld = 0, out_zstride = 0;
   int sm_count = 148;
+  int pair_relay = 1;      // pair mode: 1 = own-barrier TMA + relayed full signal, 0 = cta_group::2 TMA onto the leader's barrier
+  int debug_skip_mma = 0;  // harness only: run the TMA / barrier pipeline without issuing MMAs
 };
 
 // Enqueues the GEMM on `st`.  Returns 0 on success; on failure fills *err.
 int gemm(const GemmDesc& d, cudaStream_t st, std::string* err);
+
+// 3-D TMA map over [Z][rows][K] (K innermost, `ld` / `zstride` in elements): box = one 128-byte K-block x box_rows x 1,
+// SWIZZLE_128B / SWIZZLE_64B (kb_bytes = 128 / 64), zero fill out of bounds.  zstride == 0 => a single z.
+int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t K, int64_t rows, int64_t Z, int64_t ld,
+             int64_t zstride, int box_rows, int kb_bytes, std::string* err);
+
+// Fused forward + head kernel for arch fc (tc_fused.cu): for every (posterior sample z, 128-input tile)
+//   H = leaky(X . W1_z^T + b1_z) in TMEM -> logits = H . Wo_z^T + bo_z -> loss head -> dlogits
+//   dH = (dlogits . Wo_z) (.) leaky'(H)   written K-major, pre-split (tf32 hi/lo) or bf16, for the backward GEMM
+// without ever writing H to HBM.  Units whose pre-activation lies inside the guard band are queued on a
+// worklist together with the sign that was assumed; fused_fixup() re-evaluates them exactly and patches dH.
+struct FusedDesc {
+  int mode = MODE_TF32X3;
+  int B = 0, D = 0, H = 0, C = 0, Z = 0;
+  Operand X, W1;                  // X: [B, D] (zstride 0); W1: [Z][H][D]
+  int head = -1;                  // RBNN_HEAD_* ; -1 = write logits only
+  const float* bank = nullptr;    // bank row of sample z: bank + (z_row0 + z) * P
+  int64_t P = 0, b1_off = 0, wo_off = 0, bo_off = 0;
+  int z_row0 = 0;
+  const int32_t* labels = nullptr;
+  const float* pbar = nullptr;
+  const float* x = nullptr;       // fp32 inputs [B, D] (exact re-evaluation)
+  const float* xnorm = nullptr;   // [B]   ||x_b||_2
+  const float* wnorm = nullptr;   // [capacity] max_j ||W1_s[j,:]||_2, indexed by bank row
+  float eps = 0.f;                // guard = eps * xnorm[b] * wnorm[row]; 0 disables the worklist
+  float* dh_hi = nullptr; float* dh_lo = nullptr; void* dh_bf = nullptr;   // [Z][B][H]
+  float* logits = nullptr;        // [Z][B][C] (head == -1)
+  unsigned long long* worklist = nullptr;   // num_items * kWorkPerItem slots
+  int kblock_bytes = 128;
+  int sm_count = 148;
+};
+constexpr int kWorkPerItem = 448;
+bool fused_supported(int H, int C);
+size_t fused_worklist_slots(int B, int Z);
+int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err);
+int fused_fixup(const FusedDesc& d, cudaStream_t st, std::string* err);
 
 // Dynamic shared memory the kernel asks for (same for both modes).
 size_t smem_bytes();

@@ -75,6 +75,7 @@ struct Case {
   const char* name;
   int mode, M, N, K, Z, BN, reduce, slots, a_per_z, epi, split_out;
 };
+static int g_kblock = 64, g_pair = 1, g_skip = 0, g_relay = 1;
 
 static float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
@@ -95,6 +96,10 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
   if (c.split_out) { CK(cudaMalloc(&out_lo, on * 4)); CK(cudaMemset(out_lo, 0xFF, on * 4)); }
 
   GemmDesc d;
+  d.kblock_bytes = g_kblock;
+  d.pair = g_pair;
+  d.debug_skip_mma = g_skip;
+  d.pair_relay = g_relay;
   d.mode = c.mode; d.M = c.M; d.N = c.N; d.K = c.K; d.Z = c.Z; d.BN = c.BN;
   d.A.hi = bf ? (void*)A.bf : (void*)A.hi; d.A.lo = A.lo; d.A.rows = c.M; d.A.ld = c.K;
   d.A.zstride = c.a_per_z ? (int64_t)c.M * c.K : 0;
@@ -172,14 +177,24 @@ int main(int argc, char** argv) {
       {"bf16 fwd", MODE_BF16, 300, 512, 784, 3, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
       {"bf16 bwd reduce_z", MODE_BF16, 300, 784, 512, 5, 208, 1, 2, 1, EPI_NONE, 0},
   };
+  const char* cm = getenv("TC_CFGS");
+  const int cfg_mask = cm ? atoi(cm) : 15;
+  g_skip = getenv("TC_SKIP_MMA") ? atoi(getenv("TC_SKIP_MMA")) : 0;
+  g_relay = getenv("TC_RELAY") ? atoi(getenv("TC_RELAY")) : 1;
+  for (int cfg = 0; cfg < 4; ++cfg) {
+  if (!((cfg_mask >> cfg) & 1)) continue;
+  g_kblock = (cfg & 1) ? 128 : 64;
+  g_pair = (cfg & 2) ? 0 : 1;
+  printf("---- K-block %d bytes, %s ----\n", g_kblock, g_pair ? "CTA pairs (cta_group::2)" : "single CTA");
   for (const Case& c : small) {
     double ms = 0;
     const double e = run_case(c, true, 0, &ms);
     const double tol = 3e-5;   // tensor-core fp32 accumulation truncates: ~5e-6 (K=784) .. 2e-5 (K=2048) of the output max
     printf("%-45s rel err %.3e  %s\n", c.name, e, e < tol ? "ok" : "FAIL");
-    if (!(e < tol)) fails++;
+    if (!(e < tol) && !g_skip) fails++;
   }
-  if (bench) {
+  if (!bench) continue;
+  {
     const Case big[] = {
         {"tf32x3 fwd 10000x512x784 Z=148 BN=256", MODE_TF32X3, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
         {"tf32x3 fwd 10000x512x784 Z=148 BN=128", MODE_TF32X3, 10000, 512, 784, 148, 128, 0, 1, 0, EPI_BIAS_LEAKY, 0},
@@ -195,8 +210,9 @@ int main(int argc, char** argv) {
       const double flop = 2.0 * c.M * c.N * (double)c.K * c.Z;
       printf("%-45s rel err %.3e  %.3f ms  %.1f TFLOP/s (algorithmic, 1 pass)\n", c.name, e, ms, flop / ms * 1e-9);
       const double tol = 3e-5;
-      if (!(e < tol)) fails++;
+      if (!(e < tol) && !g_skip) fails++;
     }
+  }
   }
   printf(fails ? "FAILED (%d)\n" : "ALL OK\n", fails);
   return fails ? 1 : 0;

@@ -187,14 +187,19 @@ TC_CONFIGS = [
 ]
 
 
+@pytest.mark.parametrize("route", ["fused", "unfused"])
 @pytest.mark.parametrize("prec,tol", [("tf32x3", REL), ("bf16", 1.0)])
 @pytest.mark.parametrize("arch,shape,hidden,C,B,S", TC_CONFIGS)
-def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol):
+def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route, monkeypatch):
     """The tensor-core engine (tcgen05 / TMA / TMEM) against the fp64 oracle: TF32x3 is parity grade
     (rel <= 1e-4, the north-star tolerance); single-pass BF16 is the throughput mode and is only held
     to a loose bound (its measured deviation is reported by bench.py)."""
     from robustbnns_b200 import _lib
     from robustbnns_b200.engine import Net
+    if route == "unfused":
+        if arch != "fc":
+            pytest.skip("fc2 has a single (unfused) route")
+        monkeypatch.setenv("RBNN_TC_UNFUSED", "1")      # arch fc: GEMM -> H in HBM -> head kernel instead of the fused kernel
     net, layout, loc, rho, bank, x, labels = _problem(arch, shape, hidden, C, B, S)
     eng = Net(arch, shape, hidden, C)
     eng.set_precision(prec)
@@ -216,7 +221,7 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol):
     rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
     e_log = rel_err(gl, rl)
     cos = float(torch.nn.functional.cosine_similarity(g.double().flatten(), ref64.flatten(), dim=0))
-    print(f"tcgen05 {prec} {arch}-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} "
+    print(f"tcgen05 {prec} {route} {arch}-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} "
           f"logits-CE {e_log:.2e} cosine {cos:.6f}")
     assert cos > 0.98
     if arch == "fc2" and prec == "tf32x3":
