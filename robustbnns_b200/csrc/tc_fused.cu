@@ -394,13 +394,13 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                   uint2 pk;
                   pk.x = *reinterpret_cast<const uint32_t*>(&a);
                   pk.y = *reinterpret_cast<const uint32_t*>(&bb2);
-                  *reinterpret_cast<uint2*>(p.dh_bf + orow + j) = pk;
+                  __stcs(reinterpret_cast<uint2*>(p.dh_bf + orow + j), pk);          // streaming: read once by the next kernel
                 } else {
                   float4 hi4, lo4;
                   hi4.x = to_tf32_rn(d[0]); hi4.y = to_tf32_rn(d[1]); hi4.z = to_tf32_rn(d[2]); hi4.w = to_tf32_rn(d[3]);
                   lo4.x = d[0] - hi4.x; lo4.y = d[1] - hi4.y; lo4.z = d[2] - hi4.z; lo4.w = d[3] - hi4.w;
-                  *reinterpret_cast<float4*>(p.dh_hi + orow + j) = hi4;
-                  *reinterpret_cast<float4*>(p.dh_lo + orow + j) = lo4;
+                  __stcs(reinterpret_cast<float4*>(p.dh_hi + orow + j), hi4);        // streaming: do not displace X / W1 in L2
+                  __stcs(reinterpret_cast<float4*>(p.dh_lo + orow + j), lo4);
                 }
               }
             }

@@ -112,7 +112,10 @@ def test_golden_hmc_attacks_and_evaluation(name, tmp_path, monkeypatch):
         xt = traj[t].cuda()
         pbar = eng.forward_probs_sum(xt, 0, S) / S
         g = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, xt, y, 0, S, pbar=pbar).cpu().reshape(g64.shape) / S
-        assert rel_err(g, g64) < REL, (t, rel_err(g, g64))
+        # late PGD states saturate the softmax: the reference's own fp32 gradient then carries a cancellation
+        # error above 1e-4 (fp32 oracle vs fp64 oracle); parity is held to 3x that error there
+        g32 = orc.attack_gradient(c.net, c.layout, c.bank, traj[t], c.labels, sched(t))
+        assert rel_err(g, g64) < max(REL, 3 * rel_err(g32, g64)), (t, rel_err(g, g64), rel_err(g32, g64))
         nxt = aa._pgd_loop(bnn, xt, x0, y, alpha, 0.5, S, False, 1).cpu()
         ref_nxt = orc.pgd_step(traj[t].double(), c.x.double(), g64, 2 / 225, 0.5)
         determined = g64.abs() > REL * g64.abs().max()
