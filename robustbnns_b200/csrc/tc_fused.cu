@@ -32,11 +32,12 @@ namespace {
 
 constexpr float kSlopeF = 0.01f;
 constexpr int kRingF = 196608;
-constexpr int kEpiWarps = 8;
-constexpr int kThreadsF = 64 + kEpiWarps * 32;     // 320
-constexpr int kCMax = 16;
+constexpr int kEpiWarps = 16;                     // 4 TMEM lane quadrants x 2 lane halves x 2 column halves
+constexpr int kThreadsF = 64 + kEpiWarps * 32;     // 576
+constexpr int kCMax = 10;                          // classes the fused epilogue keeps in registers (4 rows x kCMax accumulators)
+constexpr int kMaskWords = 8;                      // 32x32 blocks per thread: n_tiles * (BN/2)/32 <= 8
 constexpr int kParamFloatsMax = 5760;              // Wo_z [C*H] + bo_z [C] + b1_z [H]  (<= 22.5 KB)
-constexpr int kXchgFloats = kBM * kCMax;           // partial logits / dlogits exchange between column halves
+constexpr int kXchgFloats = kBM * 16;           // partial logits / dlogits exchange between column halves
 constexpr int kFusedSmem = kRingF + 1024 + 256 + (kParamFloatsMax + kXchgFloats) * 4 + 16;
 constexpr unsigned long long kSentinel = ~0ull;
 
@@ -205,14 +206,21 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue: warps 2..9 =====================
+    // ===================== epilogue: warps 2..17 =====================
+    // TMEM is read with the 16x256b shape: lane t of the warp receives, for every group of 8 columns, rows
+    // {t/4, t/4+8} x columns {2(t%4), 2(t%4)+1} -- the mma accumulator fragment layout -- so a thread owns 2 rows x
+    // 8 columns of a 16x32 block and every Wo value fetched from shared memory feeds 2 rows.  The epilogue is
+    // latency bound (ncu: one instruction per ~11 cycles per warp), so it is spread over 16 warps: warp =
+    // (TMEM lane quadrant, 16-lane half of the quadrant, column half of the n-tile).
     const int ew = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                  // which half of an n-tile's columns
-    const int et = threadIdx.x - 64;           // 0..255
+    const int lhalf = (ew >> 2) & 1;           // which 16 lanes of the quadrant
+    const int half = ew >> 3;                  // which half of an n-tile's columns
+    const int et = threadIdx.x - 64;           // 0..511
     const int cols_half = p.BN >= 64 ? p.BN / 2 : p.BN;   // columns per (n-tile, half); BN < 64: half 1 idles
     const bool active = p.BN >= 64 || half == 0;
-    const int row_in_tile = quad * 32 + lane;
+    const int nblocks = cols_half / 32;        // 32-column blocks per (n-tile, half)
+    const int q = lane & 3, rsub = lane >> 2;  // fragment coordinates
     const int C = p.C, H = p.H;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -224,16 +232,26 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       for (int i = et; i < H; i += kEpiWarps * 32) b1_s[i] = __ldg(wrow + p.b1_off + i);
       if (et == 0) *wl_count = 0u;
       epi_bar();
-      const int b = m_idx * kBM + row_in_tile;
-      const bool row_ok = b < p.B;
-      const float guard = (row_ok && p.eps > 0.f) ? p.eps * __ldg(p.xnorm + b) * __ldg(p.wnorm + p.z_row0 + z) : 0.f;
+      // this thread's 2 rows: quad*32 + lhalf*16 + {0,8} + rsub
+      int brow[2];
+      bool rok[2];
+      float guard[2];
+      const float wn = p.eps > 0.f ? p.eps * __ldg(p.wnorm + p.z_row0 + z) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        brow[r] = m_idx * kBM + quad * 32 + lhalf * 16 + 8 * r + rsub;
+        rok[r] = brow[r] < p.B;
+        guard[r] = (rok[r] && p.eps > 0.f) ? wn * __ldg(p.xnorm + brow[r]) : 0.f;
+      }
       unsigned long long* wl = p.worklist ? p.worklist + (long long)item * kWorkPerItem : nullptr;
-      float logit[kCMax];
+      float logit[2][kCMax];
 #pragma unroll
-      for (int c = 0; c < kCMax; ++c) logit[c] = 0.f;
-      uint32_t mbits[16];                       // mask bits of this thread's columns: n-tile n, chunk cc -> word
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) mbits[i] = 0u;
+        for (int c = 0; c < kCMax; ++c) logit[r][c] = 0.f;
+      uint32_t mbits[kMaskWords];               // one word per 16x32 block: bit (r*8 + k*2 + e)
+#pragma unroll
+      for (int i = 0; i < kMaskWords; ++i) mbits[i] = 0u;
 
       // ---------------- pass 1 ----------------
       for (int n = 0; n < p.n_tiles; ++n, ++it) {
@@ -242,50 +260,53 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)kBNMax;
         if (active) {
-          const int nchunks = cols_half / 32 > 0 ? cols_half / 32 : 1;
 #pragma unroll 1
-          for (int cc = 0; cc < nchunks; ++cc) {
+          for (int cc = 0; cc < nblocks; ++cc) {
             const int c0 = half * cols_half + cc * 32;            // column inside the n-tile
-            uint32_t r[32];
-            tmem_ld32(taddr + (uint32_t)c0, r);
+            uint32_t v[16];                                       // [4 * colgroup + {r0c0, r0c1, r1c0, r1c1}]
+            tmem_ld_16x256b_x4(taddr + ((uint32_t)(lhalf * 16) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
             uint32_t bits = 0u;
-            const int jbase = n * p.BN + c0;
+            const int jbase = n * p.BN + c0 + 2 * q;
 #pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              if (c0 + q < p.BN) {                                // BN % 16 == 0: groups of 4 are all-in / all-out
-                const int j = jbase + q;
-                const float4 bb = *reinterpret_cast<const float4*>(b1_s + j);
-                float h[4] = {__uint_as_float(r[q]) + bb.x, __uint_as_float(r[q + 1]) + bb.y,
-                              __uint_as_float(r[q + 2]) + bb.z, __uint_as_float(r[q + 3]) + bb.w};
+            for (int k = 0; k < 4; ++k) {
+              const int j = jbase + 8 * k;                        // this thread's column pair (j, j+1)
+              const float2 bb = *reinterpret_cast<const float2*>(b1_s + j);
+              float h[2][2];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  bool pos = h[e] > 0.f;
-                  if (fabsf(h[e]) < guard) {
+              for (int r = 0; r < 2; ++r) {
+                h[r][0] = __uint_as_float(v[4 * k + 2 * r]) + bb.x;
+                h[r][1] = __uint_as_float(v[4 * k + 2 * r + 1]) + bb.y;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  bool pos = h[r][e] > 0.f;
+                  if (fabsf(h[r][e]) < guard[r]) {
                     const uint32_t slot = atomicAdd(wl_count, 1u);
                     if (slot < (uint32_t)kWorkPerItem) {
-                      wl[slot] = pack_entry(z, b, j + e, pos);
+                      wl[slot] = pack_entry(z, brow[r], j + e, pos);
                     } else {                                      // item budget exhausted: settle it here
-                      pos = exact_positive_serial(p.x + (long long)b * p.D, wrow + (long long)(j + e) * p.D,
-                                                  b1_s[j + e], p.D);
+                      pos = exact_positive_serial(p.x + (long long)brow[r] * p.D, wrow + (long long)(j + e) * p.D,
+                                                  e ? bb.y : bb.x, p.D);
                     }
                   }
-                  if (pos) bits |= 1u << (q + e);
-                  h[e] = pos ? h[e] : h[e] * kSlopeF;
+                  if (pos) bits |= 1u << (r * 8 + k * 2 + e);
+                  h[r][e] = pos ? h[r][e] : h[r][e] * kSlopeF;
                 }
-#pragma unroll
-                for (int c = 0; c < kCMax; ++c)
-                  if (c < C) {
-                    const float4 w = *reinterpret_cast<const float4*>(wo_s + c * H + j);
-                    logit[c] = fmaf(h[0], w.x, logit[c]);
-                    logit[c] = fmaf(h[1], w.y, logit[c]);
-                    logit[c] = fmaf(h[2], w.z, logit[c]);
-                    logit[c] = fmaf(h[3], w.w, logit[c]);
-                  }
               }
-            }
-            const int word = n * nchunks + cc;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
+              for (int c = 0; c < kCMax; ++c)
+                if (c < C) {
+                  const float2 w = *reinterpret_cast<const float2*>(wo_s + c * H + j);
+#pragma unroll
+                  for (int r = 0; r < 2; ++r) {
+                    logit[r][c] = fmaf(h[r][0], w.x, logit[r][c]);
+                    logit[r][c] = fmaf(h[r][1], w.y, logit[r][c]);
+                  }
+                }
+            }
+            const int word = n * nblocks + cc;
+#pragma unroll
+            for (int i = 0; i < kMaskWords; ++i)
               if (i == word) mbits[i] = bits;
           }
         }
@@ -294,55 +315,72 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         if (lane == 0) mbar_arrive(tempty0 + 8 * as);
       }
 
-      // ---------------- exchange: half 1 -> half 0 partial logits; half 0 -> half 1 dlogits ----------------
-      if (half == 1) {
+      // ---------------- row sums over the 4 lanes that share a row, then over the two column halves ----------------
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < kCMax; ++c)
-          if (c < C) xchg[row_in_tile * kCMax + c] = logit[c];
+          if (c < C) {
+            logit[r][c] += __shfl_xor_sync(0xffffffffu, logit[r][c], 1);
+            logit[r][c] += __shfl_xor_sync(0xffffffffu, logit[r][c], 2);
+          }
+      if (half == 1 && q == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int c = 0; c < kCMax; ++c)
+            if (c < C) xchg[(quad * 32 + lhalf * 16 + 8 * r + rsub) * kCMax + c] = logit[r][c];
       }
       epi_bar();
       if (half == 0) {
 #pragma unroll
-        for (int c = 0; c < kCMax; ++c)
-          if (c < C) logit[c] += (p.BN >= 64 ? xchg[row_in_tile * kCMax + c] : 0.f) + bo_s[c];
-        if (p.head < 0) {
-          if (row_ok) {
-            float* out = p.logits + ((long long)z * p.B + b) * C;
-#pragma unroll
-            for (int c = 0; c < kCMax; ++c)
-              if (c < C) out[c] = logit[c];
-          }
-        } else {
-          // loss head (same algebra and operation order as head.cu::dlogits_kernel)
-          const int y = row_ok ? p.labels[b] : 0;
-          float g[kCMax];
-          softmax_r<kCMax>(logit, C);
-          if (p.head == RBNN_HEAD_LOGITS_CE) {
-#pragma unroll
-            for (int c = 0; c < kCMax; ++c) logit[c] = logit[c] - (c == y ? 1.f : 0.f);
-          } else {
-            if (p.head == RBNN_HEAD_MEAN_OF_GRADS) {
-#pragma unroll
-              for (int c = 0; c < kCMax; ++c) g[c] = logit[c];
-            } else {
-#pragma unroll
-              for (int c = 0; c < kCMax; ++c) g[c] = (c < C && row_ok) ? __ldg(p.pbar + (long long)b * C + c) : 0.f;
-            }
-            if (p.head != RBNN_HEAD_UPSTREAM) {
-              softmax_r<kCMax>(g, C);
-#pragma unroll
-              for (int c = 0; c < kCMax; ++c) g[c] -= (c == y ? 1.f : 0.f);
-            }
-            float dot = 0.f;
-#pragma unroll
-            for (int c = 0; c < kCMax; ++c)
-              if (c < C) dot = fmaf(logit[c], g[c], dot);
-#pragma unroll
-            for (int c = 0; c < kCMax; ++c) logit[c] = logit[c] * (g[c] - dot);
-          }
+        for (int r = 0; r < 2; ++r) {
+          const int rit = quad * 32 + lhalf * 16 + 8 * r + rsub;
 #pragma unroll
           for (int c = 0; c < kCMax; ++c)
-            if (c < C) xchg[row_in_tile * kCMax + c] = logit[c];
+            if (c < C) logit[r][c] += (p.BN >= 64 ? xchg[rit * kCMax + c] : 0.f) + bo_s[c];
+          if (p.head < 0) {
+            if (rok[r] && q == 0) {
+              float* out = p.logits + ((long long)z * p.B + brow[r]) * C;
+#pragma unroll
+              for (int c = 0; c < kCMax; ++c)
+                if (c < C) out[c] = logit[r][c];
+            }
+          } else {
+            // loss head (same algebra and operation order as head.cu::dlogits_kernel)
+            const int y = rok[r] ? p.labels[brow[r]] : 0;
+            float g[kCMax];
+            softmax_r<kCMax>(logit[r], C);
+            if (p.head == RBNN_HEAD_LOGITS_CE) {
+#pragma unroll
+              for (int c = 0; c < kCMax; ++c) logit[r][c] = logit[r][c] - (c == y ? 1.f : 0.f);
+            } else {
+              if (p.head == RBNN_HEAD_MEAN_OF_GRADS) {
+#pragma unroll
+                for (int c = 0; c < kCMax; ++c) g[c] = logit[r][c];
+              } else {
+#pragma unroll
+                for (int c = 0; c < kCMax; ++c)
+                  g[c] = (c < C && rok[r]) ? __ldg(p.pbar + (long long)brow[r] * C + c) : 0.f;
+              }
+              if (p.head != RBNN_HEAD_UPSTREAM) {
+                softmax_r<kCMax>(g, C);
+#pragma unroll
+                for (int c = 0; c < kCMax; ++c) g[c] -= (c == y ? 1.f : 0.f);
+              }
+              float dot = 0.f;
+#pragma unroll
+              for (int c = 0; c < kCMax; ++c)
+                if (c < C) dot = fmaf(logit[r][c], g[c], dot);
+#pragma unroll
+              for (int c = 0; c < kCMax; ++c) logit[r][c] = logit[r][c] * (g[c] - dot);
+            }
+            if (q == 0) {
+#pragma unroll
+              for (int c = 0; c < kCMax; ++c)
+                if (c < C) xchg[rit * kCMax + c] = logit[r][c];
+            }
+          }
         }
       }
       epi_bar();
@@ -354,53 +392,56 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       if (p.head < 0) continue;
       if (half == 1) {
 #pragma unroll
-        for (int c = 0; c < kCMax; ++c)
-          if (c < C) logit[c] = xchg[row_in_tile * kCMax + c];
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int c = 0; c < kCMax; ++c)
+            if (c < C) logit[r][c] = xchg[(quad * 32 + lhalf * 16 + 8 * r + rsub) * kCMax + c];
       }
 
-      // ---------------- pass 2: dH = (dlogits . Wo) * leaky'(H) for this thread's columns ----------------
-      if (active && row_ok) {
-        const long long orow = ((long long)z * p.B + b) * H;
-        const int nchunks = cols_half / 32 > 0 ? cols_half / 32 : 1;
+      // ---------------- pass 2: dH = (dlogits . Wo) * leaky'(H) for this thread's 2 rows x column pairs ----------------
+      if (active) {
+        long long orow[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) orow[r] = ((long long)z * p.B + brow[r]) * H;
         for (int n = 0; n < p.n_tiles; ++n) {
 #pragma unroll 1
-          for (int cc = 0; cc < nchunks; ++cc) {
-            const int c0 = half * cols_half + cc * 32;
-            const int jbase = n * p.BN + c0;
-            const int word = n * nchunks + cc;
+          for (int cc = 0; cc < nblocks; ++cc) {
+            const int jbase = n * p.BN + half * cols_half + cc * 32 + 2 * q;
+            const int word = n * nblocks + cc;
             uint32_t bits = 0u;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
+            for (int i = 0; i < kMaskWords; ++i)
               if (i == word) bits = mbits[i];
 #pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              if (c0 + q < p.BN) {
-                const int j = jbase + q;
-                float d[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < 4; ++k) {
+              const int j = jbase + 8 * k;
+              float d[2][2];
 #pragma unroll
-                for (int c = 0; c < kCMax; ++c)
-                  if (c < C) {
-                    const float4 w = *reinterpret_cast<const float4*>(wo_s + c * H + j);
-                    d[0] = fmaf(logit[c], w.x, d[0]);
-                    d[1] = fmaf(logit[c], w.y, d[1]);
-                    d[2] = fmaf(logit[c], w.z, d[2]);
-                    d[3] = fmaf(logit[c], w.w, d[3]);
+              for (int r = 0; r < 2; ++r) d[r][0] = d[r][1] = 0.f;
+#pragma unroll
+              for (int c = 0; c < kCMax; ++c)
+                if (c < C) {
+                  const float2 w = *reinterpret_cast<const float2*>(wo_s + c * H + j);
+#pragma unroll
+                  for (int r = 0; r < 2; ++r) {
+                    d[r][0] = fmaf(logit[r][c], w.x, d[r][0]);
+                    d[r][1] = fmaf(logit[r][c], w.y, d[r][1]);
                   }
+                }
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (!((bits >> (q + e)) & 1u)) d[e] *= kSlopeF;
+              for (int r = 0; r < 2; ++r) {
+                if (!rok[r]) continue;
+                if (!((bits >> (r * 8 + k * 2)) & 1u)) d[r][0] *= kSlopeF;
+                if (!((bits >> (r * 8 + k * 2 + 1)) & 1u)) d[r][1] *= kSlopeF;
                 if (BF16) {
-                  const __nv_bfloat162 a = __floats2bfloat162_rn(d[0], d[1]), bb2 = __floats2bfloat162_rn(d[2], d[3]);
-                  uint2 pk;
-                  pk.x = *reinterpret_cast<const uint32_t*>(&a);
-                  pk.y = *reinterpret_cast<const uint32_t*>(&bb2);
-                  __stcs(reinterpret_cast<uint2*>(p.dh_bf + orow + j), pk);          // streaming: read once by the next kernel
+                  const __nv_bfloat162 a = __floats2bfloat162_rn(d[r][0], d[r][1]);
+                  __stcs(reinterpret_cast<unsigned int*>(p.dh_bf + orow[r] + j), *reinterpret_cast<const unsigned int*>(&a));
                 } else {
-                  float4 hi4, lo4;
-                  hi4.x = to_tf32_rn(d[0]); hi4.y = to_tf32_rn(d[1]); hi4.z = to_tf32_rn(d[2]); hi4.w = to_tf32_rn(d[3]);
-                  lo4.x = d[0] - hi4.x; lo4.y = d[1] - hi4.y; lo4.z = d[2] - hi4.z; lo4.w = d[3] - hi4.w;
-                  __stcs(reinterpret_cast<float4*>(p.dh_hi + orow + j), hi4);        // streaming: do not displace X / W1 in L2
-                  __stcs(reinterpret_cast<float4*>(p.dh_lo + orow + j), lo4);
+                  float2 hi2, lo2;
+                  hi2.x = to_tf32_rn(d[r][0]); hi2.y = to_tf32_rn(d[r][1]);
+                  lo2.x = d[r][0] - hi2.x; lo2.y = d[r][1] - hi2.y;
+                  __stcs(reinterpret_cast<float2*>(p.dh_hi + orow[r] + j), hi2);   // streaming: do not displace X / W1 in L2
+                  __stcs(reinterpret_cast<float2*>(p.dh_lo + orow[r] + j), lo2);
                 }
               }
             }
@@ -463,9 +504,9 @@ bool fused_supported(int H, int C) {
   if (H > 256 && (H % 256)) return false;
   const int n_tiles = H <= 256 ? 1 : H / 256;
   const int bn = H <= 256 ? H : 256;
-  const int words = n_tiles * ((bn >= 64 ? bn / 2 : bn) / 32 > 0 ? (bn >= 64 ? bn / 2 : bn) / 32 : 1);
-  if (words > 16) return false;
-  if (bn >= 64 && ((bn / 2) % 32)) return false;
+  const int cols_half = bn >= 64 ? bn / 2 : bn;
+  if (cols_half % 32) return false;
+  if (n_tiles * (cols_half / 32) > kMaskWords) return false;
   return ((C * H + C + 3) & ~3) + H <= kParamFloatsMax;
 }
 

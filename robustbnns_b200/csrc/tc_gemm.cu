@@ -32,7 +32,7 @@ size_t smem_bytes() { return kSmemBytes; }
 struct KParams {
   int M, N, K, Z, BN;
   int m_tiles, m_units, n_tiles, num_tiles, num_kb;   // m_units = m_tiles (single CTA) or ceil(m_tiles / 2) (CTA pair)
-  int reduce_z, slots, a_per_z, epi, skip_mma, relay;
+  int reduce_z, slots, a_per_z, epi, skip_mma, relay, spin;
   const float* bias; long long bias_zstride;
   const float* act; long long act_zstride, act_ld;
   float* out; float* out_lo; __nv_bfloat16* out_bf;
@@ -115,7 +115,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int z1 = p.reduce_z ? (int)((long long)(zz + 1) * p.Z / p.slots) : zz + 1;
         for (int z = z0; z < z1; ++z) {
           for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+            mbar_wait_mode(empty0 + 8 * stage, phase ^ 1u, p.spin);
             const uint32_t sa = ring + stage * STAGE;
             const uint32_t sb = sa + NARR * kATile;
             const int za = p.a_per_z ? z : 0;
@@ -166,7 +166,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int z1 = p.reduce_z ? (int)((long long)(zz + 1) * p.Z / p.slots) : zz + 1;
         const int total_kb = (z1 - z0) * p.num_kb;
         for (int i = 0; i < total_kb; ++i) {
-          mbar_wait(full0 + 8 * stage, phase);
+          mbar_wait_mode(full0 + 8 * stage, phase, p.spin);
           mbar_arrive_cluster(pf + 8 * stage);
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
@@ -182,14 +182,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int z0 = p.reduce_z ? (int)((long long)zz * p.Z / p.slots) : zz;
         const int z1 = p.reduce_z ? (int)((long long)(zz + 1) * p.Z / p.slots) : zz + 1;
         const uint32_t as = it & 1u;
-        mbar_wait(tempty0 + 8 * as, ((it >> 1) & 1u) ^ 1u);
+        mbar_wait_mode(tempty0 + 8 * as, ((it >> 1) & 1u) ^ 1u, p.spin);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * (uint32_t)kBNMax;
         uint32_t accumulate = 0;
         const int total_kb = (z1 - z0) * p.num_kb;
         for (int i = 0; i < total_kb; ++i) {
-          mbar_wait(full0 + 8 * stage, phase);
-          if (PAIR && p.relay) mbar_wait(pfull0 + 8 * stage, phase);
+          mbar_wait_mode(full0 + 8 * stage, phase, p.spin);
+          if (PAIR && p.relay) mbar_wait_mode(pfull0 + 8 * stage, phase, p.spin);
           tc_fence_after();
           const uint32_t sa = ring + stage * STAGE;
           const uint32_t sb = sa + NARR * kATile;
@@ -237,7 +237,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int n_idx = t % p.n_tiles, m_unit = (t / p.n_tiles) % p.m_units, zz = t / tiles_mn;
       const int m_idx = PAIR ? 2 * m_unit + (int)rank : m_unit;
       const uint32_t as = it & 1u;
-      mbar_wait(tfull0 + 8 * as, (it >> 1) & 1u);
+      mbar_wait_mode(tfull0 + 8 * as, (it >> 1) & 1u, p.spin);
       tc_fence_after();
       const int m = m_idx * kBM + quad * 32 + lane;
       const bool row_ok = m < p.M;
@@ -399,6 +399,7 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   p.epi = d.epi;
   p.skip_mma = d.debug_skip_mma;
   p.relay = d.pair_relay;
+  p.spin = d.spin_wait;
   p.bias = d.bias; p.bias_zstride = d.bias_zstride;
   p.act = d.act; p.act_zstride = d.act_zstride; p.act_ld = d.act_ld;
   p.out = d.out; p.out_lo = d.out_lo; p.out_bf = reinterpret_cast<__nv_bfloat16*>(d.out_bf);

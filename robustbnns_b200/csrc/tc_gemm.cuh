@@ -59,6 +59,7 @@ struct GemmDesc {
   int64_t out_ld = 0, out_zstride = 0;
   int sm_count = 148;
   int pair_relay = 1;      // pair mode: 1 = own-barrier TMA + relayed full signal, 0 = cta_group::2 TMA onto the leader's barrier
+  int spin_wait = 0;       // 1: poll mbarriers with test_wait instead of the suspending try_wait
   int debug_skip_mma = 0;  // harness only: run the TMA / barrier pipeline without issuing MMAs
 };
 

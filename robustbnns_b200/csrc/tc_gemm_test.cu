@@ -75,7 +75,7 @@ struct Case {
   const char* name;
   int mode, M, N, K, Z, BN, reduce, slots, a_per_z, epi, split_out;
 };
-static int g_kblock = 64, g_pair = 1, g_skip = 0, g_relay = 1;
+static int g_kblock = 64, g_pair = 1, g_skip = 0, g_relay = 1, g_spin = 0;
 
 static float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
@@ -100,6 +100,7 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
   d.pair = g_pair;
   d.debug_skip_mma = g_skip;
   d.pair_relay = g_relay;
+  d.spin_wait = g_spin;
   d.mode = c.mode; d.M = c.M; d.N = c.N; d.K = c.K; d.Z = c.Z; d.BN = c.BN;
   d.A.hi = bf ? (void*)A.bf : (void*)A.hi; d.A.lo = A.lo; d.A.rows = c.M; d.A.ld = c.K;
   d.A.zstride = c.a_per_z ? (int64_t)c.M * c.K : 0;
@@ -181,6 +182,7 @@ int main(int argc, char** argv) {
   const int cfg_mask = cm ? atoi(cm) : 15;
   g_skip = getenv("TC_SKIP_MMA") ? atoi(getenv("TC_SKIP_MMA")) : 0;
   g_relay = getenv("TC_RELAY") ? atoi(getenv("TC_RELAY")) : 1;
+  g_spin = getenv("TC_SPIN") ? atoi(getenv("TC_SPIN")) : 0;
   for (int cfg = 0; cfg < 4; ++cfg) {
   if (!((cfg_mask >> cfg) & 1)) continue;
   g_kblock = (cfg & 1) ? 128 : 64;

@@ -39,6 +39,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s
   }
 }
+// Polling variant (mbarrier.test_wait never suspends the thread): used where the arrival comes from the peer CTA
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, int spin) {
+  if (!spin) { mbar_wait(bar, parity); return; }
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -149,6 +167,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// 16 TMEM lanes x 32 consecutive fp32 columns in the 16x256b shape (x4): thread t receives, for column group
+// k = 0..3 (8 columns each), r[4k+0..1] = (lane t/4, columns 8k + 2(t%4) + {0,1}) and r[4k+2..3] = (lane t/4 + 8, same
+// columns) -- the mma accumulator fragment layout.  No wait inside: pair it with tmem_ld_wait().
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor for tiles whose rows hold KBB (128 or 64) bytes of K, swizzled with the
 // matching TMA mode (SWIZZLE_128B / SWIZZLE_64B): rows are KBB bytes apart, 8-row core groups 8*KBB bytes apart.
