@@ -44,8 +44,10 @@ enum { RBNN_ARCH_FC = 0, RBNN_ARCH_FC2 = 1, RBNN_ARCH_CONV = 2 };
 
 /* GEMM engines.  FP32 = CUDA-core FFMA (reference-class rounding, any shape);
  * TF32X3 = tcgen05 kind::tf32 with a 3-term split (fp32-class accuracy);
- * BF16 = tcgen05 kind::f16 single pass (throughput mode, NOT parity-grade). */
-enum { RBNN_PREC_FP32 = 0, RBNN_PREC_TF32X3 = 1, RBNN_PREC_BF16 = 2 };
+ * BF16 = tcgen05 kind::f16 single pass (throughput mode, NOT parity-grade);
+ * F16X3 = tcgen05 kind::f16 with a 3-term split of power-of-two-scaled fp16 hi/lo
+ *         operands (fp32-class accuracy at twice the TF32X3 rate; arch fc only). */
+enum { RBNN_PREC_FP32 = 0, RBNN_PREC_TF32X3 = 1, RBNN_PREC_BF16 = 2, RBNN_PREC_F16X3 = 3 };
 
 /* Which scalar loss the input gradient is taken of. */
 enum {

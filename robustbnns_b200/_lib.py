@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librbnn.so")
 
 ARCH = {"fc": 0, "fc2": 1, "conv": 2}
-PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2}
+PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "f16x3": 3}
 HEAD_MEAN_OF_GRADS, HEAD_GRAD_OF_MEAN, HEAD_LOGITS_CE, HEAD_UPSTREAM = 0, 1, 2, 3
 
 _p = C.c_void_p

@@ -393,9 +393,12 @@ int64_t rbnn_net_param_count(const rbnn_net* n) { return n ? n->L.P : -1; }
 
 int rbnn_net_set_precision(rbnn_net* n, int prec) {
   RBNN_CHECK(n != nullptr, "null net handle");
-  RBNN_CHECK(prec == RBNN_PREC_FP32 || prec == RBNN_PREC_TF32X3 || prec == RBNN_PREC_BF16, "unknown precision %d", prec);
+  RBNN_CHECK(prec == RBNN_PREC_FP32 || prec == RBNN_PREC_TF32X3 || prec == RBNN_PREC_BF16 || prec == RBNN_PREC_F16X3,
+             "unknown precision %d", prec);
   if (prec != RBNN_PREC_FP32)
     RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%8==0 and H>=32 on sm_100 only");
+  if (prec == RBNN_PREC_F16X3)
+    RBNN_CHECK(tc_f16x3_supported(n), "F16X3 covers arch fc with hidden sizes the fused forward+head kernel supports");
   n->prec = prec;
   return 0;
 }

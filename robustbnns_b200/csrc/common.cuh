@@ -56,6 +56,17 @@ struct TcMat {
   float *hi = nullptr, *lo = nullptr;      // tf32 split:  w = hi + lo, hi = rn_tf32(w)
   float *thi = nullptr, *tlo = nullptr;    // the same, transposed
   void *bf = nullptr, *tbf = nullptr;      // bf16 variants
+  void *h_hi = nullptr, *h_lo = nullptr;   // F16X3: fp16 split of s_w * w (s_w = TcScales::s_w1, a power of two)
+  void *th_hi = nullptr, *th_lo = nullptr; // the same, transposed
+};
+
+// Device-resident operand-range bookkeeping of the F16X3 engine (fp16 has 5 exponent bits: operands are scaled by
+// powers of two so that their largest element sits in [2^8, 2^9)).  The host never reads it.
+struct TcScales {
+  unsigned maxw1_bits;   // max |W1| over every bank row re-laid so far (float bits; monotone)
+  unsigned maxwo_bits;   // max |Wo| likewise (bounds dH)
+  int frozen;            // s_w1 has been fixed (the derived copies of clean rows depend on it)
+  float s_w1;            // power-of-two scale of the fp16 copies of W1 / W1^T
 };
 
 struct TcBank {
@@ -64,6 +75,9 @@ struct TcBank {
   int nmat = 0;
   TcMat mat[2];
   float* wnorm = nullptr;   // [capacity] max_j ||W1_s[j,:]||_2 (guard band of the fused forward kernel)
+  TcScales* scales = nullptr;     // device (F16X3)
+  int* overflow_host = nullptr;   // mapped pinned flag: a later row exceeded the fp16 range under the frozen s_w1
+  int* overflow_dev = nullptr;    // device alias of overflow_host
   uint8_t* dirty = nullptr; // host flags per row (derived copies stale)
 };
 
@@ -157,6 +171,7 @@ int add_inplace(rbnn_net* net, float* dst, const float* src, int64_t n, cudaStre
 
 // ---- tc_fc.cu (tcgen05 FC path) -----------------------------------------------------------
 int tc_supported(const rbnn_net* net);
+int tc_f16x3_supported(const rbnn_net* net);
 void tc_bank_free(rbnn_net* net);
 int tc_fc_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_t* d_labels, int B, int s0, int s1,
                          const float* d_pbar, float* d_out_sum, cudaStream_t st);

@@ -8,8 +8,10 @@
 // which is lossGradients.py:29-40 / adversarialAttacks.py:74-78 for all inputs and samples at once,
 // input gradients only (no weight gradients).  Operands of the tensor-core GEMMs are kept K-major:
 // the bank's weight matrices are re-laid once per refresh as [S,R,C] and transposed [S,C,R] copies,
-// split into tf32 hi/lo pairs (RBNN_PREC_TF32X3) or rounded to bf16 (RBNN_PREC_BF16).
+// split into tf32 hi/lo pairs (RBNN_PREC_TF32X3), into power-of-two-scaled fp16 hi/lo pairs (RBNN_PREC_F16X3,
+// arch fc) or rounded to bf16 (RBNN_PREC_BF16).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
@@ -88,6 +90,118 @@ __global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64
         thi[o] = h;
         tlo[o] = v - h;
       }
+    }
+  }
+}
+
+// ---- F16X3 operand scaling ---------------------------------------------------------------------------
+// fp16 keeps 11 significant bits over 2^-14 .. 2^16 only, so every F16X3 operand is multiplied by a power of two
+// (exact) that puts its largest element in [2^8, 2^9): hi = rn_f16(s v) carries the leading 11 bits, lo =
+// rn_f16(s v - hi) the next 11; elements below 2^-16 of the maximum lose relative (not absolute) precision, which
+// a dot product does not see.  All scales live in device memory; nothing is read back by the host.
+constexpr int kF16TargetExp = 9;
+
+__device__ __forceinline__ float pow2_scale_for(float maxabs) {     // s = 2^k with s * maxabs in [2^8, 2^9)
+  if (!(maxabs > 0.f) || !isfinite(maxabs)) return 1.f;
+  int e;
+  frexpf(maxabs, &e);                                               // maxabs = m 2^e, m in [0.5, 1)
+  return ldexpf(1.f, kF16TargetExp - e);
+}
+
+// *out_bits = max(*out_bits, max_i |v_i|) as float bits (non-negative floats order like unsigned integers);
+// `count` segments of `len` floats, segment i at base + i * stride
+__global__ void __launch_bounds__(256)
+maxabs_kernel(const float* __restrict__ base, int64_t stride, int64_t len, int count, unsigned* __restrict__ out_bits) {
+  __shared__ float red[8];
+  float m = 0.f;
+  const int64_t total = len * count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t seg = i / len, o = i - seg * len;
+    m = fmaxf(m, fabsf(__ldg(base + seg * stride + o)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    if (!(m == m)) m = __int_as_float(0x7f800000);                  // NaN weights -> "infinite" range -> overflow flag
+    atomicMax(out_bits, __float_as_uint(m));
+  }
+}
+
+// after the maxima of the dirty rows are in: fix s_w1 on first use, afterwards only check that the frozen scale
+// still keeps every |W1| inside the fp16 range (2^6 head room); otherwise raise the sticky host-visible flag
+__global__ void freeze_scales_kernel(TcScales* sc, int* overflow) {
+  const float mw = __uint_as_float(sc->maxw1_bits);
+  if (!sc->frozen) {
+    sc->s_w1 = pow2_scale_for(mw);
+    sc->frozen = 1;
+  }
+  if (!(mw * sc->s_w1 < 32768.f)) {
+    *overflow = 1;
+    __threadfence_system();
+  }
+}
+
+// per call: [0] s_x, [1] 1 / (s_x s_w1) (forward unscale), [2] dH scale, [3] 1 / (dH scale * s_w1) (backward unscale)
+// |dH| <= 2 max|g| max|Wo| with max|g| <= 1 for the built-in heads (g = softmax(.) - e_y) and max|d_pbar| for UPSTREAM
+__global__ void call_scales_kernel(const TcScales* sc, const unsigned* xmax_bits, const unsigned* gmax_bits,
+                                   float* out) {
+  const float sx = pow2_scale_for(__uint_as_float(*xmax_bits));
+  const float gmax = gmax_bits ? __uint_as_float(*gmax_bits) : 1.f;
+  const float sd = pow2_scale_for(2.f * gmax * __uint_as_float(sc->maxwo_bits));
+  out[0] = sx;
+  out[1] = 1.f / (sx * sc->s_w1);
+  out[2] = sd;
+  out[3] = 1.f / (sd * sc->s_w1);
+}
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// x[n] -> fp16 hi/lo of s_x * x
+__global__ void split_f16_kernel(const float* __restrict__ x, const float* __restrict__ call_sc,
+                                 __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4) {
+  const float s = __ldg(call_sc);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    __half h[4], l[4];
+    split_f16(v.x * s, h[0], l[0]); split_f16(v.y * s, h[1], l[1]);
+    split_f16(v.z * s, h[2], l[2]); split_f16(v.w * s, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// F16X3 twin of relayout_kernel: [s][R][C] and transposed [s][C][R] fp16 hi/lo copies of s_w1 * W
+__global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0,
+                                    const TcScales* __restrict__ sc, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    __half* __restrict__ thi, __half* __restrict__ tlo) {
+  __shared__ float tile[32][33];
+  const float sw = sc->s_w1;
+  const int s = s0 + blockIdx.z;
+  const float* __restrict__ src = bank + (int64_t)s * P + off;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = blockIdx.y * 32 + i;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = __ldg(src + (int64_t)r * C + c) * sw;
+      const int64_t o = ((int64_t)s * R + r) * C + c;
+      split_f16(v, hi[o], lo[o]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c2 = blockIdx.x * 32 + i;
+    if (r2 < R && c2 < C) {
+      const int64_t o = ((int64_t)s * C + c2) * R + r2;
+      split_f16(tile[threadIdx.x][i], thi[o], tlo[o]);
     }
   }
 }
@@ -380,14 +494,24 @@ int tc_supported(const rbnn_net* n) {
   return n->cc_major == 10;
 }
 
+// F16X3 rides on the fused forward+head kernel (dH is produced and scaled inside it): arch fc only
+int tc_f16x3_supported(const rbnn_net* n) {
+  return tc_supported(n) && n->arch == RBNN_ARCH_FC && n->L.w1 == 0 && tc::fused_supported(n->H, n->C);
+}
+
 void tc_bank_free(rbnn_net* n) {
   for (int i = 0; i < 2; ++i) {
     TcMat& m = n->tc.mat[i];
     cudaFree(m.hi); cudaFree(m.lo); cudaFree(m.thi); cudaFree(m.tlo); cudaFree(m.bf); cudaFree(m.tbf);
+    cudaFree(m.h_hi); cudaFree(m.h_lo); cudaFree(m.th_hi); cudaFree(m.th_lo);
     m = TcMat();
   }
   cudaFree(n->tc.wnorm);
   n->tc.wnorm = nullptr;
+  cudaFree(n->tc.scales);
+  n->tc.scales = nullptr;
+  if (n->tc.overflow_host) cudaFreeHost(n->tc.overflow_host);
+  n->tc.overflow_host = n->tc.overflow_dev = nullptr;
   delete[] n->tc.dirty;
   n->tc.dirty = nullptr;
   n->tc.capacity = 0;
@@ -397,7 +521,18 @@ void tc_bank_free(rbnn_net* n) {
 // Bring the derived copies of bank rows [s0, s1) up to date (all rows after a capacity / precision change).
 static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
   TcBank& tc = n->tc;
-  const bool bf = n->prec == RBNN_PREC_BF16;
+  const bool bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
+  if (f16 && tc.overflow_host && *(volatile int*)tc.overflow_host) {
+    // a row re-laid after s_w1 was frozen did not fit the fp16 range: results since then are invalid.  Start over
+    // (new scale from all rows) and tell the caller.
+    RBNN_CUDA(cudaDeviceSynchronize());
+    *tc.overflow_host = 0;
+    RBNN_CUDA(cudaMemset(tc.scales, 0, sizeof(TcScales)));
+    std::fill(tc.dirty, tc.dirty + tc.capacity, (uint8_t)1);
+    set_error("F16X3: bank rows uploaded after the operand scale was fixed exceed the fp16 range (> 64x the earlier "
+              "maximum |w|); the results of calls since that upload are invalid.  The scale has been reset: repeat the call");
+    return 1;
+  }
   if (tc.capacity < n->capacity || tc.mode != n->prec) {
     RBNN_CUDA(cudaDeviceSynchronize());
     tc_bank_free(n);
@@ -410,6 +545,11 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       if (bf) {
         RBNN_CUDA(cudaMalloc(&m.bf, elems * 2));
         RBNN_CUDA(cudaMalloc(&m.tbf, elems * 2));
+      } else if (f16) {
+        RBNN_CUDA(cudaMalloc(&m.h_hi, elems * 2));
+        RBNN_CUDA(cudaMalloc(&m.h_lo, elems * 2));
+        RBNN_CUDA(cudaMalloc(&m.th_hi, elems * 2));
+        RBNN_CUDA(cudaMalloc(&m.th_lo, elems * 2));
       } else {
         RBNN_CUDA(cudaMalloc(&m.hi, elems * 4));
         RBNN_CUDA(cudaMalloc(&m.lo, elems * 4));
@@ -418,10 +558,40 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       }
     }
     RBNN_CUDA(cudaMalloc(&tc.wnorm, (size_t)n->capacity * sizeof(float)));
+    if (f16) {
+      RBNN_CUDA(cudaMalloc(&tc.scales, sizeof(TcScales)));
+      RBNN_CUDA(cudaMemset(tc.scales, 0, sizeof(TcScales)));
+      RBNN_CUDA(cudaHostAlloc(&tc.overflow_host, sizeof(int), cudaHostAllocMapped));
+      *tc.overflow_host = 0;
+      RBNN_CUDA(cudaHostGetDevicePointer(&tc.overflow_dev, tc.overflow_host, 0));
+    }
     tc.dirty = new uint8_t[n->capacity];
     std::fill(tc.dirty, tc.dirty + n->capacity, (uint8_t)1);
     tc.capacity = n->capacity;
     tc.mode = n->prec;
+  }
+  if (f16) {
+    // operand ranges of the dirty rows first (W1 fixes / checks the frozen scale, Wo bounds dH)
+    bool any = false;
+    for (int s = s0; s < s1;) {
+      if (!tc.dirty[s]) { ++s; continue; }
+      int e = s;
+      while (e < s1 && tc.dirty[e]) ++e;
+      const int64_t P = n->L.P;
+      maxabs_kernel<<<n->sm_count * 4, 256, 0, st>>>(n->bank + (int64_t)s * P + n->L.w1, P, (int64_t)n->H * n->D, e - s,
+                                                     &tc.scales->maxw1_bits);
+      maxabs_kernel<<<n->sm_count, 256, 0, st>>>(n->bank + (int64_t)s * P + n->L.wo, P, (int64_t)n->C * n->H, e - s,
+                                                 &tc.scales->maxwo_bits);
+      n->launches += 2;
+      RBNN_CUDA(cudaGetLastError());
+      any = true;
+      s = e;
+    }
+    if (any) {
+      freeze_scales_kernel<<<1, 1, 0, st>>>(tc.scales, tc.overflow_dev);
+      n->launches++;
+      RBNN_CUDA(cudaGetLastError());
+    }
   }
   int s = s0;
   while (s < s1) {
@@ -431,9 +601,14 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
     for (int i = 0; i < tc.nmat; ++i) {
       TcMat& m = tc.mat[i];
       dim3 grid((m.C + 31) / 32, (m.R + 31) / 32, e - s);
-      relayout_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, s, m.hi, m.lo, m.thi, m.tlo,
-                                                    reinterpret_cast<__nv_bfloat16*>(m.bf),
-                                                    reinterpret_cast<__nv_bfloat16*>(m.tbf));
+      if (f16)
+        relayout_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, s, tc.scales,
+                                                          reinterpret_cast<__half*>(m.h_hi), reinterpret_cast<__half*>(m.h_lo),
+                                                          reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo));
+      else
+        relayout_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, s, m.hi, m.lo, m.thi, m.tlo,
+                                                      reinterpret_cast<__nv_bfloat16*>(m.bf),
+                                                      reinterpret_cast<__nv_bfloat16*>(m.tbf));
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }
@@ -447,7 +622,7 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
 }
 
 static int run_gemm(rbnn_net* n, tc::GemmDesc& d, int tag, cudaStream_t st) {
-  d.mode = n->prec == RBNN_PREC_BF16 ? tc::MODE_BF16 : tc::MODE_TF32X3;
+  d.mode = n->prec == RBNN_PREC_BF16 ? tc::MODE_BF16 : (n->prec == RBNN_PREC_F16X3 ? tc::MODE_F16X3 : tc::MODE_TF32X3);
   d.sm_count = n->sm_count;
   std::string err;
   if (tag) RBNN_TRY(timing_begin(n, tag, st));
@@ -477,6 +652,10 @@ struct FcWs {
   // per call
   float *x_hi = nullptr, *x_lo = nullptr;
   __nv_bfloat16* x_bf = nullptr;
+  __half *x_h16 = nullptr, *x_l16 = nullptr;                  // F16X3: fp16 split of s_x * x
+  float* call_sc = nullptr;                                   // F16X3: the call's 4 scale scalars (call_scales_kernel)
+  unsigned* max_bits = nullptr;                               // F16X3: [0] max|x|, [1] max|d_pbar| (UPSTREAM head)
+  __half *dtop_h16 = nullptr, *dtop_l16 = nullptr;            // F16X3: dH as scaled fp16 hi/lo
   // per chunk of Z samples ([Z, B, H] each)
   float *h1 = nullptr, *h1_lo = nullptr, *h2 = nullptr;       // tf32x3/fc2: h1 holds the hi part (sign == sign of H1)
   __nv_bfloat16 *h1_bf = nullptr;
@@ -489,15 +668,16 @@ struct FcWs {
 
 // arch fc with a hidden layer the fused forward+head kernel covers: H never goes to HBM
 static bool use_fused(const rbnn_net* n) {
-  return n->arch == RBNN_ARCH_FC && n->L.w1 == 0 && tc::fused_supported(n->H, n->C) && !n->tc_unfused;
+  return n->arch == RBNN_ARCH_FC && n->L.w1 == 0 && tc::fused_supported(n->H, n->C) &&
+         (!n->tc_unfused || n->prec == RBNN_PREC_F16X3);
 }
 
 static size_t fc_per_z_bytes(const rbnn_net* n, int B, bool grad) {
-  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
+  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const size_t bh = pad256((size_t)B * n->H * 4), bh2 = pad256((size_t)B * n->H * 2);
   if (use_fused(n)) {
     if (!grad) return pad256((size_t)B * n->C * 4);
-    return (bf ? bh2 : 2 * bh) + pad256(tc::fused_worklist_slots(B, 1) * 8);
+    return (bf ? bh2 : (f16 ? 2 * bh2 : 2 * bh)) + pad256(tc::fused_worklist_slots(B, 1) * 8);
   }
   size_t per = bh;                                   // h1 (fp32 or hi)
   if (two) per += (bf ? bh2 : bh) + bh;              // h1 lo / bf16 + h2
@@ -574,20 +754,31 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
 static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, const int32_t* labels, const float* pbar,
                        int B, int z0, int Z, float* logits, cudaStream_t st) {
   const int H = n->H, D = n->D;
-  const bool bf = n->prec == RBNN_PREC_BF16;
+  const bool bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const TcMat& m1 = n->tc.mat[0];
   tc::FusedDesc f;
-  f.mode = bf ? tc::MODE_BF16 : tc::MODE_TF32X3;
+  f.mode = bf ? tc::MODE_BF16 : (f16 ? tc::MODE_F16X3 : tc::MODE_TF32X3);
   f.B = B; f.D = D; f.H = H; f.C = n->C; f.Z = Z;
-  f.X.hi = bf ? (const void*)w.x_bf : (const void*)w.x_hi; f.X.lo = w.x_lo; f.X.rows = B; f.X.ld = D;
-  if (bf) f.W1.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * D;
-  else { f.W1.hi = m1.hi + (int64_t)z0 * H * D; f.W1.lo = m1.lo + (int64_t)z0 * H * D; }
+  f.X.rows = B; f.X.ld = D;
+  if (bf) {
+    f.X.hi = w.x_bf;
+    f.W1.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * D;
+  } else if (f16) {
+    f.X.hi = w.x_h16; f.X.lo = w.x_l16;
+    f.W1.hi = reinterpret_cast<const __half*>(m1.h_hi) + (int64_t)z0 * H * D;
+    f.W1.lo = reinterpret_cast<const __half*>(m1.h_lo) + (int64_t)z0 * H * D;
+    f.unscale = w.call_sc + 1; f.dh_scale = w.call_sc + 2;
+  } else {
+    f.X.hi = w.x_hi; f.X.lo = w.x_lo;
+    f.W1.hi = m1.hi + (int64_t)z0 * H * D; f.W1.lo = m1.lo + (int64_t)z0 * H * D;
+  }
   f.W1.rows = H; f.W1.ld = D; f.W1.zstride = (int64_t)H * D;
   f.head = head;
   f.bank = n->bank; f.P = n->L.P; f.b1_off = n->L.b1; f.wo_off = n->L.wo; f.bo_off = n->L.bo; f.z_row0 = z0;
   f.labels = labels; f.pbar = pbar;
   f.x = x; f.xnorm = w.xnorm; f.wnorm = n->tc.wnorm; f.eps = kGuardEpsFused;
-  f.dh_hi = w.dtop_hi; f.dh_lo = w.dtop_lo; f.dh_bf = w.dtop_bf; f.logits = logits;
+  f.dh_hi = f16 ? (void*)w.dtop_h16 : (void*)w.dtop_hi; f.dh_lo = f16 ? (void*)w.dtop_l16 : (void*)w.dtop_lo;
+  f.dh_bf = w.dtop_bf; f.logits = logits;
   f.worklist = w.worklist;
   f.sm_count = n->sm_count;
   std::string err;
@@ -627,9 +818,24 @@ static int launch_head(rbnn_net* n, bool grad, int head, const float* top, int z
   return 0;
 }
 
-static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, cudaStream_t st) {
+// pbar_for_scale: the UPSTREAM head's d_pbar [B*C] (its magnitude bounds dH), else nullptr
+static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const float* pbar_for_scale, int64_t pbar_count,
+                   cudaStream_t st) {
   const int64_t n4 = count / 4;
   const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
+  if (n->prec == RBNN_PREC_F16X3) {
+    RBNN_CUDA(cudaMemsetAsync(w.max_bits, 0, 2 * sizeof(unsigned), st));
+    maxabs_kernel<<<n->sm_count * 2, 256, 0, st>>>(x, 0, count, 1, w.max_bits);
+    if (pbar_for_scale) {
+      maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar_for_scale, 0, pbar_count, 1, w.max_bits + 1);
+      n->launches++;
+    }
+    call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, pbar_for_scale ? w.max_bits + 1 : nullptr, w.call_sc);
+    split_f16_kernel<<<blocks, 256, 0, st>>>(x, w.call_sc, w.x_h16, w.x_l16, n4);
+    n->launches += 3;
+    RBNN_CUDA(cudaGetLastError());
+    return 0;
+  }
   split_kernel<<<blocks, 256, 0, st>>>(x, w.x_hi, w.x_lo, w.x_bf, n4);
   n->launches++;
   RBNN_CUDA(cudaGetLastError());
@@ -646,10 +852,10 @@ static int tc_batch_rows(const rbnn_net* n, int B, bool grad) {
 static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1,
                         const float* pbar, float* out_sum, cudaStream_t st) {
   const int H = n->H, D = n->D;
-  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
+  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const int S = s1 - s0;
   const size_t per = fc_per_z_bytes(n, B, true);
-  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : 2 * pad256((size_t)B * D * 4);
+  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : (f16 ? 2 * pad256((size_t)B * D * 2) + 512 : 2 * pad256((size_t)B * D * 4));
   const size_t out_bytes = pad256((size_t)B * D * 4);
   // samples per chunk: as many as the budget allows; the backward reduce cuts a chunk into `slots`
   // K-concatenated ranges of ~4 samples (bounds the tensor-core accumulation chain, fills the SMs)
@@ -674,15 +880,20 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   Arena ar(n);
   FcWs w;
   if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
-  else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
+  else if (f16) {
+    w.x_h16 = ar.take<__half>((size_t)B * D); w.x_l16 = ar.take<__half>((size_t)B * D);
+    w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2);
+  } else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
+  RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
   if (!fused) w.h1 = ar.take<float>(zbh);
   if (two) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
     w.h2 = ar.take<float>(zbh);
   }
   if (bf) w.dtop_bf = ar.take<__nv_bfloat16>(zbh);
+  else if (f16) { w.dtop_h16 = ar.take<__half>(zbh); w.dtop_l16 = ar.take<__half>(zbh); }
   else { w.dtop_hi = ar.take<float>(zbh); w.dtop_lo = ar.take<float>(zbh); }
   if (two) {
     if (bf) w.d1_bf = ar.take<__nv_bfloat16>(zbh);
@@ -691,7 +902,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   if (fused && !bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc));
   w.xnorm = ar.take<float>((size_t)B);
   w.partial = ar.take<float>((size_t)slots * B * D);
-  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, st));
+  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, head == RBNN_HEAD_UPSTREAM ? pbar : nullptr, (int64_t)B * n->C, st));
   if (fused && !bf) {
     xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
     n->launches++;
@@ -709,8 +920,8 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
       RBNN_TRY(fc_forward_chunk_tc(n, w, x, B, z0, Z, &top, st));
       RBNN_TRY(launch_head(n, true, head, top, z0, Z, labels, pbar, B, nullptr, w.dtop_hi, w.dtop_lo, w.dtop_bf, st));
     }
-    const void* dfirst_hi = bf ? (const void*)w.dtop_bf : (const void*)w.dtop_hi;
-    const void* dfirst_lo = w.dtop_lo;
+    const void* dfirst_hi = bf ? (const void*)w.dtop_bf : (f16 ? (const void*)w.dtop_h16 : (const void*)w.dtop_hi);
+    const void* dfirst_lo = f16 ? (const void*)w.dtop_l16 : (const void*)w.dtop_lo;
     if (two) {
       // dH1 = (dH2 . W2) (.) leaky'(H1): per-z GEMM with K = H over the transposed copy of W2
       const TcMat& m2 = n->tc.mat[1];
@@ -734,7 +945,11 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     r.M = B; r.N = D; r.K = H; r.Z = Z; r.BN = bn_b;
     r.A.hi = dfirst_hi; r.A.lo = dfirst_lo; r.A.rows = B; r.A.ld = H; r.A.zstride = (int64_t)B * H;
     if (bf) r.B.hi = reinterpret_cast<const __nv_bfloat16*>(m1.tbf) + (int64_t)z0 * D * H;
-    else { r.B.hi = m1.thi + (int64_t)z0 * D * H; r.B.lo = m1.tlo + (int64_t)z0 * D * H; }
+    else if (f16) {
+      r.B.hi = reinterpret_cast<const __half*>(m1.th_hi) + (int64_t)z0 * D * H;
+      r.B.lo = reinterpret_cast<const __half*>(m1.th_lo) + (int64_t)z0 * D * H;
+      r.unscale = w.call_sc + 3;
+    } else { r.B.hi = m1.thi + (int64_t)z0 * D * H; r.B.lo = m1.tlo + (int64_t)z0 * D * H; }
     r.B.rows = D; r.B.ld = H; r.B.zstride = (int64_t)D * H;
     r.reduce_z = 1; r.slots = sl;
     r.out = w.partial; r.out_ld = D; r.out_zstride = (int64_t)B * D;
@@ -764,26 +979,30 @@ int tc_fc_input_grad_sum(rbnn_net* n, int head, const float* x, const int32_t* l
 static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, float* out_logits,
                            cudaStream_t st) {
   const int H = n->H, D = n->D, C = n->C;
-  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
+  const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const int S = s1 - s0;
   const size_t per = fc_per_z_bytes(n, B, false);
-  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : 2 * pad256((size_t)B * D * 4);
+  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : (f16 ? 2 * pad256((size_t)B * D * 2) + 512 : 2 * pad256((size_t)B * D * 4));
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
   const int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / per, (size_t)S));
   RBNN_TRY(ws_reserve(n, x_bytes + per * zc));
   Arena ar(n);
   FcWs w;
   if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
-  else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
+  else if (f16) {
+    w.x_h16 = ar.take<__half>((size_t)B * D); w.x_l16 = ar.take<__half>((size_t)B * D);
+    w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2);
+  } else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
+  RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
   if (!fused) w.h1 = ar.take<float>(zbh);
   if (two) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
     w.h2 = ar.take<float>(zbh);
   }
   w.logits = ar.take<float>((size_t)zc * B * C);
-  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, st));
+  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, st));
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
     float* lg = out_logits ? out_logits : w.logits;

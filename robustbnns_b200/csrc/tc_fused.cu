@@ -8,7 +8,7 @@
 //   work item = (sample z, tile of 128 inputs); per item the hidden dimension is cut into n-tiles of
 //   BN <= 256 columns that alternate between the two TMEM accumulator stages.
 //   warp 0      TMA producer (X tile + W1_z tile K-blocks, SWIZZLE_128B ring)
-//   warp 1      tcgen05.mma issuer (kind::tf32 x3 passes or kind::f16)
+//   warp 1      tcgen05.mma issuer (kind::tf32 x3 passes, kind::f16 x3 passes on scaled fp16 hi/lo, or kind::f16 on bf16)
 //   warps 2..9  epilogue: warp = (TMEM lane quadrant, column half).  Pass 1 (per n-tile, overlapping the next
 //               n-tile's MMAs): tcgen05.ld -> +b1 -> LeakyReLU -> mask bit, partial logits += h * Wo (Wo_z in
 //               shared memory), guard-band check.  After the last n-tile the two column halves exchange their
@@ -20,6 +20,7 @@
 // exactly (fp64 accumulation) and rescales dH[z, b, j] when the sign was wrong.  Each item owns kWorkPerItem
 // slots of the worklist (no global atomics, deterministic); an item that overflows evaluates inline.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "../../include/rbnn.h"
 #include "tc_gemm.cuh"
@@ -47,7 +48,8 @@ struct FParams {
   const float* bank; long long P, b1_off, wo_off, bo_off; int z_row0;
   const int32_t* labels; const float* pbar;
   const float* x; const float* xnorm; const float* wnorm; float eps;
-  float* dh_hi; float* dh_lo; __nv_bfloat16* dh_bf; float* logits;
+  void* dh_hi; void* dh_lo; __nv_bfloat16* dh_bf; float* logits;
+  const float* unscale; const float* dh_scale;      // F16X3 device scalars (see FusedDesc)
   unsigned long long* worklist;
 };
 
@@ -81,18 +83,20 @@ __device__ __forceinline__ void softmax_r(float (&v)[C_MAX], int C) {
     if (c < C) v[c] *= inv;
 }
 
-template <bool BF16, int KBB>
+template <int MODE, int KBB>
 __global__ void __launch_bounds__(kThreadsF, 1)
 fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                 const FParams p) {
+  constexpr bool BF16 = MODE == MODE_BF16;
+  constexpr bool F16K = MODE != MODE_TF32X3;            // kind::f16 MMAs on 2-byte operands
   constexpr int NARR = BF16 ? 1 : 2;
   constexpr int kATileF = kBM * KBB, kBTileF = kBNMax * KBB;
   constexpr int STAGE = NARR * (kATileF + kBTileF);
   constexpr int NSTAGE = kRingF / STAGE;
-  constexpr int KBE = KBB / (BF16 ? 2 : 4);
+  constexpr int KBE = KBB / (F16K ? 2 : 4);
   constexpr int KSTEPS = KBB / 32;
-  constexpr uint32_t FMT = BF16 ? 1u : 2u;
+  constexpr uint32_t FMT = MODE == MODE_BF16 ? 1u : (MODE == MODE_F16X3 ? 0u : 2u);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -192,9 +196,9 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
               const uint64_t a_lo = smem_desc<KBB>(sa + kATileF), b_lo = smem_desc<KBB>(sb + kBTileF);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                tc_mma<false>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
-                tc_mma<false>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                tc_mma<false>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                tc_mma<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
                 accumulate = 1;
               }
             }
@@ -222,6 +226,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int nblocks = cols_half / 32;        // 32-column blocks per (n-tile, half)
     const int q = lane & 3, rsub = lane >> 2;  // fragment coordinates
     const int C = p.C, H = p.H;
+    const float unscale = (MODE == MODE_F16X3) ? __ldg(p.unscale) : 1.f;     // 1 / (s_X s_W1)
+    const float dh_scale = (MODE == MODE_F16X3) ? __ldg(p.dh_scale) : 1.f;   // dH -> fp16 range
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int z = item / p.m_tiles, m_idx = item % p.m_tiles;
@@ -275,8 +281,13 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
               float h[2][2];
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
-                h[r][0] = __uint_as_float(v[4 * k + 2 * r]) + bb.x;
-                h[r][1] = __uint_as_float(v[4 * k + 2 * r + 1]) + bb.y;
+                if (MODE == MODE_F16X3) {
+                  h[r][0] = fmaf(__uint_as_float(v[4 * k + 2 * r]), unscale, bb.x);
+                  h[r][1] = fmaf(__uint_as_float(v[4 * k + 2 * r + 1]), unscale, bb.y);
+                } else {
+                  h[r][0] = __uint_as_float(v[4 * k + 2 * r]) + bb.x;
+                  h[r][1] = __uint_as_float(v[4 * k + 2 * r + 1]) + bb.y;
+                }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   bool pos = h[r][e] > 0.f;
@@ -436,12 +447,21 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                 if (BF16) {
                   const __nv_bfloat162 a = __floats2bfloat162_rn(d[r][0], d[r][1]);
                   __stcs(reinterpret_cast<unsigned int*>(p.dh_bf + orow[r] + j), *reinterpret_cast<const unsigned int*>(&a));
+                } else if (MODE == MODE_F16X3) {
+                  const float s0 = d[r][0] * dh_scale, s1 = d[r][1] * dh_scale;
+                  const __half2 hi2 = __floats2half2_rn(s0, s1);
+                  const float2 hf = __half22float2(hi2);
+                  const __half2 lo2 = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+                  __stcs(reinterpret_cast<unsigned int*>(reinterpret_cast<__half*>(p.dh_hi) + orow[r] + j),
+                         *reinterpret_cast<const unsigned int*>(&hi2));
+                  __stcs(reinterpret_cast<unsigned int*>(reinterpret_cast<__half*>(p.dh_lo) + orow[r] + j),
+                         *reinterpret_cast<const unsigned int*>(&lo2));
                 } else {
                   float2 hi2, lo2;
                   hi2.x = to_tf32_rn(d[r][0]); hi2.y = to_tf32_rn(d[r][1]);
                   lo2.x = d[r][0] - hi2.x; lo2.y = d[r][1] - hi2.y;
-                  __stcs(reinterpret_cast<float2*>(p.dh_hi + orow[r] + j), hi2);   // streaming: do not displace X / W1 in L2
-                  __stcs(reinterpret_cast<float2*>(p.dh_lo + orow[r] + j), lo2);
+                  __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_hi) + orow[r] + j), hi2);   // streaming: do not displace X / W1 in L2
+                  __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_lo) + orow[r] + j), lo2);
                 }
               }
             }
@@ -461,10 +481,11 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 
 // One warp per worklist slot batch: exact re-evaluation of the queued pre-activations; where the sign the
 // epilogue assumed was wrong, dH[z, b, j] is rescaled by slope^(+-1) in place.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 fixup_kernel(const unsigned long long* __restrict__ wl, long long nslots, const float* __restrict__ x,
              const float* __restrict__ bank, long long P, long long b1_off, int z_row0, int B, int D, int H,
-             float* __restrict__ dh_hi, float* __restrict__ dh_lo) {
+             void* __restrict__ dh_hi_v, void* __restrict__ dh_lo_v) {
   const int lane = threadIdx.x & 31;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long base = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nslots;
@@ -487,11 +508,23 @@ fixup_kernel(const unsigned long long* __restrict__ wl, long long nslots, const 
       const bool pos = (float)(s + (double)__ldg(wrow + b1_off + j)) > 0.f;
       if (pos != assumed_pos && lane == 0) {
         const long long o = ((long long)z * B + b) * H + j;
-        float v = dh_hi[o] + dh_lo[o];
-        v = pos ? v * 100.f : v * kSlopeF;          // undo / apply the LeakyReLU slope
-        const float hi = to_tf32_rn(v);
-        dh_hi[o] = hi;
-        dh_lo[o] = v - hi;
+        if (F16) {                                   // scaled fp16 hi/lo pair (the scale is a power of two: it commutes)
+          __half* dh_hi = reinterpret_cast<__half*>(dh_hi_v);
+          __half* dh_lo = reinterpret_cast<__half*>(dh_lo_v);
+          float v = __half2float(dh_hi[o]) + __half2float(dh_lo[o]);
+          v = pos ? v * 100.f : v * kSlopeF;
+          const __half hi = __float2half_rn(v);
+          dh_hi[o] = hi;
+          dh_lo[o] = __float2half_rn(v - __half2float(hi));
+        } else {
+          float* dh_hi = reinterpret_cast<float*>(dh_hi_v);
+          float* dh_lo = reinterpret_cast<float*>(dh_lo_v);
+          float v = dh_hi[o] + dh_lo[o];
+          v = pos ? v * 100.f : v * kSlopeF;          // undo / apply the LeakyReLU slope
+          const float hi = to_tf32_rn(v);
+          dh_hi[o] = hi;
+          dh_lo[o] = v - hi;
+        }
       }
     }
   }
@@ -515,17 +548,23 @@ size_t fused_worklist_slots(int B, int Z) { return (size_t)Z * ((B + kBM - 1) / 
 int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   std::string local;
   if (!err) err = &local;
-  const bool bf16 = d.mode == MODE_BF16;
+  const bool bf16 = d.mode == MODE_BF16, f16x3 = d.mode == MODE_F16X3;
+  const int dt = bf16 ? DT_BF16 : (f16x3 ? DT_F16 : DT_F32);
   if (d.B <= 0 || d.Z <= 0) return 0;
   if (!fused_supported(d.H, d.C)) { *err = "fused_forward_head: unsupported hidden / class size"; return 1; }
+  if (d.mode < 0 || d.mode > MODE_F16X3) { *err = "fused_forward_head: unknown mode"; return 1; }
+  if (f16x3 && (!d.unscale || !d.dh_scale)) { *err = "fused_forward_head: F16X3 needs the scale scalars"; return 1; }
   const int kbb = d.kblock_bytes == 128 ? 128 : 64;
-  auto kern = bf16 ? (kbb == 128 ? fc_fused_kernel<true, 128> : fc_fused_kernel<true, 64>)
-                   : (kbb == 128 ? fc_fused_kernel<false, 128> : fc_fused_kernel<false, 64>);
-  static bool attr_done[2][2] = {{false, false}, {false, false}};
-  if (!attr_done[bf16][kbb == 128]) {
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FParams);
+  static const kern_t kerns[3][2] = {{fc_fused_kernel<MODE_TF32X3, 64>, fc_fused_kernel<MODE_TF32X3, 128>},
+                                     {fc_fused_kernel<MODE_BF16, 64>, fc_fused_kernel<MODE_BF16, 128>},
+                                     {fc_fused_kernel<MODE_F16X3, 64>, fc_fused_kernel<MODE_F16X3, 128>}};
+  kern_t kern = kerns[d.mode][kbb == 128];
+  static bool attr_done[3][2] = {};
+  if (!attr_done[d.mode][kbb == 128]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem);
     if (e != cudaSuccess) { *err = std::string("fused_forward_head: cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
-    attr_done[bf16][kbb == 128] = true;
+    attr_done[d.mode][kbb == 128] = true;
   }
   FParams p{};
   p.B = d.B; p.D = d.D; p.H = d.H; p.C = d.C; p.Z = d.Z;
@@ -533,7 +572,7 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   p.n_tiles = d.H <= 256 ? 1 : d.H / 256;
   p.m_tiles = (d.B + kBM - 1) / kBM;
   p.num_items = p.m_tiles * d.Z;
-  const int kbe = kbb / (bf16 ? 2 : 4);
+  const int kbe = kbb / (dt == DT_F32 ? 4 : 2);
   p.num_kb = (d.D + kbe - 1) / kbe;
   p.head = d.head;
   p.bank = d.bank; p.P = d.P; p.b1_off = d.b1_off; p.wo_off = d.wo_off; p.bo_off = d.bo_off; p.z_row0 = d.z_row0;
@@ -542,6 +581,7 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   p.eps = (bf16 || !d.worklist || d.head < 0) ? 0.f : d.eps;
   p.dh_hi = d.dh_hi; p.dh_lo = d.dh_lo; p.dh_bf = reinterpret_cast<__nv_bfloat16*>(d.dh_bf); p.logits = d.logits;
   p.worklist = p.eps > 0.f ? d.worklist : nullptr;
+  p.unscale = d.unscale; p.dh_scale = d.dh_scale;
   if (d.head >= 0 && (bf16 ? !d.dh_bf : (!d.dh_hi || !d.dh_lo))) { *err = "fused_forward_head: missing dH output"; return 1; }
   if (d.head < 0 && !d.logits) { *err = "fused_forward_head: missing logits output"; return 1; }
   if (d.head >= 0 && d.head != RBNN_HEAD_MEAN_OF_GRADS && d.head != RBNN_HEAD_LOGITS_CE && !d.pbar) {
@@ -549,11 +589,11 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
     return 1;
   }
   CUtensorMap mAh, mAl, mBh, mBl;
-  if (make_map(&mAh, d.X.hi, bf16, d.D, d.B, 1, d.X.ld, 0, kBM, kbb, err)) return 1;
-  if (make_map(&mBh, d.W1.hi, bf16, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, p.BN, kbb, err)) return 1;
+  if (make_map(&mAh, d.X.hi, dt, d.D, d.B, 1, d.X.ld, 0, kBM, kbb, err)) return 1;
+  if (make_map(&mBh, d.W1.hi, dt, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, p.BN, kbb, err)) return 1;
   if (!bf16) {
-    if (make_map(&mAl, d.X.lo, false, d.D, d.B, 1, d.X.ld, 0, kBM, kbb, err)) return 1;
-    if (make_map(&mBl, d.W1.lo, false, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, p.BN, kbb, err)) return 1;
+    if (make_map(&mAl, d.X.lo, dt, d.D, d.B, 1, d.X.ld, 0, kBM, kbb, err)) return 1;
+    if (make_map(&mBl, d.W1.lo, dt, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, p.BN, kbb, err)) return 1;
   } else {
     mAl = mAh;
     mBl = mBh;
@@ -570,8 +610,12 @@ int fused_fixup(const FusedDesc& d, cudaStream_t st, std::string* err) {
   const long long nslots = (long long)fused_worklist_slots(d.B, d.Z);
   const long long warps = (nslots + 31) / 32;
   const unsigned blocks = (unsigned)std::min<long long>((warps + 7) / 8, (long long)d.sm_count * 8);
-  fixup_kernel<<<blocks, 256, 0, st>>>(d.worklist, nslots, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
-                                       d.dh_hi, d.dh_lo);
+  if (d.mode == MODE_F16X3)
+    fixup_kernel<true><<<blocks, 256, 0, st>>>(d.worklist, nslots, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
+                                               d.dh_hi, d.dh_lo);
+  else
+    fixup_kernel<false><<<blocks, 256, 0, st>>>(d.worklist, nslots, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
+                                                d.dh_hi, d.dh_lo);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("fused_fixup launch: ") + cudaGetErrorString(e);

@@ -3,7 +3,8 @@
 // Per CTA (persistent, tiles handed out round-robin):
 //   warp 0, lane 0 : TMA producer  - cp.async.bulk.tensor.3d of the A / B K-blocks (128 B of K per row,
 //                    SWIZZLE_128B) into a ring of shared-memory stages, completion on `full` mbarriers
-//   warp 1, lane 0 : MMA issuer    - tcgen05.mma.cta_group::1 (kind::tf32 x3 passes, or kind::f16),
+//   warp 1, lane 0 : MMA issuer    - tcgen05.mma.cta_group::1 (kind::tf32 x3 passes, kind::f16 x3 passes on
+//                    scaled fp16 hi/lo operands, or one kind::f16 pass on bf16),
 //                    128 x BN x (8|16) per instruction, accumulating in TMEM; tcgen05.commit frees the
 //                    stage (`empty`) and, after the last K-block, publishes the accumulator (`tmem_full`)
 //   warps 2..5     : epilogue      - tcgen05.ld 32 lanes x 32 columns at a time, bias / LeakyReLU / mask,
@@ -24,7 +25,7 @@ namespace rbnn {
 namespace tc {
 
 constexpr float kSlope = 0.01f;            // nn.LeakyReLU() default (model_nn.py:68-69)
-constexpr int kRingBytes = 196608;         // operand ring: TF32X3 2 x 96 KB (128 B K-blocks) or 4 x 48 KB (64 B K-blocks)
+constexpr int kRingBytes = 196608;         // operand ring: TF32X3 / F16X3 2 x 96 KB (128 B K-blocks) or 4 x 48 KB (64 B K-blocks)
 constexpr int kSmemBytes = kRingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 size_t smem_bytes() { return kSmemBytes; }
@@ -33,6 +34,7 @@ struct KParams {
   int M, N, K, Z, BN;
   int m_tiles, m_units, n_tiles, num_tiles, num_kb;   // m_units = m_tiles (single CTA) or ceil(m_tiles / 2) (CTA pair)
   int reduce_z, slots, a_per_z, epi, skip_mma, relay, spin;
+  const float* unscale;
   const float* bias; long long bias_zstride;
   const float* act; long long act_zstride, act_ld;
   float* out; float* out_lo; __nv_bfloat16* out_bf;
@@ -46,19 +48,21 @@ struct KParams {
 // each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for both,
 // each CTA's TMEM receives its 128 accumulator rows.  Per SM that halves the B traffic from L2 and the B reads
 // from shared memory, which is what bounds the single-CTA kernel.
-template <bool BF16, int KBB, bool PAIR>
+template <int MODE, int KBB, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const KParams p) {
+  constexpr bool BF16 = MODE == MODE_BF16;                 // single pass, one array per operand
+  constexpr bool F16K = MODE != MODE_TF32X3;               // kind::f16 MMAs on 2-byte operands
   constexpr int NARR = BF16 ? 1 : 2;                       // arrays per operand (hi[, lo])
   constexpr int kATile = kBM * KBB;                        // bytes of one A K-block tile (128 rows)
   constexpr int kBTile = (PAIR ? kBNMax / 2 : kBNMax) * KBB;   // B K-block tile held by this CTA
   constexpr int STAGE = NARR * (kATile + kBTile);
   constexpr int NSTAGE = kRingBytes / STAGE;               // TF32X3: 2/4 (single), 3/6 (pair) for KBB 128/64
-  constexpr int KBE = KBB / (BF16 ? 2 : 4);                // elements of K per K-block
+  constexpr int KBE = KBB / (F16K ? 2 : 4);                // elements of K per K-block
   constexpr int KSTEPS = KBB / 32;                         // UMMA K-steps (32 bytes of K each) per K-block
-  constexpr uint32_t FMT = BF16 ? 1u : 2u;                 // UMMA operand format: BF16 = 1, TF32 = 2
+  constexpr uint32_t FMT = MODE == MODE_BF16 ? 1u : (MODE == MODE_F16X3 ? 0u : 2u);   // UMMA operand format: F16 = 0, BF16 = 1, TF32 = 2
   constexpr int NCTA = PAIR ? 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
@@ -208,13 +212,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k) {      // small cross terms first, then the leading term
               if (PAIR) {
-                tc_mma_pair<false>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
-                tc_mma_pair<false>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                tc_mma_pair<false>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                tc_mma_pair<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
               } else {
-                tc_mma<false>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
-                tc_mma<false>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                tc_mma<false>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                tc_mma<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
               }
               accumulate = 1;
             }
@@ -232,6 +236,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // ===================== epilogue (warps 2..5 <-> TMEM lane quadrants 2,3,0,1) =====================
     const int quad = warp & 3;
     const uint32_t tempty_leader = PAIR ? mapa_u32(tempty0, 0u) : tempty0;
+    const float unscale = p.unscale ? __ldg(p.unscale) : 1.f;   // F16X3: 1 / (operand scales), a power of two
     uint32_t it = 0;
     for (int t = unit; t < p.num_tiles; t += num_units, ++it) {
       const int n_idx = t % p.n_tiles, m_unit = (t / p.n_tiles) % p.m_units, zz = t / tiles_mn;
@@ -256,6 +261,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (c0 + j >= p.BN || n >= p.N) break;           // BN % 16 == 0 and N % 4 == 0: groups of 4 are all-in or all-out
           float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                         __uint_as_float(r[j + 3])};
+          if (MODE == MODE_F16X3) { v[0] *= unscale; v[1] *= unscale; v[2] *= unscale; v[3] *= unscale; }
           if (p.epi == EPI_BIAS_LEAKY || p.epi == EPI_BIAS) {
             // scalar loads: bank rows are P floats apart, so bias_z is only 4-byte aligned
             v[0] += __ldg(bias + n); v[1] += __ldg(bias + n + 1); v[2] += __ldg(bias + n + 2); v[3] += __ldg(bias + n + 3);
@@ -324,11 +330,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 // 3-D map over [Z][rows][K] (K innermost); box = one K-block (128 B) x box_rows x 1; zero fill out of bounds.
-int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t K, int64_t rows, int64_t Z, int64_t ld,
+int make_map(CUtensorMap* map, const void* base, int dtype, int64_t K, int64_t rows, int64_t Z, int64_t ld,
              int64_t zstride, int box_rows, int kb_bytes, std::string* err) {
   auto fn = encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled is not available from the driver"; return 1; }
-  const int64_t es = bf16 ? 2 : 4;
+  const int64_t es = dtype == DT_F32 ? 4 : 2;
   if (zstride == 0) Z = 1;
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)Z};
   cuuint64_t strides[2] = {(cuuint64_t)(ld * es), (cuuint64_t)((zstride ? zstride : rows * ld) * es)};
@@ -338,7 +344,9 @@ int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t K, int64_t r
     *err = "tc::gemm: operand base / strides must be 16-byte aligned";
     return 1;
   }
-  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+  const CUtensorMapDataType dt = dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, 3,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   kb_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -351,8 +359,12 @@ int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t K, int64_t r
 int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   std::string local;
   if (!err) err = &local;
-  const bool bf16 = d.mode == MODE_BF16;
+  const bool bf16 = d.mode == MODE_BF16, f16x3 = d.mode == MODE_F16X3;
+  const int dt = bf16 ? DT_BF16 : (f16x3 ? DT_F16 : DT_F32);
   if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.Z <= 0) return 0;
+  if (d.mode != MODE_TF32X3 && d.mode != MODE_BF16 && d.mode != MODE_F16X3) { *err = "tc::gemm: unknown mode"; return 1; }
+  if (f16x3 && !d.unscale) { *err = "tc::gemm: F16X3 needs the unscale scalar"; return 1; }
+  if (f16x3 && d.out_lo) { *err = "tc::gemm: F16X3 has no pre-split output"; return 1; }
   if (d.BN < 16 || d.BN > kBNMax || (d.BN & 15)) { *err = "tc::gemm: BN must be a multiple of 16 in [16,256]"; return 1; }
   if (d.N & 3) { *err = "tc::gemm: N must be a multiple of 4"; return 1; }
   if (!d.A.hi || !d.B.hi || (!bf16 && (!d.A.lo || !d.B.lo))) { *err = "tc::gemm: missing operand array"; return 1; }
@@ -361,25 +373,27 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   const int kbb = d.kblock_bytes == 128 ? 128 : 64;
   const bool pair = d.pair && (d.BN % 32 == 0 || d.BN % 16 == 0) && ((d.BN / 2) % 8 == 0) && d.sm_count >= 2;
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
-  static const kern_t kerns[2][2][2] = {
-      {{tc_gemm_kernel<false, 64, false>, tc_gemm_kernel<false, 64, true>},
-       {tc_gemm_kernel<false, 128, false>, tc_gemm_kernel<false, 128, true>}},
-      {{tc_gemm_kernel<true, 64, false>, tc_gemm_kernel<true, 64, true>},
-       {tc_gemm_kernel<true, 128, false>, tc_gemm_kernel<true, 128, true>}}};
-  kern_t kern = kerns[bf16][kbb == 128][pair];
-  static bool attr_done[2][2][2] = {};
-  if (!attr_done[bf16][kbb == 128][pair]) {
+  static const kern_t kerns[3][2][2] = {
+      {{tc_gemm_kernel<MODE_TF32X3, 64, false>, tc_gemm_kernel<MODE_TF32X3, 64, true>},
+       {tc_gemm_kernel<MODE_TF32X3, 128, false>, tc_gemm_kernel<MODE_TF32X3, 128, true>}},
+      {{tc_gemm_kernel<MODE_BF16, 64, false>, tc_gemm_kernel<MODE_BF16, 64, true>},
+       {tc_gemm_kernel<MODE_BF16, 128, false>, tc_gemm_kernel<MODE_BF16, 128, true>}},
+      {{tc_gemm_kernel<MODE_F16X3, 64, false>, tc_gemm_kernel<MODE_F16X3, 64, true>},
+       {tc_gemm_kernel<MODE_F16X3, 128, false>, tc_gemm_kernel<MODE_F16X3, 128, true>}}};
+  kern_t kern = kerns[d.mode][kbb == 128][pair];
+  static bool attr_done[3][2][2] = {};
+  if (!attr_done[d.mode][kbb == 128][pair]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { *err = std::string("tc::gemm: cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
-    attr_done[bf16][kbb == 128][pair] = true;
+    attr_done[d.mode][kbb == 128][pair] = true;
   }
 
   CUtensorMap mAh, mAl, mBh, mBl;
-  if (make_map(&mAh, d.A.hi, bf16, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
-  if (make_map(&mBh, d.B.hi, bf16, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
+  if (make_map(&mAh, d.A.hi, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
+  if (make_map(&mBh, d.B.hi, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   if (!bf16) {
-    if (make_map(&mAl, d.A.lo, false, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
-    if (make_map(&mBl, d.B.lo, false, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
+    if (make_map(&mAl, d.A.lo, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
+    if (make_map(&mBl, d.B.lo, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   } else {
     mAl = mAh;
     mBl = mBh;
@@ -393,13 +407,14 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   p.reduce_z = d.reduce_z ? 1 : 0;
   p.slots = d.reduce_z ? d.slots : 1;
   p.num_tiles = p.m_units * p.n_tiles * (d.reduce_z ? d.slots : d.Z);
-  const int kbe = kbb / (bf16 ? 2 : 4);
+  const int kbe = kbb / (dt == DT_F32 ? 4 : 2);
   p.num_kb = (d.K + kbe - 1) / kbe;
   p.a_per_z = d.A.zstride != 0;
   p.epi = d.epi;
   p.skip_mma = d.debug_skip_mma;
   p.relay = d.pair_relay;
   p.spin = d.spin_wait;
+  p.unscale = f16x3 ? d.unscale : nullptr;
   p.bias = d.bias; p.bias_zstride = d.bias_zstride;
   p.act = d.act; p.act_zstride = d.act_zstride; p.act_ld = d.act_ld;
   p.out = d.out; p.out_lo = d.out_lo; p.out_bf = reinterpret_cast<__nv_bfloat16*>(d.out_bf);

@@ -13,6 +13,10 @@
 //   TF32X3 : every fp32 operand is pre-split into hi = rn_tf32(x) and lo = x - hi (both fp32 arrays);
 //            D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi with kind::tf32 => fp32-class accuracy (~2^-21).
 //   BF16   : single kind::f16 pass on bf16 operands (throughput mode, not parity grade).
+//   F16X3  : every fp32 operand is scaled by a power of two (so that its largest element sits near 2^9) and
+//            pre-split into fp16 hi = rn_f16(s x) and lo = rn_f16(s x - hi); the same 3-term sum with kind::f16
+//            MMAs on fp16 operands => the same ~22 significant bits as TF32X3 at twice the MMA rate and half the
+//            operand bytes.  The epilogue multiplies the accumulator by *unscale = 1 / (s_A s_B) (device scalar).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -29,9 +33,10 @@ constexpr int kThreads = 192;       // warp 0: TMA producer, warp 1: MMA issuer 
 constexpr int kTmemCols = 512;      // 2 accumulator stages x 256 fp32 columns
 
 enum { EPI_NONE = 0, EPI_BIAS_LEAKY = 1, EPI_MASK = 2, EPI_BIAS = 3 };
-enum { MODE_TF32X3 = 0, MODE_BF16 = 1 };
+enum { MODE_TF32X3 = 0, MODE_BF16 = 1, MODE_F16X3 = 2 };
+enum { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };   // element type of a TMA map
 
-// One GEMM operand: [Z][rows][K] with K contiguous.  `lo` is the tf32 residual array (TF32X3 only).
+// One GEMM operand: [Z][rows][K] with K contiguous.  `lo` is the residual array (TF32X3: fp32, F16X3: fp16).
 struct Operand {
   const void* hi = nullptr;
   const void* lo = nullptr;
@@ -50,6 +55,7 @@ struct GemmDesc {
   int reduce_z = 0;      // 1: sum over z; the z range is cut into `slots` contiguous pieces -> out[slot]
   int slots = 1;
   int epi = EPI_NONE;
+  const float* unscale = nullptr;   // F16X3: device scalar the accumulator is multiplied by before the epilogue (1 / operand scales)
   const float* bias = nullptr; int64_t bias_zstride = 0;                 // bias[z][n]
   const float* act = nullptr; int64_t act_zstride = 0; int64_t act_ld = 0; // EPI_MASK: acc *= act>0 ? 1 : slope
   // outputs, [z or slot][m][n] with leading dimension out_ld (elements) and z stride out_zstride:
@@ -68,12 +74,12 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err);
 
 // 3-D TMA map over [Z][rows][K] (K innermost, `ld` / `zstride` in elements): box = one 128-byte K-block x box_rows x 1,
 // SWIZZLE_128B / SWIZZLE_64B (kb_bytes = 128 / 64), zero fill out of bounds.  zstride == 0 => a single z.
-int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t K, int64_t rows, int64_t Z, int64_t ld,
+int make_map(CUtensorMap* map, const void* base, int dtype, int64_t K, int64_t rows, int64_t Z, int64_t ld,
              int64_t zstride, int box_rows, int kb_bytes, std::string* err);
 
 // Fused forward + head kernel for arch fc (tc_fused.cu): for every (posterior sample z, 128-input tile)
 //   H = leaky(X . W1_z^T + b1_z) in TMEM -> logits = H . Wo_z^T + bo_z -> loss head -> dlogits
-//   dH = (dlogits . Wo_z) (.) leaky'(H)   written K-major, pre-split (tf32 hi/lo) or bf16, for the backward GEMM
+//   dH = (dlogits . Wo_z) (.) leaky'(H)   written K-major, pre-split (tf32 or scaled fp16 hi/lo) or bf16, for the backward GEMM
 // without ever writing H to HBM.  Units whose pre-activation lies inside the guard band are queued on a
 // worklist together with the sign that was assumed; fused_fixup() re-evaluates them exactly and patches dH.
 struct FusedDesc {
@@ -90,7 +96,9 @@ struct FusedDesc {
   const float* xnorm = nullptr;   // [B]   ||x_b||_2
   const float* wnorm = nullptr;   // [capacity] max_j ||W1_s[j,:]||_2, indexed by bank row
   float eps = 0.f;                // guard = eps * xnorm[b] * wnorm[row]; 0 disables the worklist
-  float* dh_hi = nullptr; float* dh_lo = nullptr; void* dh_bf = nullptr;   // [Z][B][H]
+  void* dh_hi = nullptr; void* dh_lo = nullptr; void* dh_bf = nullptr;   // [Z][B][H]; hi/lo: fp32 (TF32X3) or fp16 (F16X3)
+  const float* unscale = nullptr;   // F16X3: device scalar 1 / (s_X s_W1) applied to the forward accumulator
+  const float* dh_scale = nullptr;  // F16X3: device scalar dH is multiplied by before the fp16 hi/lo split
   float* logits = nullptr;        // [Z][B][C] (head == -1)
   unsigned long long* worklist = nullptr;   // num_items * kWorkPerItem slots
   int kblock_bytes = 128;

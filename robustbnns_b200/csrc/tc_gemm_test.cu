@@ -10,6 +10,7 @@
 #include <vector>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "tc_gemm.cuh"
 
@@ -53,9 +54,26 @@ __global__ void fill_kernel(float* hi, float* lo, __nv_bfloat16* bf, int64_t n, 
   }
 }
 
+// F16X3 operands: fp16 hi/lo of s * v (s a power of two)
+__global__ void fill_f16_kernel(__half* hi, __half* lo, int64_t n, uint32_t seed, float scale, float s) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = val(i, seed, scale) * s;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 struct Dev {
   float *hi = nullptr, *lo = nullptr;
   __nv_bfloat16* bf = nullptr;
+  __half *h16 = nullptr, *l16 = nullptr;
+  void init_f16(float s) {
+    CK(cudaMalloc(&h16, n * 2));
+    CK(cudaMalloc(&l16, n * 2));
+    fill_f16_kernel<<<1184, 256>>>(h16, l16, n, seed, scale, s);
+    CK(cudaGetLastError());
+  }
   int64_t n = 0;
   uint32_t seed;
   float scale;
@@ -68,7 +86,7 @@ struct Dev {
     CK(cudaGetLastError());
   }
   float at(int64_t i) const { return val(i, seed, scale); }
-  void free_() { cudaFree(hi); cudaFree(lo); cudaFree(bf); }
+  void free_() { cudaFree(hi); cudaFree(lo); cudaFree(bf); cudaFree(h16); cudaFree(l16); }
 };
 
 struct Case {
@@ -81,11 +99,20 @@ static float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v));
 
 // returns max |err| / max |ref| over the checked entries
 static double run_case(const Case& c, bool full_check, int timing_iters, double* ms_out) {
-  const bool bf = c.mode == MODE_BF16;
+  const bool bf = c.mode == MODE_BF16, f16 = c.mode == MODE_F16X3;
   Dev A, B, bias, act;
   const int64_t a_z = c.a_per_z ? c.Z : 1;
   A.init(a_z * c.M * c.K, 11, 2.0f, bf);
   B.init((int64_t)c.Z * c.N * c.K, 22, 0.2f, bf);
+  const float sA = 256.f, sB = 4096.f;     // |A| < 1 -> < 2^8, |B| < 0.1 -> < 2^9
+  float* unscale = nullptr;
+  if (f16) {
+    A.init_f16(sA);
+    B.init_f16(sB);
+    const float u = 1.f / (sA * sB);
+    CK(cudaMalloc(&unscale, 4));
+    CK(cudaMemcpy(unscale, &u, 4, cudaMemcpyHostToDevice));
+  }
   bias.init((int64_t)c.Z * c.N + 1, 33, 1.0f, false);
   const int out_z = c.reduce ? c.slots : c.Z;
   act.init((int64_t)out_z * c.M * c.N, 44, 1.0f, false);
@@ -103,8 +130,10 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
   d.spin_wait = g_spin;
   d.mode = c.mode; d.M = c.M; d.N = c.N; d.K = c.K; d.Z = c.Z; d.BN = c.BN;
   d.A.hi = bf ? (void*)A.bf : (void*)A.hi; d.A.lo = A.lo; d.A.rows = c.M; d.A.ld = c.K;
+  d.unscale = unscale;
   d.A.zstride = c.a_per_z ? (int64_t)c.M * c.K : 0;
   d.B.hi = bf ? (void*)B.bf : (void*)B.hi; d.B.lo = B.lo; d.B.rows = c.N; d.B.ld = c.K; d.B.zstride = (int64_t)c.N * c.K;
+  if (f16) { d.A.hi = A.h16; d.A.lo = A.l16; d.B.hi = B.h16; d.B.lo = B.l16; }
   d.reduce_z = c.reduce; d.slots = c.slots; d.epi = c.epi;
   d.bias = bias.hi + 1; d.bias_zstride = c.N;     // +1: bias rows are only 4-byte aligned in the bank
   d.act = act.hi; d.act_zstride = (int64_t)c.M * c.N; d.act_ld = c.N;
@@ -162,7 +191,7 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
     max_ref = fmax(max_ref, fabs(acc));
   }
   A.free_(); B.free_(); bias.free_(); act.free_();
-  cudaFree(out); cudaFree(out_lo);
+  cudaFree(out); cudaFree(out_lo); cudaFree(unscale);
   return max_err / fmax(max_ref, 1e-30);
 }
 
@@ -175,6 +204,10 @@ int main(int argc, char** argv) {
       {"tf32x3 mask epilogue, split output", MODE_TF32X3, 200, 512, 512, 2, 256, 0, 1, 1, EPI_MASK, 1},
       {"tf32x3 tiny M=7, H=64", MODE_TF32X3, 7, 64, 784, 4, 64, 0, 1, 0, EPI_BIAS, 0},
       {"tf32x3 one tile, many z (phase wrap)", MODE_TF32X3, 128, 256, 64, 9, 256, 1, 1, 1, EPI_NONE, 0},
+      {"f16x3 fwd ragged M, K tail, bias+leaky", MODE_F16X3, 300, 512, 784, 3, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+      {"f16x3 bwd reduce_z, BN=208, N tail", MODE_F16X3, 300, 784, 512, 5, 208, 1, 2, 1, EPI_NONE, 0},
+      {"f16x3 tiny M=7, H=64", MODE_F16X3, 7, 64, 784, 4, 64, 0, 1, 0, EPI_BIAS, 0},
+      {"f16x3 one tile, many z (phase wrap)", MODE_F16X3, 128, 256, 64, 9, 256, 1, 1, 1, EPI_NONE, 0},
       {"bf16 fwd", MODE_BF16, 300, 512, 784, 3, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
       {"bf16 bwd reduce_z", MODE_BF16, 300, 784, 512, 5, 208, 1, 2, 1, EPI_NONE, 0},
   };
@@ -203,6 +236,9 @@ int main(int argc, char** argv) {
         {"tf32x3 bwd 10000x784x512 Z=148 BN=208 s37", MODE_TF32X3, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
         {"tf32x3 bwd 10000x784x512 Z=148 BN=256 s37", MODE_TF32X3, 10000, 784, 512, 148, 256, 1, 37, 1, EPI_NONE, 0},
         {"tf32x3 bwd 10000x784x512 Z=148 BN=112 s21", MODE_TF32X3, 10000, 784, 512, 148, 112, 1, 21, 1, EPI_NONE, 0},
+        {"f16x3 fwd 10000x512x784 Z=148 BN=256", MODE_F16X3, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+        {"f16x3 bwd 10000x784x512 Z=148 BN=208 s37", MODE_F16X3, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
+        {"f16x3 bwd 10000x784x512 Z=148 BN=256 s37", MODE_F16X3, 10000, 784, 512, 148, 256, 1, 37, 1, EPI_NONE, 0},
         {"bf16 fwd 10000x512x784 Z=148 BN=256", MODE_BF16, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
         {"bf16 bwd 10000x784x512 Z=148 BN=208 s37", MODE_BF16, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
     };

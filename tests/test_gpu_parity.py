@@ -115,10 +115,12 @@ def test_golden_hmc_attacks_and_evaluation(name, tmp_path, monkeypatch):
         # late PGD states saturate the softmax: the reference's own fp32 gradient then carries a cancellation
         # error above 1e-4 (fp32 oracle vs fp64 oracle); parity is held to 3x that error there
         g32 = orc.attack_gradient(c.net, c.layout, c.bank, traj[t], c.labels, sched(t))
-        assert rel_err(g, g64) < max(REL, 3 * rel_err(g32, g64)), (t, rel_err(g, g64), rel_err(g32, g64))
+        tol_t = max(REL, 3 * rel_err(g32, g64))
+        assert rel_err(g, g64) < tol_t, (t, rel_err(g, g64), rel_err(g32, g64))
         nxt = aa._pgd_loop(bnn, xt, x0, y, alpha, 0.5, S, False, 1).cpu()
         ref_nxt = orc.pgd_step(traj[t].double(), c.x.double(), g64, 2 / 225, 0.5)
-        determined = g64.abs() > REL * g64.abs().max()
+        # the sign of a pixel's gradient is determined only above the gradient tolerance that holds at this state
+        determined = g64.abs() > tol_t * g64.abs().max()
         bad = ((nxt.double() - ref_nxt).abs() > 1e-6) & determined
         assert float(bad.float().sum() / determined.float().sum().clamp_min(1)) <= 2e-3, t
 
@@ -191,7 +193,7 @@ TC_CONFIGS = [
 
 
 @pytest.mark.parametrize("route", ["fused", "unfused"])
-@pytest.mark.parametrize("prec,tol", [("tf32x3", REL), ("bf16", 1.0)])
+@pytest.mark.parametrize("prec,tol", [("tf32x3", REL), ("f16x3", REL), ("bf16", 1.0)])
 @pytest.mark.parametrize("arch,shape,hidden,C,B,S", TC_CONFIGS)
 def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route, monkeypatch):
     """The tensor-core engine (tcgen05 / TMA / TMEM) against the fp64 oracle: TF32x3 is parity grade
@@ -199,6 +201,8 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     to a loose bound (its measured deviation is reported by bench.py)."""
     from robustbnns_b200 import _lib
     from robustbnns_b200.engine import Net
+    if prec == "f16x3" and (arch != "fc" or route == "unfused"):
+        pytest.skip("F16X3 rides on the fused forward+head kernel (arch fc)")
     if route == "unfused":
         if arch != "fc":
             pytest.skip("fc2 has a single (unfused) route")
@@ -212,7 +216,7 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     ref_p = orc.bnn_forward(net, layout, bank, x, range(S)).detach()
     assert rel_err(probs, ref_p) < tol
     assert rel_err(eng.forward_logits(x, 1).cpu(),
-                   orc.bnn_forward_avg_posterior(net, layout, bank[1], x).detach()) < max(tol, 1e-4) * (1 if prec == "tf32x3" else 0.25)
+                   orc.bnn_forward_avg_posterior(net, layout, bank[1], x).detach()) < max(tol, 1e-4) * (0.25 if prec == "bf16" else 1)
     g = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S).cpu().reshape(x.shape) / S
     ref64 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)
     e_mean = rel_err(g, ref64)
