@@ -25,7 +25,11 @@ namespace rbnn {
 namespace tc {
 
 constexpr float kSlope = 0.01f;            // nn.LeakyReLU() default (model_nn.py:68-69)
-constexpr int kRingBytes = 196608;         // operand ring: TF32X3 / F16X3 2 x 96 KB (128 B K-blocks) or 4 x 48 KB (64 B K-blocks)
+// operand ring: as many K-block stages as fit.  A stage holds NARR x (128 + BNT) rows of 128 (64) bytes, BNT = the
+// B-tile capacity the kernel was instantiated for: 256 rows -> 2 x 96 KB, 160 rows -> 3 x 72 KB, 128 -> 3 x 64 KB.
+// The MMAs of a stage and its TMA refill cannot overlap, so with S stages the K-block period is
+// max(T_mma, (T_mma + T_tma) / S): narrower tiles with a third stage beat wide tiles with two.
+constexpr int kRingBytes = 221184;
 constexpr int kSmemBytes = kRingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 size_t smem_bytes() { return kSmemBytes; }
@@ -48,7 +52,7 @@ struct KParams {
 // each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for both,
 // each CTA's TMEM receives its 128 accumulator rows.  Per SM that halves the B traffic from L2 and the B reads
 // from shared memory, which is what bounds the single-CTA kernel.
-template <int MODE, int KBB, bool PAIR>
+template <int MODE, int KBB, bool PAIR, int BNT>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -57,9 +61,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   constexpr bool F16K = MODE != MODE_TF32X3;               // kind::f16 MMAs on 2-byte operands
   constexpr int NARR = BF16 ? 1 : 2;                       // arrays per operand (hi[, lo])
   constexpr int kATile = kBM * KBB;                        // bytes of one A K-block tile (128 rows)
-  constexpr int kBTile = (PAIR ? kBNMax / 2 : kBNMax) * KBB;   // B K-block tile held by this CTA
+  constexpr int kBTile = (PAIR ? BNT / 2 : BNT) * KBB;     // B K-block tile held by this CTA
   constexpr int STAGE = NARR * (kATile + kBTile);
-  constexpr int NSTAGE = kRingBytes / STAGE;               // TF32X3: 2/4 (single), 3/6 (pair) for KBB 128/64
+  constexpr int NSTAGE = (kRingBytes / STAGE) > 8 ? 8 : (kRingBytes / STAGE);
   constexpr int KBE = KBB / (F16K ? 2 : 4);                // elements of K per K-block
   constexpr int KSTEPS = KBB / 32;                         // UMMA K-steps (32 bytes of K each) per K-block
   constexpr uint32_t FMT = MODE == MODE_BF16 ? 1u : (MODE == MODE_F16X3 ? 0u : 2u);   // UMMA operand format: F16 = 0, BF16 = 1, TF32 = 2
@@ -374,18 +378,28 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   const bool pair = d.pair && (d.BN % 32 == 0 || d.BN % 16 == 0) && ((d.BN / 2) % 8 == 0) && d.sm_count >= 2;
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
   static const kern_t kerns[3][2][2] = {
-      {{tc_gemm_kernel<MODE_TF32X3, 64, false>, tc_gemm_kernel<MODE_TF32X3, 64, true>},
-       {tc_gemm_kernel<MODE_TF32X3, 128, false>, tc_gemm_kernel<MODE_TF32X3, 128, true>}},
-      {{tc_gemm_kernel<MODE_BF16, 64, false>, tc_gemm_kernel<MODE_BF16, 64, true>},
-       {tc_gemm_kernel<MODE_BF16, 128, false>, tc_gemm_kernel<MODE_BF16, 128, true>}},
-      {{tc_gemm_kernel<MODE_F16X3, 64, false>, tc_gemm_kernel<MODE_F16X3, 64, true>},
-       {tc_gemm_kernel<MODE_F16X3, 128, false>, tc_gemm_kernel<MODE_F16X3, 128, true>}}};
+      {{tc_gemm_kernel<MODE_TF32X3, 64, false, 256>, tc_gemm_kernel<MODE_TF32X3, 64, true, 256>},
+       {tc_gemm_kernel<MODE_TF32X3, 128, false, 256>, tc_gemm_kernel<MODE_TF32X3, 128, true, 256>}},
+      {{tc_gemm_kernel<MODE_BF16, 64, false, 256>, tc_gemm_kernel<MODE_BF16, 64, true, 256>},
+       {tc_gemm_kernel<MODE_BF16, 128, false, 256>, tc_gemm_kernel<MODE_BF16, 128, true, 256>}},
+      {{tc_gemm_kernel<MODE_F16X3, 64, false, 256>, tc_gemm_kernel<MODE_F16X3, 64, true, 256>},
+       {tc_gemm_kernel<MODE_F16X3, 128, false, 256>, tc_gemm_kernel<MODE_F16X3, 128, true, 256>}}};
+  // narrow-tile instantiations (single CTA, 128 B K-blocks): a smaller B-tile capacity buys more pipeline stages
+  static const kern_t narrow[3][3] = {
+      {tc_gemm_kernel<MODE_TF32X3, 128, false, 112>, tc_gemm_kernel<MODE_TF32X3, 128, false, 128>, tc_gemm_kernel<MODE_TF32X3, 128, false, 160>},
+      {tc_gemm_kernel<MODE_BF16, 128, false, 112>, tc_gemm_kernel<MODE_BF16, 128, false, 128>, tc_gemm_kernel<MODE_BF16, 128, false, 160>},
+      {tc_gemm_kernel<MODE_F16X3, 128, false, 112>, tc_gemm_kernel<MODE_F16X3, 128, false, 128>, tc_gemm_kernel<MODE_F16X3, 128, false, 160>}};
   kern_t kern = kerns[d.mode][kbb == 128][pair];
-  static bool attr_done[3][2][2] = {};
-  if (!attr_done[d.mode][kbb == 128][pair]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { *err = std::string("tc::gemm: cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
-    attr_done[d.mode][kbb == 128][pair] = true;
+  if (!pair && kbb == 128 && d.BN <= 160) kern = narrow[d.mode][d.BN <= 112 ? 0 : (d.BN <= 128 ? 1 : 2)];
+  {
+    static std::map<kern_t, bool> attr_set;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!attr_set[kern]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) { *err = std::string("tc::gemm: cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+      attr_set[kern] = true;
+    }
   }
 
   CUtensorMap mAh, mAl, mBh, mBl;

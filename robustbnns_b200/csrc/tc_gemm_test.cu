@@ -208,6 +208,9 @@ int main(int argc, char** argv) {
       {"f16x3 bwd reduce_z, BN=208, N tail", MODE_F16X3, 300, 784, 512, 5, 208, 1, 2, 1, EPI_NONE, 0},
       {"f16x3 tiny M=7, H=64", MODE_F16X3, 7, 64, 784, 4, 64, 0, 1, 0, EPI_BIAS, 0},
       {"f16x3 one tile, many z (phase wrap)", MODE_F16X3, 128, 256, 64, 9, 256, 1, 1, 1, EPI_NONE, 0},
+      {"f16x3 bwd reduce_z, BN=160 (3 stages)", MODE_F16X3, 300, 784, 512, 5, 160, 1, 2, 1, EPI_NONE, 0},
+      {"f16x3 bwd reduce_z, BN=112 (3 stages)", MODE_F16X3, 300, 784, 512, 5, 112, 1, 2, 1, EPI_NONE, 0},
+      {"tf32x3 fwd BN=128 (3 stages)", MODE_TF32X3, 300, 512, 784, 3, 128, 0, 1, 0, EPI_BIAS_LEAKY, 0},
       {"bf16 fwd", MODE_BF16, 300, 512, 784, 3, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
       {"bf16 bwd reduce_z", MODE_BF16, 300, 784, 512, 5, 208, 1, 2, 1, EPI_NONE, 0},
   };
@@ -221,7 +224,9 @@ int main(int argc, char** argv) {
   g_kblock = (cfg & 1) ? 128 : 64;
   g_pair = (cfg & 2) ? 0 : 1;
   printf("---- K-block %d bytes, %s ----\n", g_kblock, g_pair ? "CTA pairs (cta_group::2)" : "single CTA");
+  const int only_mode = getenv("TC_MODE") ? atoi(getenv("TC_MODE")) : -1;   // restrict to one precision mode
   for (const Case& c : small) {
+    if (only_mode >= 0 && c.mode != only_mode) continue;
     double ms = 0;
     const double e = run_case(c, true, 0, &ms);
     const double tol = 3e-5;   // tensor-core fp32 accumulation truncates: ~5e-6 (K=784) .. 2e-5 (K=2048) of the output max
@@ -239,10 +244,16 @@ int main(int argc, char** argv) {
         {"f16x3 fwd 10000x512x784 Z=148 BN=256", MODE_F16X3, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
         {"f16x3 bwd 10000x784x512 Z=148 BN=208 s37", MODE_F16X3, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
         {"f16x3 bwd 10000x784x512 Z=148 BN=256 s37", MODE_F16X3, 10000, 784, 512, 148, 256, 1, 37, 1, EPI_NONE, 0},
+        {"f16x3 bwd 10000x784x512 Z=148 BN=160 s37", MODE_F16X3, 10000, 784, 512, 148, 160, 1, 37, 1, EPI_NONE, 0},
+        {"f16x3 bwd 10000x784x512 Z=148 BN=112 s37", MODE_F16X3, 10000, 784, 512, 148, 112, 1, 37, 1, EPI_NONE, 0},
+        {"f16x3 bwd 10000x784x512 Z=148 BN=128 s37", MODE_F16X3, 10000, 784, 512, 148, 128, 1, 37, 1, EPI_NONE, 0},
+        {"f16x3 fwd 10000x512x784 Z=148 BN=128", MODE_F16X3, 10000, 512, 784, 148, 128, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+        {"tf32x3 bwd 10000x784x512 Z=148 BN=160 s37", MODE_TF32X3, 10000, 784, 512, 148, 160, 1, 37, 1, EPI_NONE, 0},
         {"bf16 fwd 10000x512x784 Z=148 BN=256", MODE_BF16, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
         {"bf16 bwd 10000x784x512 Z=148 BN=208 s37", MODE_BF16, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
     };
     for (const Case& c : big) {
+      if (only_mode >= 0 && c.mode != only_mode) continue;
       double ms = 0;
       const double e = run_case(c, false, 3, &ms);
       const double flop = 2.0 * c.M * c.N * (double)c.K * c.Z;
