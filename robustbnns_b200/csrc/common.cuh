@@ -53,6 +53,7 @@ struct ParamLayout {
 struct TcMat {
   int64_t off = 0;          // offset of the [R, C] matrix inside a bank row
   int R = 0, C = 0;
+  int ld = 0;               // row pitch (elements) of the forward copies: C rounded up to whole 128-byte lines
   float *hi = nullptr, *lo = nullptr;      // tf32 split:  w = hi + lo, hi = rn_tf32(w)
   float *thi = nullptr, *tlo = nullptr;    // the same, transposed
   void *bf = nullptr, *tbf = nullptr;      // bf16 variants

@@ -29,30 +29,31 @@ __device__ __forceinline__ float tf32_rn(float v) {
 }
 
 // ---- operand preparation --------------------------------------------------------------------------
-// x[n] -> hi/lo (tf32 split) or bf16
+// x[B][D] -> hi/lo (tf32 split) or bf16 copies with row pitch ld4 * 4 elements (rows start on 128-byte lines, see k_pitch)
 __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
-                             __nv_bfloat16* __restrict__ bf, int64_t n4) {
+                             __nv_bfloat16* __restrict__ bf, int64_t n4, int d4, int ld4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const int64_t row = i / d4, o = row * ld4 + (i - row * d4);
     if (bf) {
       const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&a);
       pk.y = *reinterpret_cast<const uint32_t*>(&b);
-      reinterpret_cast<uint2*>(bf)[i] = pk;
+      reinterpret_cast<uint2*>(bf)[o] = pk;
     } else {
       float4 h, l;
       h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
       l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-      reinterpret_cast<float4*>(hi)[i] = h;
-      reinterpret_cast<float4*>(lo)[i] = l;
+      reinterpret_cast<float4*>(hi)[o] = h;
+      reinterpret_cast<float4*>(lo)[o] = l;
     }
   }
 }
 
 // bank row s, matrix [R, C] at `off`  ->  [s][R][C] and transposed [s][C][R] copies (32x32 smem tiles)
 // grid: (C/32 ceil, R/32 ceil, count), block (32, 8)
-__global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0,
+__global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int ld, int s0,
                                 float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ thi,
                                 float* __restrict__ tlo, __nv_bfloat16* __restrict__ bf,
                                 __nv_bfloat16* __restrict__ tbf) {
@@ -65,7 +66,7 @@ __global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64
     float v = 0.f;
     if (r < R && c < C) {
       v = __ldg(src + (int64_t)r * C + c);
-      const int64_t o = ((int64_t)s * R + r) * C + c;
+      const int64_t o = ((int64_t)s * R + r) * ld + c;      // forward copy: row pitch ld >= C
       if (bf) {
         bf[o] = __float2bfloat16(v);
       } else {
@@ -164,20 +165,21 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 
 // x[n] -> fp16 hi/lo of s_x * x
 __global__ void split_f16_kernel(const float* __restrict__ x, const float* __restrict__ call_sc,
-                                 __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4) {
+                                 __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4, int d4, int ld4) {
   const float s = __ldg(call_sc);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const int64_t row = i / d4, o = row * ld4 + (i - row * d4);
     __half h[4], l[4];
     split_f16(v.x * s, h[0], l[0]); split_f16(v.y * s, h[1], l[1]);
     split_f16(v.z * s, h[2], l[2]); split_f16(v.w * s, h[3], l[3]);
-    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
-    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
+    reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(l);
   }
 }
 
 // F16X3 twin of relayout_kernel: [s][R][C] and transposed [s][C][R] fp16 hi/lo copies of s_w1 * W
-__global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0,
+__global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int ld, int s0,
                                     const TcScales* __restrict__ sc, __half* __restrict__ hi, __half* __restrict__ lo,
                                     __half* __restrict__ thi, __half* __restrict__ tlo) {
   __shared__ float tile[32][33];
@@ -190,7 +192,7 @@ __global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, i
     float v = 0.f;
     if (r < R && c < C) {
       v = __ldg(src + (int64_t)r * C + c) * sw;
-      const int64_t o = ((int64_t)s * R + r) * C + c;
+      const int64_t o = ((int64_t)s * R + r) * ld + c;
       split_f16(v, hi[o], lo[o]);
     }
     tile[i][threadIdx.x] = v;
@@ -494,6 +496,14 @@ int tc_supported(const rbnn_net* n) {
   return n->cc_major == 10;
 }
 
+// Row pitch (elements) of a K-major operand copy with K elements per row: rows start on 128-byte lines, so that a
+// 128-byte TMA box row is one L2 line.  (784 fp16 = 1568 B rows straddle two lines per box row and halve the TMA
+// rate -- measured: the first-layer forward ran its operand pipeline at half the rate of the backward one.)
+static int k_pitch(const rbnn_net* n, int K) {
+  const int per_line = n->prec == RBNN_PREC_TF32X3 ? 32 : 64;
+  return (K + per_line - 1) / per_line * per_line;
+}
+
 // F16X3 rides on the fused forward+head kernel (dH is produced and scaled inside it): arch fc only
 int tc_f16x3_supported(const rbnn_net* n) {
   return tc_supported(n) && n->arch == RBNN_ARCH_FC && n->L.w1 == 0 && tc::fused_supported(n->H, n->C);
@@ -537,24 +547,24 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
     RBNN_CUDA(cudaDeviceSynchronize());
     tc_bank_free(n);
     tc.nmat = n->arch == RBNN_ARCH_FC2 ? 2 : 1;
-    tc.mat[0].off = n->L.w1; tc.mat[0].R = n->H; tc.mat[0].C = n->D;
-    if (tc.nmat == 2) { tc.mat[1].off = n->L.w2; tc.mat[1].R = n->H; tc.mat[1].C = n->H; }
+    tc.mat[0].off = n->L.w1; tc.mat[0].R = n->H; tc.mat[0].C = n->D; tc.mat[0].ld = k_pitch(n, n->D);
+    if (tc.nmat == 2) { tc.mat[1].off = n->L.w2; tc.mat[1].R = n->H; tc.mat[1].C = n->H; tc.mat[1].ld = n->H; }
     for (int i = 0; i < tc.nmat; ++i) {
       TcMat& m = tc.mat[i];
-      const size_t elems = (size_t)n->capacity * m.R * m.C;
+      const size_t elems = (size_t)n->capacity * m.R * m.ld, telems = (size_t)n->capacity * m.R * m.C;
       if (bf) {
         RBNN_CUDA(cudaMalloc(&m.bf, elems * 2));
-        RBNN_CUDA(cudaMalloc(&m.tbf, elems * 2));
+        RBNN_CUDA(cudaMalloc(&m.tbf, telems * 2));
       } else if (f16) {
         RBNN_CUDA(cudaMalloc(&m.h_hi, elems * 2));
         RBNN_CUDA(cudaMalloc(&m.h_lo, elems * 2));
-        RBNN_CUDA(cudaMalloc(&m.th_hi, elems * 2));
-        RBNN_CUDA(cudaMalloc(&m.th_lo, elems * 2));
+        RBNN_CUDA(cudaMalloc(&m.th_hi, telems * 2));
+        RBNN_CUDA(cudaMalloc(&m.th_lo, telems * 2));
       } else {
         RBNN_CUDA(cudaMalloc(&m.hi, elems * 4));
         RBNN_CUDA(cudaMalloc(&m.lo, elems * 4));
-        RBNN_CUDA(cudaMalloc(&m.thi, elems * 4));
-        RBNN_CUDA(cudaMalloc(&m.tlo, elems * 4));
+        RBNN_CUDA(cudaMalloc(&m.thi, telems * 4));
+        RBNN_CUDA(cudaMalloc(&m.tlo, telems * 4));
       }
     }
     RBNN_CUDA(cudaMalloc(&tc.wnorm, (size_t)n->capacity * sizeof(float)));
@@ -602,11 +612,11 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       TcMat& m = tc.mat[i];
       dim3 grid((m.C + 31) / 32, (m.R + 31) / 32, e - s);
       if (f16)
-        relayout_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, s, tc.scales,
+        relayout_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, m.ld, s, tc.scales,
                                                           reinterpret_cast<__half*>(m.h_hi), reinterpret_cast<__half*>(m.h_lo),
                                                           reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo));
       else
-        relayout_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, s, m.hi, m.lo, m.thi, m.tlo,
+        relayout_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, m.ld, s, m.hi, m.lo, m.thi, m.tlo,
                                                       reinterpret_cast<__nv_bfloat16*>(m.bf),
                                                       reinterpret_cast<__nv_bfloat16*>(m.tbf));
       n->launches++;
@@ -718,10 +728,10 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
   const TcMat& m1 = n->tc.mat[0];
   tc::GemmDesc g;
   g.M = B; g.N = H; g.K = D; g.Z = Z; g.BN = pick_bn(H);
-  g.A.hi = bf ? (const void*)w.x_bf : (const void*)w.x_hi; g.A.lo = w.x_lo; g.A.rows = B; g.A.ld = D; g.A.zstride = 0;
-  if (bf) g.B.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * D;
-  else { g.B.hi = m1.hi + (int64_t)z0 * H * D; g.B.lo = m1.lo + (int64_t)z0 * H * D; }
-  g.B.rows = H; g.B.ld = D; g.B.zstride = (int64_t)H * D;
+  g.A.hi = bf ? (const void*)w.x_bf : (const void*)w.x_hi; g.A.lo = w.x_lo; g.A.rows = B; g.A.ld = m1.ld; g.A.zstride = 0;
+  if (bf) g.B.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * m1.ld;
+  else { g.B.hi = m1.hi + (int64_t)z0 * H * m1.ld; g.B.lo = m1.lo + (int64_t)z0 * H * m1.ld; }
+  g.B.rows = H; g.B.ld = m1.ld; g.B.zstride = (int64_t)H * m1.ld;
   g.epi = tc::EPI_BIAS_LEAKY;
   g.bias = n->bank + (int64_t)z0 * P + n->L.b1; g.bias_zstride = P;
   g.out = w.h1; g.out_ld = H; g.out_zstride = (int64_t)B * H;
@@ -759,20 +769,20 @@ static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, con
   tc::FusedDesc f;
   f.mode = bf ? tc::MODE_BF16 : (f16 ? tc::MODE_F16X3 : tc::MODE_TF32X3);
   f.B = B; f.D = D; f.H = H; f.C = n->C; f.Z = Z;
-  f.X.rows = B; f.X.ld = D;
+  f.X.rows = B; f.X.ld = m1.ld;
   if (bf) {
     f.X.hi = w.x_bf;
-    f.W1.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * D;
+    f.W1.hi = reinterpret_cast<const __nv_bfloat16*>(m1.bf) + (int64_t)z0 * H * m1.ld;
   } else if (f16) {
     f.X.hi = w.x_h16; f.X.lo = w.x_l16;
-    f.W1.hi = reinterpret_cast<const __half*>(m1.h_hi) + (int64_t)z0 * H * D;
-    f.W1.lo = reinterpret_cast<const __half*>(m1.h_lo) + (int64_t)z0 * H * D;
+    f.W1.hi = reinterpret_cast<const __half*>(m1.h_hi) + (int64_t)z0 * H * m1.ld;
+    f.W1.lo = reinterpret_cast<const __half*>(m1.h_lo) + (int64_t)z0 * H * m1.ld;
     f.unscale = w.call_sc + 1; f.dh_scale = w.call_sc + 2;
   } else {
     f.X.hi = w.x_hi; f.X.lo = w.x_lo;
-    f.W1.hi = m1.hi + (int64_t)z0 * H * D; f.W1.lo = m1.lo + (int64_t)z0 * H * D;
+    f.W1.hi = m1.hi + (int64_t)z0 * H * m1.ld; f.W1.lo = m1.lo + (int64_t)z0 * H * m1.ld;
   }
-  f.W1.rows = H; f.W1.ld = D; f.W1.zstride = (int64_t)H * D;
+  f.W1.rows = H; f.W1.ld = m1.ld; f.W1.zstride = (int64_t)H * m1.ld;
   f.head = head;
   f.bank = n->bank; f.P = n->L.P; f.b1_off = n->L.b1; f.wo_off = n->L.wo; f.bo_off = n->L.bo; f.z_row0 = z0;
   f.labels = labels; f.pbar = pbar;
@@ -822,6 +832,7 @@ static int launch_head(rbnn_net* n, bool grad, int head, const float* top, int z
 static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const float* pbar_for_scale, int64_t pbar_count,
                    cudaStream_t st) {
   const int64_t n4 = count / 4;
+  const int d4 = n->D / 4, ld4 = n->tc.mat[0].ld / 4;      // the copies take the row pitch of the W1 copies
   const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
   if (n->prec == RBNN_PREC_F16X3) {
     RBNN_CUDA(cudaMemsetAsync(w.max_bits, 0, 2 * sizeof(unsigned), st));
@@ -831,12 +842,12 @@ static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const fl
       n->launches++;
     }
     call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, pbar_for_scale ? w.max_bits + 1 : nullptr, w.call_sc);
-    split_f16_kernel<<<blocks, 256, 0, st>>>(x, w.call_sc, w.x_h16, w.x_l16, n4);
+    split_f16_kernel<<<blocks, 256, 0, st>>>(x, w.call_sc, w.x_h16, w.x_l16, n4, d4, ld4);
     n->launches += 3;
     RBNN_CUDA(cudaGetLastError());
     return 0;
   }
-  split_kernel<<<blocks, 256, 0, st>>>(x, w.x_hi, w.x_lo, w.x_bf, n4);
+  split_kernel<<<blocks, 256, 0, st>>>(x, w.x_hi, w.x_lo, w.x_bf, n4, d4, ld4);
   n->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -855,7 +866,8 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const int S = s1 - s0;
   const size_t per = fc_per_z_bytes(n, B, true);
-  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : (f16 ? 2 * pad256((size_t)B * D * 2) + 512 : 2 * pad256((size_t)B * D * 4));
+  const size_t ldx = (size_t)k_pitch(n, D);
+  const size_t x_bytes = bf ? pad256((size_t)B * ldx * 2) : (f16 ? 2 * pad256((size_t)B * ldx * 2) + 512 : 2 * pad256((size_t)B * ldx * 4));
   const size_t out_bytes = pad256((size_t)B * D * 4);
   // samples per chunk: as many as the budget allows; the backward reduce cuts a chunk into `slots`
   // K-concatenated ranges of ~4 samples (bounds the tensor-core accumulation chain, fills the SMs)
@@ -879,11 +891,11 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots + pad256((size_t)B * 4) + 4096));
   Arena ar(n);
   FcWs w;
-  if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
+  if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * ldx);
   else if (f16) {
-    w.x_h16 = ar.take<__half>((size_t)B * D); w.x_l16 = ar.take<__half>((size_t)B * D);
+    w.x_h16 = ar.take<__half>((size_t)B * ldx); w.x_l16 = ar.take<__half>((size_t)B * ldx);
     w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2);
-  } else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
+  } else { w.x_hi = ar.take<float>((size_t)B * ldx); w.x_lo = ar.take<float>((size_t)B * ldx); }
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
   RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
@@ -903,7 +915,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   w.xnorm = ar.take<float>((size_t)B);
   w.partial = ar.take<float>((size_t)slots * B * D);
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, head == RBNN_HEAD_UPSTREAM ? pbar : nullptr, (int64_t)B * n->C, st));
-  if (fused && !bf) {
+  if (fused) {       // row norms: guard band (parity modes) and the activation range of the fused head
     xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
     n->launches++;
     RBNN_CUDA(cudaGetLastError());
@@ -982,17 +994,18 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const int S = s1 - s0;
   const size_t per = fc_per_z_bytes(n, B, false);
-  const size_t x_bytes = bf ? pad256((size_t)B * D * 2) : (f16 ? 2 * pad256((size_t)B * D * 2) + 512 : 2 * pad256((size_t)B * D * 4));
+  const size_t ldx = (size_t)k_pitch(n, D);
+  const size_t x_bytes = bf ? pad256((size_t)B * ldx * 2) : (f16 ? 2 * pad256((size_t)B * ldx * 2) + 512 : 2 * pad256((size_t)B * ldx * 4));
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
   const int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / per, (size_t)S));
-  RBNN_TRY(ws_reserve(n, x_bytes + per * zc));
+  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + pad256((size_t)B * 4)));
   Arena ar(n);
   FcWs w;
-  if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * D);
+  if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * ldx);
   else if (f16) {
-    w.x_h16 = ar.take<__half>((size_t)B * D); w.x_l16 = ar.take<__half>((size_t)B * D);
+    w.x_h16 = ar.take<__half>((size_t)B * ldx); w.x_l16 = ar.take<__half>((size_t)B * ldx);
     w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2);
-  } else { w.x_hi = ar.take<float>((size_t)B * D); w.x_lo = ar.take<float>((size_t)B * D); }
+  } else { w.x_hi = ar.take<float>((size_t)B * ldx); w.x_lo = ar.take<float>((size_t)B * ldx); }
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
   RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
@@ -1002,7 +1015,13 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
     w.h2 = ar.take<float>(zbh);
   }
   w.logits = ar.take<float>((size_t)zc * B * C);
+  w.xnorm = ar.take<float>((size_t)B);
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, st));
+  if (fused) {
+    xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
+    n->launches++;
+    RBNN_CUDA(cudaGetLastError());
+  }
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
     float* lg = out_logits ? out_logits : w.logits;

@@ -21,6 +21,7 @@
 // slots of the worklist (no global atomics, deterministic); an item that overflows evaluates inline.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "../../include/rbnn.h"
 #include "tc_gemm.cuh"
@@ -35,11 +36,16 @@ constexpr float kSlopeF = 0.01f;
 constexpr int kRingF = 196608;
 constexpr int kEpiWarps = 16;                     // 4 TMEM lane quadrants x 2 lane halves x 2 column halves
 constexpr int kThreadsF = 64 + kEpiWarps * 32;     // 576
-constexpr int kCMax = 10;                          // classes the fused epilogue keeps in registers (4 rows x kCMax accumulators)
+constexpr int kCMax = 10;                          // classes the fused epilogue covers (two mma.sync class groups: 0-7, 8-15)
+constexpr int kHMax = 512;                         // hidden units the staged parameters cover
 constexpr int kMaskWords = 8;                      // 32x32 blocks per thread: n_tiles * (BN/2)/32 <= 8
-constexpr int kParamFloatsMax = 5760;              // Wo_z [C*H] + bo_z [C] + b1_z [H]  (<= 22.5 KB)
-constexpr int kXchgFloats = kBM * 16;           // partial logits / dlogits exchange between column halves
-constexpr int kFusedSmem = kRingF + 1024 + 256 + (kParamFloatsMax + kXchgFloats) * 4 + 16;
+constexpr int kWoRows = kCMax + 1;                 // + the zero row the padding classes read
+constexpr int kWoHalfs = kWoRows * (kHMax + 8);    // one fp16 copy (hi or lo) of s_wo * Wo_z, rows padded by 8 halfs
+constexpr int kWoPerThread = (kCMax * kHMax + kEpiWarps * 32 - 1) / (kEpiWarps * 32);
+constexpr int kXchgFloats = kBM * 16;              // partial logits / dlogits exchange between column halves
+// shared memory after the ring and the barriers: Wo16 hi | Wo16 lo | b1 [kHMax] | bo [16] | red [2 * kEpiWarps] | xchg
+constexpr int kFusedSmem = kRingF + 1024 + 256 + 2 * kWoHalfs * 2 + (kHMax + 16 + 2 * kEpiWarps + kXchgFloats) * 4 + 16;
+static_assert(kFusedSmem <= 232448, "fused kernel exceeds the 227 KB shared memory of an sm_100 CTA");
 constexpr unsigned long long kSentinel = ~0ull;
 
 struct FParams {
@@ -50,6 +56,7 @@ struct FParams {
   const float* x; const float* xnorm; const float* wnorm; float eps;
   void* dh_hi; void* dh_lo; __nv_bfloat16* dh_bf; float* logits;
   const float* unscale; const float* dh_scale;      // F16X3 device scalars (see FusedDesc)
+  int debug;                                         // timing experiments (RBNN_FUSED_DEBUG): 1 no dH stores, 2 no pass 2, 4 no pass-1 math
   unsigned long long* worklist;
 };
 
@@ -65,6 +72,69 @@ __device__ bool exact_positive_serial(const float* __restrict__ x, const float* 
   double s = 0.0;
   for (int d = 0; d < D; ++d) s = fma((double)__ldg(x + d), (double)__ldg(w + d), s);
   return (float)(s + (double)bias) > 0.f;
+}
+
+// s = 2^k with s * maxabs in [2^8, 2^9) (1 for zero / denormal-range / non-finite maxima): exact scaling into the
+// range where an fp16 hi/lo pair keeps 22 significant bits
+__device__ __forceinline__ float pow2_scale(float maxabs) {
+  const uint32_t eb = (__float_as_uint(maxabs) >> 23) & 0xFFu;
+  return (eb < 8u || eb == 255u) ? 1.f : __uint_as_float((262u - eb) << 23);
+}
+// (x, y) -> packed fp16 pairs hi = rn(x, y), lo = rn((x, y) - hi); the lower half holds x
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// c[16x8] += a[16x16] . b[16x8], fp16 operands from registers, fp32 accumulation
+__device__ __forceinline__ void hmma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 4 x 4 transpose of 32-bit words across the 4 lanes (q = lane % 4) that share a fragment row: on return a[k] of lane q is
+// what lane k held in a[q].  Turns "2 columns of each of 4 column groups" into "8 consecutive columns of group q".
+__device__ __forceinline__ void quad_transpose(uint32_t (&a)[4], int q) {
+  const bool odd = q & 1, up = q & 2;
+  uint32_t s0 = odd ? a[0] : a[1], s1 = odd ? a[2] : a[3];
+  s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+  s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  if (odd) { a[0] = s0; a[2] = s1; } else { a[1] = s0; a[3] = s1; }
+  uint32_t t0 = up ? a[0] : a[2], t1 = up ? a[1] : a[3];
+  t0 = __shfl_xor_sync(0xffffffffu, t0, 2);
+  t1 = __shfl_xor_sync(0xffffffffu, t1, 2);
+  if (up) { a[0] = t0; a[1] = t1; } else { a[2] = t0; a[3] = t1; }
+}
+__device__ __forceinline__ void st_cs_u4(void* ptr, const uint32_t (&a)[4]) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
+}
+
+// softmax over the classes of one row spread over the 4 lanes that share it (4 class slots per lane)
+__device__ __forceinline__ void softmax_quad(float (&v)[4], const bool (&valid)[4]) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (valid[i]) mx = fmaxf(mx, v[i]);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[i] = valid[i] ? expf(v[i] - mx) : 0.f; sum += v[i]; }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] *= inv;
 }
 
 template <int C_MAX>
@@ -107,10 +177,12 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   uint8_t* gen = smem_raw + (bars - raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 16 * NSTAGE + 32);
   uint32_t* wl_count = reinterpret_cast<uint32_t*>(gen + 16 * NSTAGE + 40);
-  float* wo_s = reinterpret_cast<float*>(gen + 256);      // [C][H]
-  float* bo_s = wo_s + p.C * p.H;                          // [C]
-  float* b1_s = wo_s + ((p.C * p.H + p.C + 3) & ~3);       // [H], 16-byte aligned
-  float* xchg = wo_s + kParamFloatsMax;                    // [128][kCMax]
+  __half* wo_hi = reinterpret_cast<__half*>(gen + 256);   // [C + 1][H + 8]: fp16 hi part of s_wo * Wo_z (row C = zeros)
+  __half* wo_lo = wo_hi + kWoHalfs;                        // the residual part
+  float* b1_s = reinterpret_cast<float*>(wo_lo + kWoHalfs);   // [H]
+  float* bo_s = b1_s + kHMax;                              // [16]
+  float* red = bo_s + 16;                                  // [2][kEpiWarps] block reductions
+  float* xchg = red + 2 * kEpiWarps;                       // [128][16] partial logits / dlogits
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -212,10 +284,14 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   } else {
     // ===================== epilogue: warps 2..17 =====================
     // TMEM is read with the 16x256b shape: lane t of the warp receives, for every group of 8 columns, rows
-    // {t/4, t/4+8} x columns {2(t%4), 2(t%4)+1} -- the mma accumulator fragment layout -- so a thread owns 2 rows x
-    // 8 columns of a 16x32 block and every Wo value fetched from shared memory feeds 2 rows.  The epilogue is
-    // latency bound (ncu: one instruction per ~11 cycles per warp), so it is spread over 16 warps: warp =
-    // (TMEM lane quadrant, 16-lane half of the quadrant, column half of the n-tile).
+    // {t/4, t/4+8} x columns {2(t%4), 2(t%4)+1} -- the mma.sync accumulator fragment layout.  That is also the
+    // A-fragment layout of mma.sync.m16n8k16 (two adjacent column groups = one 16x16 A tile), so the two small
+    // GEMMs of the head run on the tensor cores straight from registers:
+    //   pass 1  logits[16 rows, classes] += act[16, 16 hidden] . Wo^T      (B fragments: ldmatrix of Wo16[c][j])
+    //   pass 2  dH[16 rows, 8 hidden]     = dlogits[16, classes] . Wo      (B fragments: ldmatrix.trans of Wo16[c][j])
+    // with every fp32 operand split into fp16 hi/lo (power-of-two scaled per row / per sample) and the usual three
+    // products, fp32 accumulation.  This replaces 20 FFMA + 5 LDS per hidden unit by 1.5 HMMA + 0.5 LDSM per 16 of them.
+    // warp = (TMEM lane quadrant, 16-lane half of the quadrant, column half of the n-tile).
     const int ew = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int lhalf = (ew >> 2) & 1;           // which 16 lanes of the quadrant
@@ -226,35 +302,81 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const int nblocks = cols_half / 32;        // 32-column blocks per (n-tile, half)
     const int q = lane & 3, rsub = lane >> 2;  // fragment coordinates
     const int C = p.C, H = p.H;
+    const int ldw = H + 8;                     // halfs per row of the staged Wo copies (+8: conflict-free ldmatrix)
     const float unscale = (MODE == MODE_F16X3) ? __ldg(p.unscale) : 1.f;     // 1 / (s_X s_W1)
     const float dh_scale = (MODE == MODE_F16X3) ? __ldg(p.dh_scale) : 1.f;   // dH -> fp16 range
+    // ldmatrix row addresses of this lane (matrix = lane / 8, row = lane % 8); class rows >= C read the zero row
+    const int lm = lane >> 3, lr = lane & 7;
+    const int c1 = min((lm >> 1) * 8 + lr, C), c2 = min((lm & 1) * 8 + lr, C);
+    const uint32_t off1 = (uint32_t)(c1 * ldw + (lm & 1) * 8) * 2u;   // pass 1: matrices (classes 0-7 | 8-15) x (k 0-7 | 8-15)
+    const uint32_t off2 = (uint32_t)(c2 * ldw + (lm >> 1) * 8) * 2u;  // pass 2: matrices (classes 0-7 | 8-15) x (8 columns | next 8)
+    const uint32_t wo_hi_a = smem_u32(wo_hi), wo_lo_a = smem_u32(wo_lo);
+    const int cls[4] = {2 * q, 2 * q + 1, 8 + 2 * q, 9 + 2 * q};      // classes of this thread's 4 accumulator slots per row
+    for (int i = et; i < ldw; i += kEpiWarps * 32) {                 // the zero row
+      wo_hi[C * ldw + i] = __float2half_rn(0.f);
+      wo_lo[C * ldw + i] = __float2half_rn(0.f);
+    }
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int z = item / p.m_tiles, m_idx = item % p.m_tiles;
       const float* __restrict__ wrow = p.bank + (long long)(p.z_row0 + z) * p.P;
+      // ---------------- stage Wo_z (fp16 hi/lo of s_wo * Wo), b1_z, bo_z ----------------
+      float wv[kWoPerThread];
+      float wmax = 0.f, bmax = 0.f;
+#pragma unroll
+      for (int u = 0; u < kWoPerThread; ++u) {
+        const int i = et + u * kEpiWarps * 32;
+        wv[u] = i < C * H ? __ldg(wrow + p.wo_off + i) : 0.f;
+        wmax = fmaxf(wmax, fabsf(wv[u]));
+      }
+      float b1v = 0.f;
+      if (et < H) { b1v = __ldg(wrow + p.b1_off + et); bmax = fabsf(b1v); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+      }
       epi_bar();                                // everyone is done with the previous item's parameters
-      for (int i = et; i < C * H; i += kEpiWarps * 32) wo_s[i] = __ldg(wrow + p.wo_off + i);
-      for (int i = et; i < C; i += kEpiWarps * 32) bo_s[i] = __ldg(wrow + p.bo_off + i);
-      for (int i = et; i < H; i += kEpiWarps * 32) b1_s[i] = __ldg(wrow + p.b1_off + i);
+      if (lane == 0) { red[ew] = wmax; red[kEpiWarps + ew] = bmax; }
+      if (et < H) b1_s[et] = b1v;
+      if (et < C) bo_s[et] = __ldg(wrow + p.bo_off + et);
       if (et == 0) *wl_count = 0u;
+      epi_bar();
+      wmax = 0.f; bmax = 0.f;
+#pragma unroll
+      for (int i = 0; i < kEpiWarps; ++i) { wmax = fmaxf(wmax, red[i]); bmax = fmaxf(bmax, red[kEpiWarps + i]); }
+      const float s_wo = pow2_scale(wmax);
+#pragma unroll
+      for (int u = 0; u < kWoPerThread; ++u) {
+        const int i = et + u * kEpiWarps * 32;
+        if (i < C * H) {
+          const int c = i / H, j = i - c * H;
+          const float v = wv[u] * s_wo;
+          const __half h = __float2half_rn(v);
+          wo_hi[c * ldw + j] = h;
+          wo_lo[c * ldw + j] = __float2half_rn(v - __half2float(h));
+        }
+      }
       epi_bar();
       // this thread's 2 rows: quad*32 + lhalf*16 + {0,8} + rsub
       int brow[2];
       bool rok[2];
-      float guard[2];
-      const float wn = p.eps > 0.f ? p.eps * __ldg(p.wnorm + p.z_row0 + z) : 0.f;
+      float guard[2], s_a[2];
+      const float wn = __ldg(p.wnorm + p.z_row0 + z);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         brow[r] = m_idx * kBM + quad * 32 + lhalf * 16 + 8 * r + rsub;
         rok[r] = brow[r] < p.B;
-        guard[r] = (rok[r] && p.eps > 0.f) ? wn * __ldg(p.xnorm + brow[r]) : 0.f;
+        const float bound = rok[r] ? wn * __ldg(p.xnorm + brow[r]) : 0.f;   // |<x_b, w_zj>| <= ||x_b|| max_j ||w_zj||
+        guard[r] = p.eps * bound;
+        s_a[r] = pow2_scale(bound + bmax);     // activations of this row -> [.., 2^9)
       }
       unsigned long long* wl = p.worklist ? p.worklist + (long long)item * kWorkPerItem : nullptr;
-      float logit[2][kCMax];
+      float acc[2][4];                          // logits: [class group][row 0: c, c+1 | row 1: c, c+1], scaled by s_a[row] s_wo
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int g = 0; g < 2; ++g)
 #pragma unroll
-        for (int c = 0; c < kCMax; ++c) logit[r][c] = 0.f;
+        for (int i = 0; i < 4; ++i) acc[g][i] = 0.f;
       uint32_t mbits[kMaskWords];               // one word per 16x32 block: bit (r*8 + k*2 + e)
 #pragma unroll
       for (int i = 0; i < kMaskWords; ++i) mbits[i] = 0u;
@@ -271,27 +393,36 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
             const int c0 = half * cols_half + cc * 32;            // column inside the n-tile
             uint32_t v[16];                                       // [4 * colgroup + {r0c0, r0c1, r1c0, r1c1}]
             tmem_ld_16x256b_x4(taddr + ((uint32_t)(lhalf * 16) << 16) + (uint32_t)c0, v);
+            // B fragments of the two 16-column K-blocks while the TMEM load is in flight
+            const uint32_t jb = (uint32_t)(n * p.BN + c0) * 2u;
+            uint32_t bh[2][4], bl[2][4];
+            ldsm_x4(wo_hi_a + off1 + jb, bh[0]);
+            ldsm_x4(wo_lo_a + off1 + jb, bl[0]);
+            ldsm_x4(wo_hi_a + off1 + jb + 32u, bh[1]);
+            ldsm_x4(wo_lo_a + off1 + jb + 32u, bl[1]);
             tmem_ld_wait();
+            if (p.debug & 4) continue;
             uint32_t bits = 0u;
             const int jbase = n * p.BN + c0 + 2 * q;
+            uint32_t ahi[4][2], alo[4][2];                        // [column group k][row]: fp16 pairs of the activations
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int j = jbase + 8 * k;                        // this thread's column pair (j, j+1)
               const float2 bb = *reinterpret_cast<const float2*>(b1_s + j);
-              float h[2][2];
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
+                float h[2];
                 if (MODE == MODE_F16X3) {
-                  h[r][0] = fmaf(__uint_as_float(v[4 * k + 2 * r]), unscale, bb.x);
-                  h[r][1] = fmaf(__uint_as_float(v[4 * k + 2 * r + 1]), unscale, bb.y);
+                  h[0] = fmaf(__uint_as_float(v[4 * k + 2 * r]), unscale, bb.x);
+                  h[1] = fmaf(__uint_as_float(v[4 * k + 2 * r + 1]), unscale, bb.y);
                 } else {
-                  h[r][0] = __uint_as_float(v[4 * k + 2 * r]) + bb.x;
-                  h[r][1] = __uint_as_float(v[4 * k + 2 * r + 1]) + bb.y;
+                  h[0] = __uint_as_float(v[4 * k + 2 * r]) + bb.x;
+                  h[1] = __uint_as_float(v[4 * k + 2 * r + 1]) + bb.y;
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                  bool pos = h[r][e] > 0.f;
-                  if (fabsf(h[r][e]) < guard[r]) {
+                  bool pos = h[e] > 0.f;
+                  if (fabsf(h[e]) < guard[r]) {
                     const uint32_t slot = atomicAdd(wl_count, 1u);
                     if (slot < (uint32_t)kWorkPerItem) {
                       wl[slot] = pack_entry(z, brow[r], j + e, pos);
@@ -301,24 +432,27 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                     }
                   }
                   if (pos) bits |= 1u << (r * 8 + k * 2 + e);
-                  h[r][e] = pos ? h[r][e] : h[r][e] * kSlopeF;
+                  h[e] = (pos ? h[e] : h[e] * kSlopeF) * s_a[r];
                 }
+                split_pair(h[0], h[1], ahi[k][r], alo[k][r]);
               }
-#pragma unroll
-              for (int c = 0; c < kCMax; ++c)
-                if (c < C) {
-                  const float2 w = *reinterpret_cast<const float2*>(wo_s + c * H + j);
-#pragma unroll
-                  for (int r = 0; r < 2; ++r) {
-                    logit[r][c] = fmaf(h[r][0], w.x, logit[r][c]);
-                    logit[r][c] = fmaf(h[r][1], w.y, logit[r][c]);
-                  }
-                }
             }
             const int word = n * nblocks + cc;
 #pragma unroll
             for (int i = 0; i < kMaskWords; ++i)
               if (i == word) mbits[i] = bits;
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {                      // 16 hidden units each
+              const uint32_t Ah[4] = {ahi[2 * kb][0], ahi[2 * kb][1], ahi[2 * kb + 1][0], ahi[2 * kb + 1][1]};
+              const uint32_t Al[4] = {alo[2 * kb][0], alo[2 * kb][1], alo[2 * kb + 1][0], alo[2 * kb + 1][1]};
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {                       // classes 0-7 | 8-15
+                if (g == 1 && C <= 8) continue;
+                hmma_16816(acc[g], Al, bh[kb][2 * g], bh[kb][2 * g + 1]);
+                hmma_16816(acc[g], Ah, bl[kb][2 * g], bl[kb][2 * g + 1]);
+                hmma_16816(acc[g], Ah, bh[kb][2 * g], bh[kb][2 * g + 1]);
+              }
+            }
           }
         }
         tc_fence_before();
@@ -326,71 +460,72 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         if (lane == 0) mbar_arrive(tempty0 + 8 * as);
       }
 
-      // ---------------- row sums over the 4 lanes that share a row, then over the two column halves ----------------
+      // ---------------- logits: sum of the two column halves, then the loss head on this thread's 2 rows x 4 classes ----------------
+      float dl[2][4];                           // [row][class slot]: logits -> dlogits
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int c = 0; c < kCMax; ++c)
-          if (c < C) {
-            logit[r][c] += __shfl_xor_sync(0xffffffffu, logit[r][c], 1);
-            logit[r][c] += __shfl_xor_sync(0xffffffffu, logit[r][c], 2);
-          }
-      if (half == 1 && q == 0) {
+      for (int r = 0; r < 2; ++r) {
+        const float inv = 1.f / (s_a[r] * s_wo);
+        dl[r][0] = acc[0][2 * r] * inv; dl[r][1] = acc[0][2 * r + 1] * inv;
+        dl[r][2] = acc[1][2 * r] * inv; dl[r][3] = acc[1][2 * r + 1] * inv;
+      }
+      const int rit0 = quad * 32 + lhalf * 16 + rsub;
+      if (half == 1) {
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int c = 0; c < kCMax; ++c)
-            if (c < C) xchg[(quad * 32 + lhalf * 16 + 8 * r + rsub) * kCMax + c] = logit[r][c];
+          for (int i = 0; i < 4; ++i) xchg[(rit0 + 8 * r) * 16 + cls[i]] = dl[r][i];
       }
       epi_bar();
       if (half == 0) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const int rit = quad * 32 + lhalf * 16 + 8 * r + rsub;
+          const int rit = rit0 + 8 * r;
+          bool valid[4];
 #pragma unroll
-          for (int c = 0; c < kCMax; ++c)
-            if (c < C) logit[r][c] += (p.BN >= 64 ? xchg[rit * kCMax + c] : 0.f) + bo_s[c];
+          for (int i = 0; i < 4; ++i) {
+            valid[i] = cls[i] < C;
+            dl[r][i] += (p.BN >= 64 ? xchg[rit * 16 + cls[i]] : 0.f) + (valid[i] ? bo_s[cls[i]] : 0.f);
+          }
           if (p.head < 0) {
-            if (rok[r] && q == 0) {
+            if (rok[r]) {
               float* out = p.logits + ((long long)z * p.B + brow[r]) * C;
 #pragma unroll
-              for (int c = 0; c < kCMax; ++c)
-                if (c < C) out[c] = logit[r][c];
+              for (int i = 0; i < 4; ++i)
+                if (valid[i]) out[cls[i]] = dl[r][i];
             }
           } else {
-            // loss head (same algebra and operation order as head.cu::dlogits_kernel)
+            // loss head (same algebra as head.cu::dlogits_kernel; the class sums run over the 4 lanes that share a row)
             const int y = rok[r] ? p.labels[brow[r]] : 0;
-            float g[kCMax];
-            softmax_r<kCMax>(logit[r], C);
+            float g[4];
+            softmax_quad(dl[r], valid);
             if (p.head == RBNN_HEAD_LOGITS_CE) {
 #pragma unroll
-              for (int c = 0; c < kCMax; ++c) logit[r][c] = logit[r][c] - (c == y ? 1.f : 0.f);
+              for (int i = 0; i < 4; ++i) dl[r][i] = valid[i] ? dl[r][i] - (cls[i] == y ? 1.f : 0.f) : 0.f;
             } else {
               if (p.head == RBNN_HEAD_MEAN_OF_GRADS) {
 #pragma unroll
-                for (int c = 0; c < kCMax; ++c) g[c] = logit[r][c];
+                for (int i = 0; i < 4; ++i) g[i] = dl[r][i];
               } else {
 #pragma unroll
-                for (int c = 0; c < kCMax; ++c)
-                  g[c] = (c < C && rok[r]) ? __ldg(p.pbar + (long long)brow[r] * C + c) : 0.f;
+                for (int i = 0; i < 4; ++i)
+                  g[i] = (valid[i] && rok[r]) ? __ldg(p.pbar + (long long)brow[r] * C + cls[i]) : 0.f;
               }
               if (p.head != RBNN_HEAD_UPSTREAM) {
-                softmax_r<kCMax>(g, C);
+                softmax_quad(g, valid);
 #pragma unroll
-                for (int c = 0; c < kCMax; ++c) g[c] -= (c == y ? 1.f : 0.f);
+                for (int i = 0; i < 4; ++i) g[i] -= (cls[i] == y ? 1.f : 0.f);
               }
               float dot = 0.f;
 #pragma unroll
-              for (int c = 0; c < kCMax; ++c)
-                if (c < C) dot = fmaf(logit[r][c], g[c], dot);
+              for (int i = 0; i < 4; ++i)
+                if (valid[i]) dot = fmaf(dl[r][i], g[i], dot);
+              dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+              dot += __shfl_xor_sync(0xffffffffu, dot, 2);
 #pragma unroll
-              for (int c = 0; c < kCMax; ++c) logit[r][c] = logit[r][c] * (g[c] - dot);
+              for (int i = 0; i < 4; ++i) dl[r][i] = valid[i] ? dl[r][i] * (g[i] - dot) : 0.f;
             }
-            if (q == 0) {
 #pragma unroll
-              for (int c = 0; c < kCMax; ++c)
-                if (c < C) xchg[rit * kCMax + c] = logit[r][c];
-            }
+            for (int i = 0; i < 4; ++i) xchg[rit * 16 + cls[i]] = dl[r][i];
           }
         }
       }
@@ -405,63 +540,83 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int c = 0; c < kCMax; ++c)
-            if (c < C) logit[r][c] = xchg[(quad * 32 + lhalf * 16 + 8 * r + rsub) * kCMax + c];
+          for (int i = 0; i < 4; ++i) dl[r][i] = xchg[(rit0 + 8 * r) * 16 + cls[i]];
       }
 
       // ---------------- pass 2: dH = (dlogits . Wo) * leaky'(H) for this thread's 2 rows x column pairs ----------------
-      if (active) {
+      if (active && !(p.debug & 2)) {
+        // A fragments: dlogits of rows (g, g+8) x classes, scaled per row into the fp16 range and split
+        uint32_t Dh[4], Dl[4];
+        float mul[2];
         long long orow[2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) orow[r] = ((long long)z * p.B + brow[r]) * H;
+        for (int r = 0; r < 2; ++r) {
+          float mx = fmaxf(fmaxf(fabsf(dl[r][0]), fabsf(dl[r][1])), fmaxf(fabsf(dl[r][2]), fabsf(dl[r][3])));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const float s_d = pow2_scale(mx);
+          split_pair(dl[r][0] * s_d, dl[r][1] * s_d, Dh[r], Dl[r]);            // classes 2q, 2q+1
+          split_pair(dl[r][2] * s_d, dl[r][3] * s_d, Dh[2 + r], Dl[2 + r]);    // classes 8+2q, 9+2q
+          mul[r] = dh_scale / (s_d * s_wo);
+          orow[r] = ((long long)z * p.B + brow[r]) * H;
+        }
         for (int n = 0; n < p.n_tiles; ++n) {
 #pragma unroll 1
           for (int cc = 0; cc < nblocks; ++cc) {
-            const int jbase = n * p.BN + half * cols_half + cc * 32 + 2 * q;
+            const int j0 = n * p.BN + half * cols_half + cc * 32;
             const int word = n * nblocks + cc;
             uint32_t bits = 0u;
 #pragma unroll
             for (int i = 0; i < kMaskWords; ++i)
               if (i == word) bits = mbits[i];
+            uint32_t whi[2][4], wlo[2][4];                        // [row][column group]: packed 16-bit pairs (hi, lo / bf16)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int j = jbase + 8 * k;
-              float d[2][2];
+            for (int gp = 0; gp < 2; ++gp) {                      // 16 columns: two 8-column groups
+              uint32_t bh[4], bl[4];
+              ldsm_x4_trans(wo_hi_a + off2 + (uint32_t)(j0 + 16 * gp) * 2u, bh);
+              ldsm_x4_trans(wo_lo_a + off2 + (uint32_t)(j0 + 16 * gp) * 2u, bl);
 #pragma unroll
-              for (int r = 0; r < 2; ++r) d[r][0] = d[r][1] = 0.f;
+              for (int gs = 0; gs < 2; ++gs) {
+                const int k = 2 * gp + gs;
+                float d[4] = {0.f, 0.f, 0.f, 0.f};                // row 0: (j, j+1), row 1: (j, j+1)
+                hmma_16816(d, Dl, bh[2 * gs], bh[2 * gs + 1]);
+                hmma_16816(d, Dh, bl[2 * gs], bl[2 * gs + 1]);
+                hmma_16816(d, Dh, bh[2 * gs], bh[2 * gs + 1]);
+                const int j = j0 + 8 * k + 2 * q;
 #pragma unroll
-              for (int c = 0; c < kCMax; ++c)
-                if (c < C) {
-                  const float2 w = *reinterpret_cast<const float2*>(wo_s + c * H + j);
-#pragma unroll
-                  for (int r = 0; r < 2; ++r) {
-                    d[r][0] = fmaf(logit[r][c], w.x, d[r][0]);
-                    d[r][1] = fmaf(logit[r][c], w.y, d[r][1]);
+                for (int r = 0; r < 2; ++r) {
+                  float d0 = d[2 * r] * mul[r], d1 = d[2 * r + 1] * mul[r];
+                  if (!((bits >> (r * 8 + k * 2)) & 1u)) d0 *= kSlopeF;
+                  if (!((bits >> (r * 8 + k * 2 + 1)) & 1u)) d1 *= kSlopeF;
+                  if (BF16) {
+                    const __nv_bfloat162 a = __floats2bfloat162_rn(d0, d1);
+                    whi[r][k] = *reinterpret_cast<const uint32_t*>(&a);
+                  } else if (MODE == MODE_F16X3) {
+                    split_pair(d0, d1, whi[r][k], wlo[r][k]);
+                  } else if (rok[r] && !(p.debug & 1)) {
+                    float2 hi2, lo2;
+                    hi2.x = to_tf32_rn(d0); hi2.y = to_tf32_rn(d1);
+                    lo2.x = d0 - hi2.x; lo2.y = d1 - hi2.y;
+                    __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_hi) + orow[r] + j), hi2);   // streaming: do not displace X / W1 in L2
+                    __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_lo) + orow[r] + j), lo2);
                   }
                 }
+              }
+            }
+            if (MODE != MODE_TF32X3) {
+              // 16-bit outputs: gather 8 consecutive columns per lane (4 x 4 word transpose over the lanes of a row), then
+              // one 16-byte streaming store per row and array -- whole 32-byte sectors instead of 4-byte pieces
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
-                if (!rok[r]) continue;
-                if (!((bits >> (r * 8 + k * 2)) & 1u)) d[r][0] *= kSlopeF;
-                if (!((bits >> (r * 8 + k * 2 + 1)) & 1u)) d[r][1] *= kSlopeF;
+                quad_transpose(whi[r], q);
+                if (!BF16) quad_transpose(wlo[r], q);
+                if (!rok[r] || (p.debug & 1)) continue;
+                const long long o = orow[r] + j0 + 8 * q;
                 if (BF16) {
-                  const __nv_bfloat162 a = __floats2bfloat162_rn(d[r][0], d[r][1]);
-                  __stcs(reinterpret_cast<unsigned int*>(p.dh_bf + orow[r] + j), *reinterpret_cast<const unsigned int*>(&a));
-                } else if (MODE == MODE_F16X3) {
-                  const float s0 = d[r][0] * dh_scale, s1 = d[r][1] * dh_scale;
-                  const __half2 hi2 = __floats2half2_rn(s0, s1);
-                  const float2 hf = __half22float2(hi2);
-                  const __half2 lo2 = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
-                  __stcs(reinterpret_cast<unsigned int*>(reinterpret_cast<__half*>(p.dh_hi) + orow[r] + j),
-                         *reinterpret_cast<const unsigned int*>(&hi2));
-                  __stcs(reinterpret_cast<unsigned int*>(reinterpret_cast<__half*>(p.dh_lo) + orow[r] + j),
-                         *reinterpret_cast<const unsigned int*>(&lo2));
+                  st_cs_u4(p.dh_bf + o, whi[r]);
                 } else {
-                  float2 hi2, lo2;
-                  hi2.x = to_tf32_rn(d[r][0]); hi2.y = to_tf32_rn(d[r][1]);
-                  lo2.x = d[r][0] - hi2.x; lo2.y = d[r][1] - hi2.y;
-                  __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_hi) + orow[r] + j), hi2);   // streaming: do not displace X / W1 in L2
-                  __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_lo) + orow[r] + j), lo2);
+                  st_cs_u4(reinterpret_cast<__half*>(p.dh_hi) + o, whi[r]);
+                  st_cs_u4(reinterpret_cast<__half*>(p.dh_lo) + o, wlo[r]);
                 }
               }
             }
@@ -540,7 +695,7 @@ bool fused_supported(int H, int C) {
   const int cols_half = bn >= 64 ? bn / 2 : bn;
   if (cols_half % 32) return false;
   if (n_tiles * (cols_half / 32) > kMaskWords) return false;
-  return ((C * H + C + 3) & ~3) + H <= kParamFloatsMax;
+  return H <= kHMax;
 }
 
 size_t fused_worklist_slots(int B, int Z) { return (size_t)Z * ((B + kBM - 1) / kBM) * kWorkPerItem; }
@@ -582,6 +737,10 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   p.dh_hi = d.dh_hi; p.dh_lo = d.dh_lo; p.dh_bf = reinterpret_cast<__nv_bfloat16*>(d.dh_bf); p.logits = d.logits;
   p.worklist = p.eps > 0.f ? d.worklist : nullptr;
   p.unscale = d.unscale; p.dh_scale = d.dh_scale;
+  {
+    static const int dbg = getenv("RBNN_FUSED_DEBUG") ? atoi(getenv("RBNN_FUSED_DEBUG")) : 0;
+    p.debug = dbg;
+  }
   if (d.head >= 0 && (bf16 ? !d.dh_bf : (!d.dh_hi || !d.dh_lo))) { *err = "fused_forward_head: missing dH output"; return 1; }
   if (d.head < 0 && !d.logits) { *err = "fused_forward_head: missing logits output"; return 1; }
   if (d.head >= 0 && d.head != RBNN_HEAD_MEAN_OF_GRADS && d.head != RBNN_HEAD_LOGITS_CE && !d.pbar) {

@@ -93,7 +93,7 @@ struct Case {
   const char* name;
   int mode, M, N, K, Z, BN, reduce, slots, a_per_z, epi, split_out;
 };
-static int g_kblock = 64, g_pair = 1, g_skip = 0, g_relay = 1, g_spin = 0;
+static int g_kblock = 64, g_pair = 1, g_skip = 0, g_relay = 1, g_spin = 0, g_ldpad = 0, g_noout = 0;
 
 static float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
@@ -102,8 +102,10 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
   const bool bf = c.mode == MODE_BF16, f16 = c.mode == MODE_F16X3;
   Dev A, B, bias, act;
   const int64_t a_z = c.a_per_z ? c.Z : 1;
-  A.init(a_z * c.M * c.K, 11, 2.0f, bf);
-  B.init((int64_t)c.Z * c.N * c.K, 22, 0.2f, bf);
+  const int per_line = c.mode == MODE_TF32X3 ? 32 : 64;          // TC_LDPAD=1: operand rows start on 128-byte lines
+  const int64_t ldk = g_ldpad ? (c.K + per_line - 1) / per_line * per_line : c.K;
+  A.init(a_z * c.M * ldk, 11, 2.0f, bf);
+  B.init((int64_t)c.Z * c.N * ldk, 22, 0.2f, bf);
   const float sA = 256.f, sB = 4096.f;     // |A| < 1 -> < 2^8, |B| < 0.1 -> < 2^9
   float* unscale = nullptr;
   if (f16) {
@@ -129,15 +131,15 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
   d.pair_relay = g_relay;
   d.spin_wait = g_spin;
   d.mode = c.mode; d.M = c.M; d.N = c.N; d.K = c.K; d.Z = c.Z; d.BN = c.BN;
-  d.A.hi = bf ? (void*)A.bf : (void*)A.hi; d.A.lo = A.lo; d.A.rows = c.M; d.A.ld = c.K;
+  d.A.hi = bf ? (void*)A.bf : (void*)A.hi; d.A.lo = A.lo; d.A.rows = c.M; d.A.ld = ldk;
   d.unscale = unscale;
-  d.A.zstride = c.a_per_z ? (int64_t)c.M * c.K : 0;
-  d.B.hi = bf ? (void*)B.bf : (void*)B.hi; d.B.lo = B.lo; d.B.rows = c.N; d.B.ld = c.K; d.B.zstride = (int64_t)c.N * c.K;
+  d.A.zstride = c.a_per_z ? (int64_t)c.M * ldk : 0;
+  d.B.hi = bf ? (void*)B.bf : (void*)B.hi; d.B.lo = B.lo; d.B.rows = c.N; d.B.ld = ldk; d.B.zstride = (int64_t)c.N * ldk;
   if (f16) { d.A.hi = A.h16; d.A.lo = A.l16; d.B.hi = B.h16; d.B.lo = B.l16; }
   d.reduce_z = c.reduce; d.slots = c.slots; d.epi = c.epi;
   d.bias = bias.hi + 1; d.bias_zstride = c.N;     // +1: bias rows are only 4-byte aligned in the bank
   d.act = act.hi; d.act_zstride = (int64_t)c.M * c.N; d.act_ld = c.N;
-  d.out = out; d.out_lo = out_lo; d.out_ld = c.N; d.out_zstride = (int64_t)c.M * c.N;
+  d.out = g_noout ? nullptr : out; d.out_lo = out_lo; d.out_ld = c.N; d.out_zstride = (int64_t)c.M * c.N;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   d.sm_count = prop.multiProcessorCount;
@@ -174,8 +176,8 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
     const int z1 = c.reduce ? (int)((long long)(zz + 1) * c.Z / c.slots) : zz + 1;
     double acc = 0;
     for (int z = z0; z < z1; ++z) {
-      const int64_t ao = (c.a_per_z ? (int64_t)z * c.M * c.K : 0) + (int64_t)m * c.K;
-      const int64_t bo = ((int64_t)z * c.N + n) * c.K;
+      const int64_t ao = (c.a_per_z ? (int64_t)z * c.M * ldk : 0) + (int64_t)m * ldk;
+      const int64_t bo = ((int64_t)z * c.N + n) * ldk;
       for (int k = 0; k < c.K; ++k) {
         float a = A.at(ao + k), b = B.at(bo + k);
         if (bf) { a = bf16_round(a); b = bf16_round(b); }
@@ -219,6 +221,8 @@ int main(int argc, char** argv) {
   g_skip = getenv("TC_SKIP_MMA") ? atoi(getenv("TC_SKIP_MMA")) : 0;
   g_relay = getenv("TC_RELAY") ? atoi(getenv("TC_RELAY")) : 1;
   g_spin = getenv("TC_SPIN") ? atoi(getenv("TC_SPIN")) : 0;
+  g_ldpad = getenv("TC_LDPAD") ? atoi(getenv("TC_LDPAD")) : 0;
+  g_noout = getenv("TC_NOOUT") ? atoi(getenv("TC_NOOUT")) : 0;    // timing only: the epilogue drains TMEM but stores nothing
   for (int cfg = 0; cfg < 4; ++cfg) {
   if (!((cfg_mask >> cfg) & 1)) continue;
   g_kblock = (cfg & 1) ? 128 : 64;
@@ -242,6 +246,8 @@ int main(int argc, char** argv) {
         {"tf32x3 bwd 10000x784x512 Z=148 BN=256 s37", MODE_TF32X3, 10000, 784, 512, 148, 256, 1, 37, 1, EPI_NONE, 0},
         {"tf32x3 bwd 10000x784x512 Z=148 BN=112 s21", MODE_TF32X3, 10000, 784, 512, 148, 112, 1, 21, 1, EPI_NONE, 0},
         {"f16x3 fwd 10000x512x784 Z=148 BN=256", MODE_F16X3, 10000, 512, 784, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+        {"f16x3 fwd 10000x512x768 Z=148 BN=256", MODE_F16X3, 10000, 512, 768, 148, 256, 0, 1, 0, EPI_BIAS_LEAKY, 0},
+        {"f16x3 fwd 10000x512x784 Z=148 BN=160", MODE_F16X3, 10000, 512, 784, 148, 160, 0, 1, 0, EPI_BIAS_LEAKY, 0},
         {"f16x3 bwd 10000x784x512 Z=148 BN=208 s37", MODE_F16X3, 10000, 784, 512, 148, 208, 1, 37, 1, EPI_NONE, 0},
         {"f16x3 bwd 10000x784x512 Z=148 BN=256 s37", MODE_F16X3, 10000, 784, 512, 148, 256, 1, 37, 1, EPI_NONE, 0},
         {"f16x3 bwd 10000x784x512 Z=148 BN=160 s37", MODE_F16X3, 10000, 784, 512, 148, 160, 1, 37, 1, EPI_NONE, 0},
