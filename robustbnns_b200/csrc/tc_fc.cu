@@ -450,27 +450,36 @@ __global__ void xnorm_kernel(const float* __restrict__ x, int B, int D, float* _
   if (lane == 0) out[b] = sqrtf(s);
 }
 
-// wnorm[s] = max_j ||W_s[j, :]||_2 over the R rows of the [R, C] matrix at `off` of bank row s; one block per s
+// wnorm[s] = max_j ||W_s[j, :]||_2 over the R rows of the [R, C] matrix at `off` of bank row s; one block per s.
+// max_bits != nullptr (F16X3): also *max_bits = max(*max_bits, max |W_s|) as float bits -- the operand range of the
+// fp16 copies, from the same pass over the weights.
 __global__ void __launch_bounds__(256)
-wnorm_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0, float* __restrict__ out) {
-  __shared__ float red[8];
+wnorm_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0, float* __restrict__ out,
+             unsigned* __restrict__ max_bits) {
+  __shared__ float red[8], redm[8];
   const int s = s0 + blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float best = 0.f;
+  float best = 0.f, mabs = 0.f;
   for (int r = warp; r < R; r += 8) {
     const float* __restrict__ w = bank + (int64_t)s * P + off + (int64_t)r * C;
     float acc = 0.f;
-    for (int c = lane; c < C; c += 32) { const float v = __ldg(w + c); acc = fmaf(v, v, acc); }
+    for (int c = lane; c < C; c += 32) { const float v = __ldg(w + c); acc = fmaf(v, v, acc); mabs = fmaxf(mabs, fabsf(v)); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     best = fmaxf(best, acc);
   }
-  if (lane == 0) red[warp] = best;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
+  if (lane == 0) { red[warp] = best; redm[warp] = mabs; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float m = 0.f;
-    for (int i = 0; i < 8; ++i) m = fmaxf(m, red[i]);
+    float m = 0.f, a = 0.f;
+    for (int i = 0; i < 8; ++i) { m = fmaxf(m, red[i]); a = fmaxf(a, redm[i]); }
     out[s] = sqrtf(m);
+    if (max_bits) {
+      if (!(m == m) || !(a == a)) a = __int_as_float(0x7f800000);     // NaN weights -> "infinite" range -> overflow flag
+      atomicMax(max_bits, __float_as_uint(a));
+    }
   }
 }
 
@@ -588,8 +597,8 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       int e = s;
       while (e < s1 && tc.dirty[e]) ++e;
       const int64_t P = n->L.P;
-      maxabs_kernel<<<n->sm_count * 4, 256, 0, st>>>(n->bank + (int64_t)s * P + n->L.w1, P, (int64_t)n->H * n->D, e - s,
-                                                     &tc.scales->maxw1_bits);
+      wnorm_kernel<<<e - s, 256, 0, st>>>(n->bank, P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C, s, tc.wnorm,
+                                          &tc.scales->maxw1_bits);
       maxabs_kernel<<<n->sm_count, 256, 0, st>>>(n->bank + (int64_t)s * P + n->L.wo, P, (int64_t)n->C * n->H, e - s,
                                                  &tc.scales->maxwo_bits);
       n->launches += 2;
@@ -622,9 +631,11 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }
-    wnorm_kernel<<<e - s, 256, 0, st>>>(n->bank, n->L.P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C, s, tc.wnorm);
-    n->launches++;
-    RBNN_CUDA(cudaGetLastError());
+    if (!f16) {        // F16X3: the row norms came with the operand-range pass above
+      wnorm_kernel<<<e - s, 256, 0, st>>>(n->bank, n->L.P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C, s, tc.wnorm, nullptr);
+      n->launches++;
+      RBNN_CUDA(cudaGetLastError());
+    }
     std::fill(tc.dirty + s, tc.dirty + e, (uint8_t)0);
     s = e;
   }
@@ -707,6 +718,9 @@ static size_t fc_per_z_bytes(const rbnn_net* n, int B, bool grad) {
 // Measured on B200: max error 5e-6 of the output max (~7e-7 ||x|| ||w||).  eps = 2^-16 = 1.5e-5 keeps a 4x margin
 // over the model and ~20x over the measurement; ~4e-4 of the units qualify.
 constexpr float kGuardEpsFused = 1.0f / 65536.0f;
+// F16X3: half the accumulation steps of TF32x3 (K = 16 per MMA) and a smaller measured error (2.9e-6 vs 5e-6 of the
+// output max on the same operands), hence half the band: 2^-17 keeps the same ~20x margin and halves the fix-up work.
+constexpr float kGuardEpsFusedF16 = 1.0f / 131072.0f;
 constexpr float kGuardEps = 1.0f / 4096.0f;   // ~50x the measured TF32x3 error bound (5e-6 of the output max)
 
 static int refine(rbnn_net* n, float* h_hi, float* h_lo, int Z, int B, const float* a_hi, const float* a_lo,
@@ -786,7 +800,7 @@ static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, con
   f.head = head;
   f.bank = n->bank; f.P = n->L.P; f.b1_off = n->L.b1; f.wo_off = n->L.wo; f.bo_off = n->L.bo; f.z_row0 = z0;
   f.labels = labels; f.pbar = pbar;
-  f.x = x; f.xnorm = w.xnorm; f.wnorm = n->tc.wnorm; f.eps = kGuardEpsFused;
+  f.x = x; f.xnorm = w.xnorm; f.wnorm = n->tc.wnorm; f.eps = f16 ? kGuardEpsFusedF16 : kGuardEpsFused;
   f.dh_hi = f16 ? (void*)w.dtop_h16 : (void*)w.dtop_hi; f.dh_lo = f16 ? (void*)w.dtop_l16 : (void*)w.dtop_lo;
   f.dh_bf = w.dtop_bf; f.logits = logits;
   f.worklist = w.worklist;

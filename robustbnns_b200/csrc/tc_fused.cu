@@ -21,6 +21,7 @@
 // slots of the worklist (no global atomics, deterministic); an item that overflows evaluates inline.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "../../include/rbnn.h"
@@ -115,8 +116,13 @@ __device__ __forceinline__ void quad_transpose(uint32_t (&a)[4], int q) {
   t1 = __shfl_xor_sync(0xffffffffu, t1, 2);
   if (up) { a[0] = t0; a[1] = t1; } else { a[2] = t0; a[3] = t1; }
 }
-__device__ __forceinline__ void st_cs_u4(void* ptr, const uint32_t (&a)[4]) {
-  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
+__device__ __forceinline__ void st_cs_u4(void* ptr, const uint32_t (&a)[4], int flavor = 0) {
+  if (flavor == 0)
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
+  else if (flavor == 1)
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
+  else
+    asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
 }
 
 // softmax over the classes of one row spread over the 4 lanes that share it (4 class slots per lane)
@@ -219,11 +225,15 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     if (lane == 0) {
       // ===================== TMA producer =====================
       uint32_t stage = 0, phase = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int z = item / p.m_tiles, m_idx = item % p.m_tiles;
         for (int n = 0; n < p.n_tiles; ++n) {
           for (int kb = 0; kb < p.num_kb; ++kb) {
+            const long long t0 = clock64();
             mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+            w_empty += clock64() - t0;
             const uint32_t fb = full0 + 8 * stage;
             mbar_expect_tx(fb, stage_tx);
             const uint32_t sa = ring + stage * STAGE;
@@ -238,6 +248,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           }
         }
       }
+      if ((p.debug & 8) && blockIdx.x == 0)
+        printf("[fused cta0] TMA producer: total %lld cyc, waiting for an empty stage %lld\n", clock64() - t_begin, w_empty);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -245,15 +257,21 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(kBM >> 4) << 24);
       uint32_t stage = 0, phase = 0, it = 0;
+      long long w_tempty = 0, w_full = 0;
+      const long long t_begin = clock64();
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         for (int n = 0; n < p.n_tiles; ++n, ++it) {
           const uint32_t as = it & 1u;
+          long long t0 = clock64();
           mbar_wait(tempty0 + 8 * as, ((it >> 1) & 1u) ^ 1u);
+          w_tempty += clock64() - t0;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * (uint32_t)kBNMax;
           uint32_t accumulate = 0;
           for (int kb = 0; kb < p.num_kb; ++kb) {
+            t0 = clock64();
             mbar_wait(full0 + 8 * stage, phase);
+            w_full += clock64() - t0;
             tc_fence_after();
             const uint32_t sa = ring + stage * STAGE;
             const uint32_t sb = sa + NARR * kATileF;
@@ -280,6 +298,9 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           tc_commit(tfull0 + 8 * as);
         }
       }
+      if ((p.debug & 8) && blockIdx.x == 0)
+        printf("[fused cta0] MMA issuer: total %lld cyc, waiting for a free accumulator %lld, for operands %lld\n",
+               clock64() - t_begin, w_tempty, w_full);
     }
   } else {
     // ===================== epilogue: warps 2..17 =====================
@@ -317,9 +338,12 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       wo_lo[C * ldw + i] = __float2half_rn(0.f);
     }
     uint32_t it = 0;
+    long long w_tfull = 0, c_stage = 0, c_p1 = 0, c_head = 0, c_p2 = 0, t_mark = clock64();
+    const long long t_begin = t_mark;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int z = item / p.m_tiles, m_idx = item % p.m_tiles;
       const float* __restrict__ wrow = p.bank + (long long)(p.z_row0 + z) * p.P;
+      { const long long t = clock64(); c_p2 += t - t_mark; t_mark = t; }
       // ---------------- stage Wo_z (fp16 hi/lo of s_wo * Wo), b1_z, bo_z ----------------
       float wv[kWoPerThread];
       float wmax = 0.f, bmax = 0.f;
@@ -381,10 +405,11 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < kMaskWords; ++i) mbits[i] = 0u;
 
+      { const long long t = clock64(); c_stage += t - t_mark; t_mark = t; }
       // ---------------- pass 1 ----------------
       for (int n = 0; n < p.n_tiles; ++n, ++it) {
         const uint32_t as = it & 1u;
-        mbar_wait(tfull0 + 8 * as, (it >> 1) & 1u);
+        { const long long t0 = clock64(); mbar_wait(tfull0 + 8 * as, (it >> 1) & 1u); w_tfull += clock64() - t0; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)kBNMax;
         if (active) {
@@ -460,6 +485,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         if (lane == 0) mbar_arrive(tempty0 + 8 * as);
       }
 
+      { const long long t = clock64(); c_p1 += t - t_mark; t_mark = t; }
       // ---------------- logits: sum of the two column halves, then the loss head on this thread's 2 rows x 4 classes ----------------
       float dl[2][4];                           // [row][class slot]: logits -> dlogits
 #pragma unroll
@@ -543,6 +569,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           for (int i = 0; i < 4; ++i) dl[r][i] = xchg[(rit0 + 8 * r) * 16 + cls[i]];
       }
 
+      { const long long t = clock64(); c_head += t - t_mark; t_mark = t; }
       // ---------------- pass 2: dH = (dlogits . Wo) * leaky'(H) for this thread's 2 rows x column pairs ----------------
       if (active && !(p.debug & 2)) {
         // A fragments: dlogits of rows (g, g+8) x classes, scaled per row into the fp16 range and split
@@ -615,8 +642,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                 if (BF16) {
                   st_cs_u4(p.dh_bf + o, whi[r]);
                 } else {
-                  st_cs_u4(reinterpret_cast<__half*>(p.dh_hi) + o, whi[r]);
-                  st_cs_u4(reinterpret_cast<__half*>(p.dh_lo) + o, wlo[r]);
+                  st_cs_u4(reinterpret_cast<__half*>(p.dh_hi) + o, whi[r], (p.debug >> 4) & 3);
+                  st_cs_u4(reinterpret_cast<__half*>(p.dh_lo) + o, wlo[r], (p.debug >> 4) & 3);
                 }
               }
             }
@@ -624,6 +651,9 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         }
       }
     }
+    if ((p.debug & 8) && blockIdx.x == 0 && et == 0)
+      printf("[fused cta0] epilogue warp 2: total %lld cyc: staging %lld, pass 1 %lld (of which waiting for the accumulator %lld), "
+             "head %lld, pass 2 %lld\n", clock64() - t_begin, c_stage, c_p1, w_tfull, c_head, c_p2 + (clock64() - t_mark));
   }
 
   tc_fence_before();
