@@ -13,6 +13,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -887,7 +889,10 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   // K-concatenated ranges of ~4 samples (bounds the tensor-core accumulation chain, fills the SMs)
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
   int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / (per + out_bytes / 4 + 1), (size_t)S));
-  const int bn_b = pick_bn(D);
+  // experiment knobs for the input-gradient GEMM: tile width and CTA pairs (cta_group::2)
+  static const int env_bn = getenv("RBNN_BWD_BN") ? atoi(getenv("RBNN_BWD_BN")) : 0;
+  static const int env_pair = getenv("RBNN_BWD_PAIR") ? atoi(getenv("RBNN_BWD_PAIR")) : 0;
+  const int bn_b = env_bn ? env_bn : pick_bn(D);
   const int tiles_mn = ((B + tc::kBM - 1) / tc::kBM) * ((D + bn_b - 1) / bn_b);
   auto slots_for = [&](int Z) {
     int best = 1;
@@ -978,6 +983,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     } else { r.B.hi = m1.thi + (int64_t)z0 * D * H; r.B.lo = m1.tlo + (int64_t)z0 * D * H; }
     r.B.rows = D; r.B.ld = H; r.B.zstride = (int64_t)D * H;
     r.reduce_z = 1; r.slots = sl;
+    r.pair = env_pair ? 1 : 0; r.pair_relay = env_pair == 2 ? 0 : 1;
     r.out = w.partial; r.out_ld = D; r.out_zstride = (int64_t)B * D;
     RBNN_TRY(run_gemm(n, r, 2, st));
     const int64_t n4 = (int64_t)B * D / 4;
