@@ -99,16 +99,20 @@ __global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64
 
 // ---- F16X3 operand scaling ---------------------------------------------------------------------------
 // fp16 keeps 11 significant bits over 2^-14 .. 2^16 only, so every F16X3 operand is multiplied by a power of two
-// (exact) that puts its largest element in [2^8, 2^9): hi = rn_f16(s v) carries the leading 11 bits, lo =
-// rn_f16(s v - hi) the next 11; elements below 2^-16 of the maximum lose relative (not absolute) precision, which
-// a dot product does not see.  All scales live in device memory; nothing is read back by the host.
-constexpr int kF16TargetExp = 9;
+// (exact) that puts its largest element just below 2^target: hi = rn_f16(s v) carries the leading 11 bits, lo =
+// rn_f16(s v - hi) the next 11; elements far below the maximum lose relative (not absolute) precision, which a dot
+// product does not see.  Operands whose maximum is known exactly when they are scaled (the inputs of a call; dH, which
+// is bounded by 2 max|g| max|Wo|) go to 2^15, the top of the fp16 range -- 2^29 of dynamic range below the maximum
+// before the lo part runs out of bits.  The W1 copies persist across calls, so their scale is fixed on first use and
+// keeps 2^6 of head room (target 2^9) for rows uploaded later.  All scales live in device memory; nothing is read
+// back by the host.
+constexpr int kF16TargetExpFrozen = 9, kF16TargetExpExact = 15;
 
-__device__ __forceinline__ float pow2_scale_for(float maxabs) {     // s = 2^k with s * maxabs in [2^8, 2^9)
+__device__ __forceinline__ float pow2_scale_for(float maxabs, int target_exp) {     // s = 2^k, s * maxabs in [2^(t-1), 2^t)
   if (!(maxabs > 0.f) || !isfinite(maxabs)) return 1.f;
   int e;
   frexpf(maxabs, &e);                                               // maxabs = m 2^e, m in [0.5, 1)
-  return ldexpf(1.f, kF16TargetExp - e);
+  return ldexpf(1.f, target_exp - e);
 }
 
 // *out_bits = max(*out_bits, max_i |v_i|) as float bits (non-negative floats order like unsigned integers);
@@ -138,7 +142,7 @@ maxabs_kernel(const float* __restrict__ base, int64_t stride, int64_t len, int c
 __global__ void freeze_scales_kernel(TcScales* sc, int* overflow) {
   const float mw = __uint_as_float(sc->maxw1_bits);
   if (!sc->frozen) {
-    sc->s_w1 = pow2_scale_for(mw);
+    sc->s_w1 = pow2_scale_for(mw, kF16TargetExpFrozen);
     sc->frozen = 1;
   }
   if (!(mw * sc->s_w1 < 32768.f)) {
@@ -151,9 +155,9 @@ __global__ void freeze_scales_kernel(TcScales* sc, int* overflow) {
 // |dH| <= 2 max|g| max|Wo| with max|g| <= 1 for the built-in heads (g = softmax(.) - e_y) and max|d_pbar| for UPSTREAM
 __global__ void call_scales_kernel(const TcScales* sc, const unsigned* xmax_bits, const unsigned* gmax_bits,
                                    float* out) {
-  const float sx = pow2_scale_for(__uint_as_float(*xmax_bits));
+  const float sx = pow2_scale_for(__uint_as_float(*xmax_bits), kF16TargetExpExact);
   const float gmax = gmax_bits ? __uint_as_float(*gmax_bits) : 1.f;
-  const float sd = pow2_scale_for(2.f * gmax * __uint_as_float(sc->maxwo_bits));
+  const float sd = pow2_scale_for(2.f * gmax * __uint_as_float(sc->maxwo_bits), kF16TargetExpExact);
   out[0] = sx;
   out[1] = 1.f / (sx * sc->s_w1);
   out[2] = sd;
@@ -889,6 +893,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   // K-concatenated ranges of ~4 samples (bounds the tensor-core accumulation chain, fills the SMs)
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
   int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / (per + out_bytes / 4 + 1), (size_t)S));
+  zc = (S + (S + zc - 1) / zc - 1) / ((S + zc - 1) / zc);      // equal chunks (1000 -> 3 x 334, not 419 + 419 + 162)
   // experiment knobs for the input-gradient GEMM: tile width and CTA pairs (cta_group::2)
   static const int env_bn = getenv("RBNN_BWD_BN") ? atoi(getenv("RBNN_BWD_BN")) : 0;
   static const int env_pair = getenv("RBNN_BWD_PAIR") ? atoi(getenv("RBNN_BWD_PAIR")) : 0;
@@ -1017,7 +1022,8 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   const size_t ldx = (size_t)k_pitch(n, D);
   const size_t x_bytes = bf ? pad256((size_t)B * ldx * 2) : (f16 ? 2 * pad256((size_t)B * ldx * 2) + 512 : 2 * pad256((size_t)B * ldx * 4));
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
-  const int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / per, (size_t)S));
+  int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / per, (size_t)S));
+  zc = (S + (S + zc - 1) / zc - 1) / ((S + zc - 1) / zc);      // equal chunks
   RBNN_TRY(ws_reserve(n, x_bytes + per * zc + pad256((size_t)B * 4)));
   Arena ar(n);
   FcWs w;

@@ -259,6 +259,41 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     eng.close()
 
 
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3"])
+@pytest.mark.parametrize("gain", [10.0, 30.0])
+def test_tcgen05_engine_on_saturated_softmax(prec, gain):
+    """Confident networks (output layer scaled up: softmax rows within 1e-6 .. 1e-30 of one-hot) make dlogits and dH
+    tiny on most rows.  F16X3 keeps its operands in the 5-bit exponent range of fp16 through power-of-two scaling: the
+    expected gradient must still match the fp64 oracle to the north-star tolerance (max-norm over the batch)."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    arch, shape, hidden, C, B, S = "fc", (1, 28, 28), 128, 10, 160, 6
+    net, layout, loc, rho, bank, x, labels = _problem(arch, shape, hidden, C, B, S)
+    off = 0
+    for key, shp in layout:
+        n = int(np.prod(shp))
+        if key in ("model.3.weight", "model.3.bias"):
+            bank[:, off:off + n] *= gain
+        off += n
+    eng = Net(arch, shape, hidden, C)
+    eng.set_precision(prec)
+    eng.upload(bank, 0)
+    p0 = orc.bnn_forward(net, layout, bank, x, [0]).detach()
+    assert float(p0.max(-1)[0].median()) > 0.99                       # the per-sample softmax rows really are saturated
+    g = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S).cpu().reshape(x.shape) / S
+    ref64 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    ref32 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S))
+    e, e32 = rel_err(g, ref64), rel_err(ref32, ref64)
+    print(f"saturated x{gain:g} {prec}: rel err {e:.2e} (fp32 oracle vs fp64: {e32:.2e})")
+    assert e < max(REL, 3 * e32)
+    pbar = eng.forward_probs_sum(x, 0, S) / S
+    ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
+    ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    ra32 = orc.attack_gradient(net, layout, bank, x, labels, range(S))
+    assert rel_err(ga, ra) < max(REL, 3 * rel_err(ra32, ra))
+    eng.close()
+
+
 def test_autograd_through_forward_matches_attack_gradient():
     from robustbnns_b200.model_bnn import BNN
     net, layout, loc, rho, bank, x, labels = _problem("fc", (1, 28, 28), 64, 10, 12, 4)
