@@ -34,16 +34,19 @@ __device__ __forceinline__ void softmax_inplace(float (&v)[C_MAX], int C) {
     if (c < C) v[c] *= inv;
 }
 
-// out_sum[b][c] += sum_z softmax(logits[z][b][:])[c]; sequential in z => deterministic
+// out_sum[b][c] += sum_z softmax(logits[z][b][:])[c].  One warp per input: lane l sums samples l, l+32, ... in order,
+// then a fixed butterfly over the lanes => deterministic, and B x 32 threads instead of B (the attack loop calls this
+// with B ~ 1000: one thread per input left most of the GPU idle).
 template <int C_MAX>
 __global__ void probs_accumulate_kernel(const float* __restrict__ logits, int Z, int B, int C,
                                         float* __restrict__ out_sum) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (b >= B) return;
   float acc[C_MAX];
 #pragma unroll
-  for (int c = 0; c < C_MAX; ++c) acc[c] = (c < C) ? out_sum[(int64_t)b * C + c] : 0.f;
-  for (int z = 0; z < Z; ++z) {
+  for (int c = 0; c < C_MAX; ++c) acc[c] = 0.f;
+  for (int z = lane; z < Z; z += 32) {
     float v[C_MAX];
     const float* row = logits + ((int64_t)z * B + b) * C;
 #pragma unroll
@@ -55,7 +58,17 @@ __global__ void probs_accumulate_kernel(const float* __restrict__ logits, int Z,
   }
 #pragma unroll
   for (int c = 0; c < C_MAX; ++c)
-    if (c < C) out_sum[(int64_t)b * C + c] = acc[c];
+    if (c < C) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+  if (lane < C) {
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c)
+      if (c == lane) v = acc[c];
+    out_sum[(int64_t)b * C + lane] += v;
+  }
 }
 
 template <int C_MAX>
@@ -100,11 +113,12 @@ __global__ void dlogits_kernel(int head, const float* __restrict__ logits, const
 int head_probs_accumulate(rbnn_net* net, const float* logits, int Z, int B, int C, float* out_sum,
                           cudaStream_t st) {
   RBNN_CHECK(C >= 1 && C <= kMaxC, "head: n_classes %d not in [1,%d]", C, kMaxC);
-  const int thr = 128;
+  const int thr = 128;                      // 4 inputs per block
+  const unsigned blocks = (unsigned)(((int64_t)B * 32 + thr - 1) / thr);
   if (C <= 16)
-    probs_accumulate_kernel<16><<<(B + thr - 1) / thr, thr, 0, st>>>(logits, Z, B, C, out_sum);
+    probs_accumulate_kernel<16><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
   else
-    probs_accumulate_kernel<32><<<(B + thr - 1) / thr, thr, 0, st>>>(logits, Z, B, C, out_sum);
+    probs_accumulate_kernel<32><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;

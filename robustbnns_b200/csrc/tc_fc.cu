@@ -456,36 +456,36 @@ __global__ void xnorm_kernel(const float* __restrict__ x, int B, int D, float* _
   if (lane == 0) out[b] = sqrtf(s);
 }
 
-// wnorm[s] = max_j ||W_s[j, :]||_2 over the R rows of the [R, C] matrix at `off` of bank row s; one block per s.
-// max_bits != nullptr (F16X3): also *max_bits = max(*max_bits, max |W_s|) as float bits -- the operand range of the
-// fp16 copies, from the same pass over the weights.
+// wnorm[s] = max_j ||W_s[j, :]||_2 over the R rows of the [R, C] matrix at `off` of bank row s.  One warp per matrix
+// row, 8 rows per block, grid (ceil(R / 8), samples); the per-sample maximum is an atomicMax on the float bits
+// (non-negative floats order like unsigned integers), so out[s0 .. s0 + samples) must be zeroed first.
+// max_bits != nullptr (F16X3): also *max_bits = max(*max_bits, max |W_s|) -- the operand range of the fp16 copies,
+// from the same pass over the weights.
 __global__ void __launch_bounds__(256)
 wnorm_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int s0, float* __restrict__ out,
              unsigned* __restrict__ max_bits) {
   __shared__ float red[8], redm[8];
-  const int s = s0 + blockIdx.x;
+  const int s = s0 + blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float best = 0.f, mabs = 0.f;
-  for (int r = warp; r < R; r += 8) {
+  const int r = blockIdx.x * 8 + warp;
+  float acc = 0.f, mabs = 0.f;
+  if (r < R) {
     const float* __restrict__ w = bank + (int64_t)s * P + off + (int64_t)r * C;
-    float acc = 0.f;
     for (int c = lane; c < C; c += 32) { const float v = __ldg(w + c); acc = fmaf(v, v, acc); mabs = fmaxf(mabs, fabsf(v)); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    best = fmaxf(best, acc);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
-  if (lane == 0) { red[warp] = best; redm[warp] = mabs; }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
+  }
+  if (lane == 0) { red[warp] = acc; redm[warp] = mabs; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float m = 0.f, a = 0.f;
     for (int i = 0; i < 8; ++i) { m = fmaxf(m, red[i]); a = fmaxf(a, redm[i]); }
-    out[s] = sqrtf(m);
-    if (max_bits) {
-      if (!(m == m) || !(a == a)) a = __int_as_float(0x7f800000);     // NaN weights -> "infinite" range -> overflow flag
-      atomicMax(max_bits, __float_as_uint(a));
-    }
+    const bool bad = !(m == m) || !(a == a);                       // NaN weights
+    atomicMax(reinterpret_cast<unsigned*>(out + s), __float_as_uint(bad ? __int_as_float(0x7f800000) : sqrtf(m)));
+    if (max_bits) atomicMax(max_bits, __float_as_uint(bad ? __int_as_float(0x7f800000) : a));   // -> overflow flag
   }
 }
 
@@ -603,8 +603,9 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       int e = s;
       while (e < s1 && tc.dirty[e]) ++e;
       const int64_t P = n->L.P;
-      wnorm_kernel<<<e - s, 256, 0, st>>>(n->bank, P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C, s, tc.wnorm,
-                                          &tc.scales->maxw1_bits);
+      RBNN_CUDA(cudaMemsetAsync(tc.wnorm + s, 0, (size_t)(e - s) * sizeof(float), st));
+      wnorm_kernel<<<dim3((tc.mat[0].R + 7) / 8, e - s), 256, 0, st>>>(n->bank, P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C,
+                                                                       s, tc.wnorm, &tc.scales->maxw1_bits);
       maxabs_kernel<<<n->sm_count, 256, 0, st>>>(n->bank + (int64_t)s * P + n->L.wo, P, (int64_t)n->C * n->H, e - s,
                                                  &tc.scales->maxwo_bits);
       n->launches += 2;
@@ -638,7 +639,9 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       RBNN_CUDA(cudaGetLastError());
     }
     if (!f16) {        // F16X3: the row norms came with the operand-range pass above
-      wnorm_kernel<<<e - s, 256, 0, st>>>(n->bank, n->L.P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C, s, tc.wnorm, nullptr);
+      RBNN_CUDA(cudaMemsetAsync(tc.wnorm + s, 0, (size_t)(e - s) * sizeof(float), st));
+      wnorm_kernel<<<dim3((tc.mat[0].R + 7) / 8, e - s), 256, 0, st>>>(n->bank, n->L.P, tc.mat[0].off, tc.mat[0].R,
+                                                                       tc.mat[0].C, s, tc.wnorm, nullptr);
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }
