@@ -100,6 +100,19 @@ RBNN_API int rbnn_bank_download(rbnn_net* net, float* h_out, int s0, int count);
  * divides by the GLOBAL number of samples after the cross-GPU allreduce.  d_x: [B, D]. */
 RBNN_API int rbnn_forward_probs_sum(rbnn_net* net, const float* d_x, int B, int s0, int s1,
                            float* d_out_sum, void* stream);
+/* Two-phase form of the attack gradient (adversarialAttacks.py:74-78 evaluates net.forward ONCE and differentiates
+ * it): the same sum as rbnn_forward_probs_sum, and the per-sample logits and LeakyReLU masks of this call stay in the
+ * handle (~104 B per sample x input), so that rbnn_input_grad_sum_kept can rebuild the gradient without a second
+ * forward pass.  When the engine has no such route (FP32 engine, fc2 / conv, batch too large for one pass) the call
+ * is a plain forward and rbnn_keep_valid() returns 0.  The kept data is invalidated when the bank rows it used are
+ * overwritten or the precision changes. */
+RBNN_API int rbnn_forward_probs_sum_keep(rbnn_net* net, const float* d_x, int B, int s0, int s1,
+                                float* d_out_sum, void* stream);
+RBNN_API int rbnn_keep_valid(const rbnn_net* net);
+/* d_out_sum[B, D] <- sum over the kept rows of dL_s/dx for the kept inputs; head = GRAD_OF_MEAN / UPSTREAM (with
+ * d_pbar as in rbnn_input_grad_sum) or MEAN_OF_GRADS. */
+RBNN_API int rbnn_input_grad_sum_kept(rbnn_net* net, int head, const int32_t* d_labels, const float* d_pbar,
+                             float* d_out_sum, void* stream);
 /* avg_posterior=True (model_bnn.py:206-216): LOGITS of bank row s. d_out: [B, C]. */
 RBNN_API int rbnn_forward_logits(rbnn_net* net, const float* d_x, int B, int s, float* d_out, void* stream);
 

@@ -38,6 +38,9 @@ SIGNATURES = {
     "rbnn_bank_sample_diag": (_i, [_p, _p, _p, _u64, _i64, _i64, _i, _i, _p]),
     "rbnn_bank_download": (_i, [_p, _p, _i, _i]),
     "rbnn_forward_probs_sum": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "rbnn_forward_probs_sum_keep": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "rbnn_keep_valid": (_i, [_p]),
+    "rbnn_input_grad_sum_kept": (_i, [_p, _i, _p, _p, _p, _p]),
     "rbnn_forward_logits": (_i, [_p, _p, _i, _i, _p, _p]),
     "rbnn_input_grad_sum": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _p]),
     "rbnn_fgsm_step": (_i, [_p, _p, _f, _p, _i64, _p]),

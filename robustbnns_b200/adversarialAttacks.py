@@ -83,10 +83,16 @@ def _bnn_input_grad(net, x, labels_i32, n_samples, avg_posterior):
         return eng.input_grad_sum(HEAD_LOGITS_CE, x, labels_i32, row, row + 1)
     n = 10 if n_samples is None else int(n_samples)      # BNN.forward's default n_samples=10 (model_bnn.py:198)
     rows, _ = net._rows(n, None)
-    pbar = eng.forward_probs_sum(x, rows[0], rows[1])
+    # the reference evaluates net.forward once and differentiates it (adversarialAttacks.py:74-78): the forward keeps
+    # the per-sample logits and LeakyReLU masks, the mean prediction is all-reduced, and the gradient pass reuses them
+    pbar = eng.forward_probs_sum(x, rows[0], rows[1], keep=True)
+    kept = eng.keep_valid
     rdist.allreduce_sum_(pbar)
     pbar *= 1.0 / n
-    g = eng.input_grad_sum(HEAD_GRAD_OF_MEAN, x, labels_i32, rows[0], rows[1], pbar=pbar)
+    if kept:
+        g = eng.input_grad_sum_kept(HEAD_GRAD_OF_MEAN, labels_i32, pbar=pbar).reshape(x.shape[0], -1)
+    else:                       # engines without a kept route (FP32 CUDA-core engine, fc2, conv): second forward inside
+        g = eng.input_grad_sum(HEAD_GRAD_OF_MEAN, x, labels_i32, rows[0], rows[1], pbar=pbar)
     rdist.allreduce_sum_(g)
     return g          # the 1/S factor does not change sign(g)
 

@@ -385,6 +385,7 @@ int rbnn_net_destroy(rbnn_net* n) {
   cudaDeviceSynchronize();
   cudaFree(n->bank); cudaFree(n->woutp); cudaFree(n->sigma); cudaFree(n->ws);
   tc_bank_free(n);
+  tc_keep_free(n);
   delete n;
   return 0;
 }
@@ -399,6 +400,7 @@ int rbnn_net_set_precision(rbnn_net* n, int prec) {
     RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%8==0 and H>=32 on sm_100 only");
   if (prec == RBNN_PREC_F16X3)
     RBNN_CHECK(tc_f16x3_supported(n), "F16X3 covers arch fc with hidden sizes the fused forward+head kernel supports");
+  if (n->prec != prec) n->keep.valid = 0;
   n->prec = prec;
   return 0;
 }
@@ -463,6 +465,7 @@ int rbnn_bank_reserve(rbnn_net* n, int capacity) {
 int rbnn_bank_capacity(const rbnn_net* n) { return n ? n->capacity : -1; }
 
 static void mark_dirty(rbnn_net* n, int s0, int count) {
+  if (n->keep.valid && s0 < n->keep.s1 && s0 + count > n->keep.s0) n->keep.valid = 0;   // the kept forward used these rows
   if (n->tc.dirty)
     for (int s = s0; s < s0 + count && s < n->tc.capacity; ++s) n->tc.dirty[s] = 1;
 }
@@ -521,6 +524,29 @@ int rbnn_forward_probs_sum(rbnn_net* n, const float* d_x, int B, int s0, int s1,
       RBNN_TRY(fc_probs_simt(n, d_x + (int64_t)b0 * n->D, nb, s0, s1, d_out_sum + (int64_t)b0 * n->C, nullptr, st));
   }
   return 0;
+}
+
+int rbnn_forward_probs_sum_keep(rbnn_net* n, const float* d_x, int B, int s0, int s1, float* d_out_sum, void* stream) {
+  RBNN_TRY(check_rows(n, s0, s1));
+  RBNN_CHECK(B >= 0, "negative batch");
+  n->keep.valid = 0;
+  if (B == 0 || s1 == s0 || n->prec == RBNN_PREC_FP32) return rbnn_forward_probs_sum(n, d_x, B, s0, s1, d_out_sum, stream);
+  DeviceGuard dg(n->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  RBNN_CUDA(cudaMemsetAsync(d_out_sum, 0, (size_t)B * n->C * sizeof(float), st));
+  return tc_fc_forward_keep(n, d_x, B, s0, s1, d_out_sum, st);
+}
+
+int rbnn_keep_valid(const rbnn_net* n) { return n ? n->keep.valid : 0; }
+
+int rbnn_input_grad_sum_kept(rbnn_net* n, int head, const int32_t* d_labels, const float* d_pbar, float* d_out_sum,
+                             void* stream) {
+  RBNN_CHECK(n != nullptr, "null net handle");
+  RBNN_CHECK(head == RBNN_HEAD_MEAN_OF_GRADS || head == RBNN_HEAD_GRAD_OF_MEAN || head == RBNN_HEAD_UPSTREAM,
+             "head %d has no kept route", head);
+  RBNN_CHECK(head == RBNN_HEAD_MEAN_OF_GRADS || d_pbar != nullptr, "GRAD_OF_MEAN / UPSTREAM need d_pbar");
+  DeviceGuard dg(n->device);
+  return tc_fc_grad_kept(n, head, d_labels, d_pbar, d_out_sum, (cudaStream_t)stream);
 }
 
 int rbnn_forward_logits(rbnn_net* n, const float* d_x, int B, int s, float* d_out, void* stream) {

@@ -82,6 +82,16 @@ struct TcBank {
   uint8_t* dirty = nullptr; // host flags per row (derived copies stale)
 };
 
+// Kept forward of the two-phase attack gradient (tc_gemm.cuh): per-sample logits and LeakyReLU masks of the last
+// rbnn_forward_probs_sum_keep call, valid until the bank rows it used change or the precision is switched.
+struct KeepCache {
+  float* logits = nullptr; size_t logits_cap = 0;       // [S][B][C] floats
+  uint32_t* masks = nullptr; size_t masks_cap = 0;      // tc::keep_mask_words(B, S) words
+  float* call_sc = nullptr;                             // F16X3: the call's 4 scale scalars, alive between the phases
+  unsigned* max_bits = nullptr;                         // F16X3: [0] max|x|, [1] max|d_pbar|
+  int valid = 0, B = 0, s0 = 0, s1 = 0;
+};
+
 struct rbnn_net {
   int arch = 0, in_ch = 1, in_h = 28, in_w = 28, D = 784, H = 512, C = 10;
   int device = 0;
@@ -100,6 +110,7 @@ struct rbnn_net {
   int sm_count = 148;
   int cc_major = 0;           // compute capability major of `device` (10 = Blackwell: tcgen05 engine usable)
   TcBank tc;
+  KeepCache keep;
   int tc_unfused = 0;         // 1: arch fc takes the unfused GEMM -> head route (RBNN_TC_UNFUSED=1; A/B testing)
   // optional per-kernel-class device timing (bench.py's roofline leg): event pairs on the launch stream
   int timing = 0;
@@ -179,5 +190,11 @@ int tc_fc_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_
 // out_sum != nullptr: out_sum[B,C] += sum_s softmax(logits_s); out_logits != nullptr (one row): logits of row s0
 int tc_fc_forward(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum, float* d_out_logits,
                   cudaStream_t st);
+// two-phase attack gradient: forward that keeps logits + masks (net->keep.valid tells whether it could), then the
+// gradient of a loss of the mean prediction from the kept data
+int tc_fc_forward_keep(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum, cudaStream_t st);
+int tc_fc_grad_kept(rbnn_net* net, int head, const int32_t* d_labels, const float* d_pbar, float* d_out_sum,
+                    cudaStream_t st);
+void tc_keep_free(rbnn_net* net);
 
 }  // namespace rbnn

@@ -785,7 +785,7 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
 
 // fused forward + head of one chunk (arch fc): dH (head >= 0) or logits (head < 0) straight from TMEM
 static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, const int32_t* labels, const float* pbar,
-                       int B, int z0, int Z, float* logits, cudaStream_t st) {
+                       int B, int z0, int Z, float* logits, cudaStream_t st, uint32_t* maskbuf = nullptr) {
   const int H = n->H, D = n->D;
   const bool bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const TcMat& m1 = n->tc.mat[0];
@@ -813,6 +813,7 @@ static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, con
   f.dh_hi = f16 ? (void*)w.dtop_h16 : (void*)w.dtop_hi; f.dh_lo = f16 ? (void*)w.dtop_l16 : (void*)w.dtop_lo;
   f.dh_bf = w.dtop_bf; f.logits = logits;
   f.worklist = w.worklist;
+  f.maskbuf = maskbuf;
   f.sm_count = n->sm_count;
   std::string err;
   if (head >= 0) RBNN_TRY(timing_begin(n, 1, st));
@@ -821,6 +822,10 @@ static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, con
   if (head >= 0) RBNN_TRY(timing_end(n, 1, st));
   if (head >= 0 && !bf) {
     if (tc::fused_fixup(f, st, &err)) { set_error("%s", err.c_str()); return 1; }
+    n->launches++;
+  }
+  if (head == -2 && !bf && w.worklist) {
+    if (tc::fused_keep_fixup(f, maskbuf, st, &err)) { set_error("%s", err.c_str()); return 1; }
     n->launches++;
   }
   return 0;
@@ -889,8 +894,9 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const int S = s1 - s0;
   const size_t per = fc_per_z_bytes(n, B, true);
+  const bool kept = x == nullptr;       // gradient pass of a kept forward (n->keep): no forward GEMM, dH from logits + masks
   const size_t ldx = (size_t)k_pitch(n, D);
-  const size_t x_bytes = bf ? pad256((size_t)B * ldx * 2) : (f16 ? 2 * pad256((size_t)B * ldx * 2) + 512 : 2 * pad256((size_t)B * ldx * 4));
+  const size_t x_bytes = kept ? 0 : (bf ? pad256((size_t)B * ldx * 2) : (f16 ? 2 * pad256((size_t)B * ldx * 2) + 512 : 2 * pad256((size_t)B * ldx * 4)));
   const size_t out_bytes = pad256((size_t)B * D * 4);
   // samples per chunk: as many as the budget allows; the backward reduce cuts a chunk into `slots`
   // K-concatenated ranges of ~4 samples (bounds the tensor-core accumulation chain, fills the SMs)
@@ -918,7 +924,8 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots + pad256((size_t)B * 4) + 4096));
   Arena ar(n);
   FcWs w;
-  if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * ldx);
+  if (kept) { w.call_sc = n->keep.call_sc; w.max_bits = n->keep.max_bits; }
+  else if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * ldx);
   else if (f16) {
     w.x_h16 = ar.take<__half>((size_t)B * ldx); w.x_l16 = ar.take<__half>((size_t)B * ldx);
     w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2);
@@ -926,6 +933,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
   RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
+  RBNN_CHECK(!kept || fused, "the kept forward exists for the fused route only");
   if (!fused) w.h1 = ar.take<float>(zbh);
   if (two) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
@@ -938,11 +946,25 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     if (bf) w.d1_bf = ar.take<__nv_bfloat16>(zbh);
     else { w.d1_hi = ar.take<float>(zbh); w.d1_lo = ar.take<float>(zbh); }
   }
-  if (fused && !bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc));
+  if (fused && !bf && !kept) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc));
   w.xnorm = ar.take<float>((size_t)B);
   w.partial = ar.take<float>((size_t)slots * B * D);
-  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, head == RBNN_HEAD_UPSTREAM ? pbar : nullptr, (int64_t)B * n->C, st));
-  if (fused) {       // row norms: guard band (parity modes) and the activation range of the fused head
+  if (kept) {
+    if (f16) {       // the dH range of THIS head (max|x| is still in keep.max_bits[0] from the forward phase)
+      const bool up = head == RBNN_HEAD_UPSTREAM;
+      if (up) {
+        RBNN_CUDA(cudaMemsetAsync(w.max_bits + 1, 0, sizeof(unsigned), st));
+        maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar, 0, (int64_t)B * n->C, 1, w.max_bits + 1);
+        n->launches++;
+      }
+      call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, up ? w.max_bits + 1 : nullptr, w.call_sc);
+      n->launches++;
+      RBNN_CUDA(cudaGetLastError());
+    }
+  } else {
+    RBNN_TRY(split_x(n, x, (int64_t)B * D, w, head == RBNN_HEAD_UPSTREAM ? pbar : nullptr, (int64_t)B * n->C, st));
+  }
+  if (fused && !kept) {       // row norms: guard band (parity modes) and the activation range of the fused head
     xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
     n->launches++;
     RBNN_CUDA(cudaGetLastError());
@@ -952,7 +974,24 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
     const int sl = Z == zc ? slots : std::min(slots, slots_for(Z));
-    if (fused) {
+    if (kept) {
+      tc::KeptDesc k;
+      k.mode = bf ? tc::MODE_BF16 : (f16 ? tc::MODE_F16X3 : tc::MODE_TF32X3);
+      k.B = B; k.H = H; k.C = n->C; k.Z = Z;
+      k.bank = n->bank; k.P = n->L.P; k.wo_off = n->L.wo; k.z_row0 = z0;
+      k.head = head; k.labels = labels; k.pbar = pbar;
+      k.logits = n->keep.logits + (size_t)(z0 - s0) * B * n->C;
+      k.masks = n->keep.masks + tc::keep_mask_words(B, z0 - s0);
+      k.dh_hi = f16 ? (void*)w.dtop_h16 : (void*)w.dtop_hi; k.dh_lo = f16 ? (void*)w.dtop_l16 : (void*)w.dtop_lo;
+      k.dh_bf = w.dtop_bf;
+      k.dh_scale = f16 ? w.call_sc + 2 : nullptr;
+      k.sm_count = n->sm_count;
+      std::string err;
+      RBNN_TRY(timing_begin(n, 1, st));
+      if (tc::dh_from_kept(k, st, &err)) { set_error("%s", err.c_str()); return 1; }
+      n->launches++;
+      RBNN_TRY(timing_end(n, 1, st));
+    } else if (fused) {
       RBNN_TRY(fused_chunk(n, w, head, x, labels, pbar, B, z0, Z, nullptr, st));
     } else {
       const float* top = nullptr;
@@ -1017,11 +1056,12 @@ int tc_fc_input_grad_sum(rbnn_net* n, int head, const float* x, const int32_t* l
 }
 
 static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, float* out_logits,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool keep = false) {
   const int H = n->H, D = n->D, C = n->C;
   const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const int S = s1 - s0;
-  const size_t per = fc_per_z_bytes(n, B, false);
+  // keep mode: logits go to n->keep (all samples), the arena holds the guard-band worklist of a chunk
+  const size_t per = keep ? pad256(tc::fused_worklist_slots(B, 1) * 8) + 256 : fc_per_z_bytes(n, B, false);
   const size_t ldx = (size_t)k_pitch(n, D);
   const size_t x_bytes = bf ? pad256((size_t)B * ldx * 2) : (f16 ? 2 * pad256((size_t)B * ldx * 2) + 512 : 2 * pad256((size_t)B * ldx * 4));
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
@@ -1033,17 +1073,20 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * ldx);
   else if (f16) {
     w.x_h16 = ar.take<__half>((size_t)B * ldx); w.x_l16 = ar.take<__half>((size_t)B * ldx);
-    w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2);
+    if (keep) { w.call_sc = n->keep.call_sc; w.max_bits = n->keep.max_bits; }
+    else { w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2); }
   } else { w.x_hi = ar.take<float>((size_t)B * ldx); w.x_lo = ar.take<float>((size_t)B * ldx); }
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
   RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
+  RBNN_CHECK(!keep || fused, "the kept forward exists for the fused route only");
   if (!fused) w.h1 = ar.take<float>(zbh);
   if (two) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
     w.h2 = ar.take<float>(zbh);
   }
-  w.logits = ar.take<float>((size_t)zc * B * C);
+  if (keep) { if (!bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc)); }
+  else w.logits = ar.take<float>((size_t)zc * B * C);
   w.xnorm = ar.take<float>((size_t)B);
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, st));
   if (fused) {
@@ -1053,8 +1096,11 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   }
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
-    float* lg = out_logits ? out_logits : w.logits;
-    if (fused) {
+    float* lg = keep ? n->keep.logits + (size_t)(z0 - s0) * B * C : (out_logits ? out_logits : w.logits);
+    if (keep) {
+      RBNN_TRY(fused_chunk(n, w, -2, x, nullptr, nullptr, B, z0, Z, lg, st,
+                           n->keep.masks + tc::keep_mask_words(B, z0 - s0)));
+    } else if (fused) {
       RBNN_TRY(fused_chunk(n, w, -1, x, nullptr, nullptr, B, z0, Z, lg, st));
     } else {
       const float* top = nullptr;
@@ -1077,6 +1123,46 @@ int tc_fc_forward(rbnn_net* n, const float* x, int B, int s0, int s1, float* out
                              out_logits ? out_logits + (int64_t)b0 * n->C : nullptr, st));
   }
   return 0;
+}
+
+void tc_keep_free(rbnn_net* n) {
+  cudaFree(n->keep.logits); cudaFree(n->keep.masks); cudaFree(n->keep.call_sc); cudaFree(n->keep.max_bits);
+  n->keep = KeepCache();
+}
+
+// Phase 1 of the two-phase attack gradient: out_sum[B, C] += sum_s softmax(logits_s) like tc_fc_forward, and the
+// per-sample logits + LeakyReLU masks stay in n->keep.  Falls back to the plain forward (keep.valid = 0) when the
+// engine / shape has no fused route or the batch does not fit one pass.
+int tc_fc_forward_keep(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, cudaStream_t st) {
+  RBNN_CHECK(tc_supported(n), "tcgen05 engine does not cover this network");
+  n->keep.valid = 0;
+  if (!use_fused(n) || tc_batch_rows(n, B, false) < B || tc_batch_rows(n, B, true) < B)
+    return tc_fc_forward(n, x, B, s0, s1, out_sum, nullptr, st);
+  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
+  KeepCache& k = n->keep;
+  const size_t need_l = (size_t)(s1 - s0) * B * n->C, need_m = tc::keep_mask_words(B, s1 - s0);
+  if (k.logits_cap < need_l || k.masks_cap < need_m) {
+    RBNN_CUDA(cudaDeviceSynchronize());
+    cudaFree(k.logits); cudaFree(k.masks);
+    k.logits = nullptr; k.masks = nullptr; k.logits_cap = k.masks_cap = 0;
+    RBNN_CUDA(cudaMalloc(&k.logits, need_l * sizeof(float)));
+    RBNN_CUDA(cudaMalloc(&k.masks, need_m * sizeof(uint32_t)));
+    k.logits_cap = need_l; k.masks_cap = need_m;
+  }
+  if (!k.call_sc) {
+    RBNN_CUDA(cudaMalloc(&k.call_sc, 4 * sizeof(float)));
+    RBNN_CUDA(cudaMalloc(&k.max_bits, 2 * sizeof(unsigned)));
+  }
+  RBNN_TRY(tc_forward_pass(n, x, B, s0, s1, out_sum, nullptr, st, true));
+  k.valid = 1; k.B = B; k.s0 = s0; k.s1 = s1;
+  return 0;
+}
+
+// Phase 2: out_sum[B, D] = sum_s dL/dx from the kept forward (head: GRAD_OF_MEAN / UPSTREAM with d_pbar, or MEAN_OF_GRADS)
+int tc_fc_grad_kept(rbnn_net* n, int head, const int32_t* labels, const float* pbar, float* out_sum, cudaStream_t st) {
+  RBNN_CHECK(n->keep.valid, "no kept forward: call rbnn_forward_probs_sum_keep first (and check rbnn_keep_valid)");
+  RBNN_CHECK(head != RBNN_HEAD_LOGITS_CE, "LOGITS_CE has no kept route");
+  return tc_grad_pass(n, head, nullptr, labels, n->keep.B, n->keep.s0, n->keep.s1, pbar, out_sum, st);
 }
 
 }  // namespace rbnn

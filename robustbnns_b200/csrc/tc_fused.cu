@@ -24,6 +24,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "../../include/rbnn.h"
 #include "tc_gemm.cuh"
 #include "tc_ptx.cuh"
@@ -57,6 +59,7 @@ struct FParams {
   const float* x; const float* xnorm; const float* wnorm; float eps;
   void* dh_hi; void* dh_lo; __nv_bfloat16* dh_bf; float* logits;
   const float* unscale; const float* dh_scale;      // F16X3 device scalars (see FusedDesc)
+  uint32_t* maskbuf;                                 // head == -2 (keep mode): [item][kMaskWords][512] LeakyReLU mask words
   int debug;                                         // timing experiments (RBNN_FUSED_DEBUG): 1 no dH stores, 2 no pass 2, 4 no pass-1 math
   unsigned long long* worklist;
 };
@@ -116,13 +119,8 @@ __device__ __forceinline__ void quad_transpose(uint32_t (&a)[4], int q) {
   t1 = __shfl_xor_sync(0xffffffffu, t1, 2);
   if (up) { a[0] = t0; a[1] = t1; } else { a[2] = t0; a[3] = t1; }
 }
-__device__ __forceinline__ void st_cs_u4(void* ptr, const uint32_t (&a)[4], int flavor = 0) {
-  if (flavor == 0)
-    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
-  else if (flavor == 1)
-    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
-  else
-    asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
+__device__ __forceinline__ void st_cs_u4(void* ptr, const uint32_t (&a)[4]) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]) : "memory");
 }
 
 // softmax over the classes of one row spread over the 4 lanes that share it (4 class slots per lane)
@@ -157,6 +155,117 @@ __device__ __forceinline__ void softmax_r(float (&v)[C_MAX], int C) {
 #pragma unroll
   for (int c = 0; c < C_MAX; ++c)
     if (c < C) v[c] *= inv;
+}
+
+
+// Loss head on one input row whose class values are spread over the 4 lanes of a fragment row (slot i of this lane
+// holds class cls[i]): l = logits (bias included) -> l = dL/dlogits.  Same algebra as head.cu::dlogits_kernel.
+__device__ __forceinline__ void head_quad(int head, float (&l)[4], const bool (&valid)[4], const int (&cls)[4], int y,
+                                          const float* __restrict__ pbar_row) {
+  float g[4];
+  softmax_quad(l, valid);
+  if (head == RBNN_HEAD_LOGITS_CE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) l[i] = valid[i] ? l[i] - (cls[i] == y ? 1.f : 0.f) : 0.f;
+    return;
+  }
+  if (head == RBNN_HEAD_MEAN_OF_GRADS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = l[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = (valid[i] && pbar_row) ? __ldg(pbar_row + cls[i]) : 0.f;
+  }
+  if (head != RBNN_HEAD_UPSTREAM) {
+    softmax_quad(g, valid);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] -= (cls[i] == y ? 1.f : 0.f);
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (valid[i]) dot = fmaf(l[i], g[i], dot);
+  dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+  dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) l[i] = valid[i] ? l[i] * (g[i] - dot) : 0.f;
+}
+
+// A fragments of pass 2: dlogits of rows (g, g+8) x classes, scaled per row into the fp16 range and split;
+// mul[r] = dh_scale / (row scale * s_wo) turns the accumulator of row r into the stored dH
+__device__ __forceinline__ void dlogits_frags(const float (&dl)[2][4], float s_wo, float dh_scale, uint32_t (&Dh)[4],
+                                              uint32_t (&Dl)[4], float (&mul)[2]) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float mx = fmaxf(fmaxf(fabsf(dl[r][0]), fabsf(dl[r][1])), fmaxf(fabsf(dl[r][2]), fabsf(dl[r][3])));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float s_d = pow2_scale(mx);
+    split_pair(dl[r][0] * s_d, dl[r][1] * s_d, Dh[r], Dl[r]);            // classes 2q, 2q+1
+    split_pair(dl[r][2] * s_d, dl[r][3] * s_d, Dh[2 + r], Dl[2 + r]);    // classes 8+2q, 9+2q
+    mul[r] = dh_scale / (s_d * s_wo);
+  }
+}
+
+// Pass 2 on one 16 x 32 block (rows g, g+8 of this lane; hidden columns j0 .. j0+31): dH = (dlogits . Wo) * leaky'(H),
+// written as fp16 hi/lo (F16X3), tf32 hi/lo (TF32X3) or bf16.  `bits`: the block's mask word, bit (r*8 + k*2 + e).
+template <int MODE>
+__device__ __forceinline__ void pass2_block(const uint32_t (&Dh)[4], const uint32_t (&Dl)[4], const float (&mul)[2],
+                                            uint32_t bits, uint32_t wo_hi_a, uint32_t wo_lo_a, uint32_t off2, int j0, int q,
+                                            const bool (&rok)[2], const long long (&orow)[2], void* dh_hi, void* dh_lo,
+                                            __nv_bfloat16* dh_bf, bool no_store) {
+  constexpr bool BF16 = MODE == MODE_BF16;
+  uint32_t whi[2][4], wlo[2][4];                        // [row][column group]: packed 16-bit pairs (hi, lo / bf16)
+#pragma unroll
+  for (int gp = 0; gp < 2; ++gp) {                      // 16 columns: two 8-column groups
+    uint32_t bh[4], bl[4];
+    ldsm_x4_trans(wo_hi_a + off2 + (uint32_t)(j0 + 16 * gp) * 2u, bh);
+    ldsm_x4_trans(wo_lo_a + off2 + (uint32_t)(j0 + 16 * gp) * 2u, bl);
+#pragma unroll
+    for (int gs = 0; gs < 2; ++gs) {
+      const int k = 2 * gp + gs;
+      float d[4] = {0.f, 0.f, 0.f, 0.f};                // row 0: (j, j+1), row 1: (j, j+1)
+      hmma_16816(d, Dl, bh[2 * gs], bh[2 * gs + 1]);
+      hmma_16816(d, Dh, bl[2 * gs], bl[2 * gs + 1]);
+      hmma_16816(d, Dh, bh[2 * gs], bh[2 * gs + 1]);
+      const int j = j0 + 8 * k + 2 * q;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float d0 = d[2 * r] * mul[r], d1 = d[2 * r + 1] * mul[r];
+        if (!((bits >> (r * 8 + k * 2)) & 1u)) d0 *= kSlopeF;
+        if (!((bits >> (r * 8 + k * 2 + 1)) & 1u)) d1 *= kSlopeF;
+        if (BF16) {
+          const __nv_bfloat162 a = __floats2bfloat162_rn(d0, d1);
+          whi[r][k] = *reinterpret_cast<const uint32_t*>(&a);
+        } else if (MODE == MODE_F16X3) {
+          split_pair(d0, d1, whi[r][k], wlo[r][k]);
+        } else if (rok[r] && !no_store) {
+          float2 hi2, lo2;
+          hi2.x = to_tf32_rn(d0); hi2.y = to_tf32_rn(d1);
+          lo2.x = d0 - hi2.x; lo2.y = d1 - hi2.y;
+          __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(dh_hi) + orow[r] + j), hi2);   // streaming: do not displace X / W1 in L2
+          __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(dh_lo) + orow[r] + j), lo2);
+        }
+      }
+    }
+  }
+  if (MODE != MODE_TF32X3) {
+    // 16-bit outputs: gather 8 consecutive columns per lane (4 x 4 word transpose over the lanes of a row), then
+    // one 16-byte streaming store per row and array -- whole 32-byte sectors instead of 4-byte pieces
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      quad_transpose(whi[r], q);
+      if (!BF16) quad_transpose(wlo[r], q);
+      if (!rok[r] || no_store) continue;
+      const long long o = orow[r] + j0 + 8 * q;
+      if (BF16) {
+        st_cs_u4(dh_bf + o, whi[r]);
+      } else {
+        st_cs_u4(reinterpret_cast<__half*>(dh_hi) + o, whi[r]);
+        st_cs_u4(reinterpret_cast<__half*>(dh_lo) + o, wlo[r]);
+      }
+    }
+  }
 }
 
 template <int MODE, int KBB>
@@ -520,36 +629,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                 if (valid[i]) out[cls[i]] = dl[r][i];
             }
           } else {
-            // loss head (same algebra as head.cu::dlogits_kernel; the class sums run over the 4 lanes that share a row)
-            const int y = rok[r] ? p.labels[brow[r]] : 0;
-            float g[4];
-            softmax_quad(dl[r], valid);
-            if (p.head == RBNN_HEAD_LOGITS_CE) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dl[r][i] = valid[i] ? dl[r][i] - (cls[i] == y ? 1.f : 0.f) : 0.f;
-            } else {
-              if (p.head == RBNN_HEAD_MEAN_OF_GRADS) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) g[i] = dl[r][i];
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  g[i] = (valid[i] && rok[r]) ? __ldg(p.pbar + (long long)brow[r] * C + cls[i]) : 0.f;
-              }
-              if (p.head != RBNN_HEAD_UPSTREAM) {
-                softmax_quad(g, valid);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) g[i] -= (cls[i] == y ? 1.f : 0.f);
-              }
-              float dot = 0.f;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (valid[i]) dot = fmaf(dl[r][i], g[i], dot);
-              dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-              dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dl[r][i] = valid[i] ? dl[r][i] * (g[i] - dot) : 0.f;
-            }
+            head_quad(p.head, dl[r], valid, cls, rok[r] ? p.labels[brow[r]] : 0,
+                      (rok[r] && p.pbar) ? p.pbar + (long long)brow[r] * C : nullptr);
 #pragma unroll
             for (int i = 0; i < 4; ++i) xchg[rit * 16 + cls[i]] = dl[r][i];
           }
@@ -560,6 +641,12 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       if (wl) {
         const uint32_t used = min(*wl_count, (uint32_t)kWorkPerItem);
         for (uint32_t i = used + et; i < (uint32_t)kWorkPerItem; i += kEpiWarps * 32) wl[i] = kSentinel;
+      }
+      if (p.head == -2 && active) {            // keep mode: the LeakyReLU masks of this item for the gradient pass
+        uint32_t* mb = p.maskbuf + (long long)item * (kMaskWords * kEpiWarps * 32);
+#pragma unroll
+        for (int i = 0; i < kMaskWords; ++i)
+          if (i < p.n_tiles * nblocks) mb[i * (kEpiWarps * 32) + et] = mbits[i];
       }
       if (p.head < 0) continue;
       if (half == 1) {
@@ -572,21 +659,12 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       { const long long t = clock64(); c_head += t - t_mark; t_mark = t; }
       // ---------------- pass 2: dH = (dlogits . Wo) * leaky'(H) for this thread's 2 rows x column pairs ----------------
       if (active && !(p.debug & 2)) {
-        // A fragments: dlogits of rows (g, g+8) x classes, scaled per row into the fp16 range and split
         uint32_t Dh[4], Dl[4];
         float mul[2];
         long long orow[2];
+        dlogits_frags(dl, s_wo, dh_scale, Dh, Dl, mul);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          float mx = fmaxf(fmaxf(fabsf(dl[r][0]), fabsf(dl[r][1])), fmaxf(fabsf(dl[r][2]), fabsf(dl[r][3])));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          const float s_d = pow2_scale(mx);
-          split_pair(dl[r][0] * s_d, dl[r][1] * s_d, Dh[r], Dl[r]);            // classes 2q, 2q+1
-          split_pair(dl[r][2] * s_d, dl[r][3] * s_d, Dh[2 + r], Dl[2 + r]);    // classes 8+2q, 9+2q
-          mul[r] = dh_scale / (s_d * s_wo);
-          orow[r] = ((long long)z * p.B + brow[r]) * H;
-        }
+        for (int r = 0; r < 2; ++r) orow[r] = ((long long)z * p.B + brow[r]) * H;
         for (int n = 0; n < p.n_tiles; ++n) {
 #pragma unroll 1
           for (int cc = 0; cc < nblocks; ++cc) {
@@ -596,57 +674,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < kMaskWords; ++i)
               if (i == word) bits = mbits[i];
-            uint32_t whi[2][4], wlo[2][4];                        // [row][column group]: packed 16-bit pairs (hi, lo / bf16)
-#pragma unroll
-            for (int gp = 0; gp < 2; ++gp) {                      // 16 columns: two 8-column groups
-              uint32_t bh[4], bl[4];
-              ldsm_x4_trans(wo_hi_a + off2 + (uint32_t)(j0 + 16 * gp) * 2u, bh);
-              ldsm_x4_trans(wo_lo_a + off2 + (uint32_t)(j0 + 16 * gp) * 2u, bl);
-#pragma unroll
-              for (int gs = 0; gs < 2; ++gs) {
-                const int k = 2 * gp + gs;
-                float d[4] = {0.f, 0.f, 0.f, 0.f};                // row 0: (j, j+1), row 1: (j, j+1)
-                hmma_16816(d, Dl, bh[2 * gs], bh[2 * gs + 1]);
-                hmma_16816(d, Dh, bl[2 * gs], bl[2 * gs + 1]);
-                hmma_16816(d, Dh, bh[2 * gs], bh[2 * gs + 1]);
-                const int j = j0 + 8 * k + 2 * q;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                  float d0 = d[2 * r] * mul[r], d1 = d[2 * r + 1] * mul[r];
-                  if (!((bits >> (r * 8 + k * 2)) & 1u)) d0 *= kSlopeF;
-                  if (!((bits >> (r * 8 + k * 2 + 1)) & 1u)) d1 *= kSlopeF;
-                  if (BF16) {
-                    const __nv_bfloat162 a = __floats2bfloat162_rn(d0, d1);
-                    whi[r][k] = *reinterpret_cast<const uint32_t*>(&a);
-                  } else if (MODE == MODE_F16X3) {
-                    split_pair(d0, d1, whi[r][k], wlo[r][k]);
-                  } else if (rok[r] && !(p.debug & 1)) {
-                    float2 hi2, lo2;
-                    hi2.x = to_tf32_rn(d0); hi2.y = to_tf32_rn(d1);
-                    lo2.x = d0 - hi2.x; lo2.y = d1 - hi2.y;
-                    __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_hi) + orow[r] + j), hi2);   // streaming: do not displace X / W1 in L2
-                    __stcs(reinterpret_cast<float2*>(reinterpret_cast<float*>(p.dh_lo) + orow[r] + j), lo2);
-                  }
-                }
-              }
-            }
-            if (MODE != MODE_TF32X3) {
-              // 16-bit outputs: gather 8 consecutive columns per lane (4 x 4 word transpose over the lanes of a row), then
-              // one 16-byte streaming store per row and array -- whole 32-byte sectors instead of 4-byte pieces
-#pragma unroll
-              for (int r = 0; r < 2; ++r) {
-                quad_transpose(whi[r], q);
-                if (!BF16) quad_transpose(wlo[r], q);
-                if (!rok[r] || (p.debug & 1)) continue;
-                const long long o = orow[r] + j0 + 8 * q;
-                if (BF16) {
-                  st_cs_u4(p.dh_bf + o, whi[r]);
-                } else {
-                  st_cs_u4(reinterpret_cast<__half*>(p.dh_hi) + o, whi[r], (p.debug >> 4) & 3);
-                  st_cs_u4(reinterpret_cast<__half*>(p.dh_lo) + o, wlo[r], (p.debug >> 4) & 3);
-                }
-              }
-            }
+            pass2_block<MODE>(Dh, Dl, mul, bits, wo_hi_a, wo_lo_a, off2, j0, q, rok, orow, p.dh_hi, p.dh_lo, p.dh_bf,
+                              (p.debug & 1) != 0);
           }
         }
       }
@@ -715,6 +744,148 @@ fixup_kernel(const unsigned long long* __restrict__ wl, long long nslots, const 
   }
 }
 
+
+// Keep mode (head == -2) fix-up: the forward pass stored the LeakyReLU masks instead of dH; where the sign the epilogue
+// assumed for a guard-band unit was wrong, flip its mask bit.  Same exact re-evaluation as fixup_kernel.
+__global__ void __launch_bounds__(256)
+fixup_mask_kernel(const unsigned long long* __restrict__ wl, long long nslots, const float* __restrict__ x,
+                  const float* __restrict__ bank, long long P, long long b1_off, int z_row0, int B, int D, int BN,
+                  int cols_half, uint32_t* __restrict__ masks) {
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (B + kBM - 1) / kBM, nblocks = cols_half / 32;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long base = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nslots;
+       base += nwarps * 32) {
+    const unsigned long long mine = base + lane < nslots ? wl[base + lane] : kSentinel;
+    unsigned valid = __ballot_sync(0xffffffffu, mine != kSentinel);
+    while (valid) {
+      const int src = __ffs(valid) - 1;
+      valid &= valid - 1;
+      const unsigned long long e = __shfl_sync(0xffffffffu, mine, src);
+      const int z = (int)(e >> 44), b = (int)((e >> 20) & 0xFFFFFF), j = (int)((e >> 4) & 0xFFFF);
+      const bool assumed_pos = (e & 1ull) != 0;
+      const float* __restrict__ xr = x + (long long)b * D;
+      const float* __restrict__ wrow = bank + (long long)(z_row0 + z) * P;
+      const float* __restrict__ w = wrow + (long long)j * D;
+      double s = 0.0;
+      for (int d = lane; d < D; d += 32) s = fma((double)__ldg(xr + d), (double)__ldg(w + d), s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const bool pos = (float)(s + (double)__ldg(wrow + b1_off + j)) > 0.f;
+      if (pos != assumed_pos && lane == 0) {
+        // (b, j) -> (item, mask word, epilogue thread, bit) of the fused kernel's fragment layout
+        const int item = z * m_tiles + b / kBM, rt = b % kBM;
+        const int quad = rt >> 5, lhalf = (rt >> 4) & 1, r = (rt >> 3) & 1, rsub = rt & 7;
+        const int n = j / BN, jn = j % BN, half = jn / cols_half, jc = jn % cols_half;
+        const int cc = jc >> 5, k = (jc >> 3) & 3, qq = (jc >> 1) & 3, ee = jc & 1;
+        const int ew = half * 8 + lhalf * 4 + ((quad + 2) & 3);
+        const int et = ew * 32 + rsub * 4 + qq;
+        atomicXor(masks + ((long long)item * kMaskWords + (n * nblocks + cc)) * (kEpiWarps * 32) + et,
+                  1u << (r * 8 + k * 2 + ee));
+      }
+    }
+  }
+}
+
+// Gradient pass of a kept forward (attacks: adversarialAttacks.py:74-78 evaluates BNN.forward once and differentiates it):
+// dH of every (sample, input) from the stored logits and LeakyReLU masks -- the loss head and pass 2 of the fused
+// kernel without its GEMM.  One CTA of 16 warps per work item at a time, same thread <-> (row, column) mapping as the
+// fused epilogue (the mask words are stored per epilogue thread).
+template <int MODE>
+__global__ void __launch_bounds__(kEpiWarps * 32, 2)
+dh_from_kept_kernel(int B, int H, int C, int num_items, int m_tiles, int head, const float* __restrict__ bank, long long P,
+                    long long wo_off, int z_row0, const int32_t* __restrict__ labels, const float* __restrict__ pbar,
+                    const float* __restrict__ logits, const uint32_t* __restrict__ masks, void* dh_hi, void* dh_lo,
+                    __nv_bfloat16* dh_bf, const float* __restrict__ dh_scale_p) {
+  __shared__ __align__(16) __half wo16[2 * kWoHalfs];
+  __shared__ float red[kEpiWarps];
+  __half* wo_hi = wo16;
+  __half* wo_lo = wo16 + kWoHalfs;
+  const int et = threadIdx.x, ew = et >> 5, lane = et & 31;
+  const int quad = (ew + 2) & 3, lhalf = (ew >> 2) & 1, half = ew >> 3;
+  const int BN = H <= 256 ? H : 256, n_tiles = H <= 256 ? 1 : H / 256;
+  const int cols_half = BN >= 64 ? BN / 2 : BN;
+  const bool active = BN >= 64 || half == 0;
+  const int nblocks = cols_half / 32;
+  const int q = lane & 3, rsub = lane >> 2;
+  const int ldw = H + 8;
+  const float dh_scale = (MODE == MODE_F16X3) ? __ldg(dh_scale_p) : 1.f;
+  const int lm = lane >> 3, lr = lane & 7;
+  const int c2 = min((lm & 1) * 8 + lr, C);
+  const uint32_t off2 = (uint32_t)(c2 * ldw + (lm >> 1) * 8) * 2u;
+  const uint32_t wo_hi_a = smem_u32(wo_hi), wo_lo_a = smem_u32(wo_lo);
+  const int cls[4] = {2 * q, 2 * q + 1, 8 + 2 * q, 9 + 2 * q};
+  for (int i = et; i < ldw; i += kEpiWarps * 32) {
+    wo_hi[C * ldw + i] = __float2half_rn(0.f);
+    wo_lo[C * ldw + i] = __float2half_rn(0.f);
+  }
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const int z = item / m_tiles, m_idx = item % m_tiles;
+    const float* __restrict__ wrow = bank + (long long)(z_row0 + z) * P;
+    float wv[kWoPerThread];
+    float wmax = 0.f;
+#pragma unroll
+    for (int u = 0; u < kWoPerThread; ++u) {
+      const int i = et + u * kEpiWarps * 32;
+      wv[u] = i < C * H ? __ldg(wrow + wo_off + i) : 0.f;
+      wmax = fmaxf(wmax, fabsf(wv[u]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    __syncthreads();                          // everyone is done with the previous item's Wo16
+    if (lane == 0) red[ew] = wmax;
+    __syncthreads();
+    wmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < kEpiWarps; ++i) wmax = fmaxf(wmax, red[i]);
+    const float s_wo = pow2_scale(wmax);
+#pragma unroll
+    for (int u = 0; u < kWoPerThread; ++u) {
+      const int i = et + u * kEpiWarps * 32;
+      if (i < C * H) {
+        const int c = i / H, j = i - c * H;
+        const float v = wv[u] * s_wo;
+        const __half h = __float2half_rn(v);
+        wo_hi[c * ldw + j] = h;
+        wo_lo[c * ldw + j] = __float2half_rn(v - __half2float(h));
+      }
+    }
+    __syncthreads();
+    int brow[2];
+    bool rok[2];
+    float dl[2][4];
+    long long orow[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      brow[r] = m_idx * kBM + quad * 32 + lhalf * 16 + 8 * r + rsub;
+      rok[r] = brow[r] < B;
+      bool valid[4];
+      const float* __restrict__ lrow = logits + ((long long)z * B + brow[r]) * C;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        valid[i] = cls[i] < C;
+        dl[r][i] = (valid[i] && rok[r]) ? __ldg(lrow + cls[i]) : 0.f;
+      }
+      head_quad(head, dl[r], valid, cls, rok[r] ? labels[brow[r]] : 0,
+                (rok[r] && pbar) ? pbar + (long long)brow[r] * C : nullptr);
+      orow[r] = ((long long)z * B + brow[r]) * H;
+    }
+    if (!active) continue;
+    uint32_t Dh[4], Dl[4];
+    float mul[2];
+    dlogits_frags(dl, s_wo, dh_scale, Dh, Dl, mul);
+    const uint32_t* __restrict__ mb = masks + (long long)item * (kMaskWords * kEpiWarps * 32) + et;
+    for (int n = 0; n < n_tiles; ++n) {
+#pragma unroll 1
+      for (int cc = 0; cc < nblocks; ++cc) {
+        const int j0 = n * BN + half * cols_half + cc * 32;
+        const uint32_t bits = __ldg(mb + (n * nblocks + cc) * (kEpiWarps * 32));
+        pass2_block<MODE>(Dh, Dl, mul, bits, wo_hi_a, wo_lo_a, off2, j0, q, rok, orow, dh_hi, dh_lo, dh_bf, false);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 bool fused_supported(int H, int C) {
@@ -763,7 +934,8 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   p.bank = d.bank; p.P = d.P; p.b1_off = d.b1_off; p.wo_off = d.wo_off; p.bo_off = d.bo_off; p.z_row0 = d.z_row0;
   p.labels = d.labels; p.pbar = d.pbar;
   p.x = d.x; p.xnorm = d.xnorm; p.wnorm = d.wnorm;
-  p.eps = (bf16 || !d.worklist || d.head < 0) ? 0.f : d.eps;
+  p.eps = (bf16 || !d.worklist || d.head == -1) ? 0.f : d.eps;      // keep mode (-2) needs exact masks too
+  p.maskbuf = d.maskbuf;
   p.dh_hi = d.dh_hi; p.dh_lo = d.dh_lo; p.dh_bf = reinterpret_cast<__nv_bfloat16*>(d.dh_bf); p.logits = d.logits;
   p.worklist = p.eps > 0.f ? d.worklist : nullptr;
   p.unscale = d.unscale; p.dh_scale = d.dh_scale;
@@ -773,6 +945,7 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   }
   if (d.head >= 0 && (bf16 ? !d.dh_bf : (!d.dh_hi || !d.dh_lo))) { *err = "fused_forward_head: missing dH output"; return 1; }
   if (d.head < 0 && !d.logits) { *err = "fused_forward_head: missing logits output"; return 1; }
+  if (d.head == -2 && !d.maskbuf) { *err = "fused_forward_head: keep mode without a mask buffer"; return 1; }
   if (d.head >= 0 && d.head != RBNN_HEAD_MEAN_OF_GRADS && d.head != RBNN_HEAD_LOGITS_CE && !d.pbar) {
     *err = "fused_forward_head: this head needs pbar";
     return 1;
@@ -810,6 +983,47 @@ int fused_fixup(const FusedDesc& d, cudaStream_t st, std::string* err) {
     if (err) *err = std::string("fused_fixup launch: ") + cudaGetErrorString(e);
     return 1;
   }
+  return 0;
+}
+
+size_t keep_mask_words(int B, int Z) { return (size_t)Z * ((B + kBM - 1) / kBM) * kMaskWords * kEpiWarps * 32; }
+
+int fused_keep_fixup(const FusedDesc& d, uint32_t* masks, cudaStream_t st, std::string* err) {
+  if (d.mode == MODE_BF16 || !d.worklist || d.eps <= 0.f || d.B <= 0 || d.Z <= 0) return 0;
+  const long long nslots = (long long)fused_worklist_slots(d.B, d.Z);
+  const long long warps = (nslots + 31) / 32;
+  const unsigned blocks = (unsigned)std::min<long long>((warps + 7) / 8, (long long)d.sm_count * 8);
+  const int BN = d.H <= 256 ? d.H : 256;
+  fixup_mask_kernel<<<blocks, 256, 0, st>>>(d.worklist, nslots, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, BN,
+                                            BN >= 64 ? BN / 2 : BN, masks);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("fused_keep_fixup launch: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  return 0;
+}
+
+int dh_from_kept(const KeptDesc& d, cudaStream_t st, std::string* err) {
+  std::string local;
+  if (!err) err = &local;
+  if (d.B <= 0 || d.Z <= 0) return 0;
+  if (!fused_supported(d.H, d.C)) { *err = "dh_from_kept: unsupported hidden / class size"; return 1; }
+  if (d.head < 0 || !d.logits || !d.masks) { *err = "dh_from_kept: missing kept forward"; return 1; }
+  if (d.mode == MODE_F16X3 && !d.dh_scale) { *err = "dh_from_kept: F16X3 needs the dH scale"; return 1; }
+  const int m_tiles = (d.B + kBM - 1) / kBM, items = m_tiles * d.Z;
+  const int grid = std::min(items, d.sm_count * 2);
+  __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(d.dh_bf);
+#define RBNN_KEPT_LAUNCH(M)                                                                                          \
+  dh_from_kept_kernel<M><<<grid, kEpiWarps * 32, 0, st>>>(d.B, d.H, d.C, items, m_tiles, d.head, d.bank, d.P, d.wo_off, \
+                                                          d.z_row0, d.labels, d.pbar, d.logits, d.masks, d.dh_hi, d.dh_lo, \
+                                                          bf, d.dh_scale)
+  if (d.mode == MODE_F16X3) RBNN_KEPT_LAUNCH(MODE_F16X3);
+  else if (d.mode == MODE_BF16) RBNN_KEPT_LAUNCH(MODE_BF16);
+  else RBNN_KEPT_LAUNCH(MODE_TF32X3);
+#undef RBNN_KEPT_LAUNCH
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("dh_from_kept launch: ") + cudaGetErrorString(e); return 1; }
   return 0;
 }
 

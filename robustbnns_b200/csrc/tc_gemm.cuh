@@ -86,7 +86,8 @@ struct FusedDesc {
   int mode = MODE_TF32X3;
   int B = 0, D = 0, H = 0, C = 0, Z = 0;
   Operand X, W1;                  // X: [B, D] (zstride 0); W1: [Z][H][D]
-  int head = -1;                  // RBNN_HEAD_* ; -1 = write logits only
+  int head = -1;                  // RBNN_HEAD_* ; -1 = write logits only; -2 = keep mode: logits + LeakyReLU masks
+  uint32_t* maskbuf = nullptr;    // keep mode: keep_mask_words(B, Z) words
   const float* bank = nullptr;    // bank row of sample z: bank + (z_row0 + z) * P
   int64_t P = 0, b1_off = 0, wo_off = 0, bo_off = 0;
   int z_row0 = 0;
@@ -109,6 +110,24 @@ bool fused_supported(int H, int C);
 size_t fused_worklist_slots(int B, int Z);
 int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err);
 int fused_fixup(const FusedDesc& d, cudaStream_t st, std::string* err);
+
+// Two-phase evaluation for the attacks (gradient of a loss of the MEAN prediction): the forward pass runs once in keep
+// mode (per-sample logits + LeakyReLU masks stay in HBM, ~104 B per unit), the mean is all-reduced, and the gradient
+// pass rebuilds dH from the kept data with the head and pass 2 of the fused kernel -- no second forward GEMM.
+size_t keep_mask_words(int B, int Z);
+int fused_keep_fixup(const FusedDesc& d, uint32_t* masks, cudaStream_t st, std::string* err);   // flips wrongly assumed mask bits
+struct KeptDesc {
+  int mode = MODE_TF32X3;
+  int B = 0, H = 0, C = 0, Z = 0;
+  const float* bank = nullptr; int64_t P = 0, wo_off = 0; int z_row0 = 0;
+  int head = 0; const int32_t* labels = nullptr; const float* pbar = nullptr;
+  const float* logits = nullptr;      // [Z][B][C]
+  const uint32_t* masks = nullptr;    // keep_mask_words(B, Z)
+  void* dh_hi = nullptr; void* dh_lo = nullptr; void* dh_bf = nullptr;   // [Z][B][H]
+  const float* dh_scale = nullptr;    // F16X3
+  int sm_count = 148;
+};
+int dh_from_kept(const KeptDesc& d, cudaStream_t st, std::string* err);
 
 // Dynamic shared memory the kernel asks for (same for both modes).
 size_t smem_bytes();

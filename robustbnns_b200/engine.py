@@ -123,11 +123,29 @@ class Net(object):
             raise ValueError("inputs of shape %s do not flatten to [B, %d]" % (tuple(x.shape), self.D))
         return x, B
 
-    def forward_probs_sum(self, x, s0, s1):
+    def forward_probs_sum(self, x, s0, s1, keep=False):
+        """sum_s softmax(f_s(x)) over bank rows [s0, s1).  keep=True asks the engine to retain the per-sample logits
+        and LeakyReLU masks for `input_grad_sum_kept` (two-phase attack gradient); `keep_valid` tells whether it did."""
         x, B = self._x(x)
         out = torch.empty((B, self.n_classes), dtype=torch.float32, device=self.device)
-        check(lib().rbnn_forward_probs_sum(self._h, C.c_void_p(x.data_ptr()), B, int(s0), int(s1),
-                                           C.c_void_p(out.data_ptr()), _stream()))
+        fn = lib().rbnn_forward_probs_sum_keep if keep else lib().rbnn_forward_probs_sum
+        if keep:
+            self.keep_serial = getattr(self, "keep_serial", 0) + 1      # identifies WHICH forward is kept
+        check(fn(self._h, C.c_void_p(x.data_ptr()), B, int(s0), int(s1), C.c_void_p(out.data_ptr()), _stream()))
+        return out
+
+    @property
+    def keep_valid(self):
+        return bool(lib().rbnn_keep_valid(self._h))
+
+    def input_grad_sum_kept(self, head, labels, pbar=None):
+        """Gradient pass of the last kept forward: [B, D] sum over its bank rows, no second forward GEMM."""
+        labels = self._dev(labels, torch.int32).reshape(-1)
+        out = torch.empty((labels.numel(), self.D), dtype=torch.float32, device=self.device)
+        pb = self._dev(pbar) if pbar is not None else None
+        check(lib().rbnn_input_grad_sum_kept(self._h, int(head), C.c_void_p(labels.data_ptr()),
+                                             C.c_void_p(pb.data_ptr() if pb is not None else 0),
+                                             C.c_void_p(out.data_ptr()), _stream()))
         return out
 
     def forward_logits(self, x, s):

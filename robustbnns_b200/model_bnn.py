@@ -76,7 +76,11 @@ class _ForwardFn(torch.autograd.Function):
     def forward(ctx, inputs, bnn, rows, n_total, generation):
         ctx.bnn, ctx.rows, ctx.n_total, ctx.generation = bnn, rows, n_total, generation
         ctx.save_for_backward(inputs)
-        return bnn._probs_mean(inputs.detach(), rows, n_total)
+        eng = bnn.engine()
+        out = eng.forward_probs_sum(inputs.detach(), rows[0], rows[1], keep=True)     # logits + masks stay for backward()
+        ctx.keep_serial = eng.keep_serial if eng.keep_valid else None
+        rdist.allreduce_sum_(out)
+        return out / float(n_total)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -87,8 +91,11 @@ class _ForwardFn(torch.autograd.Function):
                                "call before backward(); call backward() first or pin a sample bank")
         eng = bnn.engine()
         labels = torch.zeros((inputs.shape[0],), dtype=torch.int32, device=eng.device)
-        g = eng.input_grad_sum(HEAD_UPSTREAM, inputs.detach(), labels, ctx.rows[0], ctx.rows[1],
-                               pbar=grad_out.contiguous())
+        if ctx.keep_serial is not None and eng.keep_valid and eng.keep_serial == ctx.keep_serial:
+            g = eng.input_grad_sum_kept(HEAD_UPSTREAM, labels, pbar=grad_out.contiguous())   # no second forward pass
+        else:
+            g = eng.input_grad_sum(HEAD_UPSTREAM, inputs.detach(), labels, ctx.rows[0], ctx.rows[1],
+                                   pbar=grad_out.contiguous())
         rdist.allreduce_sum_(g)
         g = (g / float(ctx.n_total)).reshape(inputs.shape)
         return g, None, None, None, None

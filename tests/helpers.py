@@ -77,7 +77,9 @@ class OracleEngine(object):
     def _x(self, x):
         return torch.as_tensor(x, dtype=torch.float32).reshape(-1, *self.input_shape)
 
-    def forward_probs_sum(self, x, s0, s1):
+    keep_valid, keep_serial = False, 0   # no kept-forward route: the drop-in takes the two-pass path
+
+    def forward_probs_sum(self, x, s0, s1, keep=False):
         x = self._x(x)
         if s1 == s0:
             return torch.zeros((x.shape[0], self.n_classes))

@@ -168,6 +168,8 @@ def test_engine_vs_oracle(arch, shape, hidden, C, B, S, ds):
     ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
     ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
     assert rel_err(ga, ra) < REL
+    # the FP32 CUDA-core engine has no kept-forward route: keep=True is a plain forward
+    assert rel_err(eng.forward_probs_sum(x, 0, S, keep=True).cpu() / S, ref_p) < REL and not eng.keep_valid
     gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, S - 1, S).cpu().reshape(x.shape)
     rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
     assert rel_err(gl, rl) < REL
@@ -224,6 +226,17 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
     ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
     e_att = rel_err(ga, ra)
+    # two-phase form (what the attacks use): forward that keeps logits + masks, then the gradient from the kept data
+    pk = eng.forward_probs_sum(x, 0, S, keep=True)
+    assert eng.keep_valid == (arch == "fc" and route == "fused")
+    if eng.keep_valid:
+        assert rel_err(pk, pbar * S) < 1e-6
+        gk = eng.input_grad_sum_kept(_lib.HEAD_GRAD_OF_MEAN, labels, pbar=pk / S).cpu().reshape(x.shape) / S
+        assert rel_err(gk, ga) < (1e-6 if prec != "bf16" else 1e-2) and rel_err(gk, ra) < tol
+        gm = eng.input_grad_sum_kept(_lib.HEAD_MEAN_OF_GRADS, labels).cpu().reshape(x.shape) / S
+        assert rel_err(gm, g) < (1e-6 if prec != "bf16" else 1e-2)
+        eng.upload(bank[0:1], 0)                   # touching a kept row invalidates the kept forward
+        assert not eng.keep_valid
     gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, S - 1, S).cpu().reshape(x.shape)
     rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
     e_log = rel_err(gl, rl)
@@ -294,16 +307,25 @@ def test_tcgen05_engine_on_saturated_softmax(prec, gain):
     eng.close()
 
 
-def test_autograd_through_forward_matches_attack_gradient():
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "tf32x3"])
+def test_autograd_through_forward_matches_attack_gradient(prec):
+    """torch autograd through BNN.forward (UPSTREAM head).  On the tensor-core engines backward() reuses the logits and
+    masks the forward kept; a second forward in between makes it fall back to the recomputing route."""
     from robustbnns_b200.model_bnn import BNN
     net, layout, loc, rho, bank, x, labels = _problem("fc", (1, 28, 28), 64, 10, 12, 4)
     bnn = BNN("mnist", 64, "leaky", "fc", "hmc", None, None, 4, 5, (1, 28, 28), 10)
     bnn.set_posterior_samples(bank)
-    xg = x.cuda().requires_grad_(True)
-    loss = torch.nn.CrossEntropyLoss(reduction="sum")(bnn.forward(xg, n_samples=4), labels.cuda())
-    loss.backward()
+    bnn.set_precision(prec)
     ref = orc.attack_gradient(net, layout, bank, x, labels, range(4), dtype=torch.float64)
-    assert rel_err(xg.grad.cpu(), ref) < REL
+    for interleave in (False, True):
+        xg = x.cuda().requires_grad_(True)
+        out = bnn.forward(xg, n_samples=4)
+        assert bnn.engine().keep_valid == (prec != "fp32")
+        if interleave:
+            bnn.forward(x.cuda()[:5].requires_grad_(True), n_samples=4)     # overwrites the kept forward
+        loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels.cuda())
+        loss.backward()
+        assert rel_err(xg.grad.cpu(), ref) < REL
 
 
 # ------------------------------------------------------------------ sampler -----------------------------
