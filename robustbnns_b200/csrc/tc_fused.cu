@@ -693,95 +693,75 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   }
 }
 
-// One warp per worklist slot batch: exact re-evaluation of the queued pre-activations; where the sign the
-// epilogue assumed was wrong, dH[z, b, j] is rescaled by slope^(+-1) in place.
-template <bool F16>
-__global__ void __launch_bounds__(256)
-fixup_kernel(const unsigned long long* __restrict__ wl, long long nslots, const float* __restrict__ x,
-             const float* __restrict__ bank, long long P, long long b1_off, int z_row0, int B, int D, int H,
-             void* __restrict__ dh_hi_v, void* __restrict__ dh_lo_v) {
-  const int lane = threadIdx.x & 31;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long base = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nslots;
-       base += nwarps * 32) {
-    const unsigned long long mine = base + lane < nslots ? wl[base + lane] : kSentinel;
-    unsigned valid = __ballot_sync(0xffffffffu, mine != kSentinel);
-    while (valid) {
-      const int src = __ffs(valid) - 1;
-      valid &= valid - 1;
-      const unsigned long long e = __shfl_sync(0xffffffffu, mine, src);
-      const int z = (int)(e >> 44), b = (int)((e >> 20) & 0xFFFFFF), j = (int)((e >> 4) & 0xFFFF);
-      const bool assumed_pos = (e & 1ull) != 0;
-      const float* __restrict__ xr = x + (long long)b * D;
-      const float* __restrict__ wrow = bank + (long long)(z_row0 + z) * P;
-      const float* __restrict__ w = wrow + (long long)j * D;            // W1 is the first tensor of a bank row
-      double s = 0.0;
-      for (int d = lane; d < D; d += 32) s = fma((double)__ldg(xr + d), (double)__ldg(w + d), s);
+// exact sign of b1[j] + <x_b, w_j>: fp64 accumulation of the exact fp32 products, one warp (all lanes return it)
+__device__ __forceinline__ bool exact_positive_warp(const float* __restrict__ xr, const float* __restrict__ w, float bias,
+                                                    int D, int lane) {
+  double s = 0.0;
+  // bank rows are only 4-byte aligned in general (P floats apart), hence scalar loads
+  for (int d = lane; d < D; d += 32) s = fma((double)__ldg(xr + d), (double)__ldg(w + d), s);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const bool pos = (float)(s + (double)__ldg(wrow + b1_off + j)) > 0.f;
-      if (pos != assumed_pos && lane == 0) {
-        const long long o = ((long long)z * B + b) * H + j;
-        if (F16) {                                   // scaled fp16 hi/lo pair (the scale is a power of two: it commutes)
-          __half* dh_hi = reinterpret_cast<__half*>(dh_hi_v);
-          __half* dh_lo = reinterpret_cast<__half*>(dh_lo_v);
-          float v = __half2float(dh_hi[o]) + __half2float(dh_lo[o]);
-          v = pos ? v * 100.f : v * kSlopeF;
-          const __half hi = __float2half_rn(v);
-          dh_hi[o] = hi;
-          dh_lo[o] = __float2half_rn(v - __half2float(hi));
-        } else {
-          float* dh_hi = reinterpret_cast<float*>(dh_hi_v);
-          float* dh_lo = reinterpret_cast<float*>(dh_lo_v);
-          float v = dh_hi[o] + dh_lo[o];
-          v = pos ? v * 100.f : v * kSlopeF;          // undo / apply the LeakyReLU slope
-          const float hi = to_tf32_rn(v);
-          dh_hi[o] = hi;
-          dh_lo[o] = v - hi;
-        }
-      }
-    }
-  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return (float)(s + (double)bias) > 0.f;
 }
 
-
-// Keep mode (head == -2) fix-up: the forward pass stored the LeakyReLU masks instead of dH; where the sign the epilogue
-// assumed for a guard-band unit was wrong, flip its mask bit.  Same exact re-evaluation as fixup_kernel.
+// Worklist fix-up.  An item's guard-band entries sit in the FIRST slots of its kWorkPerItem-slot segment, so a
+// slot-parallel sweep leaves one warp with all the work of an item: instead one block per item (grid-stride), every
+// warp reads the segment 32 slots at a time and takes the entries whose index is congruent to its own.
+//   MASK = false: dH[z, b, j] is rescaled by slope^(+-1) in place when the sign the epilogue assumed was wrong
+//   MASK = true : keep mode, the stored LeakyReLU mask bit is flipped instead
+template <bool F16, bool MASK>
 __global__ void __launch_bounds__(256)
-fixup_mask_kernel(const unsigned long long* __restrict__ wl, long long nslots, const float* __restrict__ x,
-                  const float* __restrict__ bank, long long P, long long b1_off, int z_row0, int B, int D, int BN,
-                  int cols_half, uint32_t* __restrict__ masks) {
-  const int lane = threadIdx.x & 31;
+fixup_kernel(const unsigned long long* __restrict__ wl, int num_items, const float* __restrict__ x,
+             const float* __restrict__ bank, long long P, long long b1_off, int z_row0, int B, int D, int H,
+             void* __restrict__ dh_hi_v, void* __restrict__ dh_lo_v, int BN, int cols_half, uint32_t* __restrict__ masks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int m_tiles = (B + kBM - 1) / kBM, nblocks = cols_half / 32;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long base = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < nslots;
-       base += nwarps * 32) {
-    const unsigned long long mine = base + lane < nslots ? wl[base + lane] : kSentinel;
-    unsigned valid = __ballot_sync(0xffffffffu, mine != kSentinel);
-    while (valid) {
-      const int src = __ffs(valid) - 1;
-      valid &= valid - 1;
-      const unsigned long long e = __shfl_sync(0xffffffffu, mine, src);
-      const int z = (int)(e >> 44), b = (int)((e >> 20) & 0xFFFFFF), j = (int)((e >> 4) & 0xFFFF);
-      const bool assumed_pos = (e & 1ull) != 0;
-      const float* __restrict__ xr = x + (long long)b * D;
-      const float* __restrict__ wrow = bank + (long long)(z_row0 + z) * P;
-      const float* __restrict__ w = wrow + (long long)j * D;
-      double s = 0.0;
-      for (int d = lane; d < D; d += 32) s = fma((double)__ldg(xr + d), (double)__ldg(w + d), s);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const bool pos = (float)(s + (double)__ldg(wrow + b1_off + j)) > 0.f;
-      if (pos != assumed_pos && lane == 0) {
-        // (b, j) -> (item, mask word, epilogue thread, bit) of the fused kernel's fragment layout
-        const int item = z * m_tiles + b / kBM, rt = b % kBM;
-        const int quad = rt >> 5, lhalf = (rt >> 4) & 1, r = (rt >> 3) & 1, rsub = rt & 7;
-        const int n = j / BN, jn = j % BN, half = jn / cols_half, jc = jn % cols_half;
-        const int cc = jc >> 5, k = (jc >> 3) & 3, qq = (jc >> 1) & 3, ee = jc & 1;
-        const int ew = half * 8 + lhalf * 4 + ((quad + 2) & 3);
-        const int et = ew * 32 + rsub * 4 + qq;
-        atomicXor(masks + ((long long)item * kMaskWords + (n * nblocks + cc)) * (kEpiWarps * 32) + et,
-                  1u << (r * 8 + k * 2 + ee));
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const unsigned long long* __restrict__ seg = wl + (long long)item * kWorkPerItem;
+    for (int base = 0; base < kWorkPerItem; base += 32) {
+      const unsigned long long mine = seg[base + lane];
+      unsigned valid = __ballot_sync(0xffffffffu, mine != kSentinel);
+      if (!valid) break;                                     // entries are packed from slot 0; the rest is sentinels
+      while (valid) {
+        const int src = __ffs(valid) - 1;
+        valid &= valid - 1;
+        if (((base + src) & 7) != warp) continue;
+        const unsigned long long e = __shfl_sync(0xffffffffu, mine, src);
+        const int z = (int)(e >> 44), b = (int)((e >> 20) & 0xFFFFFF), j = (int)((e >> 4) & 0xFFFF);
+        const bool assumed_pos = (e & 1ull) != 0;
+        const float* __restrict__ wrow = bank + (long long)(z_row0 + z) * P;
+        const bool pos = exact_positive_warp(x + (long long)b * D, wrow + (long long)j * D, __ldg(wrow + b1_off + j), D, lane);
+        if (pos == assumed_pos || lane != 0) continue;
+        if (MASK) {
+          // (b, j) -> (item, mask word, epilogue thread, bit) of the fused kernel's fragment layout
+          const int rt = b % kBM;
+          const int quad = rt >> 5, lhalf = (rt >> 4) & 1, r = (rt >> 3) & 1, rsub = rt & 7;
+          const int n = j / BN, jn = j % BN, half = jn / cols_half, jc = jn % cols_half;
+          const int cc = jc >> 5, k = (jc >> 3) & 3, qq = (jc >> 1) & 3, ee = jc & 1;
+          const int ew = half * 8 + lhalf * 4 + ((quad + 2) & 3);
+          const int et = ew * 32 + rsub * 4 + qq;
+          atomicXor(masks + ((long long)(z * m_tiles + b / kBM) * kMaskWords + (n * nblocks + cc)) * (kEpiWarps * 32) + et,
+                    1u << (r * 8 + k * 2 + ee));
+        } else {
+          const long long o = ((long long)z * B + b) * H + j;
+          if (F16) {                                   // scaled fp16 hi/lo pair (the scale is a power of two: it commutes)
+            __half* dh_hi = reinterpret_cast<__half*>(dh_hi_v);
+            __half* dh_lo = reinterpret_cast<__half*>(dh_lo_v);
+            float v = __half2float(dh_hi[o]) + __half2float(dh_lo[o]);
+            v = pos ? v * 100.f : v * kSlopeF;
+            const __half hi = __float2half_rn(v);
+            dh_hi[o] = hi;
+            dh_lo[o] = __float2half_rn(v - __half2float(hi));
+          } else {
+            float* dh_hi = reinterpret_cast<float*>(dh_hi_v);
+            float* dh_lo = reinterpret_cast<float*>(dh_lo_v);
+            float v = dh_hi[o] + dh_lo[o];
+            v = pos ? v * 100.f : v * kSlopeF;          // undo / apply the LeakyReLU slope
+            const float hi = to_tf32_rn(v);
+            dh_hi[o] = hi;
+            dh_lo[o] = v - hi;
+          }
+        }
       }
     }
   }
@@ -969,15 +949,14 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
 
 int fused_fixup(const FusedDesc& d, cudaStream_t st, std::string* err) {
   if (d.mode == MODE_BF16 || !d.worklist || d.head < 0 || d.eps <= 0.f || d.B <= 0 || d.Z <= 0) return 0;
-  const long long nslots = (long long)fused_worklist_slots(d.B, d.Z);
-  const long long warps = (nslots + 31) / 32;
-  const unsigned blocks = (unsigned)std::min<long long>((warps + 7) / 8, (long long)d.sm_count * 8);
+  const int items = d.Z * ((d.B + kBM - 1) / kBM);
+  const unsigned blocks = (unsigned)std::min(items, d.sm_count * 8);
   if (d.mode == MODE_F16X3)
-    fixup_kernel<true><<<blocks, 256, 0, st>>>(d.worklist, nslots, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
-                                               d.dh_hi, d.dh_lo);
+    fixup_kernel<true, false><<<blocks, 256, 0, st>>>(d.worklist, items, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
+                                                      d.dh_hi, d.dh_lo, 0, 32, nullptr);
   else
-    fixup_kernel<false><<<blocks, 256, 0, st>>>(d.worklist, nslots, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
-                                                d.dh_hi, d.dh_lo);
+    fixup_kernel<false, false><<<blocks, 256, 0, st>>>(d.worklist, items, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
+                                                       d.dh_hi, d.dh_lo, 0, 32, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("fused_fixup launch: ") + cudaGetErrorString(e);
@@ -990,12 +969,11 @@ size_t keep_mask_words(int B, int Z) { return (size_t)Z * ((B + kBM - 1) / kBM) 
 
 int fused_keep_fixup(const FusedDesc& d, uint32_t* masks, cudaStream_t st, std::string* err) {
   if (d.mode == MODE_BF16 || !d.worklist || d.eps <= 0.f || d.B <= 0 || d.Z <= 0) return 0;
-  const long long nslots = (long long)fused_worklist_slots(d.B, d.Z);
-  const long long warps = (nslots + 31) / 32;
-  const unsigned blocks = (unsigned)std::min<long long>((warps + 7) / 8, (long long)d.sm_count * 8);
+  const int items = d.Z * ((d.B + kBM - 1) / kBM);
+  const unsigned blocks = (unsigned)std::min(items, d.sm_count * 8);
   const int BN = d.H <= 256 ? d.H : 256;
-  fixup_mask_kernel<<<blocks, 256, 0, st>>>(d.worklist, nslots, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, BN,
-                                            BN >= 64 ? BN / 2 : BN, masks);
+  fixup_kernel<false, true><<<blocks, 256, 0, st>>>(d.worklist, items, d.x, d.bank, d.P, d.b1_off, d.z_row0, d.B, d.D, d.H,
+                                                    nullptr, nullptr, BN, BN >= 64 ? BN / 2 : BN, masks);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("fused_keep_fixup launch: ") + cudaGetErrorString(e);
