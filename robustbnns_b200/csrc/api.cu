@@ -396,7 +396,10 @@ int rbnn_net_set_precision(rbnn_net* n, int prec) {
   RBNN_CHECK(n != nullptr, "null net handle");
   RBNN_CHECK(prec == RBNN_PREC_FP32 || prec == RBNN_PREC_TF32X3 || prec == RBNN_PREC_BF16 || prec == RBNN_PREC_F16X3,
              "unknown precision %d", prec);
-  if (prec != RBNN_PREC_FP32)
+  if (prec != RBNN_PREC_FP32 && n->arch == RBNN_ARCH_CONV)
+    RBNN_CHECK(prec == RBNN_PREC_TF32X3 && tc_conv_supported(n),
+               "arch conv: the tcgen05 engine offers TF32X3 (implicit-GEMM conv2) on sm_100 only");
+  else if (prec != RBNN_PREC_FP32)
     RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%8==0 and H>=32 on sm_100 only");
   if (prec == RBNN_PREC_F16X3)
     RBNN_CHECK(tc_f16x3_supported(n), "F16X3 covers arch fc with hidden sizes the fused forward+head kernel supports");
@@ -514,6 +517,7 @@ int rbnn_forward_probs_sum(rbnn_net* n, const float* d_x, int B, int s0, int s1,
   cudaStream_t st = (cudaStream_t)stream;
   RBNN_CUDA(cudaMemsetAsync(d_out_sum, 0, (size_t)B * n->C * sizeof(float), st));
   if (s1 == s0) return 0;
+  if (n->prec != RBNN_PREC_FP32 && n->arch == RBNN_ARCH_CONV) return tc_conv_forward(n, d_x, B, s0, s1, d_out_sum, nullptr, st);
   if (n->prec != RBNN_PREC_FP32) return tc_fc_forward(n, d_x, B, s0, s1, d_out_sum, nullptr, st);
   const int bc = batch_chunk(n, B, false);
   for (int b0 = 0; b0 < B; b0 += bc) {
@@ -530,7 +534,8 @@ int rbnn_forward_probs_sum_keep(rbnn_net* n, const float* d_x, int B, int s0, in
   RBNN_TRY(check_rows(n, s0, s1));
   RBNN_CHECK(B >= 0, "negative batch");
   n->keep.valid = 0;
-  if (B == 0 || s1 == s0 || n->prec == RBNN_PREC_FP32) return rbnn_forward_probs_sum(n, d_x, B, s0, s1, d_out_sum, stream);
+  if (B == 0 || s1 == s0 || n->prec == RBNN_PREC_FP32 || n->arch == RBNN_ARCH_CONV)
+    return rbnn_forward_probs_sum(n, d_x, B, s0, s1, d_out_sum, stream);
   DeviceGuard dg(n->device);
   cudaStream_t st = (cudaStream_t)stream;
   RBNN_CUDA(cudaMemsetAsync(d_out_sum, 0, (size_t)B * n->C * sizeof(float), st));
@@ -554,6 +559,7 @@ int rbnn_forward_logits(rbnn_net* n, const float* d_x, int B, int s, float* d_ou
   if (B <= 0) return 0;
   DeviceGuard dg(n->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n->prec != RBNN_PREC_FP32 && n->arch == RBNN_ARCH_CONV) return tc_conv_forward(n, d_x, B, s, s + 1, nullptr, d_out, st);
   if (n->prec != RBNN_PREC_FP32) return tc_fc_forward(n, d_x, B, s, s + 1, nullptr, d_out, st);
   const int bc = batch_chunk(n, B, false);
   for (int b0 = 0; b0 < B; b0 += bc) {
@@ -580,6 +586,8 @@ int rbnn_input_grad_sum(rbnn_net* n, int head, const float* d_x, const int32_t* 
     RBNN_CUDA(cudaMemsetAsync(d_out_sum, 0, (size_t)B * n->D * sizeof(float), st));
     return 0;
   }
+  if (n->prec != RBNN_PREC_FP32 && n->arch == RBNN_ARCH_CONV)
+    return tc_conv_input_grad_sum(n, head, d_x, d_labels, B, s0, s1, d_pbar, d_out_sum, st);
   if (n->prec != RBNN_PREC_FP32) return tc_fc_input_grad_sum(n, head, d_x, d_labels, B, s0, s1, d_pbar, d_out_sum, st);
   const int bc = batch_chunk(n, B, true);
   for (int b0 = 0; b0 < B; b0 += bc) {

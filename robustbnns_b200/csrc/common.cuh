@@ -54,6 +54,8 @@ struct TcMat {
   int64_t off = 0;          // offset of the [R, C] matrix inside a bank row
   int R = 0, C = 0;
   int ld = 0;               // row pitch (elements) of the forward copies: C rounded up to whole 128-byte lines
+  int perm25 = 0;           // conv2 filters [H][32][5][5]: the forward copy stores a row's 800 columns tap-major,
+                            // (ky, kx, c) instead of (c, ky, kx) -- the K order of the implicit GEMM (tc_conv.cu)
   float *hi = nullptr, *lo = nullptr;      // tf32 split:  w = hi + lo, hi = rn_tf32(w)
   float *thi = nullptr, *tlo = nullptr;    // the same, transposed
   void *bf = nullptr, *tbf = nullptr;      // bf16 variants
@@ -172,7 +174,10 @@ int conv1_pool_fwd(rbnn_net* net, const float* x, const float* bank, int s0, int
                    uint8_t* idx1, cudaStream_t st);
 int im2col_conv2(rbnn_net* net, const float* p1, int ZB, float* col, cudaStream_t st);
 int pool2_fwd(rbnn_net* net, const float* a2, int ZB, int H, float* p2, cudaStream_t st);
-int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, float* dz2, cudaStream_t st);
+int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, float* dz2, cudaStream_t st,
+              float* dz2_lo = nullptr);
+int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, float* hi, float* lo, cudaStream_t st);
+int conv2_refine(rbnn_net* net, float* a2, const float* p1, int s0, int Z, int B, float eps, cudaStream_t st);
 int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, float* g1, cudaStream_t st);
 int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,
                   float* dx_sum, int accumulate, cudaStream_t st);
@@ -196,5 +201,14 @@ int tc_fc_forward_keep(rbnn_net* net, const float* d_x, int B, int s0, int s1, f
 int tc_fc_grad_kept(rbnn_net* net, int head, const int32_t* d_labels, const float* d_pbar, float* d_out_sum,
                     cudaStream_t st);
 void tc_keep_free(rbnn_net* net);
+// derived tensor-core operand copies of bank rows [s0, s1) brought up to date (lazily, per dirty row)
+int tc_bank_refresh(rbnn_net* net, int s0, int s1, cudaStream_t st);
+
+// ---- tc_conv.cu (tcgen05 conv path, TF32X3) --------------------------------------------------
+int tc_conv_supported(const rbnn_net* net);
+int tc_conv_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_t* d_labels, int B, int s0, int s1,
+                           const float* d_pbar, float* d_out_sum, cudaStream_t st);
+int tc_conv_forward(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum, float* d_out_logits,
+                    cudaStream_t st);
 
 }  // namespace rbnn

@@ -104,8 +104,15 @@ int pool2_fwd(rbnn_net* net, const float* a2, int ZB, int H, float* p2, cudaStre
 }
 
 // dZ2[zb][pos][h] = leaky'(A2) * sum over the <=4 windows containing pos whose first-max is pos
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+// dz2_lo != nullptr: the result is written tf32-split (hi = rn_tf32(v), lo = v - hi) for the tcgen05 dgrad GEMM
 __global__ void pool2_bwd_kernel(const float* __restrict__ a2, const float* __restrict__ dp2, int64_t total, int H,
-                                 float* __restrict__ dz2) {
+                                 float* __restrict__ dz2, float* __restrict__ dz2_lo) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int h = (int)(i % H);
@@ -131,12 +138,20 @@ __global__ void pool2_bwd_kernel(const float* __restrict__ a2, const float* __re
       if (by == y && bx == x) acc += __ldg(dp2 + (zb * 49 + wy * 7 + wx) * H + h);
     }
   const float a = __ldg(A + pos * H);
-  dz2[i] = a > 0.f ? acc : acc * kLeakySlope;
+  const float v = a > 0.f ? acc : acc * kLeakySlope;
+  if (dz2_lo) {
+    const float h = tf32_rn(v);
+    dz2[i] = h;
+    dz2_lo[i] = v - h;
+  } else {
+    dz2[i] = v;
+  }
 }
 
-int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, float* dz2, cudaStream_t st) {
+int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, float* dz2, cudaStream_t st,
+              float* dz2_lo) {
   const int64_t total = (int64_t)ZB * 64 * H;
-  pool2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a2, dp2, total, H, dz2);
+  pool2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a2, dp2, total, H, dz2, dz2_lo);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -226,6 +241,111 @@ conv1_bwd_sum_kernel(const float* __restrict__ g1, const uint8_t* __restrict__ i
 int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,
                   float* dx_sum, int accumulate, cudaStream_t st) {
   conv1_bwd_sum_kernel<<<B, 256, 0, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, dx_sum, accumulate);
+  net->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- tcgen05 route (tc_conv.cu): operand preparation and guard-band refinement of conv2 ---------------------
+// P1[zb][c][y][x] (fp32, CHW) -> channels-last tf32-split copies hi/lo[zb][y][x][c]: a pixel's 32 channels are the
+// 128-byte K-block row of the implicit GEMM.  One block per image, transposed through shared memory.
+__global__ void __launch_bounds__(256)
+p1_split_hwc_kernel(const float* __restrict__ p1, float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float t[32 * 145];
+  const int64_t zb = blockIdx.x;
+  for (int i = threadIdx.x; i < 4608; i += blockDim.x) t[(i / 144) * 145 + i % 144] = __ldg(p1 + zb * 4608 + i);
+  __syncthreads();
+  for (int o = threadIdx.x; o < 4608; o += blockDim.x) {
+    const int c = o & 31, px = o >> 5;
+    const float v = t[c * 145 + px];
+    const float h = tf32_rn(v);
+    hi[zb * 4608 + o] = h;
+    lo[zb * 4608 + o] = v - h;
+  }
+}
+
+int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, float* hi, float* lo, cudaStream_t st) {
+  p1_split_hwc_kernel<<<ZB, 256, 0, st>>>(p1, hi, lo);
+  net->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// The input gradient is discontinuous in the conv2 pre-activations in two ways: LeakyReLU (the sign of the
+// pre-activation) and MaxPool2d(2, stride 1) (which of the 4 window entries is the largest, model_nn.py:102-103).
+// The tensor-core GEMM errs by ~5e-6 of the output maximum, so every A2 entry whose pre-activation is within
+// eps * max|pre| (of this image) of ZERO or of one of its 8 spatial NEIGHBOURS in the same channel (the entries it
+// shares a pooling window with) is recomputed exactly -- fp64 accumulation of the fp32 products over the 5x5x32 patch,
+// CUDA cores -- and rewritten in place.  Afterwards every sign and every window arg-max agrees with exact arithmetic.
+// Values written concurrently by other warps differ from the ones they replace by far less than the band, so the
+// unsynchronised neighbour reads are harmless.  One block per (sample, image); A2 is [zb][64 positions][H].
+__global__ void __launch_bounds__(256)
+conv2_refine_kernel(float* __restrict__ a2, const float* __restrict__ p1, const float* __restrict__ bank, int64_t P,
+                    int64_t cw2, int64_t cb2, int s0, int B, int H, float eps) {
+  __shared__ float ps[4608];
+  __shared__ float red[8];
+  const int zb = blockIdx.x, z = zb / B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* A = a2 + (int64_t)zb * 64 * H;
+  for (int i = threadIdx.x; i < 4608; i += blockDim.x) ps[i] = __ldg(p1 + (int64_t)zb * 4608 + i);
+  float m = 0.f;
+  for (int i = threadIdx.x; i < 64 * H; i += blockDim.x) {
+    const float v = A[i];
+    m = fmaxf(m, v > 0.f ? v : -100.f * v);        // |pre-activation| (LeakyReLU inverted)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  const float guard = eps * m;
+  const float* __restrict__ wrow = bank + (int64_t)(s0 + z) * P;
+  for (int pos = warp; pos < 64; pos += 8) {
+    const int y = pos >> 3, x = pos & 7;
+    for (int h0 = 0; h0 < H; h0 += 32) {
+      const int h = h0 + lane;
+      bool flag = false;
+      if (h < H) {
+        const float v = A[pos * H + h];
+        const float pre = v > 0.f ? v : 100.f * v;
+        flag = fabsf(pre) < guard;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            if ((dy == 0 && dx == 0) || yy < 0 || yy > 7 || xx < 0 || xx > 7) continue;
+            const float vn = A[(yy * 8 + xx) * H + h];
+            const float pn = vn > 0.f ? vn : 100.f * vn;
+            flag = flag || fabsf(pre - pn) < guard;
+          }
+      }
+      unsigned any = __ballot_sync(0xffffffffu, flag);
+      while (any) {
+        const int src = __ffs(any) - 1;
+        any &= any - 1;
+        const int hh = h0 + src;
+        const float* __restrict__ w = wrow + cw2 + (int64_t)hh * 800;
+        double s = 0.0;
+        for (int k = lane; k < 800; k += 32) {
+          const int c = k / 25, r = k - 25 * c, ky = r / 5, kx = r - 5 * ky;
+          s = fma((double)ps[c * 144 + (y + ky) * 12 + x + kx], (double)__ldg(w + k), s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s += (double)__ldg(wrow + cb2 + hh);
+        float val = (float)s;
+        val = val > 0.f ? val : val * kLeakySlope;
+        if (lane == src) A[pos * H + hh] = val;
+      }
+    }
+  }
+}
+
+int conv2_refine(rbnn_net* net, float* a2, const float* p1, int s0, int Z, int B, float eps, cudaStream_t st) {
+  conv2_refine_kernel<<<Z * B, 256, 0, st>>>(a2, p1, net->bank, net->L.P, net->L.cw2, net->L.cb2, s0, B, net->H, eps);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;

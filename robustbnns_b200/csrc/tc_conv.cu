@@ -1,0 +1,193 @@
+// The tcgen05 engine for the convolutional net (arch conv, model_nn.py:98-106), precision RBNN_PREC_TF32X3.
+// Per chunk of posterior samples z and inputs b:
+//   conv1 + LeakyReLU + MaxPool2d(2)          direct CUDA-core kernel (K = 25, < 1 % of the FLOPs)        conv.cu
+//   conv2 = Conv2d(32, H, 5) + bias + LeakyReLU   IMPLICIT GEMM on tcgen05: A tiles are 5-D TMA boxes of the
+//                                                 channels-last pooled map (one box per filter tap, no im2col
+//                                                 matrix), B = W2_z as [H][(ky, kx, c)], fp32 accumulators in TMEM
+//   guard-band refinement                     exact re-evaluation of the entries whose LeakyReLU sign or pooling
+//                                             arg-max the tensor-core rounding could flip                     conv.cu
+//   MaxPool2d(2, stride 1), Linear(49H, C), loss head, their input gradients     CUDA-core kernels (3 % of the FLOPs)
+//   conv2 dgrad  dcol = dZ2 . W2_z  (K = H)   tcgen05 GEMM over the transposed weight copies, then col2im + conv1 backward
+// This is lossGradients.py:29-40 / adversarialAttacks.py:74-78 for the conv BNN, input gradients only.
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace rbnn {
+
+// ~50x the measured TF32x3 error (5e-6 of the output maximum), as for the unfused FC route (tc_fc.cu)
+constexpr float kConvGuardEps = 1.0f / 4096.0f;
+
+int tc_conv_supported(const rbnn_net* n) {
+  return n->arch == RBNN_ARCH_CONV && n->cc_major == 10 && (n->H % 16) == 0;
+}
+
+namespace {
+
+struct ConvTcBufs {
+  float *p1 = nullptr, *p1h = nullptr, *p1l = nullptr, *a2 = nullptr, *p2 = nullptr, *logits = nullptr;
+  float *dlogits = nullptr, *dp2 = nullptr, *dzh = nullptr, *dzl = nullptr, *dcol = nullptr, *g1 = nullptr;
+  uint8_t* idx1 = nullptr;
+};
+
+size_t bytes_per_zb(const rbnn_net* n, bool grad) {
+  const size_t H = n->H, C = n->C;
+  size_t per = 3 * 4608 * 4 + 4608 + 64 * H * 4 + 49 * H * 4 + C * 4;
+  if (grad) per += C * 4 + 49 * H * 4 + 2 * 64 * H * 4 + 64 * 800 * 4 + 4608 * 4;
+  return per + 64;
+}
+
+void carve(rbnn_net* n, Arena& ar, int ZB, bool grad, ConvTcBufs& c) {
+  const size_t H = n->H, C = n->C;
+  c.p1 = ar.take<float>((size_t)ZB * 4608);
+  c.p1h = ar.take<float>((size_t)ZB * 4608);
+  c.p1l = ar.take<float>((size_t)ZB * 4608);
+  c.idx1 = ar.take<uint8_t>((size_t)ZB * 4608);
+  c.a2 = ar.take<float>((size_t)ZB * 64 * H);
+  c.p2 = ar.take<float>((size_t)ZB * 49 * H);
+  c.logits = ar.take<float>((size_t)ZB * C);
+  if (grad) {
+    c.dlogits = ar.take<float>((size_t)ZB * C);
+    c.dp2 = ar.take<float>((size_t)ZB * 49 * H);
+    c.dzh = ar.take<float>((size_t)ZB * 64 * H);
+    c.dzl = ar.take<float>((size_t)ZB * 64 * H);
+    c.dcol = ar.take<float>((size_t)ZB * 64 * 800);
+    c.g1 = ar.take<float>((size_t)ZB * 4608);
+  }
+}
+
+int run_tc(rbnn_net* n, tc::GemmDesc& d, int tag, cudaStream_t st) {
+  d.mode = tc::MODE_TF32X3;
+  d.sm_count = n->sm_count;
+  std::string err;
+  RBNN_TRY(timing_begin(n, tag, st));
+  if (tc::gemm(d, st, &err)) {
+    set_error("%s", err.c_str());
+    return 1;
+  }
+  n->launches++;
+  RBNN_TRY(timing_end(n, tag, st));
+  return 0;
+}
+
+int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs& c, float* logits, cudaStream_t st) {
+  const int H = n->H, C = n->C;
+  const int64_t P = n->L.P;
+  const float* rows = n->bank + (int64_t)z0 * P;
+  const TcMat& m = n->tc.mat[0];
+  RBNN_TRY(conv1_pool_fwd(n, x, n->bank, z0, Z, B, c.p1, c.idx1, st));
+  RBNN_TRY(p1_split_hwc(n, c.p1, Z * B, c.p1h, c.p1l, st));
+  tc::GemmDesc g;
+  g.M = B * 64; g.N = H; g.K = 800; g.Z = Z; g.BN = std::min(H, 256);
+  g.conv_images = B;
+  g.A.hi = c.p1h; g.A.lo = c.p1l; g.A.rows = g.M; g.A.ld = 800; g.A.zstride = (int64_t)B * 4608;
+  g.B.hi = m.hi + (int64_t)z0 * H * m.ld; g.B.lo = m.lo + (int64_t)z0 * H * m.ld;
+  g.B.rows = H; g.B.ld = m.ld; g.B.zstride = (int64_t)H * m.ld;
+  g.epi = tc::EPI_BIAS_LEAKY;
+  g.bias = rows + n->L.cb2; g.bias_zstride = P;
+  g.out = c.a2; g.out_ld = H; g.out_zstride = (int64_t)B * 64 * H;
+  RBNN_TRY(run_tc(n, g, 1, st));
+  RBNN_TRY(conv2_refine(n, c.a2, c.p1, z0, Z, B, kConvGuardEps, st));
+  RBNN_TRY(pool2_fwd(n, c.a2, Z * B, H, c.p2, st));
+  GemmArgs o{};
+  o.A = c.p2; o.lda = 49 * H; o.sAz = (int64_t)B * 49 * H;
+  o.B = n->woutp + (int64_t)z0 * C * 49 * H; o.ldb = 49 * H; o.sBz = (int64_t)C * 49 * H;
+  o.bias = rows + n->L.bo; o.sbz = P;
+  o.C = logits; o.ldc = C; o.sCz = (int64_t)B * C;
+  o.M = B; o.N = C; o.K = 49 * H; o.Z = Z; o.epi = EPI_BIAS;
+  RBNN_TRY(gemm_simt(n, o, st));
+  return 0;
+}
+
+int grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1, const float* pbar,
+              float* out_sum, cudaStream_t st) {
+  const int H = n->H, C = n->C;
+  const size_t per = bytes_per_zb(n, true) * (size_t)B + 8192;
+  const int zc = (int)std::max<size_t>(1, std::min<size_t>(n->ws_budget / per, (size_t)(s1 - s0)));
+  RBNN_TRY(ws_reserve(n, per * zc));
+  const TcMat& m = n->tc.mat[0];
+  bool first = true;
+  for (int z0 = s0; z0 < s1; z0 += zc) {
+    const int Z = std::min(zc, s1 - z0);
+    Arena ar(n);
+    ConvTcBufs c;
+    carve(n, ar, Z * B, true, c);
+    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, c.logits, st));
+    RBNN_TRY(head_dlogits(n, head, c.logits, labels, pbar, Z, B, C, c.dlogits, st));
+    GemmArgs g{};
+    g.b_kn = 1;
+    g.A = c.dlogits; g.lda = C; g.sAz = (int64_t)B * C;
+    g.B = n->woutp + (int64_t)z0 * C * 49 * H; g.ldb = 49 * H; g.sBz = (int64_t)C * 49 * H;
+    g.C = c.dp2; g.ldc = 49 * H; g.sCz = (int64_t)B * 49 * H;
+    g.M = B; g.N = 49 * H; g.K = C; g.Z = Z; g.epi = EPI_NONE;
+    RBNN_TRY(gemm_simt(n, g, st));
+    RBNN_TRY(pool2_bwd(n, c.a2, c.dp2, Z * B, H, c.dzh, st, c.dzl));
+    // dcol[z][b * 64 + pos][c * 25 + ky * 5 + kx] = sum_h dZ2[z][b * 64 + pos][h] W2_z[h][c][ky][kx]
+    tc::GemmDesc d;
+    d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = 160;
+    d.A.hi = c.dzh; d.A.lo = c.dzl; d.A.rows = d.M; d.A.ld = H; d.A.zstride = (int64_t)B * 64 * H;
+    d.B.hi = m.thi + (int64_t)z0 * 800 * H; d.B.lo = m.tlo + (int64_t)z0 * 800 * H;
+    d.B.rows = 800; d.B.ld = H; d.B.zstride = (int64_t)800 * H;
+    d.epi = tc::EPI_NONE;
+    d.out = c.dcol; d.out_ld = 800; d.out_zstride = (int64_t)B * 64 * 800;
+    RBNN_TRY(run_tc(n, d, 2, st));
+    RBNN_TRY(col2im_conv2(n, c.dcol, c.p1, Z * B, c.g1, st));
+    RBNN_TRY(conv1_bwd_sum(n, c.g1, c.idx1, n->bank, z0, Z, B, out_sum, first ? 0 : 1, st));
+    first = false;
+  }
+  return 0;
+}
+
+int probs_pass(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, float* out_logits, cudaStream_t st) {
+  const int C = n->C;
+  const size_t per = bytes_per_zb(n, false) * (size_t)B + 8192;
+  const int zc = (int)std::max<size_t>(1, std::min<size_t>(n->ws_budget / per, (size_t)(s1 - s0)));
+  RBNN_TRY(ws_reserve(n, per * zc));
+  for (int z0 = s0; z0 < s1; z0 += zc) {
+    const int Z = std::min(zc, s1 - z0);
+    Arena ar(n);
+    ConvTcBufs c;
+    carve(n, ar, Z * B, false, c);
+    float* lg = out_logits ? out_logits : c.logits;
+    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, lg, st));
+    if (out_sum) RBNN_TRY(head_probs_accumulate(n, lg, Z, B, C, out_sum, st));
+  }
+  return 0;
+}
+
+// inputs per pass such that one posterior sample fits the workspace budget
+int batch_rows(const rbnn_net* n, int B, bool grad) {
+  const size_t rows = std::max<size_t>(1, n->ws_budget / (bytes_per_zb(n, grad) + 64));
+  return (int)std::min<size_t>(rows, (size_t)B);
+}
+
+}  // namespace
+
+int tc_conv_input_grad_sum(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1,
+                           const float* pbar, float* out_sum, cudaStream_t st) {
+  RBNN_CHECK(tc_conv_supported(n) && n->prec == RBNN_PREC_TF32X3, "the tcgen05 conv engine runs TF32X3 on sm_100 only");
+  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
+  const int bc = batch_rows(n, B, true);
+  for (int b0 = 0; b0 < B; b0 += bc) {
+    const int nb = std::min(bc, B - b0);
+    RBNN_TRY(grad_pass(n, head, x + (int64_t)b0 * n->D, labels + b0, nb, s0, s1, pbar ? pbar + (int64_t)b0 * n->C : nullptr,
+                       out_sum + (int64_t)b0 * n->D, st));
+  }
+  return 0;
+}
+
+int tc_conv_forward(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, float* out_logits,
+                    cudaStream_t st) {
+  RBNN_CHECK(tc_conv_supported(n) && n->prec == RBNN_PREC_TF32X3, "the tcgen05 conv engine runs TF32X3 on sm_100 only");
+  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
+  const int bc = batch_rows(n, B, false);
+  for (int b0 = 0; b0 < B; b0 += bc) {
+    const int nb = std::min(bc, B - b0);
+    RBNN_TRY(probs_pass(n, x + (int64_t)b0 * n->D, nb, s0, s1, out_sum ? out_sum + (int64_t)b0 * n->C : nullptr,
+                        out_logits ? out_logits + (int64_t)b0 * n->C : nullptr, st));
+  }
+  return 0;
+}
+
+}  // namespace rbnn

@@ -55,10 +55,11 @@ __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi
 
 // bank row s, matrix [R, C] at `off`  ->  [s][R][C] and transposed [s][C][R] copies (32x32 smem tiles)
 // grid: (C/32 ceil, R/32 ceil, count), block (32, 8)
+// perm25: forward-copy column (c, tap) -> (tap, c) for the conv2 filters (C = 32 * 25), see TcMat::perm25
 __global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int ld, int s0,
                                 float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ thi,
                                 float* __restrict__ tlo, __nv_bfloat16* __restrict__ bf,
-                                __nv_bfloat16* __restrict__ tbf) {
+                                __nv_bfloat16* __restrict__ tbf, int perm25) {
   __shared__ float tile[32][33];
   const int s = s0 + blockIdx.z;
   const float* __restrict__ src = bank + (int64_t)s * P + off;
@@ -68,7 +69,8 @@ __global__ void relayout_kernel(const float* __restrict__ bank, int64_t P, int64
     float v = 0.f;
     if (r < R && c < C) {
       v = __ldg(src + (int64_t)r * C + c);
-      const int64_t o = ((int64_t)s * R + r) * ld + c;      // forward copy: row pitch ld >= C
+      const int cf = perm25 ? (c % 25) * 32 + c / 25 : c;
+      const int64_t o = ((int64_t)s * R + r) * ld + cf;     // forward copy: row pitch ld >= C
       if (bf) {
         bf[o] = __float2bfloat16(v);
       } else {
@@ -544,7 +546,7 @@ void tc_bank_free(rbnn_net* n) {
 }
 
 // Bring the derived copies of bank rows [s0, s1) up to date (all rows after a capacity / precision change).
-static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
+int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
   TcBank& tc = n->tc;
   const bool bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   if (f16 && tc.overflow_host && *(volatile int*)tc.overflow_host) {
@@ -563,6 +565,9 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
     tc_bank_free(n);
     tc.nmat = n->arch == RBNN_ARCH_FC2 ? 2 : 1;
     tc.mat[0].off = n->L.w1; tc.mat[0].R = n->H; tc.mat[0].C = n->D; tc.mat[0].ld = k_pitch(n, n->D);
+    if (n->arch == RBNN_ARCH_CONV) {      // the conv2 filters [H][32*5*5]; conv1 and the output layer stay on CUDA cores
+      tc.mat[0].off = n->L.cw2; tc.mat[0].C = 800; tc.mat[0].ld = 800; tc.mat[0].perm25 = 1;
+    }
     if (tc.nmat == 2) { tc.mat[1].off = n->L.w2; tc.mat[1].R = n->H; tc.mat[1].C = n->H; tc.mat[1].ld = n->H; }
     for (int i = 0; i < tc.nmat; ++i) {
       TcMat& m = tc.mat[i];
@@ -634,7 +639,7 @@ static int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       else
         relayout_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, m.ld, s, m.hi, m.lo, m.thi, m.tlo,
                                                       reinterpret_cast<__nv_bfloat16*>(m.bf),
-                                                      reinterpret_cast<__nv_bfloat16*>(m.tbf));
+                                                      reinterpret_cast<__nv_bfloat16*>(m.tbf), m.perm25);
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }

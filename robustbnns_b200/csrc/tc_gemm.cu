@@ -38,6 +38,7 @@ struct KParams {
   int M, N, K, Z, BN;
   int m_tiles, m_units, n_tiles, num_tiles, num_kb;   // m_units = m_tiles (single CTA) or ceil(m_tiles / 2) (CTA pair)
   int reduce_z, slots, a_per_z, epi, skip_mma, relay, spin;
+  int conv_a;                 // A tiles are 5-D boxes of a channels-last 12x12x32 map (implicit GEMM of the 5x5 convolution)
   const float* unscale;
   const float* bias; long long bias_zstride;
   const float* act; long long act_zstride, act_ld;
@@ -148,6 +149,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 tma_load_3d_pair(sa + kATile, &tmAl, fb, kb * KBE, m_idx * kBM, za);
                 tma_load_3d_pair(sb + kBTile, &tmBl, fb, kb * KBE, n_idx * p.BN + (int)rank * bn_cta, z);
               }
+            } else if (MODE == MODE_TF32X3 && KBB == 128 && p.conv_a) {
+              // implicit GEMM: K-block kb = filter tap (ky, kx); the 128 tile rows are the 8x8 output positions of two
+              // images, i.e. the box {32 channels, x in [kx, kx+8), y in [ky, ky+8), images 2 m_idx .. +1} of the map
+              const uint32_t fb = full0 + 8 * stage;
+              const int ky = kb / 5, kx = kb - 5 * ky;
+              mbar_expect_tx(fb, stage_tx);
+              tma_load_5d(sa, &tmAh, fb, 0, kx, ky, 2 * m_idx, z);
+              tma_load_3d(sb, &tmBh, fb, kb * KBE, n_idx * p.BN, z);
+              tma_load_5d(sa + kATile, &tmAl, fb, 0, kx, ky, 2 * m_idx, z);
+              tma_load_3d(sb + kBTile, &tmBl, fb, kb * KBE, n_idx * p.BN, z);
             } else {
               const uint32_t fb = full0 + 8 * stage;
               mbar_expect_tx(fb, stage_tx);
@@ -360,6 +371,26 @@ int make_map(CUtensorMap* map, const void* base, int dtype, int64_t K, int64_t r
   return 0;
 }
 
+// 5-D map over channels-last activations [Z][images][12][12][32] fp32: box = {32 channels, 8, 8, 2 images, 1}, i.e. the
+// 128 rows x 128 bytes of one filter tap of the implicit GEMM (rows ordered image, oy, ox), SWIZZLE_128B.
+static int make_map_conv_a(CUtensorMap* map, const void* base, int64_t images, int64_t Z, std::string* err) {
+  auto fn = encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled is not available from the driver"; return 1; }
+  cuuint64_t dims[5] = {32u, 12u, 12u, (cuuint64_t)images, (cuuint64_t)Z};
+  cuuint64_t strides[4] = {128u, 12u * 128u, 144u * 128u, (cuuint64_t)images * 144u * 128u};
+  cuuint32_t box[5] = {32u, 8u, 8u, 2u, 1u};
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  if (reinterpret_cast<uintptr_t>(base) & 127) { *err = "tc::gemm: conv activations must be 128-byte aligned"; return 1; }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    *err = "cuTensorMapEncodeTiled (conv activations) failed with CUresult " + std::to_string((int)r);
+    return 1;
+  }
+  return 0;
+}
+
 int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   std::string local;
   if (!err) err = &local;
@@ -375,6 +406,11 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   if (d.reduce_z && (d.slots < 1 || d.slots > d.Z)) { *err = "tc::gemm: slots must be in [1, Z]"; return 1; }
 
   const int kbb = d.kblock_bytes == 128 ? 128 : 64;
+  if (d.conv_images > 0 && (d.mode != MODE_TF32X3 || kbb != 128 || d.pair || d.K != 800 || d.reduce_z ||
+                            d.M != d.conv_images * 64)) {
+    *err = "tc::gemm: the implicit-GEMM conv operand needs TF32X3, 128-byte K-blocks, single CTAs, K = 800, M = 64 * images";
+    return 1;
+  }
   const bool pair = d.pair && (d.BN % 32 == 0 || d.BN % 16 == 0) && ((d.BN / 2) % 8 == 0) && d.sm_count >= 2;
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KParams);
   static const kern_t kerns[3][2][2] = {
@@ -403,10 +439,14 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   }
 
   CUtensorMap mAh, mAl, mBh, mBl;
-  if (make_map(&mAh, d.A.hi, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
+  if (d.conv_images > 0) {
+    if (make_map_conv_a(&mAh, d.A.hi, d.conv_images, d.Z, err)) return 1;
+  } else if (make_map(&mAh, d.A.hi, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
   if (make_map(&mBh, d.B.hi, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   if (!bf16) {
-    if (make_map(&mAl, d.A.lo, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
+    if (d.conv_images > 0) {
+      if (make_map_conv_a(&mAl, d.A.lo, d.conv_images, d.Z, err)) return 1;
+    } else if (make_map(&mAl, d.A.lo, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
     if (make_map(&mBl, d.B.lo, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   } else {
     mAl = mAh;
@@ -424,6 +464,7 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   const int kbe = kbb / (dt == DT_F32 ? 4 : 2);
   p.num_kb = (d.K + kbe - 1) / kbe;
   p.a_per_z = d.A.zstride != 0;
+  p.conv_a = d.conv_images > 0;
   p.epi = d.epi;
   p.skip_mma = d.debug_skip_mma;
   p.relay = d.pair_relay;

@@ -67,6 +67,12 @@ struct GemmDesc {
   int pair_relay = 1;      // pair mode: 1 = own-barrier TMA + relayed full signal, 0 = cta_group::2 TMA onto the leader's barrier
   int spin_wait = 0;       // 1: poll mbarriers with test_wait instead of the suspending try_wait
   int debug_skip_mma = 0;  // harness only: run the TMA / barrier pipeline without issuing MMAs
+  // Implicit-GEMM A operand of the second convolution (model_nn.py:101, Conv2d(32, H, 5) on the pooled 32x12x12 map):
+  // conv_images > 0 says A.hi / A.lo are channels-last activations [Z][conv_images][12][12][32] (fp32, tf32-split) and
+  // the GEMM row m = image * 64 + oy * 8 + ox is the 5x5x32 patch at output position (oy, ox): K-block kb = (ky, kx)
+  // is ONE 5-D TMA box {32 channels, 8 x, 8 y, 2 images} at offset (kx, ky) -- no im2col matrix is ever written.
+  // K = 800 ordered (ky, kx, c); B rows must be stored in that order.  TF32X3, single CTA only.
+  int conv_images = 0;
 };
 
 // Enqueues the GEMM on `st`.  Returns 0 on success; on failure fills *err.

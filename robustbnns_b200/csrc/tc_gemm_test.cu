@@ -197,6 +197,69 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
   return max_err / fmax(max_ref, 1e-30);
 }
 
+// Implicit-GEMM operand of the 5x5 convolution (GemmDesc::conv_images): A = channels-last maps [Z][images][12][12][32],
+// B = [Z][H][800] with K ordered (ky, kx, c); out[z][image * 64 + oy * 8 + ox][h] vs a double-precision host reference.
+static double run_conv_case(int images, int Z, int H, int BN, int timing_iters, double* ms_out) {
+  Dev A, B, bias;
+  A.init((int64_t)Z * images * 144 * 32, 55, 2.0f, false);
+  B.init((int64_t)Z * H * 800, 66, 0.2f, false);
+  bias.init((int64_t)Z * H + 1, 77, 1.0f, false);
+  const int M = images * 64;
+  const int64_t on = (int64_t)Z * M * H;
+  float* out = nullptr;
+  CK(cudaMalloc(&out, on * 4));
+  CK(cudaMemset(out, 0xFF, on * 4));
+  GemmDesc d;
+  d.mode = MODE_TF32X3; d.M = M; d.N = H; d.K = 800; d.Z = Z; d.BN = BN;
+  d.conv_images = images;
+  d.A.hi = A.hi; d.A.lo = A.lo; d.A.rows = M; d.A.ld = 800; d.A.zstride = (int64_t)images * 144 * 32;
+  d.B.hi = B.hi; d.B.lo = B.lo; d.B.rows = H; d.B.ld = 800; d.B.zstride = (int64_t)H * 800;
+  d.epi = EPI_BIAS_LEAKY;
+  d.bias = bias.hi + 1; d.bias_zstride = H;
+  d.out = out; d.out_ld = H; d.out_zstride = (int64_t)M * H;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  d.sm_count = prop.multiProcessorCount;
+  std::string err;
+  if (gemm(d, 0, &err)) { printf("conv: gemm failed: %s\n", err.c_str()); exit(3); }
+  CK(cudaDeviceSynchronize());
+  if (timing_iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < timing_iters; ++i) gemm(d, 0, &err);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / timing_iters;
+  }
+  std::vector<float> h(on), hb((int64_t)Z * H);
+  CK(cudaMemcpy(h.data(), out, on * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hb.data(), bias.hi + 1, hb.size() * 4, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_ref = 0;
+  const int64_t nchk = on <= 400000 ? on : 8192;
+  for (int64_t q = 0; q < nchk; ++q) {
+    const int64_t idx = nchk == on ? q : (int64_t)(hash32(q, 778) % (uint64_t)on);
+    const int z = (int)(idx / ((int64_t)M * H));
+    const int m = (int)((idx / H) % M), n = (int)(idx % H);
+    const int img = m / 64, oy = (m % 64) / 8, ox = m % 8;
+    double acc = 0;
+    for (int ky = 0; ky < 5; ++ky)
+      for (int kx = 0; kx < 5; ++kx)
+        for (int c = 0; c < 32; ++c)
+          acc += (double)A.at((((int64_t)z * images + img) * 144 + (oy + ky) * 12 + ox + kx) * 32 + c) *
+                 (double)B.at(((int64_t)z * H + n) * 800 + (ky * 5 + kx) * 32 + c);
+    acc += hb[(int64_t)z * H + n];
+    acc = acc > 0 ? acc : acc * 0.01;
+    max_err = fmax(max_err, fabs((double)h[idx] - acc));
+    max_ref = fmax(max_ref, fabs(acc));
+  }
+  A.free_(); B.free_(); bias.free_();
+  cudaFree(out);
+  return max_err / fmax(max_ref, 1e-30);
+}
+
 int main(int argc, char** argv) {
   const bool bench = argc > 1 && !strcmp(argv[1], "bench");
   int fails = 0;
@@ -268,6 +331,23 @@ int main(int argc, char** argv) {
       if (!(e < tol) && !g_skip) fails++;
     }
   }
+  }
+  if (!getenv("TC_NO_CONV")) {
+    printf("---- implicit-GEMM conv operand (5-D TMA boxes), TF32X3, single CTA ----\n");
+    const int cc[][4] = {{5, 3, 64, 64}, {2, 2, 512, 256}, {7, 2, 128, 128}, {1, 4, 32, 32}};
+    for (const auto& c : cc) {
+      double ms = 0;
+      const double e = run_conv_case(c[0], c[1], c[2], c[3], 0, &ms);
+      printf("conv images=%d Z=%d H=%d BN=%d                      rel err %.3e  %s\n", c[0], c[1], c[2], c[3], e, e < 3e-5 ? "ok" : "FAIL");
+      if (!(e < 3e-5)) fails++;
+    }
+    if (bench) {
+      double ms = 0;
+      const double e = run_conv_case(100, 50, 512, 256, 3, &ms);
+      printf("conv images=100 Z=50 H=512 BN=256 (cfg4)           rel err %.3e  %.3f ms  %.1f TFLOP/s (algorithmic, 1 pass)\n", e, ms,
+             2.0 * 6400 * 512 * 800.0 * 50 / ms * 1e-9);
+      if (!(e < 3e-5)) fails++;
+    }
   }
   printf(fails ? "FAILED (%d)\n" : "ALL OK\n", fails);
   return fails ? 1 : 0;

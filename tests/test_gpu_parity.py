@@ -272,6 +272,83 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     eng.close()
 
 
+TC_CONV_CONFIGS = [
+    ((1, 28, 28), 32, 10, 9, 3),        # odd batch: the last 128-row tile holds one image + out-of-bounds zeros
+    ((1, 28, 28), 64, 10, 17, 4),
+    ((1, 28, 28), 512, 10, 4, 2),       # the real model_idx=0 width (two 256-column tiles)
+    ((1, 28, 28), 16, 10, 2, 5),        # narrowest legal hidden size: K = 16 < one K-block in the dgrad GEMM
+]
+
+
+@pytest.mark.parametrize("shape,hidden,C,B,S", TC_CONV_CONFIGS)
+def test_tcgen05_conv_engine_vs_oracle(shape, hidden, C, B, S):
+    """arch conv on the tensor cores (TF32X3): conv2 as an implicit GEMM over 5-D TMA boxes, its input gradient as a
+    tcgen05 GEMM, LeakyReLU signs and pooling arg-maxes settled exactly inside the guard band -- against the fp64 oracle
+    at the north-star tolerance."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    net, layout, loc, rho, bank, x, labels = _problem("conv", shape, hidden, C, B, S)
+    eng = Net("conv", shape, hidden, C)
+    for bad in ("f16x3", "bf16"):
+        with pytest.raises(RuntimeError):
+            eng.set_precision(bad)
+    eng.set_precision("tf32x3")
+    assert eng.precision == "tf32x3"
+    eng.upload(bank, 0)
+    probs = eng.forward_probs_sum(x, 0, S).cpu() / S
+    ref_p = orc.bnn_forward(net, layout, bank, x, range(S)).detach()
+    assert rel_err(probs, ref_p) < REL
+    assert rel_err(eng.forward_logits(x, 1).cpu(), orc.bnn_forward_avg_posterior(net, layout, bank[1], x).detach()) < REL
+    g = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S).cpu().reshape(x.shape) / S
+    ref64 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    e_mean = rel_err(g, ref64)
+    pbar = eng.forward_probs_sum(x, 0, S) / S
+    ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
+    ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    e_att = rel_err(ga, ra)
+    gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, S - 1, S).cpu().reshape(x.shape)
+    rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
+    e_log = rel_err(gl, rl)
+    print(f"tcgen05 conv-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} logits-CE {e_log:.2e}")
+    assert max(e_mean, e_att, e_log) < REL
+    # no kept-forward route for conv: keep=True is a plain forward
+    assert rel_err(eng.forward_probs_sum(x, 0, S, keep=True).cpu() / S, ref_p) < REL and not eng.keep_valid
+    ga_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S // 2)
+    gb_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, S // 2, S)
+    assert rel_err((ga_ + gb_).cpu().reshape(x.shape) / S, g) < 1e-5
+    eng.upload(bank[0:1], 1)                       # row 1 <- row 0: the derived filter copies must follow
+    g11 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 1, 2).cpu()
+    g00 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, 1).cpu()
+    assert torch.equal(g11, g00)
+    eng.set_precision("fp32")                      # the CUDA-core engine on the same handle
+    g32 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, 1).cpu()
+    assert rel_err(g32, g00) < REL
+    eng.close()
+
+
+def test_golden_hmc_conv_on_tcgen05(tmp_path, monkeypatch):
+    """The reference's own outputs for the conv BNN (golden vectors) reproduced by the tensor-core conv engine:
+    probabilities, expected loss gradients, FGSM examples, evaluation counts bit-exact."""
+    from robustbnns_b200 import adversarialAttacks as aa
+    from robustbnns_b200 import lossGradients as lg
+    monkeypatch.chdir(tmp_path)
+    c = Case("hmc_conv16_fmnist")
+    S = c.bank.shape[0]
+    bnn = _bnn(c, "hmc", S)
+    bnn.set_posterior_samples(c.bank)
+    bnn.set_precision("tf32x3")
+    assert rel_err(bnn.forward(c.x, n_samples=S).cpu(), c.t("probs")) < REL
+    assert rel_err(lg.expected_loss_gradients(bnn, c.x, c.labels, S).cpu(), c.t("loss_gradient")) < REL
+    hyper = {"epsilon": float(c.z["eps"])}
+    adv = aa.attack(net=bnn, x_test=c.x, y_test=c.y, dataset_name=c.dataset, device="cuda", method="fgsm",
+                    filename="a", savedir="a", hyperparams=hyper, n_samples=S)
+    ref = c.t("fgsm_hyper_adv")
+    assert _mismatch_fraction(adv, ref) <= 2e-3
+    o, a, rob = aa.attack_evaluation(net=bnn, x_test=c.x, x_attack=ref, y_test=c.y, device="cuda", n_samples=S)
+    assert [o, a] == c.z["fgsm_hyper_eval"].tolist()
+    assert float((rob.cpu() - c.t("fgsm_hyper_rob")).abs().max()) <= REL      # probabilities from tensor-core logits
+
+
 @pytest.mark.parametrize("prec", ["tf32x3", "f16x3"])
 @pytest.mark.parametrize("gain", [10.0, 30.0])
 def test_tcgen05_engine_on_saturated_softmax(prec, gain):
