@@ -215,36 +215,38 @@ static int fc_probs_simt(rbnn_net* n, const float* x, int B, int s0, int s1, flo
 // conv on the CUDA-core engine (im2col + GEMM for conv2)
 // ------------------------------------------------------------------------------------------
 struct ConvBufs {
-  float *p1, *col, *a2, *p2, *logits, *dlogits, *dp2, *dz2, *g1;
+  float *p1, *col, *a2, *logits, *dlogits, *dz2, *g1, *partial;
   uint8_t* idx1;
+  int parts;
 };
 
 static size_t conv_bytes_per_zb(const rbnn_net* n, bool grad) {
   const size_t H = n->H, C = n->C;
-  size_t per = 4608 * 4 + 4608 + 64 * 800 * 4 + 64 * H * 4 + 49 * H * 4 + C * 4;
-  if (grad) per += C * 4 + 49 * H * 4 + 64 * H * 4 + 4608 * 4;
+  size_t per = 4608 * 4 + 4608 + 64 * 800 * 4 + 64 * H * 4 + C * 4;
+  if (grad) per += C * 4 + 64 * H * 4 + 4608 * 4 + 784 * 4 /* share of the conv1-backward partials */;
   return per + 64;
 }
 
-static void conv_carve(rbnn_net* n, Arena& ar, int ZB, bool grad, ConvBufs& c) {
-  const size_t H = n->H, C = n->C;
+static void conv_carve(rbnn_net* n, Arena& ar, int Z, int B, bool grad, ConvBufs& c) {
+  const size_t H = n->H, C = n->C, ZB = (size_t)Z * B;
+  c.partial = nullptr; c.parts = 1;
   c.p1 = ar.take<float>((size_t)ZB * 4608);
   c.idx1 = ar.take<uint8_t>((size_t)ZB * 4608);
   c.col = ar.take<float>((size_t)ZB * 64 * 800);
   c.a2 = ar.take<float>((size_t)ZB * 64 * H);
-  c.p2 = ar.take<float>((size_t)ZB * 49 * H);
   c.logits = ar.take<float>((size_t)ZB * C);
   if (grad) {
     c.dlogits = ar.take<float>((size_t)ZB * C);
-    c.dp2 = ar.take<float>((size_t)ZB * 49 * H);
     c.dz2 = ar.take<float>((size_t)ZB * 64 * H);
     c.g1 = ar.take<float>((size_t)ZB * 4608);
+    c.parts = conv1_bwd_parts(n, Z, B);
+    if (c.parts > 1) c.partial = ar.take<float>((size_t)c.parts * B * 784);
   }
 }
 
 static int conv_forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvBufs& c, float* logits,
                               cudaStream_t st) {
-  const int H = n->H, C = n->C;
+  const int H = n->H;
   const int64_t P = n->L.P;
   const float* rows = n->bank + (int64_t)z0 * P;
   RBNN_TRY(conv1_pool_fwd(n, x, n->bank, z0, Z, B, c.p1, c.idx1, st));
@@ -256,14 +258,7 @@ static int conv_forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z,
   g.C = c.a2; g.ldc = H; g.sCz = (int64_t)B * 64 * H;
   g.M = B * 64; g.N = H; g.K = 800; g.Z = Z; g.epi = EPI_BIAS_LEAKY;
   RBNN_TRY(gemm_simt(n, g, st));
-  RBNN_TRY(pool2_fwd(n, c.a2, Z * B, H, c.p2, st));
-  GemmArgs o{};
-  o.A = c.p2; o.lda = 49 * H; o.sAz = (int64_t)B * 49 * H;
-  o.B = n->woutp + (int64_t)z0 * C * 49 * H; o.ldb = 49 * H; o.sBz = (int64_t)C * 49 * H;
-  o.bias = rows + n->L.bo; o.sbz = P;
-  o.C = logits; o.ldc = C; o.sCz = (int64_t)B * C;
-  o.M = B; o.N = C; o.K = 49 * H; o.Z = Z; o.epi = EPI_BIAS;
-  RBNN_TRY(gemm_simt(n, o, st));
+  RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, st));
   return 0;
 }
 
@@ -279,18 +274,11 @@ static int conv_grad_simt(rbnn_net* n, int head, const float* x, const int32_t* 
     const int Z = std::min(zc, s1 - z0);
     Arena ar(n);
     ConvBufs c{};
-    conv_carve(n, ar, Z * B, true, c);
+    conv_carve(n, ar, Z, B, true, c);
     RBNN_TRY(conv_forward_chunk(n, x, B, z0, Z, c, c.logits, st));
     RBNN_TRY(head_dlogits(n, head, c.logits, labels, pbar, Z, B, C, c.dlogits, st));
     const float* rows = n->bank + (int64_t)z0 * P;
-    GemmArgs g{};
-    g.b_kn = 1;
-    g.A = c.dlogits; g.lda = C; g.sAz = (int64_t)B * C;
-    g.B = n->woutp + (int64_t)z0 * C * 49 * H; g.ldb = 49 * H; g.sBz = (int64_t)C * 49 * H;
-    g.C = c.dp2; g.ldc = 49 * H; g.sCz = (int64_t)B * 49 * H;
-    g.M = B; g.N = 49 * H; g.K = C; g.Z = Z; g.epi = EPI_NONE;
-    RBNN_TRY(gemm_simt(n, g, st));
-    RBNN_TRY(pool2_bwd(n, c.a2, c.dp2, Z * B, H, c.dz2, st));
+    RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dz2, nullptr, st));
     GemmArgs d{};
     d.b_kn = 1;
     d.A = c.dz2; d.lda = H; d.sAz = (int64_t)B * 64 * H;
@@ -299,7 +287,7 @@ static int conv_grad_simt(rbnn_net* n, int head, const float* x, const int32_t* 
     d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.epi = EPI_NONE;
     RBNN_TRY(gemm_simt(n, d, st));
     RBNN_TRY(col2im_conv2(n, c.col, c.p1, Z * B, c.g1, st));
-    RBNN_TRY(conv1_bwd_sum(n, c.g1, c.idx1, n->bank, z0, Z, B, out_sum, first ? 0 : 1, st));
+    RBNN_TRY(conv1_bwd_sum(n, c.g1, c.idx1, n->bank, z0, Z, B, out_sum, first ? 0 : 1, st, c.partial, c.parts));
     first = false;
   }
   return 0;
@@ -315,7 +303,7 @@ static int conv_probs_simt(rbnn_net* n, const float* x, int B, int s0, int s1, f
     const int Z = std::min(zc, s1 - z0);
     Arena ar(n);
     ConvBufs c{};
-    conv_carve(n, ar, Z * B, false, c);
+    conv_carve(n, ar, Z, B, false, c);
     float* lg = out_logits ? out_logits : c.logits;
     RBNN_TRY(conv_forward_chunk(n, x, B, z0, Z, c, lg, st));
     if (out_sum) RBNN_TRY(head_probs_accumulate(n, lg, Z, B, C, out_sum, st));

@@ -179,8 +179,14 @@ int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, f
 int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, float* hi, float* lo, cudaStream_t st);
 int conv2_refine(rbnn_net* net, float* a2, const float* p1, int s0, int Z, int B, float eps, cudaStream_t st);
 int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, float* g1, cudaStream_t st);
+// partial != nullptr && parts > 1: the sample range is cut into `parts` slices (partial: [parts][B][784] floats)
 int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,
-                  float* dx_sum, int accumulate, cudaStream_t st);
+                  float* dx_sum, int accumulate, cudaStream_t st, float* partial = nullptr, int parts = 1);
+int conv1_bwd_parts(const rbnn_net* net, int Z, int B);
+// MaxPool2d(2, stride 1) + Linear(49H, C) and their input gradient, fused (the pooled map / its gradient stay on chip)
+int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* logits, cudaStream_t st);
+int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, float* dz2,
+                    float* dz2_lo, cudaStream_t st);
 
 // ---- attack.cu --------------------------------------------------------------------------
 int scale_inplace(rbnn_net* net, float* p, float scale, int64_t n, cudaStream_t st);

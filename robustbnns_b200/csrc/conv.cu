@@ -6,6 +6,8 @@
 // Internal activation layouts after conv2 are position-major / channel-minor (HWC) so the GEMM
 // output is consumed as is; model.7.weight is permuted once per bank row to match (sampler.cu).
 // Max-pool ties route to the FIRST maximum in window scan order, as torch's max_pool2d does.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace rbnn {
@@ -159,30 +161,39 @@ int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, f
 
 // ---- col2im (gather) + leaky' of the pooled conv1 activation ---------------------------------
 // G1[zb][c][iy][ix] = leaky'(P1) * sum_{ky,kx} dcol[(zb*64 + (iy-ky)*8 + (ix-kx))][c*25+ky*5+kx]
-__global__ void col2im_conv2_kernel(const float* __restrict__ dcol, const float* __restrict__ p1, int64_t total,
-                                    float* __restrict__ g1) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int ix = (int)(i % 12), iy = (int)((i / 12) % 12), c = (int)((i / 144) % 32);
-  const int64_t zb = i / 4608;
-  float acc = 0.f;
-#pragma unroll
-  for (int ky = 0; ky < 5; ++ky) {
-    const int oy = iy - ky;
-    if (oy < 0 || oy > 7) continue;
-#pragma unroll
-    for (int kx = 0; kx < 5; ++kx) {
-      const int ox = ix - kx;
-      if (ox < 0 || ox > 7) continue;
-      acc += __ldg(dcol + (zb * 64 + oy * 8 + ox) * 800 + c * 25 + ky * 5 + kx);
-    }
+// One block per (image, group of 4 channels): the image's 64 x 100 slice of dcol is staged in shared memory with
+// coalesced 400-byte runs, then gathered (the direct gather strides 3200 bytes between neighbouring threads).
+__global__ void __launch_bounds__(256)
+col2im_conv2_kernel(const float* __restrict__ dcol, const float* __restrict__ p1, float* __restrict__ g1) {
+  __shared__ float t[64 * 100];
+  const int64_t zb = blockIdx.x;
+  const int cg = blockIdx.y;
+  for (int i = threadIdx.x; i < 6400; i += blockDim.x) {
+    const int pos = i / 100, j = i - pos * 100;
+    t[i] = __ldg(dcol + (zb * 64 + pos) * 800 + cg * 100 + j);
   }
-  g1[i] = __ldg(p1 + i) > 0.f ? acc : acc * kLeakySlope;
+  __syncthreads();
+  for (int o = threadIdx.x; o < 4 * 144; o += blockDim.x) {
+    const int cl = o / 144, r = o - cl * 144, iy = r / 12, ix = r - iy * 12;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      const int oy = iy - ky;
+      if (oy < 0 || oy > 7) continue;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const int ox = ix - kx;
+        if (ox < 0 || ox > 7) continue;
+        acc += t[(oy * 8 + ox) * 100 + cl * 25 + ky * 5 + kx];
+      }
+    }
+    const int64_t gi = zb * 4608 + (cg * 4 + cl) * 144 + r;
+    g1[gi] = __ldg(p1 + gi) > 0.f ? acc : acc * kLeakySlope;
+  }
 }
 
 int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, float* g1, cudaStream_t st) {
-  const int64_t total = (int64_t)ZB * 4608;
-  col2im_conv2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dcol, p1, total, g1);
+  col2im_conv2_kernel<<<dim3(ZB, 8), 256, 0, st>>>(dcol, p1, g1);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -193,12 +204,16 @@ int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, floa
 __global__ void __launch_bounds__(256)
 conv1_bwd_sum_kernel(const float* __restrict__ g1, const uint8_t* __restrict__ idx1, const float* __restrict__ bank,
                      int64_t P, int64_t cw1, int s0, int Z, int B, float* __restrict__ dx, int accumulate) {
+  // gridDim.y > 1: block (b, zi) sums the samples of its slice of [0, Z) into the partial buffer dx[zi][b][784]
+  // (reduced in a fixed order by conv1_reduce_kernel); gridDim.y == 1: the whole range straight into dx[b][784]
   __shared__ float gs[4608];
   __shared__ uint8_t is[4608];
   __shared__ float ws[800];
   const int b = blockIdx.x;
+  const int z_begin = (int)((long long)blockIdx.y * Z / gridDim.y), z_end = (int)((long long)(blockIdx.y + 1) * Z / gridDim.y);
+  dx += (int64_t)blockIdx.y * B * 784;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int z = 0; z < Z; ++z) {
+  for (int z = z_begin; z < z_end; ++z) {
     const int64_t zb = (int64_t)z * B + b;
     __syncthreads();
     for (int i = threadIdx.x; i < 4608; i += blockDim.x) {
@@ -238,9 +253,217 @@ conv1_bwd_sum_kernel(const float* __restrict__ g1, const uint8_t* __restrict__ i
   }
 }
 
+// dx[i] = (accumulate ? dx[i] : 0) + sum_p partial[p][i], fixed order
+__global__ void conv1_reduce_kernel(const float* __restrict__ partial, int parts, int64_t n, float* __restrict__ dx,
+                                    int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = accumulate ? dx[i] : 0.f;
+  for (int p = 0; p < parts; ++p) s += __ldg(partial + (int64_t)p * n + i);
+  dx[i] = s;
+}
+
+// slices of the sample range one image's blocks are cut into (fills the SMs when the batch is small)
+int conv1_bwd_parts(const rbnn_net* net, int Z, int B) {
+  const int want = (4 * net->sm_count + B - 1) / B;
+  return std::max(1, std::min(std::min(want, Z), 32));
+}
+
 int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,
-                  float* dx_sum, int accumulate, cudaStream_t st) {
-  conv1_bwd_sum_kernel<<<B, 256, 0, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, dx_sum, accumulate);
+                  float* dx_sum, int accumulate, cudaStream_t st, float* partial, int parts) {
+  if (!partial || parts <= 1) {
+    conv1_bwd_sum_kernel<<<B, 256, 0, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, dx_sum, accumulate);
+    net->launches++;
+    RBNN_CUDA(cudaGetLastError());
+    return 0;
+  }
+  conv1_bwd_sum_kernel<<<dim3(B, parts), 256, 0, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, partial, 0);
+  const int64_t n = (int64_t)B * 784;
+  conv1_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, parts, n, dx_sum, accumulate);
+  net->launches += 2;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- MaxPool2d(2, stride 1) + Linear(49H, C), fused ------------------------------------------------
+// logits[zb][c] = bo_z[c] + sum_{p, h} max(A2 window p)[h] * woutp_z[c][p*H + h]      (model_nn.py:103-106)
+// The pooled map is never written: a block owns kPoolImgs images of one sample, so every output weight it
+// loads is used for all of them; thread-strided partial sums, then a fixed-order block reduction (deterministic).
+constexpr int kPoolImgs = 4;
+
+template <int C_MAX>
+__global__ void __launch_bounds__(256)
+pool2_logits_kernel(const float* __restrict__ a2, const float* __restrict__ woutp, const float* __restrict__ bank,
+                    int64_t P, int64_t bo_off, int s0, int B, int H, int C, float* __restrict__ logits) {
+  __shared__ float red[8][kPoolImgs][C_MAX];
+  const int z = blockIdx.y, b0 = blockIdx.x * kPoolImgs;
+  const int F = 49 * H;
+  const float* __restrict__ W = woutp + (int64_t)(s0 + z) * C * F;
+  const float* __restrict__ A = a2 + ((int64_t)z * B + b0) * 64 * H;
+  const int nimg = min(kPoolImgs, B - b0);
+  float acc[kPoolImgs][C_MAX];
+#pragma unroll
+  for (int q = 0; q < kPoolImgs; ++q)
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c) acc[q][c] = 0.f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const int p = i / H, h = i - p * H;
+    const int py = p / 7, px = p - 7 * py;
+    const int o = (py * 8 + px) * H + h;
+    float v[kPoolImgs];
+#pragma unroll
+    for (int q = 0; q < kPoolImgs; ++q) {
+      v[q] = 0.f;
+      if (q < nimg) {
+        const float* base = A + (int64_t)q * 64 * H + o;
+        v[q] = fmaxf(fmaxf(__ldg(base), __ldg(base + H)), fmaxf(__ldg(base + 8 * H), __ldg(base + 9 * H)));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c)
+      if (c < C) {
+        const float w = __ldg(W + (int64_t)c * F + i);
+#pragma unroll
+        for (int q = 0; q < kPoolImgs; ++q) acc[q][c] = fmaf(v[q], w, acc[q][c]);
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < kPoolImgs; ++q)
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c) {
+      float t = acc[q][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) red[warp][q][c] = t;
+    }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nimg * C; j += blockDim.x) {
+    const int q = j / C, c = j - q * C;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][q][c];
+    logits[((int64_t)z * B + b0 + q) * C + c] = t + __ldg(bank + (int64_t)(s0 + z) * P + bo_off + c);
+  }
+}
+
+int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* logits, cudaStream_t st) {
+  dim3 grid((B + kPoolImgs - 1) / kPoolImgs, Z);
+  if (net->C <= 16)
+    pool2_logits_kernel<16><<<grid, 256, 0, st>>>(a2, net->woutp, net->bank, net->L.P, net->L.bo, s0, B, net->H, net->C, logits);
+  else
+    pool2_logits_kernel<32><<<grid, 256, 0, st>>>(a2, net->woutp, net->bank, net->L.P, net->L.bo, s0, B, net->H, net->C, logits);
+  net->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- input gradient of Linear(49H, C) + MaxPool2d(2, stride 1) + LeakyReLU, fused ---------------------
+// dZ2[zb][pos][h] = leaky'(A2[pos][h]) * sum over the <= 4 windows w containing pos whose FIRST maximum (scan order,
+// as torch's max_pool2d) is pos of  sum_c dlogits[zb][c] * woutp_z[c][w*H + h]          -- dP2 is never written.
+// A thread owns one channel h of kBwdImgs images and walks the 7x7 windows row by row: every output weight is loaded
+// once per block (window-major; the position-major form re-read each weight from L2 four times), the two A2 rows a
+// window row touches and their gradient accumulators live in registers (all indices static after unrolling), and a
+// position receives its <= 4 contributions in the fixed order (wy-1,wx-1), (wy-1,wx), (wy,wx-1), (wy,wx).
+// dz2_lo != nullptr: the result is written tf32-split (hi = rn_tf32(v), lo = v - hi) for the tcgen05 dgrad GEMM.
+constexpr int kBwdImgs = 2;
+
+template <int C_MAX>
+__global__ void __launch_bounds__(128)
+pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ dlogits, const float* __restrict__ woutp,
+                       int s0, int B, int H, int C, float* __restrict__ dz2, float* __restrict__ dz2_lo) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const int z = blockIdx.z, b0 = blockIdx.y * kBwdImgs;
+  const int nimg = min(kBwdImgs, B - b0);
+  const int64_t F = (int64_t)49 * H;
+  const float* __restrict__ W = woutp + (int64_t)(s0 + z) * C * F + h;
+  float dl[kBwdImgs][C_MAX];
+  const float* A[kBwdImgs];
+  int64_t obase[kBwdImgs];
+#pragma unroll
+  for (int q = 0; q < kBwdImgs; ++q) {
+    const int64_t zb = (int64_t)z * B + b0 + min(q, nimg - 1);
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c) dl[q][c] = (q < nimg && c < C) ? __ldg(dlogits + zb * C + c) : 0.f;
+    obase[q] = zb * 64 * H + h;
+    A[q] = a2 + obase[q];
+  }
+  float r0[kBwdImgs][8], r1[kBwdImgs][8], acc0[kBwdImgs][8], acc1[kBwdImgs][8];
+#pragma unroll
+  for (int q = 0; q < kBwdImgs; ++q)
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      r0[q][x] = __ldg(A[q] + (int64_t)x * H);
+      acc0[q][x] = 0.f;
+      acc1[q][x] = 0.f;
+    }
+  auto store_row = [&](int row) {
+#pragma unroll
+    for (int q = 0; q < kBwdImgs; ++q) {
+      if (q >= nimg) continue;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const float v = r0[q][x] > 0.f ? acc0[q][x] : acc0[q][x] * kLeakySlope;
+        const int64_t o = obase[q] + (int64_t)(row * 8 + x) * H;
+        if (dz2_lo) {
+          const float hv = tf32_rn(v);
+          dz2[o] = hv;
+          dz2_lo[o] = v - hv;
+        } else {
+          dz2[o] = v;
+        }
+      }
+    }
+  };
+#pragma unroll 1
+  for (int wy = 0; wy < 7; ++wy) {
+#pragma unroll
+    for (int q = 0; q < kBwdImgs; ++q)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) r1[q][x] = __ldg(A[q] + (int64_t)((wy + 1) * 8 + x) * H);
+#pragma unroll
+    for (int wx = 0; wx < 7; ++wx) {
+      float wv[C_MAX];
+#pragma unroll
+      for (int c = 0; c < C_MAX; ++c) wv[c] = c < C ? __ldg(W + (int64_t)c * F + (int64_t)(wy * 7 + wx) * H) : 0.f;
+#pragma unroll
+      for (int q = 0; q < kBwdImgs; ++q) {
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < C_MAX; ++c) d = fmaf(dl[q][c], wv[c], d);
+        float best = r0[q][wx];
+        int k = 0;
+        if (r0[q][wx + 1] > best) { best = r0[q][wx + 1]; k = 1; }
+        if (r1[q][wx] > best) { best = r1[q][wx]; k = 2; }
+        if (r1[q][wx + 1] > best) { k = 3; }
+        acc0[q][wx] += k == 0 ? d : 0.f;
+        acc0[q][wx + 1] += k == 1 ? d : 0.f;
+        acc1[q][wx] += k == 2 ? d : 0.f;
+        acc1[q][wx + 1] += k == 3 ? d : 0.f;
+      }
+    }
+    store_row(wy);
+#pragma unroll
+    for (int q = 0; q < kBwdImgs; ++q)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        acc0[q][x] = acc1[q][x];
+        acc1[q][x] = 0.f;
+        r0[q][x] = r1[q][x];
+      }
+  }
+  store_row(7);
+}
+
+int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, float* dz2,
+                    float* dz2_lo, cudaStream_t st) {
+  const int threads = std::min(128, (net->H + 31) / 32 * 32);
+  dim3 grid((net->H + threads - 1) / threads, (B + kBwdImgs - 1) / kBwdImgs, Z);
+  if (net->C <= 16)
+    pool2_bwd_fused_kernel<16><<<grid, threads, 0, st>>>(a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo);
+  else
+    pool2_bwd_fused_kernel<32><<<grid, threads, 0, st>>>(a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -274,20 +497,26 @@ int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, float* hi, float* lo, c
 // The input gradient is discontinuous in the conv2 pre-activations in two ways: LeakyReLU (the sign of the
 // pre-activation) and MaxPool2d(2, stride 1) (which of the 4 window entries is the largest, model_nn.py:102-103).
 // The tensor-core GEMM errs by ~5e-6 of the output maximum, so every A2 entry whose pre-activation is within
-// eps * max|pre| (of this image) of ZERO or of one of its 8 spatial NEIGHBOURS in the same channel (the entries it
-// shares a pooling window with) is recomputed exactly -- fp64 accumulation of the fp32 products over the 5x5x32 patch,
-// CUDA cores -- and rewritten in place.  Afterwards every sign and every window arg-max agrees with exact arithmetic.
-// Values written concurrently by other warps differ from the ones they replace by far less than the band, so the
-// unsynchronised neighbour reads are harmless.  One block per (sample, image); A2 is [zb][64 positions][H].
+// guard = eps * max|pre| (of this image) of ZERO, or that is one of two or more entries of a pooling window within
+// guard of that window's maximum (a near-tie for the arg-max), is recomputed exactly -- fp64 accumulation of the fp32
+// products over the 5x5x32 patch, CUDA cores -- and rewritten in place.  Afterwards every sign and every window
+// arg-max agrees with exact arithmetic.  Two phases (flags from the untouched GEMM output, then the re-evaluation), so
+// the recomputed set and hence the result are deterministic.  One block per (sample, image); A2 is [zb][64][H].
 __global__ void __launch_bounds__(256)
 conv2_refine_kernel(float* __restrict__ a2, const float* __restrict__ p1, const float* __restrict__ bank, int64_t P,
                     int64_t cw2, int64_t cb2, int s0, int B, int H, float eps) {
   __shared__ float ps[4608];
+  __shared__ short tab[800];          // filter element k = (c, ky, kx) -> offset of its input inside the 32x12x12 map
   __shared__ float red[8];
+  __shared__ unsigned fl[64 * 64];    // recompute flags, one bit per (position, channel); H <= 2048
   const int zb = blockIdx.x, z = zb / B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* A = a2 + (int64_t)zb * 64 * H;
   for (int i = threadIdx.x; i < 4608; i += blockDim.x) ps[i] = __ldg(p1 + (int64_t)zb * 4608 + i);
+  for (int k = threadIdx.x; k < 800; k += blockDim.x) {
+    const int c = k / 25, r = k - 25 * c, ky = r / 5, kx = r - 5 * ky;
+    tab[k] = (short)(c * 144 + ky * 12 + kx);
+  }
   float m = 0.f;
   for (int i = threadIdx.x; i < 64 * H; i += blockDim.x) {
     const float v = A[i];
@@ -302,6 +531,8 @@ conv2_refine_kernel(float* __restrict__ a2, const float* __restrict__ p1, const 
   for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
   const float guard = eps * m;
   const float* __restrict__ wrow = bank + (int64_t)(s0 + z) * P;
+  const int hw = (H + 31) >> 5;                 // 32-channel words per position
+  // phase 1: flags from the untouched GEMM output (=> the set that gets recomputed is deterministic)
   for (int pos = warp; pos < 64; pos += 8) {
     const int y = pos >> 3, x = pos & 7;
     for (int h0 = 0; h0 < H; h0 += 32) {
@@ -312,34 +543,47 @@ conv2_refine_kernel(float* __restrict__ a2, const float* __restrict__ p1, const 
         const float pre = v > 0.f ? v : 100.f * v;
         flag = fabsf(pre) < guard;
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
+        for (int wy = y - 1; wy <= y; ++wy)
 #pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            const int yy = y + dy, xx = x + dx;
-            if ((dy == 0 && dx == 0) || yy < 0 || yy > 7 || xx < 0 || xx > 7) continue;
-            const float vn = A[(yy * 8 + xx) * H + h];
-            const float pn = vn > 0.f ? vn : 100.f * vn;
-            flag = flag || fabsf(pre - pn) < guard;
+          for (int wx = x - 1; wx <= x; ++wx) {
+            if (wy < 0 || wy > 6 || wx < 0 || wx > 6) continue;
+            float q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float vn = A[((wy + (j >> 1)) * 8 + wx + (j & 1)) * H + h];
+              q[j] = vn > 0.f ? vn : 100.f * vn;
+            }
+            const float top = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])) - guard;
+            const int near = (q[0] > top) + (q[1] > top) + (q[2] > top) + (q[3] > top);
+            flag = flag || (near >= 2 && pre > top);
           }
       }
-      unsigned any = __ballot_sync(0xffffffffu, flag);
-      while (any) {
-        const int src = __ffs(any) - 1;
-        any &= any - 1;
-        const int hh = h0 + src;
-        const float* __restrict__ w = wrow + cw2 + (int64_t)hh * 800;
-        double s = 0.0;
-        for (int k = lane; k < 800; k += 32) {
-          const int c = k / 25, r = k - 25 * c, ky = r / 5, kx = r - 5 * ky;
-          s = fma((double)ps[c * 144 + (y + ky) * 12 + x + kx], (double)__ldg(w + k), s);
-        }
+      const unsigned any = __ballot_sync(0xffffffffu, flag);
+      if (lane == 0) fl[pos * hw + (h0 >> 5)] = any;
+    }
+  }
+  __syncthreads();
+  // phase 2: exact re-evaluation of the flagged entries, one warp per entry
+  for (int wi = warp; wi < 64 * hw; wi += 8) {
+    unsigned any = fl[wi];
+    if (!any) continue;
+    const int pos = wi / hw, h0 = (wi - pos * hw) << 5;
+    const int y = pos >> 3, x = pos & 7;
+    const float* __restrict__ patch = ps + y * 12 + x;
+    while (any) {
+      const int src = __ffs(any) - 1;
+      any &= any - 1;
+      const int hh = h0 + src;
+      const float* __restrict__ w = wrow + cw2 + (int64_t)hh * 800;
+      double s = 0.0;
+#pragma unroll 5
+      for (int k = lane; k < 800; k += 32) s = fma((double)patch[tab[k]], (double)__ldg(w + k), s);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        s += (double)__ldg(wrow + cb2 + hh);
-        float val = (float)s;
-        val = val > 0.f ? val : val * kLeakySlope;
-        if (lane == src) A[pos * H + hh] = val;
-      }
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      s += (double)__ldg(wrow + cb2 + hh);
+      float val = (float)s;
+      val = val > 0.f ? val : val * kLeakySlope;
+      if (lane == src) A[pos * H + hh] = val;
     }
   }
 }

@@ -6,7 +6,7 @@
 //                                                 matrix), B = W2_z as [H][(ky, kx, c)], fp32 accumulators in TMEM
 //   guard-band refinement                     exact re-evaluation of the entries whose LeakyReLU sign or pooling
 //                                             arg-max the tensor-core rounding could flip                     conv.cu
-//   MaxPool2d(2, stride 1), Linear(49H, C), loss head, their input gradients     CUDA-core kernels (3 % of the FLOPs)
+//   MaxPool2d(2, stride 1) + Linear(49H, C) (fused), loss head, their input gradients (fused)   CUDA cores (3 % of the FLOPs)
 //   conv2 dgrad  dcol = dZ2 . W2_z  (K = H)   tcgen05 GEMM over the transposed weight copies, then col2im + conv1 backward
 // This is lossGradients.py:29-40 / adversarialAttacks.py:74-78 for the conv BNN, input gradients only.
 #include <algorithm>
@@ -20,40 +20,41 @@ namespace rbnn {
 constexpr float kConvGuardEps = 1.0f / 4096.0f;
 
 int tc_conv_supported(const rbnn_net* n) {
-  return n->arch == RBNN_ARCH_CONV && n->cc_major == 10 && (n->H % 16) == 0;
+  return n->arch == RBNN_ARCH_CONV && n->cc_major == 10 && (n->H % 16) == 0 && n->H <= 2048;
 }
 
 namespace {
 
 struct ConvTcBufs {
-  float *p1 = nullptr, *p1h = nullptr, *p1l = nullptr, *a2 = nullptr, *p2 = nullptr, *logits = nullptr;
-  float *dlogits = nullptr, *dp2 = nullptr, *dzh = nullptr, *dzl = nullptr, *dcol = nullptr, *g1 = nullptr;
+  float *p1 = nullptr, *p1h = nullptr, *p1l = nullptr, *a2 = nullptr, *logits = nullptr;
+  float *dlogits = nullptr, *dzh = nullptr, *dzl = nullptr, *dcol = nullptr, *g1 = nullptr, *partial = nullptr;
   uint8_t* idx1 = nullptr;
+  int parts = 1;
 };
 
 size_t bytes_per_zb(const rbnn_net* n, bool grad) {
   const size_t H = n->H, C = n->C;
-  size_t per = 3 * 4608 * 4 + 4608 + 64 * H * 4 + 49 * H * 4 + C * 4;
-  if (grad) per += C * 4 + 49 * H * 4 + 2 * 64 * H * 4 + 64 * 800 * 4 + 4608 * 4;
+  size_t per = 3 * 4608 * 4 + 4608 + 64 * H * 4 + C * 4;
+  if (grad) per += C * 4 + 2 * 64 * H * 4 + 64 * 800 * 4 + 4608 * 4;
   return per + 64;
 }
 
-void carve(rbnn_net* n, Arena& ar, int ZB, bool grad, ConvTcBufs& c) {
-  const size_t H = n->H, C = n->C;
+void carve(rbnn_net* n, Arena& ar, int Z, int B, bool grad, ConvTcBufs& c) {
+  const size_t H = n->H, C = n->C, ZB = (size_t)Z * B;
   c.p1 = ar.take<float>((size_t)ZB * 4608);
   c.p1h = ar.take<float>((size_t)ZB * 4608);
   c.p1l = ar.take<float>((size_t)ZB * 4608);
   c.idx1 = ar.take<uint8_t>((size_t)ZB * 4608);
   c.a2 = ar.take<float>((size_t)ZB * 64 * H);
-  c.p2 = ar.take<float>((size_t)ZB * 49 * H);
   c.logits = ar.take<float>((size_t)ZB * C);
   if (grad) {
     c.dlogits = ar.take<float>((size_t)ZB * C);
-    c.dp2 = ar.take<float>((size_t)ZB * 49 * H);
     c.dzh = ar.take<float>((size_t)ZB * 64 * H);
     c.dzl = ar.take<float>((size_t)ZB * 64 * H);
     c.dcol = ar.take<float>((size_t)ZB * 64 * 800);
     c.g1 = ar.take<float>((size_t)ZB * 4608);
+    c.parts = conv1_bwd_parts(n, Z, B);
+    if (c.parts > 1) c.partial = ar.take<float>((size_t)c.parts * B * 784);
   }
 }
 
@@ -72,7 +73,7 @@ int run_tc(rbnn_net* n, tc::GemmDesc& d, int tag, cudaStream_t st) {
 }
 
 int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs& c, float* logits, cudaStream_t st) {
-  const int H = n->H, C = n->C;
+  const int H = n->H;
   const int64_t P = n->L.P;
   const float* rows = n->bank + (int64_t)z0 * P;
   const TcMat& m = n->tc.mat[0];
@@ -89,21 +90,14 @@ int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs&
   g.out = c.a2; g.out_ld = H; g.out_zstride = (int64_t)B * 64 * H;
   RBNN_TRY(run_tc(n, g, 1, st));
   RBNN_TRY(conv2_refine(n, c.a2, c.p1, z0, Z, B, kConvGuardEps, st));
-  RBNN_TRY(pool2_fwd(n, c.a2, Z * B, H, c.p2, st));
-  GemmArgs o{};
-  o.A = c.p2; o.lda = 49 * H; o.sAz = (int64_t)B * 49 * H;
-  o.B = n->woutp + (int64_t)z0 * C * 49 * H; o.ldb = 49 * H; o.sBz = (int64_t)C * 49 * H;
-  o.bias = rows + n->L.bo; o.sbz = P;
-  o.C = logits; o.ldc = C; o.sCz = (int64_t)B * C;
-  o.M = B; o.N = C; o.K = 49 * H; o.Z = Z; o.epi = EPI_BIAS;
-  RBNN_TRY(gemm_simt(n, o, st));
+  RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, st));
   return 0;
 }
 
 int grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1, const float* pbar,
               float* out_sum, cudaStream_t st) {
   const int H = n->H, C = n->C;
-  const size_t per = bytes_per_zb(n, true) * (size_t)B + 8192;
+  const size_t per = bytes_per_zb(n, true) * (size_t)B + 8192 + (size_t)B * 784 * 4;   // + this sample's share of the conv1-backward partials (<= 1 slice per sample)
   const int zc = (int)std::max<size_t>(1, std::min<size_t>(n->ws_budget / per, (size_t)(s1 - s0)));
   RBNN_TRY(ws_reserve(n, per * zc));
   const TcMat& m = n->tc.mat[0];
@@ -112,17 +106,10 @@ int grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int 
     const int Z = std::min(zc, s1 - z0);
     Arena ar(n);
     ConvTcBufs c;
-    carve(n, ar, Z * B, true, c);
+    carve(n, ar, Z, B, true, c);
     RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, c.logits, st));
     RBNN_TRY(head_dlogits(n, head, c.logits, labels, pbar, Z, B, C, c.dlogits, st));
-    GemmArgs g{};
-    g.b_kn = 1;
-    g.A = c.dlogits; g.lda = C; g.sAz = (int64_t)B * C;
-    g.B = n->woutp + (int64_t)z0 * C * 49 * H; g.ldb = 49 * H; g.sBz = (int64_t)C * 49 * H;
-    g.C = c.dp2; g.ldc = 49 * H; g.sCz = (int64_t)B * 49 * H;
-    g.M = B; g.N = 49 * H; g.K = C; g.Z = Z; g.epi = EPI_NONE;
-    RBNN_TRY(gemm_simt(n, g, st));
-    RBNN_TRY(pool2_bwd(n, c.a2, c.dp2, Z * B, H, c.dzh, st, c.dzl));
+    RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dzh, c.dzl, st));
     // dcol[z][b * 64 + pos][c * 25 + ky * 5 + kx] = sum_h dZ2[z][b * 64 + pos][h] W2_z[h][c][ky][kx]
     tc::GemmDesc d;
     d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = 160;
@@ -133,7 +120,7 @@ int grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int 
     d.out = c.dcol; d.out_ld = 800; d.out_zstride = (int64_t)B * 64 * 800;
     RBNN_TRY(run_tc(n, d, 2, st));
     RBNN_TRY(col2im_conv2(n, c.dcol, c.p1, Z * B, c.g1, st));
-    RBNN_TRY(conv1_bwd_sum(n, c.g1, c.idx1, n->bank, z0, Z, B, out_sum, first ? 0 : 1, st));
+    RBNN_TRY(conv1_bwd_sum(n, c.g1, c.idx1, n->bank, z0, Z, B, out_sum, first ? 0 : 1, st, c.partial, c.parts));
     first = false;
   }
   return 0;
@@ -148,7 +135,7 @@ int probs_pass(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_su
     const int Z = std::min(zc, s1 - z0);
     Arena ar(n);
     ConvTcBufs c;
-    carve(n, ar, Z * B, false, c);
+    carve(n, ar, Z, B, false, c);
     float* lg = out_logits ? out_logits : c.logits;
     RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, lg, st));
     if (out_sum) RBNN_TRY(head_probs_accumulate(n, lg, Z, B, C, out_sum, st));
