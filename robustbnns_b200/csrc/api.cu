@@ -215,14 +215,14 @@ static int fc_probs_simt(rbnn_net* n, const float* x, int B, int s0, int s1, flo
 // conv on the CUDA-core engine (im2col + GEMM for conv2)
 // ------------------------------------------------------------------------------------------
 struct ConvBufs {
-  float *p1, *col, *a2, *logits, *dlogits, *dz2, *g1, *partial;
+  float *p1, *col, *a2, *logits, *lpart, *dlogits, *dz2, *g1, *partial;
   uint8_t* idx1;
   int parts;
 };
 
 static size_t conv_bytes_per_zb(const rbnn_net* n, bool grad) {
   const size_t H = n->H, C = n->C;
-  size_t per = 4608 * 4 + 4608 + 64 * 800 * 4 + 64 * H * 4 + C * 4;
+  size_t per = 4608 * 4 + 4608 + 64 * 800 * 4 + 64 * H * 4 + C * 4 + (H / 128 + 1) * C * 4;
   if (grad) per += C * 4 + 64 * H * 4 + 4608 * 4 + 784 * 4 /* share of the conv1-backward partials */;
   return per + 64;
 }
@@ -235,6 +235,7 @@ static void conv_carve(rbnn_net* n, Arena& ar, int Z, int B, bool grad, ConvBufs
   c.col = ar.take<float>((size_t)ZB * 64 * 800);
   c.a2 = ar.take<float>((size_t)ZB * 64 * H);
   c.logits = ar.take<float>((size_t)ZB * C);
+  c.lpart = ar.take<float>((size_t)pool2_logits_chunks(n) * ZB * C);
   if (grad) {
     c.dlogits = ar.take<float>((size_t)ZB * C);
     c.dz2 = ar.take<float>((size_t)ZB * 64 * H);
@@ -258,7 +259,7 @@ static int conv_forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z,
   g.C = c.a2; g.ldc = H; g.sCz = (int64_t)B * 64 * H;
   g.M = B * 64; g.N = H; g.K = 800; g.Z = Z; g.epi = EPI_BIAS_LEAKY;
   RBNN_TRY(gemm_simt(n, g, st));
-  RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, st));
+  RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, c.lpart, st));
   return 0;
 }
 
@@ -440,7 +441,7 @@ int rbnn_bank_reserve(rbnn_net* n, int capacity) {
   }
   n->bank = nb;
   if (n->arch == RBNN_ARCH_CONV) {
-    const size_t row = (size_t)n->C * 49 * n->H;
+    const size_t row = (size_t)conv_class_pitch(n->C) * 49 * n->H;
     float* nw = nullptr;
     RBNN_CUDA(cudaMalloc(&nw, (size_t)capacity * row * sizeof(float)));
     if (n->woutp) {

@@ -102,7 +102,8 @@ struct rbnn_net {
   // bank
   int capacity = 0;
   float* bank = nullptr;      // [capacity, P]
-  float* woutp = nullptr;     // conv only: [capacity, C, 49H] output weights permuted to (pos, h) order
+  float* woutp = nullptr;     // conv only: [capacity][49H (pos, h)][CP] output weights, classes innermost and zero-padded to
+                              // CP = conv_class_pitch(C) so that one (pos, h) entry is CP/4 16-byte loads (sampler.cu)
   float* sigma = nullptr;     // [P] scratch: softplus(rho) of the last sample_diag call
   // workspace arena
   char* ws = nullptr;
@@ -168,6 +169,7 @@ int head_dlogits(rbnn_net* net, int head, const float* logits, const int32_t* la
 int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
                 int64_t stride, int s0, int count, cudaStream_t st);
 int conv_permute_wout(rbnn_net* net, int s0, int count, cudaStream_t st);
+inline int conv_class_pitch(int C) { return C <= 4 ? 4 : (C <= 12 ? 12 : (C <= 16 ? 16 : 32)); }
 
 // ---- conv.cu ----------------------------------------------------------------------------
 int conv1_pool_fwd(rbnn_net* net, const float* x, const float* bank, int s0, int Z, int B, float* p1,
@@ -184,7 +186,8 @@ int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const flo
                   float* dx_sum, int accumulate, cudaStream_t st, float* partial = nullptr, int parts = 1);
 int conv1_bwd_parts(const rbnn_net* net, int Z, int B);
 // MaxPool2d(2, stride 1) + Linear(49H, C) and their input gradient, fused (the pooled map / its gradient stay on chip)
-int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* logits, cudaStream_t st);
+int pool2_logits_chunks(const rbnn_net* net);
+int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* logits, float* partial, cudaStream_t st);
 int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, float* dz2,
                     float* dz2_lo, cudaStream_t st);
 

@@ -287,45 +287,67 @@ int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const flo
 
 // ---- MaxPool2d(2, stride 1) + Linear(49H, C), fused ------------------------------------------------
 // logits[zb][c] = bo_z[c] + sum_{p, h} max(A2 window p)[h] * woutp_z[c][p*H + h]      (model_nn.py:103-106)
-// The pooled map is never written: a block owns kPoolImgs images of one sample, so every output weight it
-// loads is used for all of them; thread-strided partial sums, then a fixed-order block reduction (deterministic).
-constexpr int kPoolImgs = 4;
+// The pooled map is never written.  A block owns kPoolImgs images of one sample (every output weight it loads is used
+// for all of them); a thread owns channels h, h + 128, ... and walks the 7x7 windows row by row with the two A2 rows a
+// window row touches in registers, so every A2 entry is loaded once (the position-major form re-read each entry for
+// its 4 windows and thrashed L1: 21 % hit rate).  Per-thread partial sums, then a fixed-order block reduction.
+constexpr int kPoolImgs = 2;
 
 template <int C_MAX>
-__global__ void __launch_bounds__(256)
-pool2_logits_kernel(const float* __restrict__ a2, const float* __restrict__ woutp, const float* __restrict__ bank,
-                    int64_t P, int64_t bo_off, int s0, int B, int H, int C, float* __restrict__ logits) {
-  __shared__ float red[8][kPoolImgs][C_MAX];
-  const int z = blockIdx.y, b0 = blockIdx.x * kPoolImgs;
-  const int F = 49 * H;
-  const float* __restrict__ W = woutp + (int64_t)(s0 + z) * C * F;
-  const float* __restrict__ A = a2 + ((int64_t)z * B + b0) * 64 * H;
+__global__ void __launch_bounds__(128)
+pool2_logits_kernel(const float* __restrict__ a2, const float* __restrict__ woutp, int s0, int B, int H, int C,
+                    float* __restrict__ partial) {
+  // grid (channel chunks of blockDim.x, image groups, samples): partial[chunk][zb][c], summed by logits_reduce_kernel
+  __shared__ float red[4][kPoolImgs][C_MAX];
+  const int z = blockIdx.z, b0 = blockIdx.y * kPoolImgs;
+  const int64_t F = (int64_t)49 * H;
   const int nimg = min(kPoolImgs, B - b0);
   float acc[kPoolImgs][C_MAX];
 #pragma unroll
   for (int q = 0; q < kPoolImgs; ++q)
 #pragma unroll
     for (int c = 0; c < C_MAX; ++c) acc[q][c] = 0.f;
-  for (int i = threadIdx.x; i < F; i += blockDim.x) {
-    const int p = i / H, h = i - p * H;
-    const int py = p / 7, px = p - 7 * py;
-    const int o = (py * 8 + px) * H + h;
-    float v[kPoolImgs];
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < H) {
+    const float4* __restrict__ W = reinterpret_cast<const float4*>(woutp + ((int64_t)(s0 + z) * F + h) * C_MAX);
+    const float* A[kPoolImgs];
 #pragma unroll
-    for (int q = 0; q < kPoolImgs; ++q) {
-      v[q] = 0.f;
-      if (q < nimg) {
-        const float* base = A + (int64_t)q * 64 * H + o;
-        v[q] = fmaxf(fmaxf(__ldg(base), __ldg(base + H)), fmaxf(__ldg(base + 8 * H), __ldg(base + 9 * H)));
+    for (int q = 0; q < kPoolImgs; ++q) A[q] = a2 + ((int64_t)z * B + b0 + min(q, nimg - 1)) * 64 * H + h;
+    float r0[kPoolImgs][8], r1[kPoolImgs][8];
+#pragma unroll
+    for (int q = 0; q < kPoolImgs; ++q)
+#pragma unroll
+      for (int x = 0; x < 8; ++x) r0[q][x] = __ldg(A[q] + (int64_t)x * H);
+#pragma unroll 1
+    for (int wy = 0; wy < 7; ++wy) {
+#pragma unroll
+      for (int q = 0; q < kPoolImgs; ++q)
+#pragma unroll
+        for (int x = 0; x < 8; ++x) r1[q][x] = __ldg(A[q] + (int64_t)((wy + 1) * 8 + x) * H);
+#pragma unroll
+      for (int wx = 0; wx < 7; ++wx) {
+        float v[kPoolImgs];
+#pragma unroll
+        for (int q = 0; q < kPoolImgs; ++q)
+          v[q] = q < nimg ? fmaxf(fmaxf(r0[q][wx], r0[q][wx + 1]), fmaxf(r1[q][wx], r1[q][wx + 1])) : 0.f;
+        const float4* __restrict__ w = W + (int64_t)(wy * 7 + wx) * H * (C_MAX / 4);
+#pragma unroll
+        for (int j = 0; j < C_MAX / 4; ++j) {
+          const float4 wv = __ldg(w + j);                 // classes 4j .. 4j+3 of this (window, channel); padding is zero
+#pragma unroll
+          for (int q = 0; q < kPoolImgs; ++q) {
+            acc[q][4 * j + 0] = fmaf(v[q], wv.x, acc[q][4 * j + 0]);
+            acc[q][4 * j + 1] = fmaf(v[q], wv.y, acc[q][4 * j + 1]);
+            acc[q][4 * j + 2] = fmaf(v[q], wv.z, acc[q][4 * j + 2]);
+            acc[q][4 * j + 3] = fmaf(v[q], wv.w, acc[q][4 * j + 3]);
+          }
+        }
       }
+#pragma unroll
+      for (int q = 0; q < kPoolImgs; ++q)
+#pragma unroll
+        for (int x = 0; x < 8; ++x) r0[q][x] = r1[q][x];
     }
-#pragma unroll
-    for (int c = 0; c < C_MAX; ++c)
-      if (c < C) {
-        const float w = __ldg(W + (int64_t)c * F + i);
-#pragma unroll
-        for (int q = 0; q < kPoolImgs; ++q) acc[q][c] = fmaf(v[q], w, acc[q][c]);
-      }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -338,22 +360,49 @@ pool2_logits_kernel(const float* __restrict__ a2, const float* __restrict__ wout
       if (lane == 0) red[warp][q][c] = t;
     }
   __syncthreads();
+  const int nwarps = blockDim.x >> 5;
   for (int j = threadIdx.x; j < nimg * C; j += blockDim.x) {
     const int q = j / C, c = j - q * C;
     float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][q][c];
-    logits[((int64_t)z * B + b0 + q) * C + c] = t + __ldg(bank + (int64_t)(s0 + z) * P + bo_off + c);
+    for (int w = 0; w < nwarps; ++w) t += red[w][q][c];
+    partial[((int64_t)blockIdx.x * gridDim.z * B + (int64_t)z * B + b0 + q) * C + c] = t;
   }
 }
 
-int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* logits, cudaStream_t st) {
-  dim3 grid((B + kPoolImgs - 1) / kPoolImgs, Z);
-  if (net->C <= 16)
-    pool2_logits_kernel<16><<<grid, 256, 0, st>>>(a2, net->woutp, net->bank, net->L.P, net->L.bo, s0, B, net->H, net->C, logits);
-  else
-    pool2_logits_kernel<32><<<grid, 256, 0, st>>>(a2, net->woutp, net->bank, net->L.P, net->L.bo, s0, B, net->H, net->C, logits);
-  net->launches++;
+// logits[zb][c] = bo_z[c] + sum_chunk partial[chunk][zb][c]   (fixed order)
+__global__ void logits_reduce_kernel(const float* __restrict__ partial, int chunks, const float* __restrict__ bank,
+                                     int64_t P, int64_t bo_off, int s0, int B, int C, int64_t n, float* __restrict__ logits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  const int z = (int)(i / ((int64_t)B * C));
+  float t = 0.f;
+  for (int k = 0; k < chunks; ++k) t += __ldg(partial + (int64_t)k * n + i);
+  logits[i] = t + __ldg(bank + (int64_t)(s0 + z) * P + bo_off + c);
+}
+
+// specialisations on the class pitch of woutp (conv_class_pitch): 4, 12 (MNIST / F-MNIST: 10 classes), 16, 32
+#define RBNN_CONV_C_DISPATCH(KERNEL, GRID, BLOCK, ...)                                      \
+  do {                                                                                      \
+    const int cp_ = conv_class_pitch(net->C);                                               \
+    if (cp_ == 4) KERNEL<4><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                            \
+    else if (cp_ == 12) KERNEL<12><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                     \
+    else if (cp_ == 16) KERNEL<16><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                     \
+    else KERNEL<32><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                    \
+  } while (0)
+
+int pool2_logits_chunks(const rbnn_net* net) { return (net->H + 127) / 128; }
+
+// partial: pool2_logits_chunks(net) * Z * B * C floats of scratch
+int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* logits, float* partial, cudaStream_t st) {
+  const int threads = std::min(128, (net->H + 31) / 32 * 32);
+  const int chunks = (net->H + threads - 1) / threads;
+  dim3 grid(chunks, (B + kPoolImgs - 1) / kPoolImgs, Z);
+  RBNN_CONV_C_DISPATCH(pool2_logits_kernel, grid, threads, a2, net->woutp, s0, B, net->H, net->C, partial);
+  const int64_t n = (int64_t)Z * B * net->C;
+  logits_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, chunks, net->bank, net->L.P, net->L.bo, s0, B,
+                                                                    net->C, n, logits);
+  net->launches += 2;
   RBNN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -377,7 +426,7 @@ pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ d
   const int z = blockIdx.z, b0 = blockIdx.y * kBwdImgs;
   const int nimg = min(kBwdImgs, B - b0);
   const int64_t F = (int64_t)49 * H;
-  const float* __restrict__ W = woutp + (int64_t)(s0 + z) * C * F + h;
+  const float4* __restrict__ W = reinterpret_cast<const float4*>(woutp + ((int64_t)(s0 + z) * F + h) * C_MAX);
   float dl[kBwdImgs][C_MAX];
   const float* A[kBwdImgs];
   int64_t obase[kBwdImgs];
@@ -426,7 +475,10 @@ pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ d
     for (int wx = 0; wx < 7; ++wx) {
       float wv[C_MAX];
 #pragma unroll
-      for (int c = 0; c < C_MAX; ++c) wv[c] = c < C ? __ldg(W + (int64_t)c * F + (int64_t)(wy * 7 + wx) * H) : 0.f;
+      for (int j = 0; j < C_MAX / 4; ++j) {
+        const float4 t = __ldg(W + (int64_t)(wy * 7 + wx) * H * (C_MAX / 4) + j);
+        wv[4 * j] = t.x; wv[4 * j + 1] = t.y; wv[4 * j + 2] = t.z; wv[4 * j + 3] = t.w;
+      }
 #pragma unroll
       for (int q = 0; q < kBwdImgs; ++q) {
         float d = 0.f;
@@ -460,10 +512,7 @@ int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0
                     float* dz2_lo, cudaStream_t st) {
   const int threads = std::min(128, (net->H + 31) / 32 * 32);
   dim3 grid((net->H + threads - 1) / threads, (B + kBwdImgs - 1) / kBwdImgs, Z);
-  if (net->C <= 16)
-    pool2_bwd_fused_kernel<16><<<grid, threads, 0, st>>>(a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo);
-  else
-    pool2_bwd_fused_kernel<32><<<grid, threads, 0, st>>>(a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo);
+  RBNN_CONV_C_DISPATCH(pool2_bwd_fused_kernel, grid, threads, a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -532,34 +581,52 @@ conv2_refine_kernel(float* __restrict__ a2, const float* __restrict__ p1, const 
   const float guard = eps * m;
   const float* __restrict__ wrow = bank + (int64_t)(s0 + z) * P;
   const int hw = (H + 31) >> 5;                 // 32-channel words per position
-  // phase 1: flags from the untouched GEMM output (=> the set that gets recomputed is deterministic)
-  for (int pos = warp; pos < 64; pos += 8) {
-    const int y = pos >> 3, x = pos & 7;
-    for (int h0 = 0; h0 < H; h0 += 32) {
-      const int h = h0 + lane;
-      bool flag = false;
-      if (h < H) {
-        const float v = A[pos * H + h];
-        const float pre = v > 0.f ? v : 100.f * v;
-        flag = fabsf(pre) < guard;
+  // phase 1: flags from the untouched GEMM output (=> the set that gets recomputed is deterministic).  A thread owns
+  // a channel and walks the 8 rows with rows y-1, y, y+1 (as pre-activations) in registers; per window row it
+  // derives thr[wx] = (two or more of the window's entries lie within guard of its maximum) ? maximum - guard : +inf,
+  // and an entry is flagged when it exceeds the threshold of any window it belongs to, or sits within guard of zero.
+  for (int h = threadIdx.x; h < hw * 32; h += blockDim.x) {
+    const bool ok = h < H;
+    const float* __restrict__ Ah = A + (ok ? h : 0);
+    float rb[8], rc[8], thrA[7], thrB[7];
 #pragma unroll
-        for (int wy = y - 1; wy <= y; ++wy)
+    for (int x = 0; x < 8; ++x) {
+      const float v = Ah[x * H];
+      rb[x] = v > 0.f ? v : 100.f * v;
+    }
 #pragma unroll
-          for (int wx = x - 1; wx <= x; ++wx) {
-            if (wy < 0 || wy > 6 || wx < 0 || wx > 6) continue;
-            float q[4];
+    for (int x = 0; x < 7; ++x) thrA[x] = __int_as_float(0x7f800000);
+#pragma unroll 1
+    for (int y = 0; y < 8; ++y) {
+      if (y < 7) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float vn = A[((wy + (j >> 1)) * 8 + wx + (j & 1)) * H + h];
-              q[j] = vn > 0.f ? vn : 100.f * vn;
-            }
-            const float top = fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])) - guard;
-            const int near = (q[0] > top) + (q[1] > top) + (q[2] > top) + (q[3] > top);
-            flag = flag || (near >= 2 && pre > top);
-          }
+        for (int x = 0; x < 8; ++x) {
+          const float v = Ah[((y + 1) * 8 + x) * H];
+          rc[x] = v > 0.f ? v : 100.f * v;
+        }
+#pragma unroll
+        for (int wx = 0; wx < 7; ++wx) {
+          const float top = fmaxf(fmaxf(rb[wx], rb[wx + 1]), fmaxf(rc[wx], rc[wx + 1])) - guard;
+          const int near = (rb[wx] > top) + (rb[wx + 1] > top) + (rc[wx] > top) + (rc[wx + 1] > top);
+          thrB[wx] = near >= 2 ? top : __int_as_float(0x7f800000);
+        }
+      } else {
+#pragma unroll
+        for (int wx = 0; wx < 7; ++wx) thrB[wx] = __int_as_float(0x7f800000);
       }
-      const unsigned any = __ballot_sync(0xffffffffu, flag);
-      if (lane == 0) fl[pos * hw + (h0 >> 5)] = any;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const float pre = rb[x];
+        bool flag = fabsf(pre) < guard;
+        if (x > 0) flag = flag || pre > thrA[x - 1] || pre > thrB[x - 1];
+        if (x < 7) flag = flag || pre > thrA[x] || pre > thrB[x];
+        const unsigned any = __ballot_sync(0xffffffffu, flag && ok);
+        if (lane == 0) fl[(y * 8 + x) * hw + (h >> 5)] = any;
+      }
+#pragma unroll
+      for (int x = 0; x < 8; ++x) rb[x] = rc[x];
+#pragma unroll
+      for (int wx = 0; wx < 7; ++wx) thrA[wx] = thrB[wx];
     }
   }
   __syncthreads();

@@ -78,23 +78,25 @@ int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t 
 }
 
 // conv: the output Linear consumes the pooled activations in (pos, h) order (HWC), the reference
-// flattens (h, pos) (CHW, model_nn.py:105-106) => keep a permuted copy of model.7.weight per row.
-__global__ void permute_wout_kernel(const float* __restrict__ bank, int64_t P, int64_t wo, int C, int H,
+// flattens (h, pos) (CHW, model_nn.py:105-106) => keep a permuted copy of model.7.weight per row, classes innermost
+// and zero-padded to a multiple of 4 (conv_class_pitch): the fused pooling kernels fetch an entry with 16-byte loads.
+__global__ void permute_wout_kernel(const float* __restrict__ bank, int64_t P, int64_t wo, int C, int CP, int H,
                                     float* __restrict__ woutp, int s0) {
   const int F = 49 * H;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)C * F) return;
+  if (i >= (int64_t)CP * F) return;
   const int s = s0 + blockIdx.y;
-  const int c = (int)(i / F), k = (int)(i % F);
+  const int k = (int)(i / CP), c = (int)(i % CP);
   const int p = k / H, h = k % H;
-  woutp[((int64_t)s * C + c) * F + k] = __ldg(bank + (int64_t)s * P + wo + (int64_t)c * F + h * 49 + p);
+  woutp[((int64_t)s * F + k) * CP + c] = c < C ? __ldg(bank + (int64_t)s * P + wo + (int64_t)c * F + h * 49 + p) : 0.f;
 }
 
 int conv_permute_wout(rbnn_net* net, int s0, int count, cudaStream_t st) {
   if (net->arch != RBNN_ARCH_CONV || count <= 0) return 0;
-  const int64_t n = (int64_t)net->C * 49 * net->H;
+  const int CP = conv_class_pitch(net->C);
+  const int64_t n = (int64_t)CP * 49 * net->H;
   dim3 grid((unsigned)((n + 255) / 256), (unsigned)count);
-  permute_wout_kernel<<<grid, 256, 0, st>>>(net->bank, net->L.P, net->L.wo, net->C, net->H, net->woutp, s0);
+  permute_wout_kernel<<<grid, 256, 0, st>>>(net->bank, net->L.P, net->L.wo, net->C, CP, net->H, net->woutp, s0);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;

@@ -16,8 +16,9 @@
 
 namespace rbnn {
 
-// ~50x the measured TF32x3 error (5e-6 of the output maximum), as for the unfused FC route (tc_fc.cu)
-constexpr float kConvGuardEps = 1.0f / 4096.0f;
+// guard band of the conv2 refinement: 2^-13 of the image's largest |pre-activation|, ~22x the measured TF32x3 error
+// (5.5e-6 of the output maximum at K = 800, tc_gemm_test.cu); ~11x for the difference of two entries (pooling ties)
+constexpr float kConvGuardEps = 1.0f / 8192.0f;
 
 int tc_conv_supported(const rbnn_net* n) {
   return n->arch == RBNN_ARCH_CONV && n->cc_major == 10 && (n->H % 16) == 0 && n->H <= 2048;
@@ -26,7 +27,7 @@ int tc_conv_supported(const rbnn_net* n) {
 namespace {
 
 struct ConvTcBufs {
-  float *p1 = nullptr, *p1h = nullptr, *p1l = nullptr, *a2 = nullptr, *logits = nullptr;
+  float *p1 = nullptr, *p1h = nullptr, *p1l = nullptr, *a2 = nullptr, *logits = nullptr, *lpart = nullptr;
   float *dlogits = nullptr, *dzh = nullptr, *dzl = nullptr, *dcol = nullptr, *g1 = nullptr, *partial = nullptr;
   uint8_t* idx1 = nullptr;
   int parts = 1;
@@ -34,7 +35,7 @@ struct ConvTcBufs {
 
 size_t bytes_per_zb(const rbnn_net* n, bool grad) {
   const size_t H = n->H, C = n->C;
-  size_t per = 3 * 4608 * 4 + 4608 + 64 * H * 4 + C * 4;
+  size_t per = 3 * 4608 * 4 + 4608 + 64 * H * 4 + C * 4 + (H / 128 + 1) * C * 4;
   if (grad) per += C * 4 + 2 * 64 * H * 4 + 64 * 800 * 4 + 4608 * 4;
   return per + 64;
 }
@@ -47,6 +48,7 @@ void carve(rbnn_net* n, Arena& ar, int Z, int B, bool grad, ConvTcBufs& c) {
   c.idx1 = ar.take<uint8_t>((size_t)ZB * 4608);
   c.a2 = ar.take<float>((size_t)ZB * 64 * H);
   c.logits = ar.take<float>((size_t)ZB * C);
+  c.lpart = ar.take<float>((size_t)pool2_logits_chunks(n) * ZB * C);
   if (grad) {
     c.dlogits = ar.take<float>((size_t)ZB * C);
     c.dzh = ar.take<float>((size_t)ZB * 64 * H);
@@ -90,7 +92,7 @@ int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs&
   g.out = c.a2; g.out_ld = H; g.out_zstride = (int64_t)B * 64 * H;
   RBNN_TRY(run_tc(n, g, 1, st));
   RBNN_TRY(conv2_refine(n, c.a2, c.p1, z0, Z, B, kConvGuardEps, st));
-  RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, st));
+  RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, c.lpart, st));
   return 0;
 }
 
