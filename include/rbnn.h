@@ -43,7 +43,8 @@ typedef struct rbnn_net rbnn_net;
 enum { RBNN_ARCH_FC = 0, RBNN_ARCH_FC2 = 1, RBNN_ARCH_CONV = 2 };
 
 /* GEMM engines.  FP32 = CUDA-core FFMA (reference-class rounding, any shape);
- * TF32X3 = tcgen05 kind::tf32 with a 3-term split (fp32-class accuracy);
+ * TF32X3 = tcgen05 kind::tf32 with a 3-term split (fp32-class accuracy; arch fc / fc2, and arch conv, where
+ *          conv2 runs as an implicit GEMM over 5-D TMA boxes and its input gradient as a tcgen05 GEMM);
  * BF16 = tcgen05 kind::f16 single pass (throughput mode, NOT parity-grade);
  * F16X3 = tcgen05 kind::f16 with a 3-term split of power-of-two-scaled fp16 hi/lo
  *         operands (fp32-class accuracy at twice the TF32X3 rate; arch fc only). */
