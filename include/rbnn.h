@@ -55,7 +55,10 @@ enum {
   RBNN_HEAD_MEAN_OF_GRADS = 0, /* lossGradients.py:29-40: per-sample CE(softmax(softmax(z_s))) */
   RBNN_HEAD_GRAD_OF_MEAN = 1,  /* adversarialAttacks.py:74-78: CE(softmax(mean_s softmax(z_s))) */
   RBNN_HEAD_LOGITS_CE = 2,     /* avg_posterior=True, model_bnn.py:206-216: CE(z) on the mean-weight net */
-  RBNN_HEAD_UPSTREAM = 3       /* autograd through BNN.forward: d_pbar holds dL/d(mean probs) [B,C] itself */
+  RBNN_HEAD_UPSTREAM = 3,      /* autograd through BNN.forward: d_pbar holds dL/d(mean probs) [B,C] itself */
+  RBNN_HEAD_LOGITS_UPSTREAM = 4 /* Ensemble_NN.forward (mean of LOGITS, model_ensemble.py:57-67): d_pbar holds
+                                   dL/d(sum of logits) [B,C]; every bank row receives it unchanged.  FP32 engine
+                                   (any architecture) and the conv TF32X3 engine. */
 };
 
 RBNN_API int rbnn_abi_version(void);
@@ -116,6 +119,11 @@ RBNN_API int rbnn_input_grad_sum_kept(rbnn_net* net, int head, const int32_t* d_
                              float* d_out_sum, void* stream);
 /* avg_posterior=True (model_bnn.py:206-216): LOGITS of bank row s. d_out: [B, C]. */
 RBNN_API int rbnn_forward_logits(rbnn_net* net, const float* d_x, int B, int s, float* d_out, void* stream);
+/* Ensemble_NN.forward (model_ensemble.py:57-67): d_out_sum[B, C] <- sum over bank rows s in [s0, s1) of the LOGITS
+ * f_{w_s}(x); the caller divides by the ensemble size.  Deterministic NN.forward (model_nn.py:126-141) is the
+ * one-row case. */
+RBNN_API int rbnn_forward_logits_sum(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum,
+                            void* stream);
 
 /* ---- a6/a7/a8/a9: input gradients ---------------------------------------------------------
  * d_out_sum[B, D] <- sum over rows s in [s0, s1) of dL_s/dx with L chosen by `head`:
@@ -126,8 +134,10 @@ RBNN_API int rbnn_forward_logits(rbnn_net* net, const float* d_x, int B, int s, 
  *                  multiplies the final sum by 1/S                (adversarialAttacks.py:74-78)
  *   LOGITS_CE    : L = CE(z_s, y) for the single row s0           (model_bnn.py:206-216)
  *   UPSTREAM     : like GRAD_OF_MEAN but g = d_pbar[B,C] is given (any loss on BNN.forward's output)
+ *   LOGITS_UPSTREAM: dL/dz_s = d_pbar[B,C] for every row (any loss on the SUM / mean of the logits: Ensemble_NN,
+ *                  deterministic NN; model_ensemble.py:57-67).  FP32 engine and the conv TF32X3 engine.
  * Sum reduction over the batch (the reference batch is always 1, so no 1/B).
- * d_labels: [B] int32 class indices. d_pbar may be NULL unless head is GRAD_OF_MEAN / UPSTREAM. */
+ * d_labels: [B] int32 class indices. d_pbar may be NULL unless head is GRAD_OF_MEAN / UPSTREAM / LOGITS_UPSTREAM. */
 RBNN_API int rbnn_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_t* d_labels, int B,
                         int s0, int s1, const float* d_pbar, float* d_out_sum, void* stream);
 

@@ -391,6 +391,62 @@ def pgd_attack(net, layout, bank, images, labels, sample_schedule: SampleSchedul
 
 
 # --------------------------------------------------------------------------
+# deterministic NN / Ensemble_NN     model_nn.py:126-141, model_ensemble.py:57-67
+# --------------------------------------------------------------------------
+def ensemble_forward(net: _Net, layout, bank: torch.Tensor, x: torch.Tensor, members: Sequence[int],
+                     dtype=torch.float32) -> torch.Tensor:
+    """Ensemble_NN.forward: mean over the selected members of the LOGITS (model_ensemble.py:62-66);
+    a single member is NN.forward (model_nn.py:126-141)."""
+    x = x.to(dtype)
+    outs = [net_logits(net, {k: v.to(dtype) for k, v in unpack(bank[int(s)], layout).items()}, x) for s in members]
+    return torch.stack(outs, 0).mean(0)
+
+
+def ensemble_attack_gradient(net, layout, bank, x, labels, members, dtype=torch.float32):
+    """d/dx CE(mean_s f_s(x), y), the loss fgsm/pgd differentiate for these nets (adversarialAttacks.py:74-78)."""
+    xs = x.to(dtype).clone().requires_grad_(True)
+    loss = nnf.cross_entropy(ensemble_forward(net, layout, bank, xs, members, dtype), labels, reduction="sum")
+    (g,) = torch.autograd.grad(loss, xs)
+    return g
+
+
+def ensemble_fgsm_attack(net, layout, bank, images, labels, members, hyperparams=None, dtype=torch.float32):
+    epsilon = hyperparams["epsilon"] if hyperparams is not None else 0.3
+    g = ensemble_attack_gradient(net, layout, bank, images, labels, members, dtype)
+    return fgsm_step(images.to(dtype), g, epsilon)
+
+
+def ensemble_pgd_attack(net, layout, bank, images, labels, members, hyperparams=None, iters=None,
+                        dtype=torch.float32):
+    images = images.to(dtype)
+    if hyperparams is not None:
+        epsilon = hyperparams["epsilon"]
+        alpha = 2 / images.flatten(1).max(dim=1)[0].reshape(-1, *([1] * (images.dim() - 1)))
+    else:
+        epsilon, alpha = 0.5, 2 / 225
+    n_it = 40 if iters is None else iters
+    original, image = images.clone(), images.clone()
+    for _ in range(n_it):
+        g = ensemble_attack_gradient(net, layout, bank, image, labels, members, dtype)
+        image = pgd_step(image, original, g, alpha, epsilon).detach()
+    return image
+
+
+def ensemble_attack_evaluation(net, layout, bank, x_test, x_attack, y_onehot, members, batch_size: int = 128):
+    """adversarialAttacks.py:151-198 for a net whose forward returns (mean) logits."""
+    labels = y_onehot.argmax(-1)
+    outs, correct = [[], []], [0.0, 0.0]
+    with torch.no_grad():
+        for which, data in enumerate((x_test, x_attack)):
+            for b0 in range(0, len(data), batch_size):
+                out = ensemble_forward(net, layout, bank, data[b0:b0 + batch_size], members)
+                correct[which] += (out.argmax(-1) == labels[b0:b0 + batch_size]).sum().item()
+                outs[which].append(out)
+        rob = softmax_robustness(torch.cat(outs[0]), torch.cat(outs[1]))
+    return 100 * correct[0] / len(x_test), 100 * correct[1] / len(x_test), rob
+
+
+# --------------------------------------------------------------------------
 # a11/a12  evaluation                                adversarialAttacks.py:30-62,151-198
 # --------------------------------------------------------------------------
 def softmax_difference(original_predictions, adversarial_predictions):

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "librbnn.so")
 
 ARCH = {"fc": 0, "fc2": 1, "conv": 2}
 PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "f16x3": 3}
-HEAD_MEAN_OF_GRADS, HEAD_GRAD_OF_MEAN, HEAD_LOGITS_CE, HEAD_UPSTREAM = 0, 1, 2, 3
+HEAD_MEAN_OF_GRADS, HEAD_GRAD_OF_MEAN, HEAD_LOGITS_CE, HEAD_UPSTREAM, HEAD_LOGITS_UPSTREAM = 0, 1, 2, 3, 4
 
 _p = C.c_void_p
 _i = C.c_int
@@ -42,6 +42,7 @@ SIGNATURES = {
     "rbnn_keep_valid": (_i, [_p]),
     "rbnn_input_grad_sum_kept": (_i, [_p, _i, _p, _p, _p, _p]),
     "rbnn_forward_logits": (_i, [_p, _p, _i, _i, _p, _p]),
+    "rbnn_forward_logits_sum": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "rbnn_input_grad_sum": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _p]),
     "rbnn_fgsm_step": (_i, [_p, _p, _f, _p, _i64, _p]),
     "rbnn_pgd_step": (_i, [_p, _p, _p, _p, _f, _p, _i, _i, _p]),

@@ -98,7 +98,10 @@ def _bnn_input_grad(net, x, labels_i32, n_samples, avg_posterior):
 
 
 def _generic_input_grad(net, image, label, n_samples, avg_posterior):
-    """The reference's autograd route for non-BNN networks (adversarialAttacks.py:73-79)."""
+    """Non-BNN networks (adversarialAttacks.py:73-79): the engine-backed `NN` / `Ensemble_NN` drop-ins answer with the
+    CUDA input-gradient pass (`input_grad`), anything else takes the reference's autograd route."""
+    if hasattr(net, "input_grad"):
+        return net.input_grad(image, label, n_samples).reshape(image.shape)
     image = image.detach().clone()
     image.requires_grad = True
     output = net.forward(inputs=image, n_samples=n_samples, avg_posterior=avg_posterior)
@@ -106,6 +109,14 @@ def _generic_input_grad(net, image, label, n_samples, avg_posterior):
     net.zero_grad()
     loss.backward()
     return image.grad.data
+
+
+def _to_net_device(net, image, label):
+    """Engine-backed deterministic nets compute on their CUDA device: move the attack's tensors there."""
+    if hasattr(net, "input_grad"):
+        dev = net.engine().device
+        return torch.as_tensor(image).to(dev), torch.as_tensor(label).to(dev)
+    return image, label
 
 
 def _prep(net, image, label):
@@ -120,6 +131,7 @@ def fgsm_attack(net, image, label, hyperparams=None, n_samples=None, avg_posteri
     `image` is [B, ch, h, w] (the reference passes B=1), `label` [B] class indices."""
     epsilon = hyperparams["epsilon"] if hyperparams is not None else 0.3
     if not isinstance(net, BNN):
+        image, label = _to_net_device(net, image, label)
         grad = _generic_input_grad(net, image, label, n_samples, avg_posterior)
         return torch.clamp(image.detach() + epsilon * grad.sign(), 0, 1)
     x, y = _prep(net, image, label)
@@ -132,8 +144,10 @@ def pgd_attack(net, image, label, hyperparams=None, n_samples=None, avg_posterio
     (adversarialAttacks.py:86-108): (eps, alpha) = (hyperparams eps, 2/image.max()) or (0.5, 2/225),
     `iters`=40 as hard-coded upstream; alpha is per image."""
     if not isinstance(net, BNN):
-        if hyperparams is not None:
-            epsilon, alpha = hyperparams["epsilon"], 2 / image.max()
+        image, label = _to_net_device(net, image, label)
+        if hyperparams is not None:          # alpha = 2 / image.max() of EACH image (the reference attacks one at a time, :89)
+            epsilon = hyperparams["epsilon"]
+            alpha = 2 / image.flatten(1).max(dim=1)[0].reshape(-1, *([1] * (image.dim() - 1)))
         else:
             epsilon, alpha = 0.5, 2 / 225
         original_image = image.detach().clone()

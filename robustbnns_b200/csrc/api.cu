@@ -519,6 +519,14 @@ int rbnn_forward_probs_sum(rbnn_net* n, const float* d_x, int B, int s0, int s1,
   return 0;
 }
 
+int rbnn_forward_logits_sum(rbnn_net* n, const float* d_x, int B, int s0, int s1, float* d_out_sum, void* stream) {
+  RBNN_CHECK(n != nullptr, "null net handle");
+  n->sum_logits = 1;                      // the per-chunk accumulation adds raw logits (head.cu)
+  const int rc = rbnn_forward_probs_sum(n, d_x, B, s0, s1, d_out_sum, stream);
+  n->sum_logits = 0;
+  return rc;
+}
+
 int rbnn_forward_probs_sum_keep(rbnn_net* n, const float* d_x, int B, int s0, int s1, float* d_out_sum, void* stream) {
   RBNN_TRY(check_rows(n, s0, s1));
   RBNN_CHECK(B >= 0, "negative batch");
@@ -564,9 +572,11 @@ int rbnn_forward_logits(rbnn_net* n, const float* d_x, int B, int s, float* d_ou
 int rbnn_input_grad_sum(rbnn_net* n, int head, const float* d_x, const int32_t* d_labels, int B, int s0, int s1,
                         const float* d_pbar, float* d_out_sum, void* stream) {
   RBNN_TRY(check_rows(n, s0, s1));
-  RBNN_CHECK(head >= RBNN_HEAD_MEAN_OF_GRADS && head <= RBNN_HEAD_UPSTREAM, "unknown head %d", head);
-  RBNN_CHECK((head != RBNN_HEAD_GRAD_OF_MEAN && head != RBNN_HEAD_UPSTREAM) || d_pbar != nullptr,
-             "GRAD_OF_MEAN / UPSTREAM need d_pbar");
+  RBNN_CHECK(head >= RBNN_HEAD_MEAN_OF_GRADS && head <= RBNN_HEAD_LOGITS_UPSTREAM, "unknown head %d", head);
+  RBNN_CHECK((head != RBNN_HEAD_GRAD_OF_MEAN && head != RBNN_HEAD_UPSTREAM && head != RBNN_HEAD_LOGITS_UPSTREAM) ||
+                 d_pbar != nullptr, "GRAD_OF_MEAN / UPSTREAM / LOGITS_UPSTREAM need d_pbar");
+  RBNN_CHECK(head != RBNN_HEAD_LOGITS_UPSTREAM || n->prec == RBNN_PREC_FP32 || n->arch == RBNN_ARCH_CONV,
+             "LOGITS_UPSTREAM (ensemble / deterministic nets) runs on the FP32 engine, or TF32X3 for arch conv");
   RBNN_CHECK(head != RBNN_HEAD_LOGITS_CE || s1 - s0 == 1, "LOGITS_CE takes exactly one bank row");
   if (B <= 0) return 0;
   DeviceGuard dg(n->device);

@@ -37,7 +37,8 @@ __device__ __forceinline__ void softmax_inplace(float (&v)[C_MAX], int C) {
 // out_sum[b][c] += sum_z softmax(logits[z][b][:])[c].  One warp per input: lane l sums samples l, l+32, ... in order,
 // then a fixed butterfly over the lanes => deterministic, and B x 32 threads instead of B (the attack loop calls this
 // with B ~ 1000: one thread per input left most of the GPU idle).
-template <int C_MAX>
+// RAW: accumulate the logits themselves (Ensemble_NN.forward averages logits, model_ensemble.py:62-66).
+template <int C_MAX, bool RAW>
 __global__ void probs_accumulate_kernel(const float* __restrict__ logits, int Z, int B, int C,
                                         float* __restrict__ out_sum) {
   const int lane = threadIdx.x & 31;
@@ -51,7 +52,7 @@ __global__ void probs_accumulate_kernel(const float* __restrict__ logits, int Z,
     const float* row = logits + ((int64_t)z * B + b) * C;
 #pragma unroll
     for (int c = 0; c < C_MAX; ++c) v[c] = (c < C) ? __ldg(row + c) : 0.f;
-    softmax_inplace<C_MAX>(v, C);
+    if (!RAW) softmax_inplace<C_MAX>(v, C);
 #pragma unroll
     for (int c = 0; c < C_MAX; ++c)
       if (c < C) acc[c] += v[c];
@@ -77,6 +78,12 @@ __global__ void dlogits_kernel(int head, const float* __restrict__ logits, const
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= (int64_t)Z * B) return;
   const int b = (int)(r % B);
+  if (head == RBNN_HEAD_LOGITS_UPSTREAM) {       // loss of the MEAN LOGITS: every sample receives d_pbar as is
+#pragma unroll
+    for (int c = 0; c < C_MAX; ++c)
+      if (c < C) dlogits[r * C + c] = __ldg(pbar + (int64_t)b * C + c);
+    return;
+  }
   const int y = labels[b];
   float p[C_MAX], g[C_MAX];
 #pragma unroll
@@ -115,10 +122,13 @@ int head_probs_accumulate(rbnn_net* net, const float* logits, int Z, int B, int 
   RBNN_CHECK(C >= 1 && C <= kMaxC, "head: n_classes %d not in [1,%d]", C, kMaxC);
   const int thr = 128;                      // 4 inputs per block
   const unsigned blocks = (unsigned)(((int64_t)B * 32 + thr - 1) / thr);
-  if (C <= 16)
-    probs_accumulate_kernel<16><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
-  else
-    probs_accumulate_kernel<32><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
+  if (net->sum_logits) {
+    if (C <= 16) probs_accumulate_kernel<16, true><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
+    else probs_accumulate_kernel<32, true><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
+  } else {
+    if (C <= 16) probs_accumulate_kernel<16, false><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
+    else probs_accumulate_kernel<32, false><<<blocks, thr, 0, st>>>(logits, Z, B, C, out_sum);
+  }
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -127,7 +137,8 @@ int head_probs_accumulate(rbnn_net* net, const float* logits, int Z, int B, int 
 int head_dlogits(rbnn_net* net, int head, const float* logits, const int32_t* labels, const float* pbar, int Z,
                  int B, int C, float* dlogits, cudaStream_t st) {
   RBNN_CHECK(C >= 1 && C <= kMaxC, "head: n_classes %d not in [1,%d]", C, kMaxC);
-  RBNN_CHECK((head != RBNN_HEAD_GRAD_OF_MEAN && head != RBNN_HEAD_UPSTREAM) || pbar != nullptr, "head: needs d_pbar");
+  RBNN_CHECK((head != RBNN_HEAD_GRAD_OF_MEAN && head != RBNN_HEAD_UPSTREAM && head != RBNN_HEAD_LOGITS_UPSTREAM) ||
+                 pbar != nullptr, "head: needs d_pbar");
   const int thr = 128;
   const int64_t rows = (int64_t)Z * B;
   const unsigned blocks = (unsigned)((rows + thr - 1) / thr);

@@ -155,6 +155,14 @@ class Net(object):
                                         _stream()))
         return out
 
+    def forward_logits_sum(self, x, s0, s1):
+        """sum_s f_s(x) (LOGITS) over bank rows [s0, s1): Ensemble_NN.forward x size (model_ensemble.py:57-67)."""
+        x, B = self._x(x)
+        out = torch.empty((B, self.n_classes), dtype=torch.float32, device=self.device)
+        check(lib().rbnn_forward_logits_sum(self._h, C.c_void_p(x.data_ptr()), B, int(s0), int(s1),
+                                            C.c_void_p(out.data_ptr()), _stream()))
+        return out
+
     def input_grad_sum(self, head, x, labels, s0, s1, pbar=None):
         x, B = self._x(x)
         labels = self._dev(labels, torch.int32).reshape(-1)

@@ -9,6 +9,7 @@ from oracle import oracle as orc
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SVI_CASES = ["svi_fc16_mnist", "svi_fc2_32_moons", "svi_conv16_mnist"]
 HMC_CASES = ["hmc_fc16_fmnist", "hmc_fc2_16_mnist", "hmc_conv16_fmnist", "hmc_fc2_32_moons"]
+ENS_CASES = ["ens_fc2_16_mnist", "ens_conv16_fmnist", "ens_fc16_mnist"]      # tests/golden/make_golden_ensemble.py
 
 
 class Case(object):

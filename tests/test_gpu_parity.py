@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import oracle as orc
-from tests.helpers import HMC_CASES, SVI_CASES, Case, rel_err
+from tests.helpers import ENS_CASES, HMC_CASES, SVI_CASES, Case, rel_err
 
 pytestmark = pytest.mark.gpu
 REL = 1e-4
@@ -123,6 +123,61 @@ def test_golden_hmc_attacks_and_evaluation(name, tmp_path, monkeypatch):
         determined = g64.abs() > tol_t * g64.abs().max()
         bad = ((nxt.double() - ref_nxt).abs() > 1e-6) & determined
         assert float(bad.float().sum() / determined.float().sum().clamp_min(1)) <= 2e-3, t
+
+
+# ------------------------------------------------------------------ deterministic NN / Ensemble_NN ----
+@pytest.mark.parametrize("name", ENS_CASES)
+def test_golden_ensemble_and_nn(name, tmp_path, monkeypatch):
+    """the reference's Ensemble_NN / NN outputs (mean logits, accuracies, FGSM / PGD examples,
+    evaluation counts, robustness) reproduced by the engine-backed drop-ins, weights read from the reference's files."""
+    from robustbnns_b200 import adversarialAttacks as aa
+    from robustbnns_b200.model_ensemble import Ensemble_NN
+    from robustbnns_b200.model_nn import NN
+    monkeypatch.chdir(tmp_path)
+    c = Case(name)
+    size, used = int(c.z["size"]), int(c.z["n_used"])
+    ens = Ensemble_NN(c.dataset if "fmnist" not in name else "fashion_mnist", c.hidden, "leaky", c.arch, 1, 0.01,
+                      c.input_shape, c.n_classes, size)
+    # the members' weight files, as the reference's NN.save(savedir=<ens name>/weights, seed=i) writes them
+    import os
+    wdir = os.path.join("tests_root", ens.name, "weights")
+    os.makedirs(wdir)
+    for i in range(size):
+        torch.save(orc.unpack(c.bank[i], c.layout), os.path.join(wdir, f"{ens.member_name}_weights_{i}.pt"))
+    ens.load("cuda", rel_path="tests_root/")
+    with pytest.raises(ValueError):
+        ens.forward(c.x, n_samples=size + 1)
+    assert rel_err(ens.forward(c.x, n_samples=used).cpu(), c.t("logits_used")) < REL
+    assert rel_err(ens.forward(c.x, n_samples=None).cpu(), c.t("logits_all")) < REL
+    nn0 = NN(ens.dataset_name, c.input_shape, c.n_classes, c.hidden, "leaky", c.arch, 0.01, 1)
+    nn0.load("cuda", savedir=os.path.join(ens.name, "weights"), seed=0, rel_path="tests_root/")
+    assert rel_err(nn0.forward(c.x).cpu(), c.t("logits_member0")) < REL
+    assert torch.equal(nn0.state_dict()[c.layout[0][0]], orc.unpack(c.bank[0], c.layout)[c.layout[0][0]])
+    loader = torch.utils.data.DataLoader(list(zip(c.x, c.y)), batch_size=4)
+    assert abs(ens.evaluate(loader, "cuda", n_samples=used) - float(c.z["evaluate_acc"])) < 1e-4
+    loader = torch.utils.data.DataLoader(list(zip(c.x, c.y)), batch_size=4)
+    assert abs(nn0.evaluate(loader, "cuda") - float(c.z["evaluate_acc_member0"])) < 1e-4
+    # gradient against the fp64 oracle
+    for net, members, ns in ((ens, range(used), used), (nn0, [0], None)):
+        g = net.input_grad(c.x, c.labels, ns).cpu().reshape(c.x.shape)
+        ref = orc.ensemble_attack_gradient(c.net, c.layout, c.bank, c.x, c.labels, members, dtype=torch.float64)
+        assert rel_err(g, ref) < REL
+    hyper = {"epsilon": float(c.z["eps"])}
+    for who, net, ns in (("ens", ens, used), ("nn", nn0, None)):
+        for method in ("fgsm", "pgd"):
+            for hname, h in (("hyper", hyper), ("default", None)):
+                adv = aa.attack(net=net, x_test=c.x, y_test=c.y, dataset_name=c.dataset, device="cuda", method=method,
+                                filename="a", savedir="a", hyperparams=h, n_samples=ns)
+                ref = c.t(f"{who}_{method}_{hname}_adv")
+                assert adv.is_cuda and adv.shape == ref.shape
+                if (method, hname) == ("pgd", "default"):     # 40 small steps: chaotic in fp32 (see the BNN test)
+                    assert float((adv.cpu() - c.x).abs().max()) <= 0.5 + 1e-6
+                else:
+                    assert _mismatch_fraction(adv, ref) <= 5e-3, (who, method, hname)
+                o, a, rob = aa.attack_evaluation(net=net, x_test=c.x, x_attack=ref, y_test=c.y, device="cuda",
+                                                 n_samples=ns)
+                assert [o, a] == c.z[f"{who}_{method}_{hname}_eval"].tolist()
+                assert float((rob.cpu() - c.t(f"{who}_{method}_{hname}_rob")).abs().max()) <= 2e-6
 
 
 # ------------------------------------------------------------------ oracle at larger sizes -------------

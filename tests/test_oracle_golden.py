@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import oracle as orc
-from tests.helpers import HMC_CASES, SVI_CASES, Case, rel_err
+from tests.helpers import ENS_CASES, HMC_CASES, SVI_CASES, Case, rel_err
 
 TOL = 1e-5  # fp32 torch vs fp32 torch, different batching/summation order only
 
@@ -83,6 +83,26 @@ def test_hmc_attacks_and_evaluation(name):
             o, a, rob = orc.attack_evaluation(c.net, c.layout, c.bank, c.x, ref, c.y, sched)
             assert [o, a] == c.z[f"{method}_{hname}_eval"].tolist()
             assert float((rob - c.t(f"{method}_{hname}_rob")).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ENS_CASES)
+def test_ensemble_and_deterministic_nets(name):
+    """Ensemble_NN / NN rows against the reference's own outputs."""
+    c = Case(name)
+    size, used = int(c.z["size"]), int(c.z["n_used"])
+    assert rel_err(orc.ensemble_forward(c.net, c.layout, c.bank, c.x, range(used)), c.t("logits_used")) < TOL
+    assert rel_err(orc.ensemble_forward(c.net, c.layout, c.bank, c.x, range(size)), c.t("logits_all")) < TOL
+    assert rel_err(orc.ensemble_forward(c.net, c.layout, c.bank, c.x, [0]), c.t("logits_member0")) < TOL
+    hyper = {"epsilon": float(c.z["eps"])}
+    for who, members in (("ens", range(used)), ("nn", [0])):
+        for method, fn in (("fgsm", orc.ensemble_fgsm_attack), ("pgd", orc.ensemble_pgd_attack)):
+            for hname, h in (("hyper", hyper), ("default", None)):
+                adv = fn(c.net, c.layout, c.bank, c.x, c.labels, members, h)
+                ref = c.t(f"{who}_{method}_{hname}_adv")
+                assert float(((adv - ref).abs() > 1e-6).float().mean()) <= 2e-3, (who, method, hname)
+                o, a, rob = orc.ensemble_attack_evaluation(c.net, c.layout, c.bank, c.x, ref, c.y, members)
+                assert [o, a] == c.z[f"{who}_{method}_{hname}_eval"].tolist()
+                assert float((rob - c.t(f"{who}_{method}_{hname}_rob")).abs().max()) <= 1e-6
 
 
 def test_softmax_difference_errors():
