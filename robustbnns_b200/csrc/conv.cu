@@ -200,56 +200,82 @@ int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, floa
 }
 
 // ---- maxpool1 backward + conv1 input gradient, summed over the chunk's samples ---------------
-// dx[b][iy][ix] (+)= sum_z sum_c sum_{ky,kx} [idx1 routes (iy-ky, ix-kx)] G1[z][b][c][.][.] * cw1[z][c][ky][kx]
-__global__ void __launch_bounds__(256)
+// dx[b][iy][ix] (+)= sum_z sum_c sum_{ky,kx} R_z[c][iy-ky][ix-kx] * cw1_z[c][ky][kx],  where R is G1 routed back through
+// MaxPool2d(2): R[c][oy][ox] = G1[c][oy/2][ox/2] if idx1 picked (oy, ox) in its 2x2 cell, else 0   (model_nn.py:98-100).
+// Per (sample, image) the routed map of 16 channels at a time is scattered into shared memory (x padded by 4 zeros on
+// both sides, row pitch 33 => conflict-free), then a thread owns a strip of 7 output pixels of one row: per (channel,
+// ky) it loads 11 map entries + 5 weights and issues 35 FMAs (the first version tested idx1 for every (pixel, tap,
+// channel): 6 instructions per FMA).  gridDim.y > 1: block (b, zi) sums its slice of the samples into
+// partial[zi][b][784] (reduced in a fixed order by conv1_reduce_kernel); gridDim.y == 1: straight into dx[b][784].
+constexpr int kC1Pitch = 33, kC1Chan = 16;
+constexpr int kC1SmemFloats = kC1Chan * 24 * kC1Pitch + 800;
+
+__global__ void __launch_bounds__(128)
 conv1_bwd_sum_kernel(const float* __restrict__ g1, const uint8_t* __restrict__ idx1, const float* __restrict__ bank,
                      int64_t P, int64_t cw1, int s0, int Z, int B, float* __restrict__ dx, int accumulate) {
-  // gridDim.y > 1: block (b, zi) sums the samples of its slice of [0, Z) into the partial buffer dx[zi][b][784]
-  // (reduced in a fixed order by conv1_reduce_kernel); gridDim.y == 1: the whole range straight into dx[b][784]
-  __shared__ float gs[4608];
-  __shared__ uint8_t is[4608];
-  __shared__ float ws[800];
+  extern __shared__ float c1sm[];
+  float* R = c1sm;                                   // [16][24][33]
+  float* ws = c1sm + kC1Chan * 24 * kC1Pitch;        // [32][25]
   const int b = blockIdx.x;
   const int z_begin = (int)((long long)blockIdx.y * Z / gridDim.y), z_end = (int)((long long)(blockIdx.y + 1) * Z / gridDim.y);
   dx += (int64_t)blockIdx.y * B * 784;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int t = threadIdx.x, iy = t >> 2, strip = t & 3;
+  const bool active = iy < 28;
+  float acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+  for (int i = t; i < kC1Chan * 24 * kC1Pitch; i += blockDim.x) R[i] = 0.f;
+  int prev[kC1Chan * 144 / 128];                     // where this thread's cells were scattered last time (-1: nowhere)
+#pragma unroll
+  for (int q = 0; q < kC1Chan * 144 / 128; ++q) prev[q] = -1;
   for (int z = z_begin; z < z_end; ++z) {
     const int64_t zb = (int64_t)z * B + b;
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4608; i += blockDim.x) {
-      gs[i] = __ldg(g1 + zb * 4608 + i);
-      is[i] = idx1[zb * 4608 + i];
-    }
-    for (int i = threadIdx.x; i < 800; i += blockDim.x) ws[i] = __ldg(bank + (int64_t)(s0 + z) * P + cw1 + i);
-    __syncthreads();
+    __syncthreads();                                 // the previous sample's readers are done with ws / R
+    for (int i = t; i < 800; i += blockDim.x) ws[i] = __ldg(bank + (int64_t)(s0 + z) * P + cw1 + i);
+#pragma unroll 1
+    for (int half = 0; half < 32 / kC1Chan; ++half) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int pix = threadIdx.x + t * 256;
-      if (pix >= 784) break;
-      const int iy = pix / 28, ix = pix % 28;
-      float a = 0.f;
-      for (int ky = 0; ky < 5; ++ky) {
-        const int oy = iy - ky;
-        if (oy < 0 || oy > 23) continue;
-        for (int kx = 0; kx < 5; ++kx) {
-          const int ox = ix - kx;
-          if (ox < 0 || ox > 23) continue;
-          const int pp = (oy >> 1) * 12 + (ox >> 1);
-          const int sub = ((oy & 1) << 1) | (ox & 1);
-#pragma unroll 8
-          for (int c = 0; c < 32; ++c)
-            if (is[c * 144 + pp] == sub) a = fmaf(gs[c * 144 + pp], ws[c * 25 + ky * 5 + kx], a);
+      for (int q = 0; q < kC1Chan * 144 / 128; ++q) {
+        const int i = t + q * 128;                   // (local channel, cell): always handled by this thread
+        const int c = i / 144, cell = i - c * 144, cy = cell / 12, cx = cell - 12 * cy;
+        const int64_t gi = zb * 4608 + (half * kC1Chan + c) * 144 + cell;
+        const int sub = idx1[gi];
+        const int o = (c * 24 + 2 * cy + (sub >> 1)) * kC1Pitch + 2 * cx + (sub & 1) + 4;
+        if (prev[q] >= 0) R[prev[q]] = 0.f;
+        R[o] = __ldg(g1 + gi);
+        prev[q] = o;
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll 2
+        for (int c = 0; c < kC1Chan; ++c) {
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) {
+            const int oy = iy - ky;
+            if (oy < 0 || oy > 23) continue;
+            const float* __restrict__ row = R + (c * 24 + oy) * kC1Pitch + strip * 7;
+            const float* __restrict__ w = ws + (half * kC1Chan + c) * 25 + ky * 5;
+            float r[11], wv[5];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) r[k] = row[k];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) wv[k] = w[k];
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) acc[j] = fmaf(r[j - kx + 4], wv[kx], acc[j]);
+          }
         }
       }
-      acc[t] += a;
+      __syncthreads();                               // readers done before the next scatter rewrites R
     }
   }
+  if (active) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int pix = threadIdx.x + t * 256;
-    if (pix >= 784) break;
-    const int64_t o = (int64_t)b * 784 + pix;
-    dx[o] = accumulate ? dx[o] + acc[t] : acc[t];
+    for (int j = 0; j < 7; ++j) {
+      const int64_t o = (int64_t)b * 784 + iy * 28 + strip * 7 + j;
+      dx[o] = accumulate ? dx[o] + acc[j] : acc[j];
+    }
   }
 }
 
@@ -271,13 +297,19 @@ int conv1_bwd_parts(const rbnn_net* net, int Z, int B) {
 
 int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,
                   float* dx_sum, int accumulate, cudaStream_t st, float* partial, int parts) {
+  const size_t smem = (size_t)kC1SmemFloats * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RBNN_CUDA(cudaFuncSetAttribute(conv1_bwd_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   if (!partial || parts <= 1) {
-    conv1_bwd_sum_kernel<<<B, 256, 0, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, dx_sum, accumulate);
+    conv1_bwd_sum_kernel<<<B, 128, smem, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, dx_sum, accumulate);
     net->launches++;
     RBNN_CUDA(cudaGetLastError());
     return 0;
   }
-  conv1_bwd_sum_kernel<<<dim3(B, parts), 256, 0, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, partial, 0);
+  conv1_bwd_sum_kernel<<<dim3(B, parts), 128, smem, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, partial, 0);
   const int64_t n = (int64_t)B * 784;
   conv1_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, parts, n, dx_sum, accumulate);
   net->launches += 2;
