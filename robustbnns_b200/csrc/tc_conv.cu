@@ -9,6 +9,9 @@
 //   MaxPool2d(2, stride 1) + Linear(49H, C) (fused), loss head, their input gradients (fused)   CUDA cores (3 % of the FLOPs)
 //   conv2 dgrad  dcol = dZ2 . W2_z  (K = H)   tcgen05 GEMM over the transposed weight copies, then col2im + conv1 backward
 // This is lossGradients.py:29-40 / adversarialAttacks.py:74-78 for the conv BNN, input gradients only.
+#include <math.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -91,7 +94,8 @@ int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs&
   g.bias = rows + n->L.cb2; g.bias_zstride = P;
   g.out = c.a2; g.out_ld = H; g.out_zstride = (int64_t)B * 64 * H;
   RBNN_TRY(run_tc(n, g, 1, st));
-  RBNN_TRY(conv2_refine(n, c.a2, c.p1, z0, Z, B, kConvGuardEps, st));
+  static const float guard_eps = getenv("RBNN_CONV_GUARD_LOG2") ? ldexpf(1.f, -atoi(getenv("RBNN_CONV_GUARD_LOG2"))) : kConvGuardEps;   // experiments
+  RBNN_TRY(conv2_refine(n, c.a2, c.p1, z0, Z, B, guard_eps, st));
   RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, c.lpart, st));
   return 0;
 }

@@ -12,7 +12,8 @@ B, S = int(os.environ.get("NB", "8")), int(os.environ.get("NS", "6"))
 shape, C = (1, 28, 28), 10
 net = orc.build_net("conv", shape, hidden, C)
 layout = orc.param_layout(net)
-g = torch.Generator().manual_seed(1)
+seed = int(os.environ.get("SEED", "1"))
+g = torch.Generator().manual_seed(seed)
 rows = []
 for key, shp in layout:
     n = 1
@@ -23,6 +24,12 @@ for key, shp in layout:
 bank = torch.cat(rows, dim=1)
 x = torch.rand((B, *shape), generator=g)
 labels = torch.randint(0, C, (B,), generator=g)
+if os.environ.get("IDX"):                      # keep a subset of the images / samples (as the full-size test does)
+    idx = torch.tensor([int(v) for v in os.environ["IDX"].split(",")])
+    x, labels, B = x[idx], labels[idx], len(idx)
+s_lo, s_hi = int(os.environ.get("S0", "0")), int(os.environ.get("S1", str(S)))
+bank = bank[s_lo:s_hi]
+S = s_hi - s_lo
 ref = torch.stack([orc.expected_loss_gradients(net, layout, bank, x, labels, [s], dtype=torch.float64) for s in range(S)])
 ref32 = torch.stack([orc.expected_loss_gradients(net, layout, bank, x, labels, [s]) for s in range(S)]).double()
 print("oracle fp32 vs fp64 per-row max rel err: %.3e" % float(((ref32 - ref).abs().flatten(2).max(-1)[0] / ref.abs().flatten(2).max(-1)[0]).max()))

@@ -332,6 +332,7 @@ TC_CONV_CONFIGS = [
     ((1, 28, 28), 64, 10, 17, 4),
     ((1, 28, 28), 512, 10, 4, 2),       # the real model_idx=0 width (two 256-column tiles)
     ((1, 28, 28), 16, 10, 2, 5),        # narrowest legal hidden size: K = 16 < one K-block in the dgrad GEMM
+    ((1, 28, 28), 1024, 10, 3, 2),      # saved_BNNs model_2 / model_4 / model_8 width (four 256-column tiles)
 ]
 
 
@@ -558,3 +559,95 @@ def test_full_size_properties_fc_headline():
     out = eng.loss_gradients_host(x.reshape(B, -1), labels, 0, S, S)
     assert rel_err(out, full.cpu().reshape(B, -1) / S) < 1e-6
     eng.close()
+
+
+def test_full_size_properties_conv_cfg4():
+    """BASELINE configs[3] shape (100 F-MNIST-shaped inputs, conv-512, 50 stored posterior samples) on the tensor-core
+    conv engine: size-independent properties plus an oracle check on a subset of the rows."""
+    import math
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    B, S, H = 100, 50, 512
+    net = orc.build_net("conv", (1, 28, 28), H, 10)
+    layout = orc.param_layout(net)
+    g = torch.Generator().manual_seed(21)
+    cols = []
+    for key, shp in layout:                         # independent networks, N(0, 1/fan_in): an HMC-like bank
+        n = int(np.prod(shp))
+        fan = n // shp[0] if len(shp) > 1 else 25
+        cols.append(torch.randn((S, n), generator=g) / math.sqrt(fan))
+    bank = torch.cat(cols, dim=1)
+    x = torch.rand((B, 1, 28, 28), generator=g)
+    labels = torch.randint(0, 10, (B,), generator=g)
+    eng = Net("conv", (1, 28, 28), H, 10)
+    eng.set_precision("tf32x3")
+    eng.upload(bank, 0)
+    xd, ld = x.cuda(), labels.cuda().to(torch.int32)
+    full = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, 0, S)
+    # (1) deterministic: a second evaluation is bit-identical
+    assert torch.equal(eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, 0, S), full)
+    # (2) linearity over the sample range (what sample sharding relies on)
+    parts = sum(eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, s, min(s + 17, S)) for s in range(0, S, 17))
+    assert rel_err(parts.cpu(), full.cpu()) < 1e-5
+    # (3) permuting the batch permutes the rows (up to the summation order of the sample slices)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
+    gp = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd[perm].contiguous(), ld[perm].contiguous(), 0, S)
+    assert rel_err(gp.cpu(), full[perm].cpu()) < 1e-5
+    # (4) 16 (sample, image) units against the fp64 oracle.  At this size a unit holds 32 768 second-layer activations
+    # competing in pooling windows, and the pooled conv1 map is stored in fp32: roughly one unit in a hundred has a
+    # window arg-max that fp32 storage decides differently from fp64 (measured with scratch/conv_dbg.py: FP32 engine
+    # 3 of 192 units, tensor-core engine 1 of 192 -- the unit (sample 4, image 63) below).  Such a unit moves by ~1e-3;
+    # all others must meet the north-star tolerance.
+    idx = torch.tensor([0, 17, 63, 99])
+    xs, ls = xd[idx.cuda()].contiguous(), ld[idx.cuda()].contiguous()
+    errs = []
+    for smp in range(3, 7):
+        got = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xs, ls, smp, smp + 1).cpu().reshape(4, 1, 28, 28).double()
+        ref = orc.expected_loss_gradients(net, layout, bank, x[idx], labels[idx], [smp], dtype=torch.float64)
+        errs.append((got - ref).abs().flatten(1).max(-1)[0] / ref.abs().flatten(1).max(-1)[0])
+    errs = torch.stack(errs)
+    assert int((errs > REL).sum()) <= 1 and float(errs.max()) < 5e-2, errs
+    # (5) probabilities: rows sum to one; mean logits of the bank == sum of single rows
+    p = eng.forward_probs_sum(xd, 0, S) / S
+    assert float((p.sum(-1) - 1).abs().max()) < 1e-5
+    ls = eng.forward_logits_sum(xd, 0, 5)
+    assert rel_err(sum(eng.forward_logits(xd, s) for s in range(5)).cpu(), ls.cpu()) < 1e-5
+    eng.close()
+
+
+def test_full_size_properties_pgd_cfg3():
+    """BASELINE configs[2] shape: Bayesian FGSM / PGD on 1000 MNIST-shaped inputs, fc 784-512-10, fresh SVI samples."""
+    from robustbnns_b200 import adversarialAttacks as aa
+    from robustbnns_b200.model_bnn import BNN
+    N, S = 1000, 100
+    net = orc.build_net("fc", (1, 28, 28), 512, 10)
+    layout = orc.param_layout(net)
+    loc, rho = orc.scaled_guide_params(layout, seed=4, rho_mean=-5.0)
+    x, y = orc.synthetic_inputs(N, (1, 28, 28), 10, seed=9)
+    labels = y.argmax(-1)
+    bnn = BNN("mnist", 512, "leaky", "fc", "svi", 1, 0.01, None, None, (1, 28, 28), 10)
+    bnn.set_guide(loc, rho)
+    bnn.set_precision("f16x3")
+    xd, yd = x.cuda(), labels.cuda()
+    for hyper, eps in (({"epsilon": 0.1}, 0.1), (None, 0.5)):
+        bnn.reseed(0)
+        adv = aa.pgd_attack(bnn, xd, yd, hyperparams=hyper, n_samples=S, iters=20)
+        assert adv.shape == xd.shape and bool(torch.isfinite(adv).all())
+        assert float(adv.min()) >= 0.0 and float(adv.max()) <= 1.0
+        assert float((adv - xd).abs().max()) <= eps + 1e-6                  # inside the L-inf ball around the originals
+        bnn.reseed(0)
+        again = aa.pgd_attack(bnn, xd, yd, hyperparams=hyper, n_samples=S, iters=20)
+        assert torch.equal(adv, again)                                      # same fresh-sample stream => identical
+    bnn.reseed(0)
+    f0 = aa.fgsm_attack(bnn, xd, yd, hyperparams={"epsilon": 0.0}, n_samples=S)
+    assert torch.equal(f0, xd)                                              # eps = 0 leaves the inputs alone
+    bnn.reseed(0)
+    f1 = aa.fgsm_attack(bnn, xd, yd, hyperparams={"epsilon": 0.2}, n_samples=S)
+    d = (f1 - xd).abs()
+    assert float(((d - 0.2).abs() < 1e-6).float().mean() + (d < 0.2 - 1e-6).float().mean()) == 1.0
+    # the attack must lower the expected probability of the true class on average (it ascends the loss)
+    bnn.reseed(1)
+    p_clean = bnn.forward(xd, n_samples=S).gather(1, yd[:, None]).mean()
+    bnn.reseed(1)
+    p_adv = bnn.forward(f1, n_samples=S).gather(1, yd[:, None]).mean()
+    assert float(p_adv) < float(p_clean)
