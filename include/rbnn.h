@@ -47,7 +47,7 @@ enum { RBNN_ARCH_FC = 0, RBNN_ARCH_FC2 = 1, RBNN_ARCH_CONV = 2 };
  *          conv2 runs as an implicit GEMM over 5-D TMA boxes and its input gradient as a tcgen05 GEMM);
  * BF16 = tcgen05 kind::f16 single pass (throughput mode, NOT parity-grade);
  * F16X3 = tcgen05 kind::f16 with a 3-term split of power-of-two-scaled fp16 hi/lo
- *         operands (fp32-class accuracy at twice the TF32X3 rate; arch fc only). */
+ *         operands (fp32-class accuracy at twice the TF32X3 rate; arch fc and arch conv). */
 enum { RBNN_PREC_FP32 = 0, RBNN_PREC_TF32X3 = 1, RBNN_PREC_BF16 = 2, RBNN_PREC_F16X3 = 3 };
 
 /* Which scalar loss the input gradient is taken of. */

@@ -279,7 +279,7 @@ static int conv_grad_simt(rbnn_net* n, int head, const float* x, const int32_t* 
     RBNN_TRY(conv_forward_chunk(n, x, B, z0, Z, c, c.logits, st));
     RBNN_TRY(head_dlogits(n, head, c.logits, labels, pbar, Z, B, C, c.dlogits, st));
     const float* rows = n->bank + (int64_t)z0 * P;
-    RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dz2, nullptr, st));
+    RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dz2, nullptr, nullptr, st));
     GemmArgs d{};
     d.b_kn = 1;
     d.A = c.dz2; d.lda = H; d.sAz = (int64_t)B * 64 * H;
@@ -386,11 +386,11 @@ int rbnn_net_set_precision(rbnn_net* n, int prec) {
   RBNN_CHECK(prec == RBNN_PREC_FP32 || prec == RBNN_PREC_TF32X3 || prec == RBNN_PREC_BF16 || prec == RBNN_PREC_F16X3,
              "unknown precision %d", prec);
   if (prec != RBNN_PREC_FP32 && n->arch == RBNN_ARCH_CONV)
-    RBNN_CHECK(prec == RBNN_PREC_TF32X3 && tc_conv_supported(n),
-               "arch conv: the tcgen05 engine offers TF32X3 (implicit-GEMM conv2) on sm_100 only");
+    RBNN_CHECK((prec == RBNN_PREC_TF32X3 || prec == RBNN_PREC_F16X3) && tc_conv_supported(n),
+               "arch conv: the tcgen05 engine offers TF32X3 and F16X3 (implicit-GEMM conv2) on sm_100 only");
   else if (prec != RBNN_PREC_FP32)
     RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%8==0 and H>=32 on sm_100 only");
-  if (prec == RBNN_PREC_F16X3)
+  if (prec == RBNN_PREC_F16X3 && n->arch != RBNN_ARCH_CONV)
     RBNN_CHECK(tc_f16x3_supported(n), "F16X3 covers arch fc with hidden sizes the fused forward+head kernel supports");
   if (n->prec != prec) n->keep.valid = 0;
   n->prec = prec;

@@ -179,7 +179,8 @@ int im2col_conv2(rbnn_net* net, const float* p1, int ZB, float* col, cudaStream_
 int pool2_fwd(rbnn_net* net, const float* a2, int ZB, int H, float* p2, cudaStream_t st);
 int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, float* dz2, cudaStream_t st,
               float* dz2_lo = nullptr);
-int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, float* hi, float* lo, cudaStream_t st);
+// f16_scale != nullptr: hi / lo are fp16 arrays holding the split of *f16_scale * P1 (F16X3), else tf32-split fp32
+int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, void* hi, void* lo, const float* f16_scale, cudaStream_t st);
 int conv2_refine(rbnn_net* net, float* a2, const float* p1, int s0, int Z, int B, float eps, cudaStream_t st);
 int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, float* g1, cudaStream_t st);
 // partial != nullptr && parts > 1: the sample range is cut into `parts` slices (partial: [parts][B][784] floats)
@@ -189,8 +190,9 @@ int conv1_bwd_parts(const rbnn_net* net, int Z, int B);
 // MaxPool2d(2, stride 1) + Linear(49H, C) and their input gradient, fused (the pooled map / its gradient stay on chip)
 int pool2_logits_chunks(const rbnn_net* net);
 int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* logits, float* partial, cudaStream_t st);
-int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, float* dz2,
-                    float* dz2_lo, cudaStream_t st);
+// dz2_lo == nullptr: fp32 result; f16_scale == nullptr: tf32 hi / lo (fp32 arrays); else fp16 hi / lo of *f16_scale * dZ2
+int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, void* dz2,
+                    void* dz2_lo, const float* f16_scale, cudaStream_t st);
 
 // ---- attack.cu --------------------------------------------------------------------------
 int scale_inplace(rbnn_net* net, float* p, float scale, int64_t n, cudaStream_t st);
@@ -214,7 +216,13 @@ void tc_keep_free(rbnn_net* net);
 // derived tensor-core operand copies of bank rows [s0, s1) brought up to date (lazily, per dirty row)
 int tc_bank_refresh(rbnn_net* net, int s0, int s1, cudaStream_t st);
 
-// ---- tc_conv.cu (tcgen05 conv path, TF32X3) --------------------------------------------------
+// F16X3 operand ranges (device-resident): *bits = max(*bits, max|p|) as float bits; out[0..3] = s_x, 1/(s_x s_w),
+// s_d, 1/(s_d s_w) with s_d from the bound dh_factor * max|g| * max|Wo| (call_scales_kernel, tc_fc.cu)
+int tc_maxabs(rbnn_net* net, const float* p, int64_t count, unsigned* bits, cudaStream_t st);
+int tc_call_scales(rbnn_net* net, const unsigned* xmax_bits, const unsigned* gmax_bits, float dh_factor, float* out,
+                   cudaStream_t st);
+
+// ---- tc_conv.cu (tcgen05 conv path, TF32X3 / F16X3) -------------------------------------------
 int tc_conv_supported(const rbnn_net* net);
 int tc_conv_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_t* d_labels, int B, int s0, int s1,
                            const float* d_pbar, float* d_out_sum, cudaStream_t st);

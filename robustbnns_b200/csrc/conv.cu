@@ -6,6 +6,8 @@
 // Internal activation layouts after conv2 are position-major / channel-minor (HWC) so the GEMM
 // output is consumed as is; model.7.weight is permuted once per bank row to match (sampler.cu).
 // Max-pool ties route to the FIRST maximum in window scan order, as torch's max_pool2d does.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -110,6 +112,12 @@ __device__ __forceinline__ float tf32_rn(float v) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
   return __uint_as_float(u);
+}
+
+// F16X3 operand split of an already scaled value: hi = rn_f16(v), lo = rn_f16(v - hi)
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
 }
 
 // dz2_lo != nullptr: the result is written tf32-split (hi = rn_tf32(v), lo = v - hi) for the tcgen05 dgrad GEMM
@@ -452,7 +460,11 @@ constexpr int kBwdImgs = 2;
 template <int C_MAX>
 __global__ void __launch_bounds__(128)
 pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ dlogits, const float* __restrict__ woutp,
-                       int s0, int B, int H, int C, float* __restrict__ dz2, float* __restrict__ dz2_lo) {
+                       int s0, int B, int H, int C, void* __restrict__ dz2v, void* __restrict__ dz2_lov,
+                       const float* __restrict__ f16_scale) {
+  float* __restrict__ dz2 = reinterpret_cast<float*>(dz2v);
+  float* __restrict__ dz2_lo = reinterpret_cast<float*>(dz2_lov);
+  const float f16s = f16_scale ? __ldg(f16_scale) : 0.f;
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   const int z = blockIdx.z, b0 = blockIdx.y * kBwdImgs;
@@ -487,7 +499,9 @@ pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ d
       for (int x = 0; x < 8; ++x) {
         const float v = r0[q][x] > 0.f ? acc0[q][x] : acc0[q][x] * kLeakySlope;
         const int64_t o = obase[q] + (int64_t)(row * 8 + x) * H;
-        if (dz2_lo) {
+        if (f16_scale) {
+          split_f16(v * f16s, reinterpret_cast<__half*>(dz2v)[o], reinterpret_cast<__half*>(dz2_lov)[o]);
+        } else if (dz2_lo) {
           const float hv = tf32_rn(v);
           dz2[o] = hv;
           dz2_lo[o] = v - hv;
@@ -540,11 +554,12 @@ pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ d
   store_row(7);
 }
 
-int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, float* dz2,
-                    float* dz2_lo, cudaStream_t st) {
+int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, void* dz2,
+                    void* dz2_lo, const float* f16_scale, cudaStream_t st) {
   const int threads = std::min(128, (net->H + 31) / 32 * 32);
   dim3 grid((net->H + threads - 1) / threads, (B + kBwdImgs - 1) / kBwdImgs, Z);
-  RBNN_CONV_C_DISPATCH(pool2_bwd_fused_kernel, grid, threads, a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo);
+  RBNN_CONV_C_DISPATCH(pool2_bwd_fused_kernel, grid, threads, a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo,
+                       f16_scale);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -554,22 +569,28 @@ int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0
 // P1[zb][c][y][x] (fp32, CHW) -> channels-last tf32-split copies hi/lo[zb][y][x][c]: a pixel's 32 channels are the
 // 128-byte K-block row of the implicit GEMM.  One block per image, transposed through shared memory.
 __global__ void __launch_bounds__(256)
-p1_split_hwc_kernel(const float* __restrict__ p1, float* __restrict__ hi, float* __restrict__ lo) {
+p1_split_hwc_kernel(const float* __restrict__ p1, void* __restrict__ hi, void* __restrict__ lo,
+                    const float* __restrict__ f16_scale) {
   __shared__ float t[32 * 145];
   const int64_t zb = blockIdx.x;
   for (int i = threadIdx.x; i < 4608; i += blockDim.x) t[(i / 144) * 145 + i % 144] = __ldg(p1 + zb * 4608 + i);
   __syncthreads();
+  const float sc = f16_scale ? __ldg(f16_scale) : 1.f;
   for (int o = threadIdx.x; o < 4608; o += blockDim.x) {
     const int c = o & 31, px = o >> 5;
     const float v = t[c * 145 + px];
-    const float h = tf32_rn(v);
-    hi[zb * 4608 + o] = h;
-    lo[zb * 4608 + o] = v - h;
+    if (f16_scale) {
+      split_f16(v * sc, reinterpret_cast<__half*>(hi)[zb * 4608 + o], reinterpret_cast<__half*>(lo)[zb * 4608 + o]);
+    } else {
+      const float h = tf32_rn(v);
+      reinterpret_cast<float*>(hi)[zb * 4608 + o] = h;
+      reinterpret_cast<float*>(lo)[zb * 4608 + o] = v - h;
+    }
   }
 }
 
-int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, float* hi, float* lo, cudaStream_t st) {
-  p1_split_hwc_kernel<<<ZB, 256, 0, st>>>(p1, hi, lo);
+int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, void* hi, void* lo, const float* f16_scale, cudaStream_t st) {
+  p1_split_hwc_kernel<<<ZB, 256, 0, st>>>(p1, hi, lo, f16_scale);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;

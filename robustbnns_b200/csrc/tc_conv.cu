@@ -1,4 +1,5 @@
-// The tcgen05 engine for the convolutional net (arch conv, model_nn.py:98-106), precision RBNN_PREC_TF32X3.
+// The tcgen05 engine for the convolutional net (arch conv, model_nn.py:98-106), precisions RBNN_PREC_TF32X3 and
+// RBNN_PREC_F16X3 (power-of-two-scaled fp16 hi/lo operands: 32 channels = one 64-byte K-block row, scales device-resident).
 // Per chunk of posterior samples z and inputs b:
 //   conv1 + LeakyReLU + MaxPool2d(2)          direct CUDA-core kernel (K = 25, < 1 % of the FLOPs)        conv.cu
 //   conv2 = Conv2d(32, H, 5) + bias + LeakyReLU   IMPLICIT GEMM on tcgen05: A tiles are 5-D TMA boxes of the
@@ -30,8 +31,11 @@ int tc_conv_supported(const rbnn_net* n) {
 namespace {
 
 struct ConvTcBufs {
-  float *p1 = nullptr, *p1h = nullptr, *p1l = nullptr, *a2 = nullptr, *logits = nullptr, *lpart = nullptr;
-  float *dlogits = nullptr, *dzh = nullptr, *dzl = nullptr, *dcol = nullptr, *g1 = nullptr, *partial = nullptr;
+  float *p1 = nullptr, *a2 = nullptr, *logits = nullptr, *lpart = nullptr;
+  void *p1h = nullptr, *p1l = nullptr, *dzh = nullptr, *dzl = nullptr;     // tf32 split (fp32 arrays) or fp16 hi / lo
+  float *dlogits = nullptr, *dcol = nullptr, *g1 = nullptr, *partial = nullptr;
+  float* call_sc = nullptr;        // F16X3: [0] s_p, [1] 1/(s_p s_w), [2] s_d, [3] 1/(s_d s_w)
+  unsigned* max_bits = nullptr;    // F16X3: [0] max|P1| of the chunk, [1] max|d_pbar|
   uint8_t* idx1 = nullptr;
   int parts = 1;
 };
@@ -46,8 +50,10 @@ size_t bytes_per_zb(const rbnn_net* n, bool grad) {
 void carve(rbnn_net* n, Arena& ar, int Z, int B, bool grad, ConvTcBufs& c) {
   const size_t H = n->H, C = n->C, ZB = (size_t)Z * B;
   c.p1 = ar.take<float>((size_t)ZB * 4608);
-  c.p1h = ar.take<float>((size_t)ZB * 4608);
+  c.p1h = ar.take<float>((size_t)ZB * 4608);      // sized for fp32; the fp16 variant uses half of it
   c.p1l = ar.take<float>((size_t)ZB * 4608);
+  c.call_sc = ar.take<float>(4);
+  c.max_bits = ar.take<unsigned>(2);
   c.idx1 = ar.take<uint8_t>((size_t)ZB * 4608);
   c.a2 = ar.take<float>((size_t)ZB * 64 * H);
   c.logits = ar.take<float>((size_t)ZB * C);
@@ -64,7 +70,7 @@ void carve(rbnn_net* n, Arena& ar, int Z, int B, bool grad, ConvTcBufs& c) {
 }
 
 int run_tc(rbnn_net* n, tc::GemmDesc& d, int tag, cudaStream_t st) {
-  d.mode = tc::MODE_TF32X3;
+  d.mode = n->prec == RBNN_PREC_F16X3 ? tc::MODE_F16X3 : tc::MODE_TF32X3;
   d.sm_count = n->sm_count;
   std::string err;
   RBNN_TRY(timing_begin(n, tag, st));
@@ -77,18 +83,35 @@ int run_tc(rbnn_net* n, tc::GemmDesc& d, int tag, cudaStream_t st) {
   return 0;
 }
 
-int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs& c, float* logits, cudaStream_t st) {
+// gmax: device [B, C] tensor whose magnitude bounds the head's g (UPSTREAM / LOGITS_UPSTREAM heads), else nullptr;
+// dh_factor: |dZ2| <= dh_factor * max|g| * max|Wout| (4 pooling windows x sum_c |dlogits_c|)
+int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs& c, float* logits, const float* gmax,
+                  float dh_factor, cudaStream_t st) {
   const int H = n->H;
   const int64_t P = n->L.P;
   const float* rows = n->bank + (int64_t)z0 * P;
   const TcMat& m = n->tc.mat[0];
+  const bool f16 = n->prec == RBNN_PREC_F16X3;
   RBNN_TRY(conv1_pool_fwd(n, x, n->bank, z0, Z, B, c.p1, c.idx1, st));
-  RBNN_TRY(p1_split_hwc(n, c.p1, Z * B, c.p1h, c.p1l, st));
+  if (f16) {        // operand ranges of this chunk -> the call's power-of-two scales (device-resident, no read-back)
+    RBNN_CUDA(cudaMemsetAsync(c.max_bits, 0, 2 * sizeof(unsigned), st));
+    RBNN_TRY(tc_maxabs(n, c.p1, (int64_t)Z * B * 4608, c.max_bits, st));
+    if (gmax) RBNN_TRY(tc_maxabs(n, gmax, (int64_t)B * n->C, c.max_bits + 1, st));
+    RBNN_TRY(tc_call_scales(n, c.max_bits, gmax ? c.max_bits + 1 : nullptr, dh_factor, c.call_sc, st));
+  }
+  RBNN_TRY(p1_split_hwc(n, c.p1, Z * B, c.p1h, c.p1l, f16 ? c.call_sc : nullptr, st));
   tc::GemmDesc g;
   g.M = B * 64; g.N = H; g.K = 800; g.Z = Z; g.BN = std::min(H, 256);
   g.conv_images = B;
   g.A.hi = c.p1h; g.A.lo = c.p1l; g.A.rows = g.M; g.A.ld = 800; g.A.zstride = (int64_t)B * 4608;
-  g.B.hi = m.hi + (int64_t)z0 * H * m.ld; g.B.lo = m.lo + (int64_t)z0 * H * m.ld;
+  if (f16) {
+    g.kblock_bytes = 64;                            // 32 fp16 channels per filter tap
+    g.B.hi = reinterpret_cast<const uint16_t*>(m.h_hi) + (int64_t)z0 * H * m.ld;
+    g.B.lo = reinterpret_cast<const uint16_t*>(m.h_lo) + (int64_t)z0 * H * m.ld;
+    g.unscale = c.call_sc + 1;
+  } else {
+    g.B.hi = m.hi + (int64_t)z0 * H * m.ld; g.B.lo = m.lo + (int64_t)z0 * H * m.ld;
+  }
   g.B.rows = H; g.B.ld = m.ld; g.B.zstride = (int64_t)H * m.ld;
   g.epi = tc::EPI_BIAS_LEAKY;
   g.bias = rows + n->L.cb2; g.bias_zstride = P;
@@ -113,14 +136,23 @@ int grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int 
     Arena ar(n);
     ConvTcBufs c;
     carve(n, ar, Z, B, true, c);
-    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, c.logits, st));
+    const bool f16 = n->prec == RBNN_PREC_F16X3;
+    const bool given = head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM;
+    const float dh_factor = head == RBNN_HEAD_LOGITS_UPSTREAM ? 4.f * (float)C : 8.f;
+    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, c.logits, given ? pbar : nullptr, dh_factor, st));
     RBNN_TRY(head_dlogits(n, head, c.logits, labels, pbar, Z, B, C, c.dlogits, st));
-    RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dzh, c.dzl, st));
+    RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dzh, c.dzl, f16 ? c.call_sc + 2 : nullptr, st));
     // dcol[z][b * 64 + pos][c * 25 + ky * 5 + kx] = sum_h dZ2[z][b * 64 + pos][h] W2_z[h][c][ky][kx]
     tc::GemmDesc d;
     d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = 160;
     d.A.hi = c.dzh; d.A.lo = c.dzl; d.A.rows = d.M; d.A.ld = H; d.A.zstride = (int64_t)B * 64 * H;
-    d.B.hi = m.thi + (int64_t)z0 * 800 * H; d.B.lo = m.tlo + (int64_t)z0 * 800 * H;
+    if (f16) {
+      d.B.hi = reinterpret_cast<const uint16_t*>(m.th_hi) + (int64_t)z0 * 800 * H;
+      d.B.lo = reinterpret_cast<const uint16_t*>(m.th_lo) + (int64_t)z0 * 800 * H;
+      d.unscale = c.call_sc + 3;
+    } else {
+      d.B.hi = m.thi + (int64_t)z0 * 800 * H; d.B.lo = m.tlo + (int64_t)z0 * 800 * H;
+    }
     d.B.rows = 800; d.B.ld = H; d.B.zstride = (int64_t)800 * H;
     d.epi = tc::EPI_NONE;
     d.out = c.dcol; d.out_ld = 800; d.out_zstride = (int64_t)B * 64 * 800;
@@ -143,7 +175,7 @@ int probs_pass(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_su
     ConvTcBufs c;
     carve(n, ar, Z, B, false, c);
     float* lg = out_logits ? out_logits : c.logits;
-    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, lg, st));
+    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, lg, nullptr, 8.f, st));
     if (out_sum) RBNN_TRY(head_probs_accumulate(n, lg, Z, B, C, out_sum, st));
   }
   return 0;
@@ -159,7 +191,8 @@ int batch_rows(const rbnn_net* n, int B, bool grad) {
 
 int tc_conv_input_grad_sum(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1,
                            const float* pbar, float* out_sum, cudaStream_t st) {
-  RBNN_CHECK(tc_conv_supported(n) && n->prec == RBNN_PREC_TF32X3, "the tcgen05 conv engine runs TF32X3 on sm_100 only");
+  RBNN_CHECK(tc_conv_supported(n) && (n->prec == RBNN_PREC_TF32X3 || n->prec == RBNN_PREC_F16X3),
+             "the tcgen05 conv engine runs TF32X3 / F16X3 on sm_100 only");
   RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
   const int bc = batch_rows(n, B, true);
   for (int b0 = 0; b0 < B; b0 += bc) {
@@ -172,7 +205,8 @@ int tc_conv_input_grad_sum(rbnn_net* n, int head, const float* x, const int32_t*
 
 int tc_conv_forward(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, float* out_logits,
                     cudaStream_t st) {
-  RBNN_CHECK(tc_conv_supported(n) && n->prec == RBNN_PREC_TF32X3, "the tcgen05 conv engine runs TF32X3 on sm_100 only");
+  RBNN_CHECK(tc_conv_supported(n) && (n->prec == RBNN_PREC_TF32X3 || n->prec == RBNN_PREC_F16X3),
+             "the tcgen05 conv engine runs TF32X3 / F16X3 on sm_100 only");
   RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
   const int bc = batch_rows(n, B, false);
   for (int b0 = 0; b0 < B; b0 += bc) {

@@ -155,11 +155,13 @@ __global__ void freeze_scales_kernel(TcScales* sc, int* overflow) {
 
 // per call: [0] s_x, [1] 1 / (s_x s_w1) (forward unscale), [2] dH scale, [3] 1 / (dH scale * s_w1) (backward unscale)
 // |dH| <= 2 max|g| max|Wo| with max|g| <= 1 for the built-in heads (g = softmax(.) - e_y) and max|d_pbar| for UPSTREAM
+// dh_factor: the bound of the hidden-layer gradient is dh_factor * max|g| * max|Wo| (2 for the FC nets; the conv net
+// passes 8: a position collects up to 4 pooling windows)
 __global__ void call_scales_kernel(const TcScales* sc, const unsigned* xmax_bits, const unsigned* gmax_bits,
-                                   float* out) {
+                                   float* out, float dh_factor) {
   const float sx = pow2_scale_for(__uint_as_float(*xmax_bits), kF16TargetExpExact);
   const float gmax = gmax_bits ? __uint_as_float(*gmax_bits) : 1.f;
-  const float sd = pow2_scale_for(2.f * gmax * __uint_as_float(sc->maxwo_bits), kF16TargetExpExact);
+  const float sd = pow2_scale_for(dh_factor * gmax * __uint_as_float(sc->maxwo_bits), kF16TargetExpExact);
   out[0] = sx;
   out[1] = 1.f / (sx * sc->s_w1);
   out[2] = sd;
@@ -189,7 +191,7 @@ __global__ void split_f16_kernel(const float* __restrict__ x, const float* __res
 // F16X3 twin of relayout_kernel: [s][R][C] and transposed [s][C][R] fp16 hi/lo copies of s_w1 * W
 __global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, int64_t off, int R, int C, int ld, int s0,
                                     const TcScales* __restrict__ sc, __half* __restrict__ hi, __half* __restrict__ lo,
-                                    __half* __restrict__ thi, __half* __restrict__ tlo) {
+                                    __half* __restrict__ thi, __half* __restrict__ tlo, int perm25) {
   __shared__ float tile[32][33];
   const float sw = sc->s_w1;
   const int s = s0 + blockIdx.z;
@@ -200,7 +202,8 @@ __global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, i
     float v = 0.f;
     if (r < R && c < C) {
       v = __ldg(src + (int64_t)r * C + c) * sw;
-      const int64_t o = ((int64_t)s * R + r) * ld + c;
+      const int cf = perm25 ? (c % 25) * 32 + c / 25 : c;     // conv2 filters: tap-major forward copy (TcMat::perm25)
+      const int64_t o = ((int64_t)s * R + r) * ld + cf;
       split_f16(v, hi[o], lo[o]);
     }
     tile[i][threadIdx.x] = v;
@@ -507,6 +510,22 @@ __global__ void reduce_slots_kernel(const float* __restrict__ partial, int npart
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------
+// F16X3 operand-range helpers for the conv engine (tc_conv.cu): *bits = max(*bits, max|p|) and the call's 4 scalars
+int tc_maxabs(rbnn_net* n, const float* p, int64_t count, unsigned* bits, cudaStream_t st) {
+  maxabs_kernel<<<n->sm_count * 2, 256, 0, st>>>(p, 0, count, 1, bits);
+  n->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tc_call_scales(rbnn_net* n, const unsigned* xmax_bits, const unsigned* gmax_bits, float dh_factor, float* out,
+                   cudaStream_t st) {
+  call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, xmax_bits, gmax_bits, out, dh_factor);
+  n->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int tc_supported(const rbnn_net* n) {
   if (n->arch != RBNN_ARCH_FC && n->arch != RBNN_ARCH_FC2) return 0;
   if ((n->D & 7) || n->H < 32 || n->C > kMaxC) return 0;
@@ -566,7 +585,7 @@ int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
     tc.nmat = n->arch == RBNN_ARCH_FC2 ? 2 : 1;
     tc.mat[0].off = n->L.w1; tc.mat[0].R = n->H; tc.mat[0].C = n->D; tc.mat[0].ld = k_pitch(n, n->D);
     if (n->arch == RBNN_ARCH_CONV) {      // the conv2 filters [H][32*5*5]; conv1 and the output layer stay on CUDA cores
-      tc.mat[0].off = n->L.cw2; tc.mat[0].C = 800; tc.mat[0].ld = 800; tc.mat[0].perm25 = 1;
+      tc.mat[0].off = n->L.cw2; tc.mat[0].C = 800; tc.mat[0].ld = k_pitch(n, 800); tc.mat[0].perm25 = 1;
     }
     if (tc.nmat == 2) { tc.mat[1].off = n->L.w2; tc.mat[1].R = n->H; tc.mat[1].C = n->H; tc.mat[1].ld = n->H; }
     for (int i = 0; i < tc.nmat; ++i) {
@@ -611,7 +630,8 @@ int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       RBNN_CUDA(cudaMemsetAsync(tc.wnorm + s, 0, (size_t)(e - s) * sizeof(float), st));
       wnorm_kernel<<<dim3((tc.mat[0].R + 7) / 8, e - s), 256, 0, st>>>(n->bank, P, tc.mat[0].off, tc.mat[0].R, tc.mat[0].C,
                                                                        s, tc.wnorm, &tc.scales->maxw1_bits);
-      maxabs_kernel<<<n->sm_count, 256, 0, st>>>(n->bank + (int64_t)s * P + n->L.wo, P, (int64_t)n->C * n->H, e - s,
+      const int64_t wo_len = (int64_t)n->C * n->H * (n->arch == RBNN_ARCH_CONV ? 49 : 1);
+      maxabs_kernel<<<n->sm_count, 256, 0, st>>>(n->bank + (int64_t)s * P + n->L.wo, P, wo_len, e - s,
                                                  &tc.scales->maxwo_bits);
       n->launches += 2;
       RBNN_CUDA(cudaGetLastError());
@@ -635,7 +655,7 @@ int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       if (f16)
         relayout_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, m.ld, s, tc.scales,
                                                           reinterpret_cast<__half*>(m.h_hi), reinterpret_cast<__half*>(m.h_lo),
-                                                          reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo));
+                                                          reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo), m.perm25);
       else
         relayout_kernel<<<grid, dim3(32, 8), 0, st>>>(n->bank, n->L.P, m.off, m.R, m.C, m.ld, s, m.hi, m.lo, m.thi, m.tlo,
                                                       reinterpret_cast<__nv_bfloat16*>(m.bf),
@@ -874,7 +894,7 @@ static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const fl
       maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar_for_scale, 0, pbar_count, 1, w.max_bits + 1);
       n->launches++;
     }
-    call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, pbar_for_scale ? w.max_bits + 1 : nullptr, w.call_sc);
+    call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, pbar_for_scale ? w.max_bits + 1 : nullptr, w.call_sc, 2.f);
     split_f16_kernel<<<blocks, 256, 0, st>>>(x, w.call_sc, w.x_h16, w.x_l16, n4, d4, ld4);
     n->launches += 3;
     RBNN_CUDA(cudaGetLastError());
@@ -962,7 +982,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
         maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar, 0, (int64_t)B * n->C, 1, w.max_bits + 1);
         n->launches++;
       }
-      call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, up ? w.max_bits + 1 : nullptr, w.call_sc);
+      call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, up ? w.max_bits + 1 : nullptr, w.call_sc, 2.f);
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }

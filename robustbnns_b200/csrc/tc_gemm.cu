@@ -149,9 +149,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 tma_load_3d_pair(sa + kATile, &tmAl, fb, kb * KBE, m_idx * kBM, za);
                 tma_load_3d_pair(sb + kBTile, &tmBl, fb, kb * KBE, n_idx * p.BN + (int)rank * bn_cta, z);
               }
-            } else if (MODE == MODE_TF32X3 && KBB == 128 && p.conv_a) {
+            } else if (((MODE == MODE_TF32X3 && KBB == 128) || (MODE == MODE_F16X3 && KBB == 64)) && p.conv_a) {
               // implicit GEMM: K-block kb = filter tap (ky, kx); the 128 tile rows are the 8x8 output positions of two
               // images, i.e. the box {32 channels, x in [kx, kx+8), y in [ky, ky+8), images 2 m_idx .. +1} of the map
+              // (32 channels = 128 bytes of fp32 / tf32, 64 bytes of fp16)
               const uint32_t fb = full0 + 8 * stage;
               const int ky = kb / 5, kx = kb - 5 * ky;
               mbar_expect_tx(fb, stage_tx);
@@ -373,17 +374,19 @@ int make_map(CUtensorMap* map, const void* base, int dtype, int64_t K, int64_t r
 
 // 5-D map over channels-last activations [Z][images][12][12][32] fp32: box = {32 channels, 8, 8, 2 images, 1}, i.e. the
 // 128 rows x 128 bytes of one filter tap of the implicit GEMM (rows ordered image, oy, ox), SWIZZLE_128B.
-static int make_map_conv_a(CUtensorMap* map, const void* base, int64_t images, int64_t Z, std::string* err) {
+static int make_map_conv_a(CUtensorMap* map, const void* base, int dtype, int64_t images, int64_t Z, std::string* err) {
   auto fn = encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled is not available from the driver"; return 1; }
+  const cuuint64_t px = dtype == DT_F32 ? 128u : 64u;      // bytes of one pixel's 32 channels
   cuuint64_t dims[5] = {32u, 12u, 12u, (cuuint64_t)images, (cuuint64_t)Z};
-  cuuint64_t strides[4] = {128u, 12u * 128u, 144u * 128u, (cuuint64_t)images * 144u * 128u};
+  cuuint64_t strides[4] = {px, 12u * px, 144u * px, (cuuint64_t)images * 144u * px};
   cuuint32_t box[5] = {32u, 8u, 8u, 2u, 1u};
   cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
   if (reinterpret_cast<uintptr_t>(base) & 127) { *err = "tc::gemm: conv activations must be 128-byte aligned"; return 1; }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  dtype == DT_F32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     *err = "cuTensorMapEncodeTiled (conv activations) failed with CUresult " + std::to_string((int)r);
     return 1;
@@ -406,9 +409,10 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   if (d.reduce_z && (d.slots < 1 || d.slots > d.Z)) { *err = "tc::gemm: slots must be in [1, Z]"; return 1; }
 
   const int kbb = d.kblock_bytes == 128 ? 128 : 64;
-  if (d.conv_images > 0 && (d.mode != MODE_TF32X3 || kbb != 128 || d.pair || d.K != 800 || d.reduce_z ||
-                            d.M != d.conv_images * 64)) {
-    *err = "tc::gemm: the implicit-GEMM conv operand needs TF32X3, 128-byte K-blocks, single CTAs, K = 800, M = 64 * images";
+  if (d.conv_images > 0 && (!((d.mode == MODE_TF32X3 && kbb == 128) || (d.mode == MODE_F16X3 && kbb == 64)) || d.pair ||
+                            d.K != 800 || d.reduce_z || d.M != d.conv_images * 64)) {
+    *err = "tc::gemm: the implicit-GEMM conv operand needs TF32X3 with 128-byte or F16X3 with 64-byte K-blocks (32 channels), "
+           "single CTAs, K = 800, M = 64 * images";
     return 1;
   }
   const bool pair = d.pair && (d.BN % 32 == 0 || d.BN % 16 == 0) && ((d.BN / 2) % 8 == 0) && d.sm_count >= 2;
@@ -440,12 +444,12 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
 
   CUtensorMap mAh, mAl, mBh, mBl;
   if (d.conv_images > 0) {
-    if (make_map_conv_a(&mAh, d.A.hi, d.conv_images, d.Z, err)) return 1;
+    if (make_map_conv_a(&mAh, d.A.hi, dt, d.conv_images, d.Z, err)) return 1;
   } else if (make_map(&mAh, d.A.hi, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
   if (make_map(&mBh, d.B.hi, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   if (!bf16) {
     if (d.conv_images > 0) {
-      if (make_map_conv_a(&mAl, d.A.lo, d.conv_images, d.Z, err)) return 1;
+      if (make_map_conv_a(&mAl, d.A.lo, dt, d.conv_images, d.Z, err)) return 1;
     } else if (make_map(&mAl, d.A.lo, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
     if (make_map(&mBl, d.B.lo, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   } else {

@@ -71,7 +71,8 @@ struct GemmDesc {
   // conv_images > 0 says A.hi / A.lo are channels-last activations [Z][conv_images][12][12][32] (fp32, tf32-split) and
   // the GEMM row m = image * 64 + oy * 8 + ox is the 5x5x32 patch at output position (oy, ox): K-block kb = (ky, kx)
   // is ONE 5-D TMA box {32 channels, 8 x, 8 y, 2 images} at offset (kx, ky) -- no im2col matrix is ever written.
-  // K = 800 ordered (ky, kx, c); B rows must be stored in that order.  TF32X3, single CTA only.
+  // K = 800 ordered (ky, kx, c); B rows must be stored in that order.  Single CTAs; TF32X3 (128-byte K-blocks) or
+  // F16X3 with kblock_bytes = 64 (32 fp16 channels; activations [..][32] fp16 hi/lo).
   int conv_images = 0;
 };
 

@@ -199,10 +199,18 @@ static double run_case(const Case& c, bool full_check, int timing_iters, double*
 
 // Implicit-GEMM operand of the 5x5 convolution (GemmDesc::conv_images): A = channels-last maps [Z][images][12][12][32],
 // B = [Z][H][800] with K ordered (ky, kx, c); out[z][image * 64 + oy * 8 + ox][h] vs a double-precision host reference.
-static double run_conv_case(int images, int Z, int H, int BN, int timing_iters, double* ms_out) {
+static double run_conv_case(int images, int Z, int H, int BN, int timing_iters, double* ms_out, int mode = MODE_TF32X3) {
   Dev A, B, bias;
   A.init((int64_t)Z * images * 144 * 32, 55, 2.0f, false);
   B.init((int64_t)Z * H * 800, 66, 0.2f, false);
+  float* unscale = nullptr;
+  if (mode == MODE_F16X3) {
+    A.init_f16(256.f);
+    B.init_f16(4096.f);
+    const float u = 1.f / (256.f * 4096.f);
+    CK(cudaMalloc(&unscale, 4));
+    CK(cudaMemcpy(unscale, &u, 4, cudaMemcpyHostToDevice));
+  }
   bias.init((int64_t)Z * H + 1, 77, 1.0f, false);
   const int M = images * 64;
   const int64_t on = (int64_t)Z * M * H;
@@ -210,10 +218,15 @@ static double run_conv_case(int images, int Z, int H, int BN, int timing_iters, 
   CK(cudaMalloc(&out, on * 4));
   CK(cudaMemset(out, 0xFF, on * 4));
   GemmDesc d;
-  d.mode = MODE_TF32X3; d.M = M; d.N = H; d.K = 800; d.Z = Z; d.BN = BN;
+  d.mode = mode; d.M = M; d.N = H; d.K = 800; d.Z = Z; d.BN = BN;
   d.conv_images = images;
   d.A.hi = A.hi; d.A.lo = A.lo; d.A.rows = M; d.A.ld = 800; d.A.zstride = (int64_t)images * 144 * 32;
   d.B.hi = B.hi; d.B.lo = B.lo; d.B.rows = H; d.B.ld = 800; d.B.zstride = (int64_t)H * 800;
+  if (mode == MODE_F16X3) {
+    d.kblock_bytes = 64;
+    d.A.hi = A.h16; d.A.lo = A.l16; d.B.hi = B.h16; d.B.lo = B.l16;
+    d.unscale = unscale;
+  }
   d.epi = EPI_BIAS_LEAKY;
   d.bias = bias.hi + 1; d.bias_zstride = H;
   d.out = out; d.out_ld = H; d.out_zstride = (int64_t)M * H;
@@ -256,7 +269,7 @@ static double run_conv_case(int images, int Z, int H, int BN, int timing_iters, 
     max_ref = fmax(max_ref, fabs(acc));
   }
   A.free_(); B.free_(); bias.free_();
-  cudaFree(out);
+  cudaFree(out); cudaFree(unscale);
   return max_err / fmax(max_ref, 1e-30);
 }
 
@@ -341,7 +354,19 @@ int main(int argc, char** argv) {
       printf("conv images=%d Z=%d H=%d BN=%d                      rel err %.3e  %s\n", c[0], c[1], c[2], c[3], e, e < 3e-5 ? "ok" : "FAIL");
       if (!(e < 3e-5)) fails++;
     }
+    printf("---- implicit-GEMM conv operand, F16X3 (64-byte K-blocks = 32 fp16 channels) ----\n");
+    for (const auto& c : cc) {
+      double ms = 0;
+      const double e = run_conv_case(c[0], c[1], c[2], c[3], 0, &ms, MODE_F16X3);
+      printf("conv f16x3 images=%d Z=%d H=%d BN=%d                rel err %.3e  %s\n", c[0], c[1], c[2], c[3], e, e < 3e-5 ? "ok" : "FAIL");
+      if (!(e < 3e-5)) fails++;
+    }
     if (bench) {
+      double ms16 = 0;
+      const double e16 = run_conv_case(100, 50, 512, 256, 3, &ms16, MODE_F16X3);
+      printf("conv f16x3 images=100 Z=50 H=512 BN=256 (cfg4)     rel err %.3e  %.3f ms  %.1f TFLOP/s (algorithmic, 1 pass)\n", e16, ms16,
+             2.0 * 6400 * 512 * 800.0 * 50 / ms16 * 1e-9);
+      if (!(e16 < 3e-5)) fails++;
       double ms = 0;
       const double e = run_conv_case(100, 50, 512, 256, 3, &ms);
       printf("conv images=100 Z=50 H=512 BN=256 (cfg4)           rel err %.3e  %.3f ms  %.1f TFLOP/s (algorithmic, 1 pass)\n", e, ms,

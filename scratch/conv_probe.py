@@ -10,7 +10,7 @@ from robustbnns_b200 import adversarialAttacks as aa
 from robustbnns_b200 import lossGradients as lg
 from robustbnns_b200.model_bnn import BNN
 
-precs = [sys.argv[1]] if len(sys.argv) > 1 else ["fp32", "tf32x3"]
+precs = [sys.argv[1]] if len(sys.argv) > 1 else ["fp32", "tf32x3", "f16x3"]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 hidden = int(os.environ.get("HIDDEN", "512"))
 n_img, n_s = 100, 50

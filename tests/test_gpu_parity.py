@@ -336,20 +336,20 @@ TC_CONV_CONFIGS = [
 ]
 
 
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3"])
 @pytest.mark.parametrize("shape,hidden,C,B,S", TC_CONV_CONFIGS)
-def test_tcgen05_conv_engine_vs_oracle(shape, hidden, C, B, S):
-    """arch conv on the tensor cores (TF32X3): conv2 as an implicit GEMM over 5-D TMA boxes, its input gradient as a
-    tcgen05 GEMM, LeakyReLU signs and pooling arg-maxes settled exactly inside the guard band -- against the fp64 oracle
-    at the north-star tolerance."""
+def test_tcgen05_conv_engine_vs_oracle(shape, hidden, C, B, S, prec):
+    """arch conv on the tensor cores (TF32X3 / F16X3): conv2 as an implicit GEMM over 5-D TMA boxes, its input gradient
+    as a tcgen05 GEMM, LeakyReLU signs and pooling arg-maxes settled exactly inside the guard band -- against the fp64
+    oracle at the north-star tolerance."""
     from robustbnns_b200 import _lib
     from robustbnns_b200.engine import Net
     net, layout, loc, rho, bank, x, labels = _problem("conv", shape, hidden, C, B, S)
     eng = Net("conv", shape, hidden, C)
-    for bad in ("f16x3", "bf16"):
-        with pytest.raises(RuntimeError):
-            eng.set_precision(bad)
-    eng.set_precision("tf32x3")
-    assert eng.precision == "tf32x3"
+    with pytest.raises(RuntimeError):
+        eng.set_precision("bf16")
+    eng.set_precision(prec)
+    assert eng.precision == prec
     eng.upload(bank, 0)
     probs = eng.forward_probs_sum(x, 0, S).cpu() / S
     ref_p = orc.bnn_forward(net, layout, bank, x, range(S)).detach()
@@ -358,6 +358,13 @@ def test_tcgen05_conv_engine_vs_oracle(shape, hidden, C, B, S):
     g = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S).cpu().reshape(x.shape) / S
     ref64 = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)
     e_mean = rel_err(g, ref64)
+    # heads whose g is handed in (autograd through forward, ensembles): the dZ2 range of F16X3 comes from max|g|
+    gu = torch.randn((B, C), generator=torch.Generator().manual_seed(3)) * 1e-3
+    got_u = eng.input_grad_sum(_lib.HEAD_LOGITS_UPSTREAM, x, labels, 0, S, pbar=gu).cpu().reshape(x.shape)
+    xs = x.double().clone().requires_grad_(True)
+    lsum = sum(orc.net_logits(net, {k: v.double() for k, v in orc.unpack(bank[s], layout).items()}, xs) for s in range(S))
+    (ref_u,) = torch.autograd.grad((lsum * gu.double()).sum(), xs)
+    assert rel_err(got_u, ref_u) < REL
     pbar = eng.forward_probs_sum(x, 0, S) / S
     ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, x, labels, 0, S, pbar=pbar).cpu().reshape(x.shape) / S
     ra = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
@@ -365,7 +372,7 @@ def test_tcgen05_conv_engine_vs_oracle(shape, hidden, C, B, S):
     gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, S - 1, S).cpu().reshape(x.shape)
     rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
     e_log = rel_err(gl, rl)
-    print(f"tcgen05 conv-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} logits-CE {e_log:.2e}")
+    print(f"tcgen05 {prec} conv-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} logits-CE {e_log:.2e}")
     assert max(e_mean, e_att, e_log) < REL
     # no kept-forward route for conv: keep=True is a plain forward
     assert rel_err(eng.forward_probs_sum(x, 0, S, keep=True).cpu() / S, ref_p) < REL and not eng.keep_valid
@@ -382,7 +389,8 @@ def test_tcgen05_conv_engine_vs_oracle(shape, hidden, C, B, S):
     eng.close()
 
 
-def test_golden_hmc_conv_on_tcgen05(tmp_path, monkeypatch):
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3"])
+def test_golden_hmc_conv_on_tcgen05(prec, tmp_path, monkeypatch):
     """The reference's own outputs for the conv BNN (golden vectors) reproduced by the tensor-core conv engine:
     probabilities, expected loss gradients, FGSM examples, evaluation counts bit-exact."""
     from robustbnns_b200 import adversarialAttacks as aa
@@ -392,7 +400,7 @@ def test_golden_hmc_conv_on_tcgen05(tmp_path, monkeypatch):
     S = c.bank.shape[0]
     bnn = _bnn(c, "hmc", S)
     bnn.set_posterior_samples(c.bank)
-    bnn.set_precision("tf32x3")
+    bnn.set_precision(prec)
     assert rel_err(bnn.forward(c.x, n_samples=S).cpu(), c.t("probs")) < REL
     assert rel_err(lg.expected_loss_gradients(bnn, c.x, c.labels, S).cpu(), c.t("loss_gradient")) < REL
     hyper = {"epsilon": float(c.z["eps"])}
