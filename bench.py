@@ -356,6 +356,46 @@ def main():
                             "per iteration as upstream, no host round-trip between iterations"}
         except Exception as e:
             log("PGD measurement failed:", e)
+        try:
+            # BASELINE configs[3] shape: conv-512 BNN, 100 F-MNIST-shaped inputs, 50 stored (HMC-like) posterior samples
+            from robustbnns_b200 import adversarialAttacks as aa
+            n_img, n_s, hid = 100, 50, 512
+            cb = BNN("fashion_mnist", hid, "leaky", "conv", "hmc", None, None, n_s, 5, SHAPE, NCLS)
+            gc = torch.Generator().manual_seed(2)
+            cols = []
+            for key, shp in cb.basenet.layout:
+                n = 1
+                for v in shp:
+                    n *= v
+                fan_c = n // shp[0] if len(shp) > 1 else 25
+                cols.append(torch.randn((n_s, n), generator=gc) / math.sqrt(fan_c))
+            cb.set_posterior_samples(torch.cat(cols, dim=1))
+            cb.set_precision("f16x3")
+            xc, yc = x_dev[:n_img].contiguous(), y_dev[:n_img].to(torch.int64)
+            lg.expected_loss_gradients(cb, xc, yc, n_s)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                lg.expected_loss_gradients(cb, xc, yc, n_s)
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / 5
+            aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=1)
+            torch.cuda.synchronize()
+            e0.record()
+            aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=4)
+            e1.record()
+            torch.cuda.synchronize()
+            pit = e0.elapsed_time(e1) / 4
+            extra["conv_cfg4"] = {"grads_per_s": n_img * n_s / (gms * 1e-3), "grad_ms": gms,
+                                  "tflops_algorithmic": n_img * n_s * 107704320 / (gms * 1e-3) / 1e12,
+                                  "pgd_ms_per_iter": pit, "pgd40_imgs_per_s": n_img / (pit * 40e-3), "engine": "f16x3",
+                                  "note": "conv-512 BNN (107.7 MFLOP per sample x input), 100 inputs x 50 stored samples: "
+                                          "conv2 as a tcgen05 implicit GEMM over 5-D TMA boxes, dgrad as a tcgen05 GEMM"}
+            del cb
+        except Exception as e:
+            log("conv measurement failed:", e)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

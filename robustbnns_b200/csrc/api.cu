@@ -531,11 +531,12 @@ int rbnn_forward_probs_sum_keep(rbnn_net* n, const float* d_x, int B, int s0, in
   RBNN_TRY(check_rows(n, s0, s1));
   RBNN_CHECK(B >= 0, "negative batch");
   n->keep.valid = 0;
-  if (B == 0 || s1 == s0 || n->prec == RBNN_PREC_FP32 || n->arch == RBNN_ARCH_CONV)
+  if (B == 0 || s1 == s0 || n->prec == RBNN_PREC_FP32)
     return rbnn_forward_probs_sum(n, d_x, B, s0, s1, d_out_sum, stream);
   DeviceGuard dg(n->device);
   cudaStream_t st = (cudaStream_t)stream;
   RBNN_CUDA(cudaMemsetAsync(d_out_sum, 0, (size_t)B * n->C * sizeof(float), st));
+  if (n->arch == RBNN_ARCH_CONV) return tc_conv_forward_keep(n, d_x, B, s0, s1, d_out_sum, st);
   return tc_fc_forward_keep(n, d_x, B, s0, s1, d_out_sum, st);
 }
 
@@ -548,6 +549,7 @@ int rbnn_input_grad_sum_kept(rbnn_net* n, int head, const int32_t* d_labels, con
              "head %d has no kept route", head);
   RBNN_CHECK(head == RBNN_HEAD_MEAN_OF_GRADS || d_pbar != nullptr, "GRAD_OF_MEAN / UPSTREAM need d_pbar");
   DeviceGuard dg(n->device);
+  if (n->arch == RBNN_ARCH_CONV) return tc_conv_grad_kept(n, head, d_labels, d_pbar, d_out_sum, (cudaStream_t)stream);
   return tc_fc_grad_kept(n, head, d_labels, d_pbar, d_out_sum, (cudaStream_t)stream);
 }
 

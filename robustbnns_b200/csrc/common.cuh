@@ -91,6 +91,8 @@ struct KeepCache {
   uint32_t* masks = nullptr; size_t masks_cap = 0;      // tc::keep_mask_words(B, S) words
   float* call_sc = nullptr;                             // F16X3: the call's 4 scale scalars, alive between the phases
   unsigned* max_bits = nullptr;                         // F16X3: [0] max|x|, [1] max|d_pbar|
+  // conv engine (tc_conv.cu): pooled conv1 map, its arg-max indices, the refined A2 and the logits of every kept unit
+  char* conv_buf = nullptr; size_t conv_cap = 0;
   int valid = 0, B = 0, s0 = 0, s1 = 0;
 };
 
@@ -228,5 +230,10 @@ int tc_conv_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int3
                            const float* d_pbar, float* d_out_sum, cudaStream_t st);
 int tc_conv_forward(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum, float* d_out_logits,
                     cudaStream_t st);
+// two-phase attack gradient for the conv net: the forward keeps P1 / arg-max indices / refined A2 / logits per unit
+// (net->keep.valid tells whether it could), the gradient pass starts from them -- no second forward
+int tc_conv_forward_keep(rbnn_net* net, const float* d_x, int B, int s0, int s1, float* d_out_sum, cudaStream_t st);
+int tc_conv_grad_kept(rbnn_net* net, int head, const int32_t* d_labels, const float* d_pbar, float* d_out_sum,
+                      cudaStream_t st);
 
 }  // namespace rbnn

@@ -40,6 +40,28 @@ struct ConvTcBufs {
   int parts = 1;
 };
 
+// views into KeepCache::conv_buf for `units` (sample, image) units
+struct KeepView {
+  float *p1 = nullptr, *a2 = nullptr, *logits = nullptr;
+  uint8_t* idx1 = nullptr;
+};
+
+size_t keep_bytes(const rbnn_net* n, size_t units) {
+  return pad256(units * 4608 * 4) + pad256(units * 64 * n->H * 4) + pad256(units * n->C * 4) + pad256(units * 4608);
+}
+
+KeepView keep_view(const rbnn_net* n, size_t units) {
+  KeepView v;
+  char* p = n->keep.conv_buf;
+  v.p1 = reinterpret_cast<float*>(p); p += pad256(units * 4608 * 4);
+  v.a2 = reinterpret_cast<float*>(p); p += pad256(units * 64 * n->H * 4);
+  v.logits = reinterpret_cast<float*>(p); p += pad256(units * n->C * 4);
+  v.idx1 = reinterpret_cast<uint8_t*>(p);
+  return v;
+}
+
+constexpr size_t kConvKeepBudget = (size_t)16 << 30;      // kept forward: at most 16 GB of HBM
+
 size_t bytes_per_zb(const rbnn_net* n, bool grad) {
   const size_t H = n->H, C = n->C;
   size_t per = 3 * 4608 * 4 + 4608 + 64 * H * 4 + C * 4 + (H / 128 + 1) * C * 4;
@@ -47,17 +69,27 @@ size_t bytes_per_zb(const rbnn_net* n, bool grad) {
   return per + 64;
 }
 
-void carve(rbnn_net* n, Arena& ar, int Z, int B, bool grad, ConvTcBufs& c) {
+// fwd / grad: which halves of the evaluation need workspace; kv != nullptr: P1, idx1, A2 and the logits live in the
+// kept-forward storage (unit offset unit0) instead of the arena
+void carve(rbnn_net* n, Arena& ar, int Z, int B, bool fwd, bool grad, ConvTcBufs& c, const KeepView* kv = nullptr,
+           size_t unit0 = 0) {
   const size_t H = n->H, C = n->C, ZB = (size_t)Z * B;
-  c.p1 = ar.take<float>((size_t)ZB * 4608);
-  c.p1h = ar.take<float>((size_t)ZB * 4608);      // sized for fp32; the fp16 variant uses half of it
-  c.p1l = ar.take<float>((size_t)ZB * 4608);
   c.call_sc = ar.take<float>(4);
   c.max_bits = ar.take<unsigned>(2);
-  c.idx1 = ar.take<uint8_t>((size_t)ZB * 4608);
-  c.a2 = ar.take<float>((size_t)ZB * 64 * H);
-  c.logits = ar.take<float>((size_t)ZB * C);
-  c.lpart = ar.take<float>((size_t)pool2_logits_chunks(n) * ZB * C);
+  if (kv) {
+    c.p1 = kv->p1 + unit0 * 4608; c.idx1 = kv->idx1 + unit0 * 4608;
+    c.a2 = kv->a2 + unit0 * 64 * H; c.logits = kv->logits + unit0 * C;
+  } else {
+    c.p1 = ar.take<float>((size_t)ZB * 4608);
+    c.idx1 = ar.take<uint8_t>((size_t)ZB * 4608);
+    c.a2 = ar.take<float>((size_t)ZB * 64 * H);
+    c.logits = ar.take<float>((size_t)ZB * C);
+  }
+  if (fwd) {
+    c.p1h = ar.take<float>((size_t)ZB * 4608);      // sized for fp32; the fp16 variant uses half of it
+    c.p1l = ar.take<float>((size_t)ZB * 4608);
+    c.lpart = ar.take<float>((size_t)pool2_logits_chunks(n) * ZB * C);
+  }
   if (grad) {
     c.dlogits = ar.take<float>((size_t)ZB * C);
     c.dzh = ar.take<float>((size_t)ZB * 64 * H);
@@ -123,42 +155,52 @@ int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs&
   return 0;
 }
 
+// loss head + input gradients of one chunk, starting from its logits, refined A2, P1 and arg-max indices
+int backward_chunk(rbnn_net* n, int head, const int32_t* labels, const float* pbar, int B, int z0, int Z, ConvTcBufs& c,
+                   float* out_sum, bool first, cudaStream_t st) {
+  const int H = n->H, C = n->C;
+  const TcMat& m = n->tc.mat[0];
+  const bool f16 = n->prec == RBNN_PREC_F16X3;
+  RBNN_TRY(head_dlogits(n, head, c.logits, labels, pbar, Z, B, C, c.dlogits, st));
+  RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dzh, c.dzl, f16 ? c.call_sc + 2 : nullptr, st));
+  // dcol[z][b * 64 + pos][c * 25 + ky * 5 + kx] = sum_h dZ2[z][b * 64 + pos][h] W2_z[h][c][ky][kx]
+  tc::GemmDesc d;
+  d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = 160;
+  d.A.hi = c.dzh; d.A.lo = c.dzl; d.A.rows = d.M; d.A.ld = H; d.A.zstride = (int64_t)B * 64 * H;
+  if (f16) {
+    d.B.hi = reinterpret_cast<const uint16_t*>(m.th_hi) + (int64_t)z0 * 800 * H;
+    d.B.lo = reinterpret_cast<const uint16_t*>(m.th_lo) + (int64_t)z0 * 800 * H;
+    d.unscale = c.call_sc + 3;
+  } else {
+    d.B.hi = m.thi + (int64_t)z0 * 800 * H; d.B.lo = m.tlo + (int64_t)z0 * 800 * H;
+  }
+  d.B.rows = 800; d.B.ld = H; d.B.zstride = (int64_t)800 * H;
+  d.epi = tc::EPI_NONE;
+  d.out = c.dcol; d.out_ld = 800; d.out_zstride = (int64_t)B * 64 * 800;
+  RBNN_TRY(run_tc(n, d, 2, st));
+  RBNN_TRY(col2im_conv2(n, c.dcol, c.p1, Z * B, c.g1, st));
+  RBNN_TRY(conv1_bwd_sum(n, c.g1, c.idx1, n->bank, z0, Z, B, out_sum, first ? 0 : 1, st, c.partial, c.parts));
+  return 0;
+}
+
+// |dZ2| <= dh_factor * max|g| * max|Wout|: 4 pooling windows x sum_c |dlogits_c| (<= 2 max|g|, or C max|g| when the
+// head hands g to the logits unchanged)
+float dh_factor_of(const rbnn_net* n, int head) { return head == RBNN_HEAD_LOGITS_UPSTREAM ? 4.f * (float)n->C : 8.f; }
+bool g_given(int head) { return head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM; }
+
 int grad_pass(rbnn_net* n, int head, const float* x, const int32_t* labels, int B, int s0, int s1, const float* pbar,
               float* out_sum, cudaStream_t st) {
-  const int H = n->H, C = n->C;
   const size_t per = bytes_per_zb(n, true) * (size_t)B + 8192 + (size_t)B * 784 * 4;   // + this sample's share of the conv1-backward partials (<= 1 slice per sample)
   const int zc = (int)std::max<size_t>(1, std::min<size_t>(n->ws_budget / per, (size_t)(s1 - s0)));
   RBNN_TRY(ws_reserve(n, per * zc));
-  const TcMat& m = n->tc.mat[0];
   bool first = true;
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
     Arena ar(n);
     ConvTcBufs c;
-    carve(n, ar, Z, B, true, c);
-    const bool f16 = n->prec == RBNN_PREC_F16X3;
-    const bool given = head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM;
-    const float dh_factor = head == RBNN_HEAD_LOGITS_UPSTREAM ? 4.f * (float)C : 8.f;
-    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, c.logits, given ? pbar : nullptr, dh_factor, st));
-    RBNN_TRY(head_dlogits(n, head, c.logits, labels, pbar, Z, B, C, c.dlogits, st));
-    RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dzh, c.dzl, f16 ? c.call_sc + 2 : nullptr, st));
-    // dcol[z][b * 64 + pos][c * 25 + ky * 5 + kx] = sum_h dZ2[z][b * 64 + pos][h] W2_z[h][c][ky][kx]
-    tc::GemmDesc d;
-    d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = 160;
-    d.A.hi = c.dzh; d.A.lo = c.dzl; d.A.rows = d.M; d.A.ld = H; d.A.zstride = (int64_t)B * 64 * H;
-    if (f16) {
-      d.B.hi = reinterpret_cast<const uint16_t*>(m.th_hi) + (int64_t)z0 * 800 * H;
-      d.B.lo = reinterpret_cast<const uint16_t*>(m.th_lo) + (int64_t)z0 * 800 * H;
-      d.unscale = c.call_sc + 3;
-    } else {
-      d.B.hi = m.thi + (int64_t)z0 * 800 * H; d.B.lo = m.tlo + (int64_t)z0 * 800 * H;
-    }
-    d.B.rows = 800; d.B.ld = H; d.B.zstride = (int64_t)800 * H;
-    d.epi = tc::EPI_NONE;
-    d.out = c.dcol; d.out_ld = 800; d.out_zstride = (int64_t)B * 64 * 800;
-    RBNN_TRY(run_tc(n, d, 2, st));
-    RBNN_TRY(col2im_conv2(n, c.dcol, c.p1, Z * B, c.g1, st));
-    RBNN_TRY(conv1_bwd_sum(n, c.g1, c.idx1, n->bank, z0, Z, B, out_sum, first ? 0 : 1, st, c.partial, c.parts));
+    carve(n, ar, Z, B, true, true, c);
+    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, c.logits, g_given(head) ? pbar : nullptr, dh_factor_of(n, head), st));
+    RBNN_TRY(backward_chunk(n, head, labels, pbar, B, z0, Z, c, out_sum, first, st));
     first = false;
   }
   return 0;
@@ -173,7 +215,7 @@ int probs_pass(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_su
     const int Z = std::min(zc, s1 - z0);
     Arena ar(n);
     ConvTcBufs c;
-    carve(n, ar, Z, B, false, c);
+    carve(n, ar, Z, B, true, false, c);
     float* lg = out_logits ? out_logits : c.logits;
     RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, lg, nullptr, 8.f, st));
     if (out_sum) RBNN_TRY(head_probs_accumulate(n, lg, Z, B, C, out_sum, st));
@@ -199,6 +241,71 @@ int tc_conv_input_grad_sum(rbnn_net* n, int head, const float* x, const int32_t*
     const int nb = std::min(bc, B - b0);
     RBNN_TRY(grad_pass(n, head, x + (int64_t)b0 * n->D, labels + b0, nb, s0, s1, pbar ? pbar + (int64_t)b0 * n->C : nullptr,
                        out_sum + (int64_t)b0 * n->D, st));
+  }
+  return 0;
+}
+
+// Phase 1 of the two-phase attack gradient (adversarialAttacks.py:74-78 evaluates net.forward once and differentiates it):
+// out_sum[B, C] += sum_s softmax(logits_s) as tc_conv_forward, and P1, its arg-max indices, the refined A2 and the
+// logits of every unit stay in net->keep.conv_buf.  Falls back to the plain forward (keep.valid = 0) when the kept
+// data would exceed kConvKeepBudget or the batch does not fit one pass.
+int tc_conv_forward_keep(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, cudaStream_t st) {
+  RBNN_CHECK(tc_conv_supported(n) && (n->prec == RBNN_PREC_TF32X3 || n->prec == RBNN_PREC_F16X3),
+             "the tcgen05 conv engine runs TF32X3 / F16X3 on sm_100 only");
+  KeepCache& k = n->keep;
+  k.valid = 0;
+  const size_t units = (size_t)(s1 - s0) * B;
+  const size_t need = keep_bytes(n, units);
+  if (need > kConvKeepBudget || batch_rows(n, B, false) < B || batch_rows(n, B, true) < B)
+    return tc_conv_forward(n, x, B, s0, s1, out_sum, nullptr, st);
+  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
+  if (k.conv_cap < need) {
+    RBNN_CUDA(cudaDeviceSynchronize());
+    cudaFree(k.conv_buf);
+    k.conv_buf = nullptr; k.conv_cap = 0;
+    RBNN_CUDA(cudaMalloc(&k.conv_buf, need));
+    k.conv_cap = need;
+  }
+  const KeepView kv = keep_view(n, units);
+  const size_t per = bytes_per_zb(n, false) * (size_t)B + 8192;
+  const int zc = (int)std::max<size_t>(1, std::min<size_t>(n->ws_budget / per, (size_t)(s1 - s0)));
+  RBNN_TRY(ws_reserve(n, per * zc));
+  for (int z0 = s0; z0 < s1; z0 += zc) {
+    const int Z = std::min(zc, s1 - z0);
+    Arena ar(n);
+    ConvTcBufs c;
+    carve(n, ar, Z, B, true, false, c, &kv, (size_t)(z0 - s0) * B);
+    RBNN_TRY(forward_chunk(n, x, B, z0, Z, c, c.logits, nullptr, 8.f, st));
+    RBNN_TRY(head_probs_accumulate(n, c.logits, Z, B, n->C, out_sum, st));
+  }
+  k.valid = 1; k.B = B; k.s0 = s0; k.s1 = s1;
+  return 0;
+}
+
+// Phase 2: out_sum[B, D] = sum_s dL/dx from the kept forward
+int tc_conv_grad_kept(rbnn_net* n, int head, const int32_t* labels, const float* pbar, float* out_sum, cudaStream_t st) {
+  KeepCache& k = n->keep;
+  RBNN_CHECK(k.valid && k.conv_buf, "no kept forward: call rbnn_forward_probs_sum_keep first (and check rbnn_keep_valid)");
+  RBNN_CHECK(head != RBNN_HEAD_LOGITS_CE, "LOGITS_CE has no kept route");
+  const int B = k.B, s0 = k.s0, s1 = k.s1;
+  const bool f16 = n->prec == RBNN_PREC_F16X3;
+  const KeepView kv = keep_view(n, (size_t)(s1 - s0) * B);
+  const size_t per = bytes_per_zb(n, true) * (size_t)B + 8192 + (size_t)B * 784 * 4;
+  const int zc = (int)std::max<size_t>(1, std::min<size_t>(n->ws_budget / per, (size_t)(s1 - s0)));
+  RBNN_TRY(ws_reserve(n, per * zc));
+  bool first = true;
+  for (int z0 = s0; z0 < s1; z0 += zc) {
+    const int Z = std::min(zc, s1 - z0);
+    Arena ar(n);
+    ConvTcBufs c;
+    carve(n, ar, Z, B, false, true, c, &kv, (size_t)(z0 - s0) * B);
+    if (f16) {          // the dZ2 range of THIS head ([0], [1] of the scalars belong to the forward and are not used here)
+      RBNN_CUDA(cudaMemsetAsync(c.max_bits, 0, 2 * sizeof(unsigned), st));
+      if (g_given(head)) RBNN_TRY(tc_maxabs(n, pbar, (int64_t)B * n->C, c.max_bits + 1, st));
+      RBNN_TRY(tc_call_scales(n, c.max_bits, g_given(head) ? c.max_bits + 1 : nullptr, dh_factor_of(n, head), c.call_sc, st));
+    }
+    RBNN_TRY(backward_chunk(n, head, labels, pbar, B, z0, Z, c, out_sum, first, st));
+    first = false;
   }
   return 0;
 }

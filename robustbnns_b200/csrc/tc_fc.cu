@@ -1152,6 +1152,7 @@ int tc_fc_forward(rbnn_net* n, const float* x, int B, int s0, int s1, float* out
 
 void tc_keep_free(rbnn_net* n) {
   cudaFree(n->keep.logits); cudaFree(n->keep.masks); cudaFree(n->keep.call_sc); cudaFree(n->keep.max_bits);
+  cudaFree(n->keep.conv_buf);
   n->keep = KeepCache();
 }
 

@@ -374,8 +374,16 @@ def test_tcgen05_conv_engine_vs_oracle(shape, hidden, C, B, S, prec):
     e_log = rel_err(gl, rl)
     print(f"tcgen05 {prec} conv-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} logits-CE {e_log:.2e}")
     assert max(e_mean, e_att, e_log) < REL
-    # no kept-forward route for conv: keep=True is a plain forward
-    assert rel_err(eng.forward_probs_sum(x, 0, S, keep=True).cpu() / S, ref_p) < REL and not eng.keep_valid
+    # two-phase form (what the attacks use): the forward keeps P1 / arg-max indices / refined A2 / logits, the gradient
+    # pass starts from them -- same kernels on the same data, so the results are identical
+    pk = eng.forward_probs_sum(x, 0, S, keep=True)
+    assert eng.keep_valid and rel_err(pk, pbar * S) < 1e-6
+    gk = eng.input_grad_sum_kept(_lib.HEAD_GRAD_OF_MEAN, labels, pbar=pk / S).cpu().reshape(x.shape) / S
+    assert torch.equal(gk, ga)
+    gm = eng.input_grad_sum_kept(_lib.HEAD_MEAN_OF_GRADS, labels).cpu().reshape(x.shape) / S
+    assert torch.equal(gm, g)
+    eng.upload(bank[0:1], 0)                       # touching a kept row invalidates the kept forward
+    assert not eng.keep_valid
     ga_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S // 2)
     gb_ = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, S // 2, S)
     assert rel_err((ga_ + gb_).cpu().reshape(x.shape) / S, g) < 1e-5
@@ -652,7 +660,7 @@ def test_full_size_properties_pgd_cfg3():
     bnn.reseed(0)
     f1 = aa.fgsm_attack(bnn, xd, yd, hyperparams={"epsilon": 0.2}, n_samples=S)
     d = (f1 - xd).abs()
-    assert float(((d - 0.2).abs() < 1e-6).float().mean() + (d < 0.2 - 1e-6).float().mean()) == 1.0
+    assert float(d.max()) <= 0.2 + 1e-6 and float(((d - 0.2).abs() < 1e-6).float().mean()) > 0.5    # full steps unless clipped
     # the attack must lower the expected probability of the true class on average (it ascends the loss)
     bnn.reseed(1)
     p_clean = bnn.forward(xd, n_samples=S).gather(1, yd[:, None]).mean()
