@@ -18,10 +18,13 @@ from tests.helpers import rel_err
 
 pytestmark = pytest.mark.gpu
 
-ARCH, SHAPE, HIDDEN, C, B, S = "fc", (1, 28, 28), 128, 10, 200, 13      # 13 samples: uneven shards (7 + 6)
+SHAPE, C = (1, 28, 28), 10
+# (architecture, hidden, inputs, samples, engine): 13 / 5 samples give uneven shards (7 + 6, 3 + 2)
+CASES = [("fc", 128, 200, 13, "fp32"), ("fc", 128, 200, 13, "f16x3"), ("conv", 32, 10, 5, "f16x3")]
 
 
-def _rank_main(rank, world, port, prec, q):
+def _rank_main(rank, world, port, case, q):
+    ARCH, HIDDEN, B, S, prec = case
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
@@ -61,8 +64,9 @@ def _rank_main(rank, world, port, prec, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x3"])
-def test_two_rank_nccl_sharding_equals_single_device_and_oracle(prec):
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%s" % (c[0], c[4]))
+def test_two_rank_nccl_sharding_equals_single_device_and_oracle(case):
+    ARCH, HIDDEN, B, S, prec = case
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
@@ -70,7 +74,7 @@ def test_two_rank_nccl_sharding_equals_single_device_and_oracle(prec):
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, prec, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, case, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
