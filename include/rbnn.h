@@ -108,7 +108,7 @@ RBNN_API int rbnn_forward_probs_sum(rbnn_net* net, const float* d_x, int B, int 
  * it): the same sum as rbnn_forward_probs_sum, and the per-sample logits and LeakyReLU masks of this call stay in the
  * handle (~104 B per sample x input), so that rbnn_input_grad_sum_kept can rebuild the gradient without a second
  * forward pass (arch conv keeps the pooled conv1 map, its arg-max indices, the refined second-layer activations and the
- * logits instead).  When the engine has no such route (FP32 engine, fc2, batch too large for one pass) the call
+ * logits, fc2 the refined hidden activations).  When the engine has no such route (FP32 engine, batch too large for one pass) the call
  * is a plain forward and rbnn_keep_valid() returns 0.  The kept data is invalidated when the bank rows it used are
  * overwritten or the precision changes. */
 RBNN_API int rbnn_forward_probs_sum_keep(rbnn_net* net, const float* d_x, int B, int s0, int s1,

@@ -91,6 +91,8 @@ struct KeepCache {
   uint32_t* masks = nullptr; size_t masks_cap = 0;      // tc::keep_mask_words(B, S) words
   float* call_sc = nullptr;                             // F16X3: the call's 4 scale scalars, alive between the phases
   unsigned* max_bits = nullptr;                         // F16X3: [0] max|x|, [1] max|d_pbar|
+  // unfused FC route (fc2, or arch fc with RBNN_TC_UNFUSED): the hidden activations H1 [, H2] of every kept unit, fp32
+  float* fc_h = nullptr; size_t fc_cap = 0;
   // conv engine (tc_conv.cu): pooled conv1 map, its arg-max indices, the refined A2 and the logits of every kept unit
   char* conv_buf = nullptr; size_t conv_cap = 0;
   int valid = 0, B = 0, s0 = 0, s1 = 0;

@@ -958,9 +958,11 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
   RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
-  RBNN_CHECK(!kept || fused, "the kept forward exists for the fused route only");
-  if (!fused) w.h1 = ar.take<float>(zbh);
-  if (two) {
+  RBNN_CHECK(!kept || fused || n->keep.fc_h, "no kept hidden activations for the unfused route");
+  const bool kept_unfused = kept && !fused;       // H1 [, H2] of every kept unit live in n->keep.fc_h
+  const size_t keep_units = (size_t)(s1 - s0) * B * H;
+  if (!fused && !kept) w.h1 = ar.take<float>(zbh);
+  if (two && !kept) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
     w.h2 = ar.take<float>(zbh);
   }
@@ -999,7 +1001,12 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
     const int sl = Z == zc ? slots : std::min(slots, slots_for(Z));
-    if (kept) {
+    if (kept_unfused) {
+      w.h1 = n->keep.fc_h + (size_t)(z0 - s0) * B * H;
+      if (two) w.h2 = n->keep.fc_h + keep_units + (size_t)(z0 - s0) * B * H;
+      RBNN_TRY(launch_head(n, true, head, two ? w.h2 : w.h1, z0, Z, labels, pbar, B, nullptr, w.dtop_hi, w.dtop_lo,
+                           w.dtop_bf, st));
+    } else if (kept) {
       tc::KeptDesc k;
       k.mode = bf ? tc::MODE_BF16 : (f16 ? tc::MODE_F16X3 : tc::MODE_TF32X3);
       k.B = B; k.H = H; k.C = n->C; k.Z = Z;
@@ -1086,7 +1093,7 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
   const int S = s1 - s0;
   // keep mode: logits go to n->keep (all samples), the arena holds the guard-band worklist of a chunk
-  const size_t per = keep ? pad256(tc::fused_worklist_slots(B, 1) * 8) + 256 : fc_per_z_bytes(n, B, false);
+  const size_t per = (keep && use_fused(n)) ? pad256(tc::fused_worklist_slots(B, 1) * 8) + 256 : fc_per_z_bytes(n, B, false);
   const size_t ldx = (size_t)k_pitch(n, D);
   const size_t x_bytes = bf ? pad256((size_t)B * ldx * 2) : (f16 ? 2 * pad256((size_t)B * ldx * 2) + 512 : 2 * pad256((size_t)B * ldx * 4));
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
@@ -1104,13 +1111,14 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
   RBNN_CHECK(!f16 || fused, "F16X3 covers arch fc with a hidden layer the fused kernel supports");
-  RBNN_CHECK(!keep || fused, "the kept forward exists for the fused route only");
-  if (!fused) w.h1 = ar.take<float>(zbh);
+  const bool keep_unfused = keep && !fused;       // H1 [, H2] go to n->keep.fc_h (all samples) instead of the arena
+  const size_t keep_units = (size_t)S * B * H;
+  if (!fused && !keep) w.h1 = ar.take<float>(zbh);
   if (two) {
     if (bf) w.h1_bf = ar.take<__nv_bfloat16>(zbh); else w.h1_lo = ar.take<float>(zbh);
-    w.h2 = ar.take<float>(zbh);
+    if (!keep) w.h2 = ar.take<float>(zbh);
   }
-  if (keep) { if (!bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc)); }
+  if (keep && fused) { if (!bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc)); }
   else w.logits = ar.take<float>((size_t)zc * B * C);
   w.xnorm = ar.take<float>((size_t)B);
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, st));
@@ -1121,8 +1129,12 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   }
   for (int z0 = s0; z0 < s1; z0 += zc) {
     const int Z = std::min(zc, s1 - z0);
-    float* lg = keep ? n->keep.logits + (size_t)(z0 - s0) * B * C : (out_logits ? out_logits : w.logits);
-    if (keep) {
+    float* lg = (keep && fused) ? n->keep.logits + (size_t)(z0 - s0) * B * C : (out_logits ? out_logits : w.logits);
+    if (keep_unfused) {
+      w.h1 = n->keep.fc_h + (size_t)(z0 - s0) * B * H;
+      if (two) w.h2 = n->keep.fc_h + keep_units + (size_t)(z0 - s0) * B * H;
+    }
+    if (keep && fused) {
       RBNN_TRY(fused_chunk(n, w, -2, x, nullptr, nullptr, B, z0, Z, lg, st,
                            n->keep.masks + tc::keep_mask_words(B, z0 - s0)));
     } else if (fused) {
@@ -1152,7 +1164,7 @@ int tc_fc_forward(rbnn_net* n, const float* x, int B, int s0, int s1, float* out
 
 void tc_keep_free(rbnn_net* n) {
   cudaFree(n->keep.logits); cudaFree(n->keep.masks); cudaFree(n->keep.call_sc); cudaFree(n->keep.max_bits);
-  cudaFree(n->keep.conv_buf);
+  cudaFree(n->keep.conv_buf); cudaFree(n->keep.fc_h);
   n->keep = KeepCache();
 }
 
@@ -1162,10 +1174,26 @@ void tc_keep_free(rbnn_net* n) {
 int tc_fc_forward_keep(rbnn_net* n, const float* x, int B, int s0, int s1, float* out_sum, cudaStream_t st) {
   RBNN_CHECK(tc_supported(n), "tcgen05 engine does not cover this network");
   n->keep.valid = 0;
-  if (!use_fused(n) || tc_batch_rows(n, B, false) < B || tc_batch_rows(n, B, true) < B)
+  if (tc_batch_rows(n, B, false) < B || tc_batch_rows(n, B, true) < B)
     return tc_fc_forward(n, x, B, s0, s1, out_sum, nullptr, st);
-  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
   KeepCache& k = n->keep;
+  if (!use_fused(n)) {
+    // unfused route (fc2, RBNN_TC_UNFUSED): keep the refined hidden activations themselves (fp32, 4 B per hidden unit)
+    const size_t need = (size_t)(s1 - s0) * B * n->H * (n->arch == RBNN_ARCH_FC2 ? 2 : 1);
+    if (need * sizeof(float) > ((size_t)16 << 30)) return tc_fc_forward(n, x, B, s0, s1, out_sum, nullptr, st);
+    RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
+    if (k.fc_cap < need) {
+      RBNN_CUDA(cudaDeviceSynchronize());
+      cudaFree(k.fc_h);
+      k.fc_h = nullptr; k.fc_cap = 0;
+      RBNN_CUDA(cudaMalloc(&k.fc_h, need * sizeof(float)));
+      k.fc_cap = need;
+    }
+    RBNN_TRY(tc_forward_pass(n, x, B, s0, s1, out_sum, nullptr, st, true));
+    k.valid = 1; k.B = B; k.s0 = s0; k.s1 = s1;
+    return 0;
+  }
+  RBNN_TRY(tc_bank_refresh(n, s0, s1, st));
   const size_t need_l = (size_t)(s1 - s0) * B * n->C, need_m = tc::keep_mask_words(B, s1 - s0);
   if (k.logits_cap < need_l || k.masks_cap < need_m) {
     RBNN_CUDA(cudaDeviceSynchronize());

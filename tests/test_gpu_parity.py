@@ -283,11 +283,12 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     e_att = rel_err(ga, ra)
     # two-phase form (what the attacks use): forward that keeps logits + masks, then the gradient from the kept data
     pk = eng.forward_probs_sum(x, 0, S, keep=True)
-    assert eng.keep_valid == (arch == "fc" and route == "fused")
+    assert eng.keep_valid          # fused route: logits + masks are kept; unfused / fc2: the hidden activations
     if eng.keep_valid:
         assert rel_err(pk, pbar * S) < 1e-6
         gk = eng.input_grad_sum_kept(_lib.HEAD_GRAD_OF_MEAN, labels, pbar=pk / S).cpu().reshape(x.shape) / S
-        assert rel_err(gk, ga) < (1e-6 if prec != "bf16" else 1e-2) and rel_err(gk, ra) < tol
+        assert rel_err(gk, ga) < (1e-6 if prec != "bf16" else 1e-2)
+        assert arch == "fc2" or rel_err(gk, ra) < tol        # fc2: ga (== gk) is held to the row criterion below
         gm = eng.input_grad_sum_kept(_lib.HEAD_MEAN_OF_GRADS, labels).cpu().reshape(x.shape) / S
         assert rel_err(gm, g) < (1e-6 if prec != "bf16" else 1e-2)
         eng.upload(bank[0:1], 0)                   # touching a kept row invalidates the kept forward
