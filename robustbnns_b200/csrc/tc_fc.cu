@@ -363,6 +363,9 @@ fc_head_kernel(int head, const float* __restrict__ Hact, const float* __restrict
 // Every unit with |pre-activation| < eps * (row max) is therefore recomputed exactly (fp64 accumulation of
 // the fp32 products, CUDA cores) and rewritten in place.  About 1e-3 of the units qualify.
 // One warp per (sample z, input b) row; H_hi (+ H_lo when the output is stored tf32-split) hold leaky(pre).
+// NCH = ceil(H / 128): the row (4 values per lane and 128-column chunk) stays in registers between the maximum pass
+// and the flag pass, so H is read once.
+template <int NCH>
 __global__ void __launch_bounds__(256)
 refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, int H, const float* __restrict__ a_hi,
               const float* __restrict__ a_lo, int64_t a_zstride, int K, const float* __restrict__ bank, int64_t P,
@@ -373,15 +376,22 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
     const int z = (int)(row / B), b = (int)(row % B);
     float* hh = Hhi + row * H;
     float* hl = Hlo ? Hlo + row * H : nullptr;
+    float v[NCH][4];
     float m = 0.f;
-    for (int j = lane * 4; j < H; j += 128) {
-      float4 v = *reinterpret_cast<const float4*>(hh + j);
-      if (hl) {
-        const float4 l = *reinterpret_cast<const float4*>(hl + j);
-        v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int j = c * 128 + lane * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < H) {
+        t = *reinterpret_cast<const float4*>(hh + j);
+        if (hl) {
+          const float4 l = *reinterpret_cast<const float4*>(hl + j);
+          t.x += l.x; t.y += l.y; t.z += l.z; t.w += l.w;
+        }
       }
-      m = fmaxf(m, fmaxf(fmaxf(v.x > 0.f ? v.x : -100.f * v.x, v.y > 0.f ? v.y : -100.f * v.y),
-                         fmaxf(v.z > 0.f ? v.z : -100.f * v.z, v.w > 0.f ? v.w : -100.f * v.w)));
+      v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m = fmaxf(m, v[c][e] > 0.f ? v[c][e] : -100.f * v[c][e]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -389,20 +399,14 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
     const float* __restrict__ ah = a_hi + (int64_t)z * a_zstride + (int64_t)b * K;
     const float* __restrict__ al = a_lo ? a_lo + (int64_t)z * a_zstride + (int64_t)b * K : nullptr;
     const float* __restrict__ wrow = bank + (int64_t)(z_row0 + z) * P;
-    for (int j0 = 0; j0 < H; j0 += 128) {
-      const int j = j0 + lane * 4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int j0 = c * 128, j = j0 + lane * 4;
       unsigned flags = 0u;
       if (j < H) {
-        float4 t = *reinterpret_cast<const float4*>(hh + j);
-        if (hl) {
-          const float4 l = *reinterpret_cast<const float4*>(hl + j);
-          t.x += l.x; t.y += l.y; t.z += l.z; t.w += l.w;
-        }
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pre = v[e] > 0.f ? v[e] : -100.f * v[e];
+          const float pre = v[c][e] > 0.f ? v[c][e] : -100.f * v[c][e];
           if (pre < guard) flags |= 1u << e;
         }
       }
@@ -414,12 +418,29 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
         const int e = __ffs(f) - 1;
         const int jj = j0 + src * 4 + e;
         const float* __restrict__ w = wrow + w_off + (int64_t)jj * K;
-        double s = 0.0;
-        for (int d = lane; d < K; d += 32) {
+        // 8 loads in flight per lane and two accumulation chains: the loop is latency bound (weights come from L2)
+        double s = 0.0, s2 = 0.0;
+        int d = lane;
+        for (; d + 224 < K; d += 256) {
+          float a[8], wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { a[u] = ah[d + 32 * u]; wv[u] = __ldg(w + d + 32 * u); }
+          if (al) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += al[d + 32 * u];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            s = fma((double)a[u], (double)wv[u], s);
+            s2 = fma((double)a[u + 1], (double)wv[u + 1], s2);
+          }
+        }
+        for (; d < K; d += 32) {
           float a = ah[d];
           if (al) a += al[d];
           s = fma((double)a, (double)__ldg(w + d), s);
         }
+        s += s2;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         s += (double)__ldg(wrow + b_off + jj);
@@ -428,7 +449,7 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
         if (lane == src) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (q == e) v[q] = val;
+            if (q == e) v[c][q] = val;
           flags &= ~(1u << e);
           changed = true;
         }
@@ -437,12 +458,12 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
       if (changed) {
         if (hl) {
           float4 h4, l4;
-          h4.x = tf32_rn(v[0]); h4.y = tf32_rn(v[1]); h4.z = tf32_rn(v[2]); h4.w = tf32_rn(v[3]);
-          l4.x = v[0] - h4.x; l4.y = v[1] - h4.y; l4.z = v[2] - h4.z; l4.w = v[3] - h4.w;
+          h4.x = tf32_rn(v[c][0]); h4.y = tf32_rn(v[c][1]); h4.z = tf32_rn(v[c][2]); h4.w = tf32_rn(v[c][3]);
+          l4.x = v[c][0] - h4.x; l4.y = v[c][1] - h4.y; l4.z = v[c][2] - h4.z; l4.w = v[c][3] - h4.w;
           *reinterpret_cast<float4*>(hh + j) = h4;
           *reinterpret_cast<float4*>(hl + j) = l4;
         } else {
-          *reinterpret_cast<float4*>(hh + j) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(hh + j) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
         }
       }
     }
@@ -761,8 +782,13 @@ static int refine(rbnn_net* n, float* h_hi, float* h_lo, int Z, int B, const flo
                   int64_t a_zstride, int K, int64_t w_off, int64_t b_off, int z0, cudaStream_t st) {
   const int64_t rows = (int64_t)Z * B;
   const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)n->sm_count * 8);
-  refine_kernel<<<blocks, 256, 0, st>>>(h_hi, h_lo, Z, B, n->H, a_hi, a_lo, a_zstride, K, n->bank, n->L.P, w_off,
-                                        b_off, z0, kGuardEps);
+#define RBNN_REFINE(NCH) refine_kernel<NCH><<<blocks, 256, 0, st>>>(h_hi, h_lo, Z, B, n->H, a_hi, a_lo, a_zstride, K, n->bank, \
+                                                                  n->L.P, w_off, b_off, z0, kGuardEps)
+  const int nch = (n->H + 127) / 128;
+  RBNN_CHECK(nch <= 16, "tcgen05 engine (unfused route): hidden sizes up to 2048");
+  if (nch <= 1) RBNN_REFINE(1); else if (nch <= 2) RBNN_REFINE(2); else if (nch <= 4) RBNN_REFINE(4);
+  else if (nch <= 8) RBNN_REFINE(8); else RBNN_REFINE(16);
+#undef RBNN_REFINE
   n->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
