@@ -896,7 +896,9 @@ static int launch_head(rbnn_net* n, bool grad, int head, const float* top, int z
                                                                 labels, pbar, B, H, C, logits, dh_hi, dh_lo, dh_bf); \
   } while (0)
   RBNN_CHECK(smem <= 200 * 1024, "tcgen05 engine: n_classes * hidden too large for the head kernel");
-  if (C <= 16) {
+  if (C <= 10) {          // MNIST / Fashion-MNIST / half-moons: no predicated padding classes
+    if (grad) RBNN_HEAD_LAUNCH(10, true); else RBNN_HEAD_LAUNCH(10, false);
+  } else if (C <= 16) {
     if (grad) RBNN_HEAD_LAUNCH(16, true); else RBNN_HEAD_LAUNCH(16, false);
   } else {
     if (grad) RBNN_HEAD_LAUNCH(32, true); else RBNN_HEAD_LAUNCH(32, false);
