@@ -57,6 +57,18 @@ class Net(object):
     def set_precision(self, name):
         check(lib().rbnn_net_set_precision(self._h, PREC[name]))
 
+    def set_best_precision(self):
+        """The fastest parity-grade engine this network has: F16X3 (arch fc with a fused hidden size, arch conv), else
+        TF32X3 (fc / fc2 with D % 8 == 0 and H >= 32), else the FP32 CUDA-core engine.  Returns its name."""
+        for cand in ("f16x3", "tf32x3"):
+            try:
+                self.set_precision(cand)
+                return cand
+            except _lib.RbnnError:
+                continue
+        self.set_precision("fp32")
+        return "fp32"
+
     @property
     def precision(self):
         code = lib().rbnn_net_get_precision(self._h)

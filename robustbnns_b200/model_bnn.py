@@ -123,6 +123,7 @@ class BNN(object):
         self.output_size = output_size
         self.rng_seed = 0
         self._engine = engine
+        self._precision = "auto"              # engine choice for an engine this object creates (set_precision)
         self._loc = self._rho = None          # SVI guide parameters, flattened [P]
         self._bank_host = None                # explicit / HMC bank [S, P] (CPU tensor)
         self._reset_rows()
@@ -147,6 +148,10 @@ class BNN(object):
             from .engine import Net
             self._engine = Net(self.basenet.architecture, self.input_shape, self.basenet.hidden_size,
                                self.output_size)
+            if self._precision == "auto":
+                self._engine.set_best_precision()
+            else:
+                self._engine.set_precision(self._precision)
         return self._engine
 
     def _reset_rows(self):
@@ -155,8 +160,14 @@ class BNN(object):
         self._scratch_generation = 0
 
     def set_precision(self, name):
-        """'fp32' (CUDA-core FFMA, default), 'tf32x3' or 'bf16' (tcgen05)."""
-        self.engine().set_precision(name)
+        """'auto' (default: the fastest parity-grade engine the network has -- 'f16x3' for arch fc / conv, 'tf32x3'
+        for fc2, 'fp32' otherwise), 'fp32' (CUDA-core FFMA), 'f16x3' / 'tf32x3' (tcgen05, fp32-class accuracy) or
+        'bf16' (tcgen05 single pass, throughput mode, not parity grade); see DESIGN.md section 4.1."""
+        self._precision = name
+        if name == "auto":
+            self.engine().set_best_precision()
+        else:
+            self.engine().set_precision(name)
 
     def reseed(self, seed):
         """Stand-in for pyro.set_rng_seed(seed) before unseeded forwards (adversarialAttacks.py:161)."""

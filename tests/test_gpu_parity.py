@@ -18,10 +18,14 @@ torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.allow_tf32 = False
 
 
-def _bnn(case, inference="svi", n_samples=None):
+def _bnn(case, inference="svi", n_samples=None, precision="fp32"):
+    """The golden-vector tests pin the FP32 CUDA-core engine (reference-class rounding); the drop-in's own default is
+    'auto' (tensor-core engines where the network has one), exercised by test_default_engine_is_the_fastest_parity_grade."""
     from robustbnns_b200.model_bnn import BNN
-    return BNN(case.dataset, case.hidden, "leaky", case.arch, inference, 1, 0.01, n_samples, 5,
-               case.input_shape, case.n_classes)
+    bnn = BNN(case.dataset, case.hidden, "leaky", case.arch, inference, 1, 0.01, n_samples, 5,
+              case.input_shape, case.n_classes)
+    bnn.set_precision(precision)
+    return bnn
 
 
 def _mismatch_fraction(a, b, tol=1e-6):
@@ -145,12 +149,17 @@ def test_golden_ensemble_and_nn(name, tmp_path, monkeypatch):
     for i in range(size):
         torch.save(orc.unpack(c.bank[i], c.layout), os.path.join(wdir, f"{ens.member_name}_weights_{i}.pt"))
     ens.load("cuda", rel_path="tests_root/")
+    if c.arch == "conv":      # conv nets default to the tensor-core engine: same mean logits at the north-star tolerance ...
+        assert ens.engine().precision == "f16x3"
+        assert rel_err(ens.forward(c.x, n_samples=used).cpu(), c.t("logits_used")) < REL
+        ens.engine().set_precision("fp32")          # ... the bit-level checks below pin the FP32 engine
     with pytest.raises(ValueError):
         ens.forward(c.x, n_samples=size + 1)
     assert rel_err(ens.forward(c.x, n_samples=used).cpu(), c.t("logits_used")) < REL
     assert rel_err(ens.forward(c.x, n_samples=None).cpu(), c.t("logits_all")) < REL
     nn0 = NN(ens.dataset_name, c.input_shape, c.n_classes, c.hidden, "leaky", c.arch, 0.01, 1)
     nn0.load("cuda", savedir=os.path.join(ens.name, "weights"), seed=0, rel_path="tests_root/")
+    nn0.engine().set_precision("fp32")
     assert rel_err(nn0.forward(c.x).cpu(), c.t("logits_member0")) < REL
     assert torch.equal(nn0.state_dict()[c.layout[0][0]], orc.unpack(c.bank[0], c.layout)[c.layout[0][0]])
     loader = torch.utils.data.DataLoader(list(zip(c.x, c.y)), batch_size=4)
@@ -476,6 +485,25 @@ def test_autograd_through_forward_matches_attack_gradient(prec):
         loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, labels.cuda())
         loss.backward()
         assert rel_err(xg.grad.cpu(), ref) < REL
+
+
+def test_default_engine_is_the_fastest_parity_grade():
+    """A BNN that creates its own engine picks F16X3 (fc-512, conv), TF32X3 (fc2) or FP32 (half-moons: D = 2)."""
+    from robustbnns_b200.model_bnn import BNN
+    from robustbnns_b200.model_nn import NN
+    for arch, shape, hidden, C, ds, want in (("fc", (1, 28, 28), 512, 10, "mnist", "f16x3"),
+                                             ("conv", (1, 28, 28), 64, 10, "mnist", "f16x3"),
+                                             ("fc2", (1, 28, 28), 128, 10, "mnist", "tf32x3"),
+                                             ("fc2", (1, 2, 1), 32, 2, "half_moons", "fp32"),
+                                             ("fc", (1, 28, 28), 16, 10, "mnist", "fp32")):
+        bnn = BNN(ds, hidden, "leaky", arch, "hmc", None, None, 2, 5, shape, C)
+        assert bnn.engine().precision == want, (arch, hidden)
+        bnn.set_precision("fp32")
+        assert bnn.engine().precision == "fp32"
+        bnn.set_precision("auto")
+        assert bnn.engine().precision == want
+    assert NN("mnist", (1, 28, 28), 10, 64, "leaky", "conv", 0.01, 1).engine().precision == "f16x3"
+    assert NN("mnist", (1, 28, 28), 10, 64, "leaky", "fc2", 0.01, 1).engine().precision == "fp32"
 
 
 # ------------------------------------------------------------------ sampler -----------------------------
