@@ -57,8 +57,7 @@ enum {
   RBNN_HEAD_LOGITS_CE = 2,     /* avg_posterior=True, model_bnn.py:206-216: CE(z) on the mean-weight net */
   RBNN_HEAD_UPSTREAM = 3,      /* autograd through BNN.forward: d_pbar holds dL/d(mean probs) [B,C] itself */
   RBNN_HEAD_LOGITS_UPSTREAM = 4 /* Ensemble_NN.forward (mean of LOGITS, model_ensemble.py:57-67): d_pbar holds
-                                   dL/d(sum of logits) [B,C]; every bank row receives it unchanged.  FP32 engine
-                                   (any architecture) and the conv TF32X3 engine. */
+                                   dL/d(sum of logits) [B,C]; every bank row receives it unchanged. */
 };
 
 RBNN_API int rbnn_abi_version(void);
@@ -136,7 +135,7 @@ RBNN_API int rbnn_forward_logits_sum(rbnn_net* net, const float* d_x, int B, int
  *   LOGITS_CE    : L = CE(z_s, y) for the single row s0           (model_bnn.py:206-216)
  *   UPSTREAM     : like GRAD_OF_MEAN but g = d_pbar[B,C] is given (any loss on BNN.forward's output)
  *   LOGITS_UPSTREAM: dL/dz_s = d_pbar[B,C] for every row (any loss on the SUM / mean of the logits: Ensemble_NN,
- *                  deterministic NN; model_ensemble.py:57-67).  FP32 engine and the conv TF32X3 engine.
+ *                  deterministic NN; model_ensemble.py:57-67).
  * Sum reduction over the batch (the reference batch is always 1, so no 1/B).
  * d_labels: [B] int32 class indices. d_pbar may be NULL unless head is GRAD_OF_MEAN / UPSTREAM / LOGITS_UPSTREAM. */
 RBNN_API int rbnn_input_grad_sum(rbnn_net* net, int head, const float* d_x, const int32_t* d_labels, int B,

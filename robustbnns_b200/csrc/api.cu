@@ -545,9 +545,9 @@ int rbnn_keep_valid(const rbnn_net* n) { return n ? n->keep.valid : 0; }
 int rbnn_input_grad_sum_kept(rbnn_net* n, int head, const int32_t* d_labels, const float* d_pbar, float* d_out_sum,
                              void* stream) {
   RBNN_CHECK(n != nullptr, "null net handle");
-  RBNN_CHECK(head == RBNN_HEAD_MEAN_OF_GRADS || head == RBNN_HEAD_GRAD_OF_MEAN || head == RBNN_HEAD_UPSTREAM,
-             "head %d has no kept route", head);
-  RBNN_CHECK(head == RBNN_HEAD_MEAN_OF_GRADS || d_pbar != nullptr, "GRAD_OF_MEAN / UPSTREAM need d_pbar");
+  RBNN_CHECK(head == RBNN_HEAD_MEAN_OF_GRADS || head == RBNN_HEAD_GRAD_OF_MEAN || head == RBNN_HEAD_UPSTREAM ||
+                 head == RBNN_HEAD_LOGITS_UPSTREAM, "head %d has no kept route", head);
+  RBNN_CHECK(head == RBNN_HEAD_MEAN_OF_GRADS || d_pbar != nullptr, "GRAD_OF_MEAN / UPSTREAM / LOGITS_UPSTREAM need d_pbar");
   DeviceGuard dg(n->device);
   if (n->arch == RBNN_ARCH_CONV) return tc_conv_grad_kept(n, head, d_labels, d_pbar, d_out_sum, (cudaStream_t)stream);
   return tc_fc_grad_kept(n, head, d_labels, d_pbar, d_out_sum, (cudaStream_t)stream);
@@ -577,8 +577,6 @@ int rbnn_input_grad_sum(rbnn_net* n, int head, const float* d_x, const int32_t* 
   RBNN_CHECK(head >= RBNN_HEAD_MEAN_OF_GRADS && head <= RBNN_HEAD_LOGITS_UPSTREAM, "unknown head %d", head);
   RBNN_CHECK((head != RBNN_HEAD_GRAD_OF_MEAN && head != RBNN_HEAD_UPSTREAM && head != RBNN_HEAD_LOGITS_UPSTREAM) ||
                  d_pbar != nullptr, "GRAD_OF_MEAN / UPSTREAM / LOGITS_UPSTREAM need d_pbar");
-  RBNN_CHECK(head != RBNN_HEAD_LOGITS_UPSTREAM || n->prec == RBNN_PREC_FP32 || n->arch == RBNN_ARCH_CONV,
-             "LOGITS_UPSTREAM (ensemble / deterministic nets) runs on the FP32 engine, or TF32X3 for arch conv");
   RBNN_CHECK(head != RBNN_HEAD_LOGITS_CE || s1 - s0 == 1, "LOGITS_CE takes exactly one bank row");
   if (B <= 0) return 0;
   DeviceGuard dg(n->device);

@@ -299,8 +299,11 @@ fc_head_kernel(int head, const float* __restrict__ Hact, const float* __restrict
     // ---- loss head: dlogits = softmax-Jacobian applied to g (see head.cu) ----
     const int y = labels[b];
     float g[C_MAX];
-    softmax_c<C_MAX>(acc, C);                 // acc = p = softmax(z)
-    if (head == RBNN_HEAD_LOGITS_CE) {
+    if (head != RBNN_HEAD_LOGITS_UPSTREAM) softmax_c<C_MAX>(acc, C);                 // acc = p = softmax(z)
+    if (head == RBNN_HEAD_LOGITS_UPSTREAM) {   // loss of the mean LOGITS (ensembles, deterministic nets): dlogits = d_pbar
+#pragma unroll
+      for (int c = 0; c < C_MAX; ++c) acc[c] = (c < C) ? __ldg(pbar + (int64_t)b * C + c) : 0.f;
+    } else if (head == RBNN_HEAD_LOGITS_CE) {
 #pragma unroll
       for (int c = 0; c < C_MAX; ++c) acc[c] = acc[c] - (c == y ? 1.f : 0.f);
     } else {
@@ -911,7 +914,7 @@ static int launch_head(rbnn_net* n, bool grad, int head, const float* top, int z
 
 // pbar_for_scale: the UPSTREAM head's d_pbar [B*C] (its magnitude bounds dH), else nullptr
 static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const float* pbar_for_scale, int64_t pbar_count,
-                   cudaStream_t st) {
+                   float dh_factor, cudaStream_t st) {
   const int64_t n4 = count / 4;
   const int d4 = n->D / 4, ld4 = n->tc.mat[0].ld / 4;      // the copies take the row pitch of the W1 copies
   const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
@@ -922,7 +925,8 @@ static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const fl
       maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar_for_scale, 0, pbar_count, 1, w.max_bits + 1);
       n->launches++;
     }
-    call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, pbar_for_scale ? w.max_bits + 1 : nullptr, w.call_sc, 2.f);
+    call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, pbar_for_scale ? w.max_bits + 1 : nullptr, w.call_sc,
+                                        dh_factor);
     split_f16_kernel<<<blocks, 256, 0, st>>>(x, w.call_sc, w.x_h16, w.x_l16, n4, d4, ld4);
     n->launches += 3;
     RBNN_CUDA(cudaGetLastError());
@@ -1006,18 +1010,22 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   w.partial = ar.take<float>((size_t)slots * B * D);
   if (kept) {
     if (f16) {       // the dH range of THIS head (max|x| is still in keep.max_bits[0] from the forward phase)
-      const bool up = head == RBNN_HEAD_UPSTREAM;
+      const bool up = head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM;
       if (up) {
         RBNN_CUDA(cudaMemsetAsync(w.max_bits + 1, 0, sizeof(unsigned), st));
         maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar, 0, (int64_t)B * n->C, 1, w.max_bits + 1);
         n->launches++;
       }
-      call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, up ? w.max_bits + 1 : nullptr, w.call_sc, 2.f);
+      call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, up ? w.max_bits + 1 : nullptr, w.call_sc,
+                                          head == RBNN_HEAD_LOGITS_UPSTREAM ? (float)n->C : 2.f);
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }
   } else {
-    RBNN_TRY(split_x(n, x, (int64_t)B * D, w, head == RBNN_HEAD_UPSTREAM ? pbar : nullptr, (int64_t)B * n->C, st));
+    // |dH| <= sum_c |dlogits_c| max|Wo|: <= 2 max|g| for the softmax heads, <= C max|g| when g goes to the logits as is
+    RBNN_TRY(split_x(n, x, (int64_t)B * D, w,
+                     (head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM) ? pbar : nullptr, (int64_t)B * n->C,
+                     head == RBNN_HEAD_LOGITS_UPSTREAM ? (float)n->C : 2.f, st));
   }
   if (fused && !kept) {       // row norms: guard band (parity modes) and the activation range of the fused head
     xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
@@ -1149,7 +1157,7 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   if (keep && fused) { if (!bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc)); }
   else w.logits = ar.take<float>((size_t)zc * B * C);
   w.xnorm = ar.take<float>((size_t)B);
-  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, st));
+  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, 2.f, st));
   if (fused) {
     xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
     n->launches++;

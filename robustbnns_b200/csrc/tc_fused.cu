@@ -163,6 +163,11 @@ __device__ __forceinline__ void softmax_r(float (&v)[C_MAX], int C) {
 __device__ __forceinline__ void head_quad(int head, float (&l)[4], const bool (&valid)[4], const int (&cls)[4], int y,
                                           const float* __restrict__ pbar_row) {
   float g[4];
+  if (head == RBNN_HEAD_LOGITS_UPSTREAM) {     // loss of the mean LOGITS (ensembles, deterministic nets): dlogits = d_pbar
+#pragma unroll
+    for (int i = 0; i < 4; ++i) l[i] = (valid[i] && pbar_row) ? __ldg(pbar_row + cls[i]) : 0.f;
+    return;
+  }
   softmax_quad(l, valid);
   if (head == RBNN_HEAD_LOGITS_CE) {
 #pragma unroll

@@ -106,8 +106,7 @@ class NN(object):
         if self._engine is None:
             from .engine import Net
             self._engine = Net(self.architecture, self.input_shape, self.hidden_size, self.output_size)
-            if self.architecture == "conv":          # the head of these nets (LOGITS_UPSTREAM) runs on FP32, or the
-                self._engine.set_best_precision()    # tensor-core conv engine
+            self._engine.set_best_precision()        # tensor-core engines where the network has one
         return self._engine
 
     def _pack(self, state_dict):

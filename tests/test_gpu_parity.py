@@ -305,6 +305,13 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     gl = eng.input_grad_sum(_lib.HEAD_LOGITS_CE, x, labels, S - 1, S).cpu().reshape(x.shape)
     rl = orc.attack_gradient_avg_posterior(net, layout, bank[S - 1], x, labels, dtype=torch.float64)
     e_log = rel_err(gl, rl)
+    # head of the ensembles / deterministic nets: g handed to the logits unchanged (its magnitude sets the F16X3 dH range)
+    gu = torch.randn((B, C), generator=torch.Generator().manual_seed(3)) * 1e-3
+    got_u = eng.input_grad_sum(_lib.HEAD_LOGITS_UPSTREAM, x, labels, 0, S, pbar=gu).cpu().reshape(x.shape)
+    xs = x.double().clone().requires_grad_(True)
+    lsum = sum(orc.net_logits(net, {k: v.double() for k, v in orc.unpack(bank[s], layout).items()}, xs) for s in range(S))
+    (ref_u,) = torch.autograd.grad((lsum * gu.double()).sum(), xs)
+    assert rel_err(got_u, ref_u) < (tol if arch != "fc2" else max(tol, 0.1))
     cos = float(torch.nn.functional.cosine_similarity(g.double().flatten(), ref64.flatten(), dim=0))
     print(f"tcgen05 {prec} {route} {arch}-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} "
           f"logits-CE {e_log:.2e} cosine {cos:.6f}")
@@ -503,7 +510,7 @@ def test_default_engine_is_the_fastest_parity_grade():
         bnn.set_precision("auto")
         assert bnn.engine().precision == want
     assert NN("mnist", (1, 28, 28), 10, 64, "leaky", "conv", 0.01, 1).engine().precision == "f16x3"
-    assert NN("mnist", (1, 28, 28), 10, 64, "leaky", "fc2", 0.01, 1).engine().precision == "fp32"
+    assert NN("mnist", (1, 28, 28), 10, 64, "leaky", "fc2", 0.01, 1).engine().precision == "tf32x3"
 
 
 # ------------------------------------------------------------------ sampler -----------------------------
