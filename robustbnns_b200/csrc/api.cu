@@ -483,6 +483,12 @@ int rbnn_bank_sample_diag(rbnn_net* n, const float* d_loc, const float* d_rho, u
   if (count == 0) return 0;
   DeviceGuard dg(n->device);
   cudaStream_t st = (cudaStream_t)stream;
+  int fused = 0;        // F16X3 / arch fc with a fixed weight scale: bank rows and operand copies in one pass
+  RBNN_TRY(tc_sample_relayout_f16(n, d_loc, d_rho, seed, sample_index0, sample_index_stride, s0, count, st, &fused));
+  if (fused) {
+    if (n->keep.valid && s0 < n->keep.s1 && s0 + count > n->keep.s0) n->keep.valid = 0;
+    return 0;
+  }
   RBNN_TRY(sample_diag(n, d_loc, d_rho, seed, sample_index0, sample_index_stride, s0, count, st));
   RBNN_TRY(conv_permute_wout(n, s0, count, st));
   mark_dirty(n, s0, count);

@@ -82,6 +82,7 @@ struct TcBank {
   int* overflow_host = nullptr;   // mapped pinned flag: a later row exceeded the fp16 range under the frozen s_w1
   int* overflow_dev = nullptr;    // device alias of overflow_host
   uint8_t* dirty = nullptr; // host flags per row (derived copies stale)
+  int frozen_host = 0;      // the F16X3 weight scale has been fixed on the device (a freeze_scales launch is enqueued)
 };
 
 // Kept forward of the two-phase attack gradient (tc_gemm.cuh): per-sample logits and LeakyReLU masks of the last
@@ -173,6 +174,9 @@ int head_dlogits(rbnn_net* net, int head, const float* logits, const int32_t* la
 // ---- sampler.cu -------------------------------------------------------------------------
 int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
                 int64_t stride, int s0, int count, cudaStream_t st);
+int sample_sigma(rbnn_net* net, const float* d_rho, cudaStream_t st);      // net->sigma = softplus(rho)
+int sample_diag_from(rbnn_net* net, const float* d_loc, uint64_t seed, int64_t sample_index0, int64_t stride, int s0,
+                     int count, int64_t elem0, cudaStream_t st);            // elements [elem0, P) of the rows
 int conv_permute_wout(rbnn_net* net, int s0, int count, cudaStream_t st);
 inline int conv_class_pitch(int C) { return C <= 4 ? 4 : (C <= 12 ? 12 : (C <= 16 ? 16 : 32)); }
 
@@ -219,6 +223,11 @@ int tc_fc_grad_kept(rbnn_net* net, int head, const int32_t* d_labels, const floa
 void tc_keep_free(rbnn_net* net);
 // derived tensor-core operand copies of bank rows [s0, s1) brought up to date (lazily, per dirty row)
 int tc_bank_refresh(rbnn_net* net, int s0, int s1, cudaStream_t st);
+// K-sample fused with the operand re-layout (arch fc, F16X3, weight scale already fixed): draws rows [s0, s0+count) and
+// writes the bank AND the fp16 hi/lo operand copies of W1 in one pass.  Returns 0 and sets *done = 1 when it ran;
+// *done = 0 means "not applicable, use sample_diag + the lazy refresh".
+int tc_sample_relayout_f16(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
+                           int64_t stride, int s0, int count, cudaStream_t st, int* done);
 
 // F16X3 operand ranges (device-resident): *bits = max(*bits, max|p|) as float bits; out[0..3] = s_x, 1/(s_x s_w),
 // s_d, 1/(s_d s_w) with s_d from the bound dh_factor * max|g| * max|Wo| (call_scales_kernel, tc_fc.cu)

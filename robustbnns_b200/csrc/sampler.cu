@@ -8,35 +8,9 @@
 // torch.nn.Softplus() defaults beta=1, threshold=20 (model_bnn.py:18).
 // The numpy restatement used by the tests is oracle/oracle.py::philox_standard_normals.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace rbnn {
-
-__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
-                                              uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-}
-
-__device__ __forceinline__ float u01(uint32_t x) {  // ((x>>9)+0.5) * 2^-23, exact in fp32, in (0,1)
-  return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f;
-}
-
-// Box-Muller on the special-function units: the angle is taken in (-pi, pi) (same distribution as (0, 2 pi)), where
-// __sinf / __cosf err by <= 2^-21.4 absolutely; __logf errs by ~2 ulp on (0, 1).  |z| <= 5.8, so a normal moves by
-// < 3e-6 against libm -- the restatement test (oracle.philox_standard_normals) allows 2e-5 sigma.
-__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& z0, float& z1) {
-  const float r = sqrtf(-2.f * __logf(u01(xa)));
-  const float t = 6.283185307179586f * u01(xb);
-  const float a = t - 3.14159265358979f;        // cos t = -cos a, sin t = -sin a
-  z0 = -r * __cosf(a);
-  z1 = -r * __sinf(a);
-}
 
 __global__ void softplus_kernel(const float* __restrict__ rho, float* __restrict__ sigma, int64_t P) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,16 +22,14 @@ __global__ void softplus_kernel(const float* __restrict__ rho, float* __restrict
 // grid: (ceil(P/4/256), count)
 __global__ void __launch_bounds__(256)
 sample_diag_kernel(const float* __restrict__ loc, const float* __restrict__ sigma, float* __restrict__ bank,
-                   int64_t P, uint32_t k0, uint32_t k1, int64_t sample_index0, int64_t stride, int s0, int vec) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                   int64_t P, uint32_t k0, uint32_t k1, int64_t sample_index0, int64_t stride, int s0, int vec,
+                   int64_t q0) {
+  const int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // q0: first quad (the tail of a row only)
   const int64_t i0 = q * 4;
   if (i0 >= P) return;
   const int64_t g = sample_index0 + (int64_t)blockIdx.y * stride;
-  uint32_t c0 = (uint32_t)q, c1 = (uint32_t)g, c2 = 0x52424E4Eu, c3 = 0u;
-  philox4x32_10(c0, c1, c2, c3, k0, k1);
   float z[4];
-  box_muller(c0, c1, z[0], z[1]);
-  box_muller(c2, c3, z[2], z[3]);
+  philox_normals4((uint32_t)q, (uint32_t)g, k0, k1, z);
   float* __restrict__ row = bank + (int64_t)(s0 + blockIdx.y) * P;
   if (vec && i0 + 3 < P) {          // P even and loc 16-byte aligned: 16-byte loads, 8-byte stores (rows are 8-byte aligned)
     const float4 sg = __ldg(reinterpret_cast<const float4*>(sigma + i0));
@@ -72,21 +44,34 @@ sample_diag_kernel(const float* __restrict__ loc, const float* __restrict__ sigm
     if (i0 + j < P) row[i0 + j] = fmaf(__ldg(sigma + i0 + j), z[j], __ldg(loc + i0 + j));
 }
 
-int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
-                int64_t stride, int s0, int count, cudaStream_t st) {
+int sample_sigma(rbnn_net* net, const float* d_rho, cudaStream_t st) {
   const int64_t P = net->L.P;
   if (!net->sigma) RBNN_CUDA(cudaMalloc(&net->sigma, P * sizeof(float)));
   softplus_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_rho, net->sigma, P);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
-  const int64_t nq = (P + 3) / 4;
+  return 0;
+}
+
+// elements [elem0, P) of the rows (elem0 % 4 == 0; 0 = whole rows); net->sigma must hold softplus(rho) (sample_sigma)
+int sample_diag_from(rbnn_net* net, const float* d_loc, uint64_t seed, int64_t sample_index0, int64_t stride, int s0,
+                     int count, int64_t elem0, cudaStream_t st) {
+  const int64_t P = net->L.P;
+  const int64_t nq = (P + 3) / 4 - elem0 / 4;
+  if (nq <= 0) return 0;
   dim3 grid((unsigned)((nq + 255) / 256), (unsigned)count);
   sample_diag_kernel<<<grid, 256, 0, st>>>(d_loc, net->sigma, net->bank, P, (uint32_t)(seed & 0xFFFFFFFFu),
                                            (uint32_t)(seed >> 32), sample_index0, stride, s0,
-                                           ((P & 1) == 0 && (reinterpret_cast<uintptr_t>(d_loc) & 15) == 0) ? 1 : 0);
+                                           ((P & 1) == 0 && (reinterpret_cast<uintptr_t>(d_loc) & 15) == 0) ? 1 : 0, elem0 / 4);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
+}
+
+int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
+                int64_t stride, int s0, int count, cudaStream_t st) {
+  RBNN_TRY(sample_sigma(net, d_rho, st));
+  return sample_diag_from(net, d_loc, seed, sample_index0, stride, s0, count, 0, st);
 }
 
 // conv: the output Linear consumes the pooled activations in (pos, h) order (HWC), the reference

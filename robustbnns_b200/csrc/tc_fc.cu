@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "tc_gemm.cuh"
 
 namespace rbnn {
@@ -216,6 +217,85 @@ __global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, i
       const int64_t o = ((int64_t)s * C + c2) * R + r2;
       split_f16(tile[threadIdx.x][i], thi[o], tlo[o]);
     }
+  }
+}
+
+// K-sample + re-layout in one pass (F16X3, scale already frozen): block = 32 rows of W1 x all C columns, looped in 32-column
+// tiles.  Per tile every thread draws the 4 normals of one Philox call (4 consecutive columns of one row: the bank's
+// element order), writes w = loc + sigma * eps to the bank row and s_w1 * w into the shared-memory tile, from which
+// the forward and transposed fp16 hi/lo copies are written as in relayout_f16_kernel.  Row norms (guard band) and
+// max|W1| (range check) come from the same registers.  grid: (ceil(R/32), count), block (32, 8); C % 4 == 0.
+__global__ void __launch_bounds__(256)
+sample_relayout_f16_kernel(const float* __restrict__ loc, const float* __restrict__ sigma, float* __restrict__ bank,
+                           int64_t P, int64_t off, int R, int C, int ld, int s0, int64_t sample_index0, int64_t stride,
+                           uint32_t k0, uint32_t k1, TcScales* __restrict__ sc, __half* __restrict__ hi,
+                           __half* __restrict__ lo, __half* __restrict__ thi, __half* __restrict__ tlo,
+                           float* __restrict__ wnorm) {
+  __shared__ float tile[32][33];
+  __shared__ float red_n[8], red_m[8];
+  const float sw = sc->s_w1;
+  const int s = s0 + blockIdx.y;
+  const uint32_t g = (uint32_t)(sample_index0 + (int64_t)blockIdx.y * stride);
+  const int r0 = blockIdx.x * 32;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int tr = tid >> 3, tg = tid & 7;              // row of the tile and 4-column group this thread draws
+  const int r = r0 + tr;
+  float* __restrict__ brow = bank + (int64_t)s * P;
+  float racc = 0.f, mabs = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + tg * 4;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R && c < C) {
+      const int64_t i = off + (int64_t)r * C + c;      // multiple of 4
+      float z[4];
+      philox_normals4((uint32_t)(i >> 2), g, k0, k1, z);
+      const float4 sg = __ldg(reinterpret_cast<const float4*>(sigma + i));
+      const float4 lc = __ldg(reinterpret_cast<const float4*>(loc + i));
+      w[0] = fmaf(sg.x, z[0], lc.x); w[1] = fmaf(sg.y, z[1], lc.y);
+      w[2] = fmaf(sg.z, z[2], lc.z); w[3] = fmaf(sg.w, z[3], lc.w);
+      float2* out = reinterpret_cast<float2*>(brow + i);          // bank rows are 8-byte aligned (P even)
+      out[0] = make_float2(w[0], w[1]);
+      out[1] = make_float2(w[2], w[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { racc = fmaf(w[j], w[j], racc); mabs = fmaxf(mabs, fabsf(w[j])); }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tile[tr][tg * 4 + j] = w[j] * sw;
+    __syncthreads();
+    const int cc = c0 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int rr = r0 + i;
+      if (rr < R && cc < C) {
+        const int64_t o = ((int64_t)s * R + rr) * ld + cc;
+        split_f16(tile[i][threadIdx.x], hi[o], lo[o]);
+      }
+    }
+    const int r2 = r0 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int c2 = c0 + i;
+      if (r2 < R && c2 < C) {
+        const int64_t o = ((int64_t)s * C + c2) * R + r2;
+        split_f16(tile[threadIdx.x][i], thi[o], tlo[o]);
+      }
+    }
+    __syncthreads();
+  }
+  // row norm: the 8 threads of a row are consecutive lanes; then the maximum over the block's 32 rows
+  racc += __shfl_xor_sync(0xffffffffu, racc, 1);
+  racc += __shfl_xor_sync(0xffffffffu, racc, 2);
+  racc += __shfl_xor_sync(0xffffffffu, racc, 4);
+#pragma unroll
+  for (int o = 8; o < 32; o <<= 1) racc = fmaxf(racc, __shfl_xor_sync(0xffffffffu, racc, o));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
+  if (threadIdx.x == 0) { red_n[threadIdx.y] = racc; red_m[threadIdx.y] = mabs; }
+  __syncthreads();
+  if (tid == 0) {
+    float m = 0.f, a = 0.f;
+    for (int i = 0; i < 8; ++i) { m = fmaxf(m, red_n[i]); a = fmaxf(a, red_m[i]); }
+    const bool bad = !(m == m) || !(a == a);
+    atomicMax(reinterpret_cast<unsigned*>(wnorm + s), __float_as_uint(bad ? __int_as_float(0x7f800000) : sqrtf(m)));
+    atomicMax(&sc->maxw1_bits, __float_as_uint(bad ? __int_as_float(0x7f800000) : a));
   }
 }
 
@@ -550,6 +630,37 @@ int tc_call_scales(rbnn_net* n, const unsigned* xmax_bits, const unsigned* gmax_
   return 0;
 }
 
+int tc_sample_relayout_f16(rbnn_net* n, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
+                           int64_t stride, int s0, int count, cudaStream_t st, int* done) {
+  *done = 0;
+  TcBank& tc = n->tc;
+  const TcMat& m = tc.mat[0];
+  if (n->prec != RBNN_PREC_F16X3 || n->arch != RBNN_ARCH_FC || tc.mode != n->prec || tc.capacity < s0 + count ||
+      tc.capacity != n->capacity || !tc.frozen_host || tc.nmat != 1 || m.off != 0 || (m.C & 3) || (n->L.P & 1) ||
+      (reinterpret_cast<uintptr_t>(d_loc) & 15) || count <= 0)
+    return 0;
+  if (tc.overflow_host && *(volatile int*)tc.overflow_host) return 0;      // let tc_bank_refresh report / reset it
+  RBNN_TRY(sample_sigma(n, d_rho, st));
+  RBNN_CUDA(cudaMemsetAsync(tc.wnorm + s0, 0, (size_t)count * sizeof(float), st));
+  dim3 grid((m.R + 31) / 32, count);
+  sample_relayout_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(
+      d_loc, n->sigma, n->bank, n->L.P, m.off, m.R, m.C, m.ld, s0, sample_index0, stride, (uint32_t)(seed & 0xFFFFFFFFu),
+      (uint32_t)(seed >> 32), tc.scales, reinterpret_cast<__half*>(m.h_hi), reinterpret_cast<__half*>(m.h_lo),
+      reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo), tc.wnorm);
+  n->launches++;
+  RBNN_CUDA(cudaGetLastError());
+  // the rest of the rows (b1, Wo, bo) with the plain sampler, then the Wo range and the scale check
+  RBNN_TRY(sample_diag_from(n, d_loc, seed, sample_index0, stride, s0, count, (int64_t)m.R * m.C, st));
+  maxabs_kernel<<<n->sm_count, 256, 0, st>>>(n->bank + (int64_t)s0 * n->L.P + n->L.wo, n->L.P, (int64_t)n->C * n->H, count,
+                                             &tc.scales->maxwo_bits);
+  freeze_scales_kernel<<<1, 1, 0, st>>>(tc.scales, tc.overflow_dev);
+  n->launches += 2;
+  RBNN_CUDA(cudaGetLastError());
+  std::fill(tc.dirty + s0, tc.dirty + s0 + count, (uint8_t)0);
+  *done = 1;
+  return 0;
+}
+
 int tc_supported(const rbnn_net* n) {
   if (n->arch != RBNN_ARCH_FC && n->arch != RBNN_ARCH_FC2) return 0;
   if ((n->D & 7) || n->H < 32 || n->C > kMaxC) return 0;
@@ -586,6 +697,7 @@ void tc_bank_free(rbnn_net* n) {
   n->tc.dirty = nullptr;
   n->tc.capacity = 0;
   n->tc.mode = -1;
+  n->tc.frozen_host = 0;
 }
 
 // Bring the derived copies of bank rows [s0, s1) up to date (all rows after a capacity / precision change).
@@ -598,6 +710,7 @@ int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
     RBNN_CUDA(cudaDeviceSynchronize());
     *tc.overflow_host = 0;
     RBNN_CUDA(cudaMemset(tc.scales, 0, sizeof(TcScales)));
+    tc.frozen_host = 0;
     std::fill(tc.dirty, tc.dirty + tc.capacity, (uint8_t)1);
     set_error("F16X3: bank rows uploaded after the operand scale was fixed exceed the fp16 range (> 64x the earlier "
               "maximum |w|); the results of calls since that upload are invalid.  The scale has been reset: repeat the call");
@@ -666,6 +779,7 @@ int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       freeze_scales_kernel<<<1, 1, 0, st>>>(tc.scales, tc.overflow_dev);
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
+      tc.frozen_host = 1;
     }
   }
   int s = s0;

@@ -541,6 +541,41 @@ def test_philox_sampler_matches_restatement_and_moments():
     eng.close()
 
 
+def test_fused_sampler_relayout_equals_two_step_path():
+    """F16X3, arch fc: once the weight scale is fixed, rbnn_bank_sample_diag draws the bank rows AND writes the fp16
+    operand copies in one kernel.  Same Philox bits as the plain sampler, and the same gradients as an engine that
+    received those rows by upload (two-step path: upload -> lazy re-layout)."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    net, layout, loc, rho, bank, x, labels = _problem("fc", (1, 28, 28), 512, 10, 130, 2)
+    S = 5
+    eng = Net("fc", (1, 28, 28), 512, 10)
+    eng.set_precision("f16x3")
+    eng.sample_diag(loc, rho, 11, 0, 0, S)                                   # first draw: plain sampler, scale not fixed yet
+    g0 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S)       # fixes the scale (lazy refresh)
+    n0 = eng.launch_count
+    eng.sample_diag(loc, rho, 11, 100, 0, S, stride=3)                       # fused path: indices 100, 103, ...
+    assert eng.launch_count - n0 <= 5                                        # softplus, fused, tail, maxabs, freeze
+    got = eng.download(0, S)
+    ref = orc.philox_bank(loc, rho, 11, [100 + 3 * i for i in range(S)])
+    # same Philox bits: libm-level differences in the normals (2e-5 sigma) plus the fp32 rounding of loc + sigma * eps
+    assert bool(((got - ref).abs() <= 2e-5 * orc.softplus(rho) + 2.4e-7 * ref.abs()).all())
+    g1 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S)
+    other = Net("fc", (1, 28, 28), 512, 10)
+    other.set_precision("f16x3")
+    other.upload(got, 0)
+    g2 = other.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 0, S)
+    assert rel_err(g1.cpu(), g2.cpu()) < 1e-6                                # (the two engines may fix different scales)
+    ref64 = orc.expected_loss_gradients(net, layout, got, x, labels, range(S), dtype=torch.float64)
+    assert rel_err(g1.cpu().reshape(x.shape) / S, ref64) < REL
+    assert not torch.equal(g0, g1)
+    # the plain sampler on the same handle (fp32 engine) draws the same rows
+    eng.set_precision("fp32")
+    eng.sample_diag(loc, rho, 11, 100, 0, S, stride=3)
+    assert torch.equal(eng.download(0, S), got)
+    eng.close(); other.close()
+
+
 # ------------------------------------------------------------------ stateless kernels -------------------
 def test_attack_and_evaluation_kernels_edge_cases():
     from robustbnns_b200 import engine as E
