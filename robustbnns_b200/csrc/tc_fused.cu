@@ -701,22 +701,10 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 // exact sign of b1[j] + <x_b, w_j>: fp64 accumulation of the exact fp32 products, one warp (all lanes return it)
 __device__ __forceinline__ bool exact_positive_warp(const float* __restrict__ xr, const float* __restrict__ w, float bias,
                                                     int D, int lane) {
-  // bank rows are only 4-byte aligned in general (P floats apart), hence scalar loads; 8 of them in flight per lane
-  // and two accumulation chains (the loop is latency bound: the weights come from L2 / HBM)
-  double s = 0.0, s2 = 0.0;
-  int d = lane;
-  for (; d + 224 < D; d += 256) {
-    float a[8], wv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { a[u] = __ldg(xr + d + 32 * u); wv[u] = __ldg(w + d + 32 * u); }
-#pragma unroll
-    for (int u = 0; u < 8; u += 2) {
-      s = fma((double)a[u], (double)wv[u], s);
-      s2 = fma((double)a[u + 1], (double)wv[u + 1], s2);
-    }
-  }
-  for (; d < D; d += 32) s = fma((double)__ldg(xr + d), (double)__ldg(w + d), s);
-  s += s2;
+  double s = 0.0;
+  // bank rows are only 4-byte aligned in general (P floats apart), hence scalar loads.  (An 8-deep software pipeline
+  // with two accumulation chains -- which halved the unfused route's refine_kernel -- made this kernel 40 % slower.)
+  for (int d = lane; d < D; d += 32) s = fma((double)__ldg(xr + d), (double)__ldg(w + d), s);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return (float)(s + (double)bias) > 0.f;
