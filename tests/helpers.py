@@ -89,6 +89,12 @@ class OracleEngine(object):
     def forward_logits(self, x, s):
         return orc.bnn_forward_avg_posterior(self.net, self.layout, self.bank[s], self._x(x))
 
+    def forward_logits_sum(self, x, s0, s1):
+        return orc.ensemble_forward(self.net, self.layout, self.bank, self._x(x), range(s0, s1)) * (s1 - s0)
+
+    def set_best_precision(self):
+        return "oracle"
+
     def input_grad_sum(self, head, x, labels, s0, s1, pbar=None):
         x = self._x(x)
         if s1 == s0:
@@ -102,6 +108,10 @@ class OracleEngine(object):
             return orc.expected_loss_gradients(self.net, self.layout, self.bank, x, labels, range(s0, s1)) * (s1 - s0)
         xs = x.clone().requires_grad_(True)
         import torch.nn.functional as nnf
+        if head == 4:                     # LOGITS_UPSTREAM: g goes to the (sum of the) logits as is
+            ls = sum(orc.net_logits(self.net, orc.unpack(self.bank[s], self.layout), xs) for s in range(s0, s1))
+            (gx,) = torch.autograd.grad((ls * torch.as_tensor(pbar).detach()).sum(), xs)
+            return gx
         ps = torch.stack([nnf.softmax(orc.net_logits(self.net, orc.unpack(self.bank[s], self.layout), xs), -1)
                           for s in range(s0, s1)]).sum(0)
         if head == 1:

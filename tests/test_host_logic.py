@@ -139,6 +139,56 @@ def test_save_load_roundtrip_reference_formats(tmp_path):
         h3.load("cpu", rel_path=str(tmp_path) + "/", filename=hb.name + "_weights")
 
 
+@pytest.mark.parametrize("name", ["ens_fc2_16_mnist", "ens_fc16_mnist"])
+def test_nn_and_ensemble_host_logic(name, tmp_path, monkeypatch):
+    """Deterministic NN / Ensemble_NN drop-ins (model_nn.py, model_ensemble.py) with the oracle standing in for the
+    engine: weight files in the reference's layout, member selection, errors, attacks and evaluation against the
+    reference's own outputs."""
+    from robustbnns_b200 import adversarialAttacks as aa
+    from robustbnns_b200.model_ensemble import Ensemble_NN
+    from robustbnns_b200.model_nn import NN
+    from tests.helpers import OracleEngine
+    monkeypatch.chdir(tmp_path)
+    c = Case(name)
+    size, used = int(c.z["size"]), int(c.z["n_used"])
+    ens = Ensemble_NN("mnist", c.hidden, "leaky", c.arch, 1, 0.01, c.input_shape, c.n_classes, size)
+    assert ens.name == "mnist_ensemble_hid=%d_act=leaky_arch=%s_size=%d" % (c.hidden, c.arch, size)   # model_ensemble.py:26-31
+    ens._engine = OracleEngine(c.arch, c.input_shape, c.hidden, c.n_classes)
+    wdir = os.path.join("w", ens.name, "weights")
+    os.makedirs(wdir)
+    for i in range(size):
+        torch.save(orc.unpack(c.bank[i], c.layout), os.path.join(wdir, "%s_weights_%d.pt" % (ens.member_name, i)))
+    ens.load("cpu", rel_path="w/")
+    with pytest.raises(ValueError):
+        ens.forward(c.x, n_samples=size + 1)
+    with pytest.raises(AttributeError):
+        ens.set_members(c.bank[:size - 1])
+    assert rel_err(ens.forward(c.x, n_samples=used), c.t("logits_used")) < 1e-5
+    assert rel_err(ens.forward(c.x, None), c.t("logits_all")) < 1e-5
+    nn0 = NN("mnist", c.input_shape, c.n_classes, c.hidden, "leaky", c.arch, 0.01, 1)
+    nn0._engine = OracleEngine(c.arch, c.input_shape, c.hidden, c.n_classes)
+    with pytest.raises(RuntimeError):
+        nn0.forward(c.x)                              # no weights installed yet
+    nn0.load("cpu", savedir=os.path.join(ens.name, "weights"), seed=0, rel_path="w/")
+    assert rel_err(nn0.forward(c.x), c.t("logits_member0")) < 1e-5
+    nn0.save(savedir="resaved", seed=3)               # the reference's file name under TESTS (model_nn.py:143-151)
+    from robustbnns_b200.savedir import TESTS
+    again = torch.load(os.path.join(TESTS, "resaved", nn0.name + "_weights_3.pt"), weights_only=False)
+    assert list(again.keys()) == [k for k, _ in c.layout] and torch.equal(again[c.layout[0][0]], nn0.state_dict()[c.layout[0][0]])
+    hyper = {"epsilon": float(c.z["eps"])}
+    for who, net, ns in (("ens", ens, used), ("nn", nn0, None)):
+        adv = aa.attack(net=net, x_test=c.x, y_test=c.y, dataset_name="mnist", device="cpu", method="fgsm",
+                        filename="a", savedir="a", hyperparams=hyper, n_samples=ns)
+        ref = c.t(f"{who}_fgsm_hyper_adv")
+        assert float(((adv - ref).abs() > 1e-6).float().mean()) <= 2e-3
+        adv = aa.attack(net=net, x_test=c.x, y_test=c.y, dataset_name="mnist", device="cpu", method="pgd",
+                        filename="a", savedir="a", hyperparams=hyper, n_samples=ns)
+        assert float(((adv - c.t(f"{who}_pgd_hyper_adv")).abs() > 1e-6).float().mean()) <= 2e-3   # per-image alpha (:89)
+        o, a, rob = aa.attack_evaluation(net=net, x_test=c.x, x_attack=ref, y_test=c.y, device="cpu", n_samples=ns)
+        assert [o, a] == c.z[f"{who}_fgsm_hyper_eval"].tolist()
+        assert float((rob - c.t(f"{who}_fgsm_hyper_rob")).abs().max()) <= 1e-6
+
+
 def _rank_main(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
