@@ -184,29 +184,55 @@ ATTACK_BATCH = 8192     # images per device pass
 
 def attack(net, x_test, y_test, dataset_name, device, method, filename, savedir=None,
            hyperparams=None, n_samples=None, avg_posterior=False):
-    """All test points at once (adversarialAttacks.py:111-143); returns [N, ch, h, w] on the device."""
+    """All test points at once (adversarialAttacks.py:111-143); returns [N, ch, h, w] on the device.
+    Multi-GPU (torch.distributed initialised, BNN with attack_sharding == "inputs", the default): every rank draws the
+    same posterior samples (global Philox indices), attacks its own block of the test points without any collective,
+    and the blocks are all-gathered at the end -- identical to the single-GPU result."""
     print(f"\nProducing {method} attacks on {dataset_name}:")
     labels = torch.as_tensor(y_test).argmax(-1)
-    adversarial_attack = []
-    for b0 in range(0, len(x_test), ATTACK_BATCH):
-        image = torch.as_tensor(x_test[b0:b0 + ATTACK_BATCH])
-        label = labels[b0:b0 + ATTACK_BATCH]
-        if not isinstance(net, BNN):
-            image, label = image.to(device), label.to(device)
-        if method == "fgsm":
-            perturbed_image = fgsm_attack(net=net, image=image, label=label, hyperparams=hyperparams,
-                                          n_samples=n_samples, avg_posterior=avg_posterior)
-        elif method == "pgd":
-            perturbed_image = pgd_attack(net=net, image=image, label=label, hyperparams=hyperparams,
-                                         n_samples=n_samples, avg_posterior=avg_posterior)
-        adversarial_attack.append(perturbed_image)
-    adversarial_attack = torch.cat(adversarial_attack)
+    rank, world = rdist.real_world()
+    shard_inputs = isinstance(net, BNN) and world > 1 and getattr(net, "attack_sharding", "inputs") == "inputs"
+    n_total = len(x_test)
+    lo, hi, per = 0, n_total, n_total
+    if shard_inputs:
+        per = (n_total + world - 1) // world
+        lo, hi = min(n_total, rank * per), min(n_total, (rank + 1) * per)
+
+    def run(lo, hi):
+        out = []
+        for b0 in range(lo, hi, ATTACK_BATCH):
+            b1 = min(hi, b0 + ATTACK_BATCH)
+            image = torch.as_tensor(x_test[b0:b1])
+            label = labels[b0:b1]
+            if not isinstance(net, BNN):
+                image, label = image.to(device), label.to(device)
+            if method == "fgsm":
+                perturbed_image = fgsm_attack(net=net, image=image, label=label, hyperparams=hyperparams,
+                                              n_samples=n_samples, avg_posterior=avg_posterior)
+            elif method == "pgd":
+                perturbed_image = pgd_attack(net=net, image=image, label=label, hyperparams=hyperparams,
+                                             n_samples=n_samples, avg_posterior=avg_posterior)
+            out.append(perturbed_image)
+        return out
+
+    if shard_inputs:
+        with rdist.replicated():
+            net._replace_rows()                      # every rank holds all the samples while it attacks its block
+            parts = run(lo, hi)
+        net._replace_rows()                          # back to sample sharding
+        eng = net.engine()
+        shape = tuple(torch.as_tensor(x_test).shape[1:])
+        local = torch.cat(parts) if parts else torch.zeros((0,) + shape, dtype=torch.float32, device=eng.device)
+        adversarial_attack = rdist.all_gather_rows(local.reshape((-1,) + shape), per, n_total)
+    else:
+        adversarial_attack = torch.cat(run(0, n_total))
 
     path = TESTS + filename + "/" if savedir is None else TESTS + savedir + "/"
     name = filename + "_" + str(method)
     # (the reference also writes two PNG grids here through matplotlib, utils.py:276-290: plotting is out of scope)
     name = name + "_attackSamp=" + str(n_samples) + "_attack.pkl" if n_samples else name + "_attack.pkl"
-    save_to_pickle(data=adversarial_attack, path=path, filename=name)
+    if rank == 0 or not shard_inputs:
+        save_to_pickle(data=adversarial_attack, path=path, filename=name)
     return adversarial_attack
 
 

@@ -7,15 +7,50 @@ only data-path collectives are sum-allreduces of [B, C] probability sums and
 [B, D] gradient sums, issued through torch.distributed (NCCL on GPUs; gloo in
 the CPU tests).
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
+_replicated = 0        # > 0 inside `replicated()`: every rank works on its own, no collectives
 
-def world():
-    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+
+def real_world():
+    """(rank, world_size) of the process group; (0, 1) when torch.distributed is not initialised."""
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def world():
+    """(rank, world_size) the sample sharding sees: (0, 1) inside `replicated()`."""
+    return (0, 1) if _replicated else real_world()
+
+
+@contextlib.contextmanager
+def replicated():
+    """INPUT sharding (the alternative): inside this context every rank holds ALL posterior
+    samples (the Philox draws are indexed by the global sample number, so all ranks draw identical banks without
+    talking to each other) and works on its own slice of the inputs -- no data-path collective at all.  Used by
+    `adversarialAttacks.attack`, whose PGD loop would otherwise all-reduce twice per iteration."""
+    global _replicated
+    _replicated += 1
+    try:
+        yield
+    finally:
+        _replicated -= 1
+
+
+def all_gather_rows(local, per_rank, n_total):
+    """Concatenate the ranks' row blocks (rank r holds rows [r * per_rank, min(n_total, (r + 1) * per_rank)))."""
+    rank, w = real_world()
+    if w == 1:
+        return local
+    pad = torch.zeros((per_rank,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(w)]
+    dist.all_gather(parts, pad)
+    return torch.cat(parts)[:n_total]
 
 
 def local_positions(n, rank, world_size):
@@ -28,7 +63,9 @@ def local_count(n, rank, world_size):
 
 
 def allreduce_sum_(t):
-    """In-place sum over ranks; no-op for a single process."""
+    """In-place sum over ranks; no-op for a single process and inside `replicated()`."""
+    if _replicated:
+        return t
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t

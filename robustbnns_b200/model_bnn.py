@@ -124,6 +124,7 @@ class BNN(object):
         self.rng_seed = 0
         self._engine = engine
         self._precision = "auto"              # engine choice for an engine this object creates (set_precision)
+        self.attack_sharding = "inputs"       # multi-GPU `attack`: shard the inputs (no collectives) or the "samples"
         self._loc = self._rho = None          # SVI guide parameters, flattened [P]
         self._bank_host = None                # explicit / HMC bank [S, P] (CPU tensor)
         self._reset_rows()
@@ -270,6 +271,13 @@ class BNN(object):
         raise NotImplementedError("posterior inference (SVI/HMC training) is outside the accelerated hot path")
 
     model = guide = _train_svi = _train_hmc = train
+
+    def _replace_rows(self):
+        """Redo the bank placement after the sharding mode changed (rdist.replicated() entered / left)."""
+        if self._bank_host is not None:
+            self.set_posterior_samples(self._bank_host)
+        else:
+            self._reset_rows()
 
     # ---- sample placement --------------------------------------------------------------------
     def _grow_pinned(self, need_local):

@@ -48,6 +48,21 @@ def _rank_main(rank, world, port, case, q):
         grads = lg.expected_loss_gradients(bnn, x, labels, S)                  # allreduce of [B, D]
         adv = aa.fgsm_attack(bnn, x, labels, hyperparams={"epsilon": 0.1}, n_samples=S)   # both, fresh draws
         assert bnn._pin_rows == len(range(rank, S, world))
+        # attack(): input sharding (every rank draws the same samples and attacks its block, one all-gather at the end)
+        # against sample sharding (two all-reduces per gradient) on the same fresh-sample stream
+        import tempfile
+        os.chdir(tempfile.mkdtemp())
+        y1h = torch.nn.functional.one_hot(labels, C).float()
+        att = {}
+        for mode in ("inputs", "samples"):
+            bnn.attack_sharding = mode
+            bnn.reseed(3)
+            att[mode] = aa.attack(net=bnn, x_test=x, y_test=y1h, dataset_name="mnist", device="cuda", method="fgsm",
+                                  filename="a", savedir="a", hyperparams={"epsilon": 0.1}, n_samples=S)
+        assert att["inputs"].shape == x.shape
+        assert float(((att["inputs"] - att["samples"]).abs() > 1e-6).float().mean()) <= 2e-3      # sign ties only
+        probs_again = bnn.forward(x, n_samples=S, seeds=seeds)          # the sample sharding is back in place
+        assert torch.equal(probs_again, probs)
         # single-device evaluation of the same global samples on this rank's GPU: no collective
         eng = Net(ARCH, SHAPE, HIDDEN, C)
         eng.set_precision(prec)

@@ -212,7 +212,19 @@ def _rank_main(rank, world, port, q):
         fr = sb.forward(s.x, n_samples=3)
         pgd = aa.pgd_attack(bnn, c.x, c.labels, hyperparams=None, n_samples=S, iters=3)
         ev = aa.attack_evaluation(bnn, c.x, c.t("fgsm_hyper_adv"), c.y, "cpu", n_samples=S)
-        q.put((rank, probs, grads, adv, sp, fr, pgd, ev[:2], ev[2]))
+        # attack(): INPUT sharding (9 images -> blocks of 5 + 4, every rank holds all samples, no collective until the
+        # final all-gather); afterwards the sample sharding is back in place
+        import tempfile
+        os.chdir(tempfile.mkdtemp())
+        hyper = {"epsilon": float(c.z["eps"])}
+        att = [aa.attack(net=bnn, x_test=c.x, y_test=c.y, dataset_name="mnist", device="cpu", method=m, filename="a",
+                         savedir="a", hyperparams=hyper, n_samples=S) for m in ("fgsm", "pgd")]
+        probs_after = bnn.forward(c.x, n_samples=S)
+        assert torch.equal(probs_after, probs)
+        bnn.attack_sharding = "samples"                                   # the all-reduce-per-iteration variant
+        att_s = aa.attack(net=bnn, x_test=c.x, y_test=c.y, dataset_name="mnist", device="cpu", method="fgsm",
+                          filename="a", savedir="a", hyperparams=hyper, n_samples=S)
+        q.put((rank, probs, grads, adv, sp, fr, pgd, ev[:2], ev[2], att, att_s))
     finally:
         dist.destroy_process_group()
 
@@ -235,7 +247,11 @@ def test_two_rank_gloo_sharding_equals_single_process():
     S = c.bank.shape[0]
     sched = lambda call: range(S)  # noqa: E731
     pgd_ref = orc.pgd_attack(c.net, c.layout, c.bank, c.x, c.labels, sched, None, iters=3)
-    for (_, probs, grads, adv, sp, fr, pgd, acc, rob) in res:
+    for (_, probs, grads, adv, sp, fr, pgd, acc, rob, att, att_s) in res:
+        assert att[0].shape == c.x.shape
+        assert float((att[0] - c.t("fgsm_hyper_adv")).abs().max()) <= 1e-6
+        assert float(((att[1] - c.t("pgd_hyper_adv")).abs() > 1e-6).float().mean()) <= 2e-3
+        assert float((att_s - c.t("fgsm_hyper_adv")).abs().max()) <= 1e-6
         assert rel_err(probs, c.t("probs")) < 1e-5
         assert rel_err(grads, c.t("loss_gradient")) < 1e-5
         assert float((adv - c.t("fgsm_hyper_adv")).abs().max()) <= 1e-6
