@@ -62,7 +62,9 @@ def _rank_main(rank, world, port, case, q):
         assert att["inputs"].shape == x.shape
         assert float(((att["inputs"] - att["samples"]).abs() > 1e-6).float().mean()) <= 2e-3      # sign ties only
         probs_again = bnn.forward(x, n_samples=S, seeds=seeds)          # the sample sharding is back in place
-        assert torch.equal(probs_again, probs)
+        # (not bit-identical on F16X3: the re-drawn rows get their guard-band row norms from the fused sampler kernel,
+        # whose summation order differs from the stand-alone norm pass)
+        assert rel_err(probs_again.cpu(), probs.cpu()) < 1e-6
         # single-device evaluation of the same global samples on this rank's GPU: no collective
         eng = Net(ARCH, SHAPE, HIDDEN, C)
         eng.set_precision(prec)
@@ -92,7 +94,7 @@ def test_two_rank_nccl_sharding_equals_single_device_and_oracle(case):
     procs = [ctx.Process(target=_rank_main, args=(r, 2, port, case, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    res = sorted([q.get(timeout=90) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
