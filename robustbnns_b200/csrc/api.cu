@@ -483,15 +483,21 @@ int rbnn_bank_sample_diag(rbnn_net* n, const float* d_loc, const float* d_rho, u
   if (count == 0) return 0;
   DeviceGuard dg(n->device);
   cudaStream_t st = (cudaStream_t)stream;
-  int fused = 0;        // F16X3 / arch fc with a fixed weight scale: bank rows and operand copies in one pass
-  RBNN_TRY(tc_sample_relayout_f16(n, d_loc, d_rho, seed, sample_index0, sample_index_stride, s0, count, st, &fused));
-  if (fused) {
-    if (n->keep.valid && s0 < n->keep.s1 && s0 + count > n->keep.s0) n->keep.valid = 0;
-    return 0;
+  constexpr int kMaxRowsPerLaunch = 32768;      // the sample index is a grid dimension (limit 65535)
+  for (int c0 = 0; c0 < count; c0 += kMaxRowsPerLaunch) {
+    const int cnt = std::min(kMaxRowsPerLaunch, count - c0);
+    const int r0 = s0 + c0;
+    const int64_t idx0 = sample_index0 + (int64_t)c0 * sample_index_stride;
+    int fused = 0;      // F16X3 / arch fc with a fixed weight scale: bank rows and operand copies in one pass
+    RBNN_TRY(tc_sample_relayout_f16(n, d_loc, d_rho, seed, idx0, sample_index_stride, r0, cnt, st, &fused));
+    if (fused) {
+      if (n->keep.valid && r0 < n->keep.s1 && r0 + cnt > n->keep.s0) n->keep.valid = 0;
+      continue;
+    }
+    RBNN_TRY(sample_diag(n, d_loc, d_rho, seed, idx0, sample_index_stride, r0, cnt, st));
+    RBNN_TRY(conv_permute_wout(n, r0, cnt, st));
+    mark_dirty(n, r0, cnt);
   }
-  RBNN_TRY(sample_diag(n, d_loc, d_rho, seed, sample_index0, sample_index_stride, s0, count, st));
-  RBNN_TRY(conv_permute_wout(n, s0, count, st));
-  mark_dirty(n, s0, count);
   return 0;
 }
 
