@@ -119,6 +119,7 @@ struct rbnn_net {
   int cc_major = 0;           // compute capability major of `device` (10 = Blackwell: tcgen05 engine usable)
   TcBank tc;
   KeepCache keep;
+  int conv1_smem_set = 0;     // conv1_bwd_sum_kernel's dynamic shared-memory attribute has been set on this device
   int sum_logits = 0;         // 1 while rbnn_forward_logits_sum runs: the forward passes accumulate raw logits, not softmax rows
   int tc_unfused = 0;         // 1: arch fc takes the unfused GEMM -> head route (RBNN_TC_UNFUSED=1; A/B testing)
   // optional per-kernel-class device timing (bench.py's roofline leg): event pairs on the launch stream

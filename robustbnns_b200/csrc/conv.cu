@@ -306,10 +306,9 @@ int conv1_bwd_parts(const rbnn_net* net, int Z, int B) {
 int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,
                   float* dx_sum, int accumulate, cudaStream_t st, float* partial, int parts) {
   const size_t smem = (size_t)kC1SmemFloats * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!net->conv1_smem_set) {       // per handle (= per device): the opt-in above 48 KB of dynamic shared memory
     RBNN_CUDA(cudaFuncSetAttribute(conv1_bwd_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    net->conv1_smem_set = 1;
   }
   if (!partial || parts <= 1) {
     conv1_bwd_sum_kernel<<<B, 128, smem, st>>>(g1, idx1, bank, net->L.P, net->L.cw1, s0, Z, B, dx_sum, accumulate);
