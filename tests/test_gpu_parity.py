@@ -494,6 +494,42 @@ def test_autograd_through_forward_matches_attack_gradient(prec):
         assert rel_err(xg.grad.cpu(), ref) < REL
 
 
+@pytest.mark.parametrize("arch,hidden,prec", [("fc", 512, "f16x3"), ("fc", 64, "tf32x3"), ("fc2", 128, "tf32x3"),
+                                              ("conv", 32, "f16x3"), ("conv", 32, "fp32"), ("fc2", 128, "fp32")])
+def test_single_image_and_empty_batch(arch, hidden, prec):
+    """The reference's own calling pattern is ONE image at a time (lossGradients.py:29-38, adversarialAttacks.py:118-131):
+    B = 1 through every engine, and the degenerate B = 0 / S = 0 calls."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    S = 3
+    net, layout, loc, rho, bank, x, labels = _problem(arch, (1, 28, 28), hidden, 10, 2, S)
+    eng = Net(arch, (1, 28, 28), hidden, 10)
+    eng.set_precision(prec)
+    eng.upload(bank, 0)
+    tol = REL if arch != "fc2" or prec == "fp32" else 1e-2
+    for i in range(2):
+        xi, yi = x[i:i + 1], labels[i:i + 1]
+        p = eng.forward_probs_sum(xi, 0, S).cpu() / S
+        assert p.shape == (1, 10) and rel_err(p, orc.bnn_forward(net, layout, bank, xi, range(S)).detach()) < tol
+        g = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xi, yi, 0, S).cpu().reshape(xi.shape) / S
+        ref = orc.expected_loss_gradients(net, layout, bank, xi, yi, range(S), dtype=torch.float64)
+        ref32 = orc.expected_loss_gradients(net, layout, bank, xi, yi, range(S))
+        assert min(rel_err(g, ref), rel_err(g, ref32)) < tol
+        pbar = eng.forward_probs_sum(xi, 0, S, keep=True) / S
+        if eng.keep_valid:
+            ga = eng.input_grad_sum_kept(_lib.HEAD_GRAD_OF_MEAN, yi, pbar=pbar).cpu().reshape(xi.shape) / S
+        else:
+            ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, xi, yi, 0, S, pbar=pbar).cpu().reshape(xi.shape) / S
+        assert rel_err(ga, orc.attack_gradient(net, layout, bank, xi, yi, range(S), dtype=torch.float64)) < tol
+    # empty batch / empty sample range
+    e = x[:0]
+    assert eng.forward_probs_sum(e, 0, S).shape == (0, 10)
+    assert eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, e, labels[:0], 0, S).numel() == 0
+    assert float(eng.forward_probs_sum(x, 2, 2).abs().max()) == 0.0
+    assert float(eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x, labels, 1, 1).abs().max()) == 0.0
+    eng.close()
+
+
 def test_default_engine_is_the_fastest_parity_grade():
     """A BNN that creates its own engine picks F16X3 (fc-512, conv), TF32X3 (fc2) or FP32 (half-moons: D = 2)."""
     from robustbnns_b200.model_bnn import BNN
