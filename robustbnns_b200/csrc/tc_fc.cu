@@ -663,7 +663,7 @@ int tc_sample_relayout_f16(rbnn_net* n, const float* d_loc, const float* d_rho, 
 
 int tc_supported(const rbnn_net* n) {
   if (n->arch != RBNN_ARCH_FC && n->arch != RBNN_ARCH_FC2) return 0;
-  if ((n->D & 7) || n->H < 32 || n->C > kMaxC) return 0;
+  if ((n->D & 7) || n->H < 32 || n->H > 2048 || n->C > kMaxC) return 0;      // refine_kernel keeps a row of <= 2048 units in registers
   return n->cc_major == 10;
 }
 
