@@ -530,6 +530,42 @@ def test_single_image_and_empty_batch(arch, hidden, prec):
     eng.close()
 
 
+def test_half_moons_grid_sweep(tmp_path, monkeypatch):
+    """BASELINE configs[0] / [4]: the half-moons over-parametrisation sweep through the grid_search_halfMoons drop-in
+    (fc2 2-H-H-2, stored posteriors in the reference's file layout, 100 test points x 100 samples) against the oracle."""
+    from robustbnns_b200 import grid_search_halfMoons as gs
+    from robustbnns_b200.adversarialAttacks import load_attack
+    from robustbnns_b200.lossGradients import load_loss_gradients
+    from robustbnns_b200.utils import load_half_moons
+    monkeypatch.chdir(tmp_path)
+    _, _, x_test, y_test, _, _ = load_half_moons()
+    S, pts, widths = 100, 100, (32, 128, 512)
+    banks = {}
+    for hidden in widths:
+        bnn = gs.MoonsBNN(hidden, "leaky", "fc2", "hmc", None, None, S, 5, 100, (1, 2, 1), 2)
+        assert bnn.engine().precision == "fp32"                       # D = 2: no tensor-core shape
+        net = orc.build_net("fc2", (1, 2, 1), hidden, 2, dataset_name="half_moons")
+        layout = orc.param_layout(net)
+        loc, rho = orc.scaled_guide_params(layout, seed=hidden, rho_mean=-2.0)
+        bank = loc + orc.softplus(rho) * torch.randn((S, loc.numel()), generator=torch.Generator().manual_seed(hidden))
+        bnn.set_posterior_samples(bank)
+        bnn.save(rel_path="w/")
+        banks[hidden] = (net, layout, bank, bnn.name)
+    gs.serial_compute_grads(list(widths), ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                            rel_path="w/", test_points=pts)
+    gs.grid_attack("fgsm", list(widths), ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S], pts,
+                   device="cuda", rel_path="w/")
+    xt, labels = torch.from_numpy(x_test[:pts]), torch.from_numpy(y_test[:pts]).argmax(-1)
+    for hidden, (net, layout, bank, name) in banks.items():
+        got = load_loss_gradients(n_samples=S, filename=name, savedir=name + "/")
+        ref = orc.expected_loss_gradients(net, layout, bank, xt, labels, range(S), dtype=torch.float64).reshape(pts, 2).numpy()
+        order = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]           # the loader shuffles the test points  # noqa: E731
+        assert got.shape == (pts, 2) and np.abs(order(got) - order(ref)).max() <= REL * np.abs(ref).max()
+        adv = load_attack("fgsm", name, n_samples=S)
+        ref_adv = orc.fgsm_attack(net, layout, bank, xt, labels, lambda call: range(S), None)
+        assert _mismatch_fraction(adv, ref_adv) <= 5e-3
+
+
 def test_default_engine_is_the_fastest_parity_grade():
     """A BNN that creates its own engine picks F16X3 (fc-512, conv), TF32X3 (fc2) or FP32 (half-moons: D = 2)."""
     from robustbnns_b200.model_bnn import BNN

@@ -189,6 +189,51 @@ def test_nn_and_ensemble_host_logic(name, tmp_path, monkeypatch):
         assert float((rob - c.t(f"{who}_fgsm_hyper_rob")).abs().max()) <= 1e-6
 
 
+def test_half_moons_grid_driver(tmp_path, monkeypatch):
+    """grid_search_halfMoons drop-in (BASELINE configs[4]) with the oracle standing in for the
+    engine: the data set equals the reference's recipe, MoonsBNN names / weight files follow the reference, and the
+    sweep's gradients and FGSM examples are the oracle's on the same stored posteriors."""
+    import numpy as np
+    from robustbnns_b200 import grid_search_halfMoons as gs
+    from robustbnns_b200.adversarialAttacks import load_attack
+    from robustbnns_b200.lossGradients import load_loss_gradients
+    from robustbnns_b200.utils import load_half_moons
+    from tests.helpers import OracleEngine
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr("robustbnns_b200.engine.Net",
+                        lambda arch, shape, hidden, C: OracleEngine(arch, shape, hidden, C, dataset="half_moons"))
+    x_train, y_train, x_test, y_test, shp, ncls = load_half_moons()
+    assert x_train.shape == (24000, 1, 2, 1) and x_test.shape == (6000, 1, 2, 1) and tuple(shp) == (1, 2, 1) and ncls == 2
+    assert float(min(x_train.min(), x_test.min())) == 0.0 and float(max(x_train.max(), x_test.max())) == 1.0
+    assert y_test.shape == (6000, 2) and set(np.unique(y_test)) == {0.0, 1.0}
+    S, pts = 4, 12
+    banks = {}
+    for hidden in (16, 32):
+        bnn = gs.MoonsBNN(hidden, "leaky", "fc2", "hmc", None, None, S, 5, 100, (1, 2, 1), 2)
+        assert bnn.name == "half_moons_bnn_hmc_hid=%d_act=leaky_arch=fc2_inp=100_samp=%d_warm=5_stepsize=0.001_numsteps=10" % (hidden, S)
+        net = orc.build_net("fc2", (1, 2, 1), hidden, 2, dataset_name="half_moons")
+        layout = orc.param_layout(net)
+        loc, rho = orc.scaled_guide_params(layout, seed=hidden, rho_mean=-2.0)
+        bank = loc + orc.softplus(rho) * torch.randn((S, loc.numel()), generator=torch.Generator().manual_seed(hidden))
+        bnn.set_posterior_samples(bank)
+        bnn.save(rel_path="w/")                                       # the reference's per-sample state-dict files
+        banks[hidden] = (net, layout, bank, bnn.name)
+    gs.serial_compute_grads([16, 32], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                            rel_path="w/", test_points=pts)
+    gs.grid_attack("fgsm", [16, 32], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S], pts,
+                   device="cpu", rel_path="w/")
+    xt, labels = torch.from_numpy(x_test[:pts]), torch.from_numpy(y_test[:pts]).argmax(-1)
+    for hidden, (net, layout, bank, name) in banks.items():
+        got = load_loss_gradients(n_samples=S, filename=name, savedir=name + "/")
+        assert got.shape == (pts, 2)                                  # squeezed, lossGradients.py:66
+        ref = orc.expected_loss_gradients(net, layout, bank, xt, labels, range(S)).reshape(pts, 2).numpy()
+        order = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]           # the loader shuffles the test points  # noqa: E731
+        assert np.abs(order(got) - order(ref)).max() <= 1e-5 * np.abs(ref).max()
+        adv = load_attack("fgsm", name, n_samples=S)
+        ref_adv = orc.fgsm_attack(net, layout, bank, xt, labels, lambda call: range(S), None)
+        assert float((adv.cpu() - ref_adv).abs().max()) <= 1e-6
+
+
 def _rank_main(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
