@@ -270,6 +270,7 @@ def _rank_main(rank, world, port, q):
         att_s = aa.attack(net=bnn, x_test=c.x, y_test=c.y, dataset_name="mnist", device="cpu", method="fgsm",
                           filename="a", savedir="a", hyperparams=hyper, n_samples=S)
         q.put((rank, probs, grads, adv, sp, fr, pgd, ev[:2], ev[2], att, att_s))
+        dist.barrier()                      # nobody tears the group down while a peer is still inside a collective
     finally:
         dist.destroy_process_group()
 
