@@ -339,6 +339,27 @@ def main():
         eng.set_precision(prec)
         step_resident()
         try:
+            # K-sample alone (HBM-bound side of the path): this rank's samples -> bank rows (+ the fp16 operand copies
+            # when the engine writes them in the same pass), achieved bytes/s against the measured HBM copy rate
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = eng.launch_count
+            e0.record()
+            for _ in range(3):
+                eng.sample_diag(bnn._loc, bnn._rho, bnn.rng_seed, rank, rows[0], local_S, stride=world)
+            e1.record()
+            torch.cuda.synchronize()
+            sms = e0.elapsed_time(e1) / 3
+            fused_copies = prec == "f16x3" and (eng.launch_count - l0) // 3 <= 5
+            nbytes = local_S * (eng.P * 4 + (784 * 512 * 8 if fused_copies else 0))
+            extra["sampler"] = {"ms": sms, "samples": local_S, "bytes": nbytes, "achieved": nbytes / (sms * 1e-3) / 1e9,
+                                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (sms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                "bound": "hbm (Philox integer work keeps it below the copy rate)",
+                                "note": "bank rows (4 P bytes per sample)" + (" + fp16 hi/lo operand copies of W1 and W1^T "
+                                        "(8 bytes per weight) written by the same kernel" if fused_copies else "")}
+        except Exception as e:
+            log("sampler measurement failed:", e)
+        try:
             from robustbnns_b200 import adversarialAttacks as aa
             n_img, n_s, iters = 1000, 100, 20          # BASELINE configs[2] shape: 1000 inputs, 20-step PGD
             xa, ya = x_dev[:n_img].contiguous(), y_dev[:n_img].to(torch.int64)
