@@ -140,6 +140,30 @@ maxabs_kernel(const float* __restrict__ base, int64_t stride, int64_t len, int c
   }
 }
 
+// contiguous variant (activations of a chunk): 16-byte loads, no per-element segment arithmetic
+__global__ void __launch_bounds__(256)
+maxabs_flat_kernel(const float* __restrict__ p, int64_t n, unsigned* __restrict__ out_bits) {
+  __shared__ float red[8];
+  float m = 0.f;
+  const int64_t n4 = (reinterpret_cast<uintptr_t>(p) & 15) ? 0 : n / 4;
+  const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(p4 + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(p + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    if (!(m == m)) m = __int_as_float(0x7f800000);
+    atomicMax(out_bits, __float_as_uint(m));
+  }
+}
+
 // after the maxima of the dirty rows are in: fix s_w1 on first use, afterwards only check that the frozen scale
 // still keeps every |W1| inside the fp16 range (2^6 head room); otherwise raise the sticky host-visible flag
 __global__ void freeze_scales_kernel(TcScales* sc, int* overflow) {
@@ -616,7 +640,8 @@ __global__ void reduce_slots_kernel(const float* __restrict__ partial, int npart
 // ------------------------------------------------------------------------------------------------------
 // F16X3 operand-range helpers for the conv engine (tc_conv.cu): *bits = max(*bits, max|p|) and the call's 4 scalars
 int tc_maxabs(rbnn_net* n, const float* p, int64_t count, unsigned* bits, cudaStream_t st) {
-  maxabs_kernel<<<n->sm_count * 2, 256, 0, st>>>(p, 0, count, 1, bits);
+  const unsigned blocks = (unsigned)std::min<int64_t>((count / 4 + 255) / 256 + 1, (int64_t)n->sm_count * 8);
+  maxabs_flat_kernel<<<blocks, 256, 0, st>>>(p, count, bits);
   n->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -1034,7 +1059,7 @@ static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const fl
   const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
   if (n->prec == RBNN_PREC_F16X3) {
     RBNN_CUDA(cudaMemsetAsync(w.max_bits, 0, 2 * sizeof(unsigned), st));
-    maxabs_kernel<<<n->sm_count * 2, 256, 0, st>>>(x, 0, count, 1, w.max_bits);
+    maxabs_flat_kernel<<<n->sm_count * 4, 256, 0, st>>>(x, count, w.max_bits);
     if (pbar_for_scale) {
       maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar_for_scale, 0, pbar_count, 1, w.max_bits + 1);
       n->launches++;
