@@ -74,8 +74,11 @@ def _rank_main(rank, world, port, case, q):
         g1 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, 0, S).reshape(x.shape) / S
         p1 = eng.forward_probs_sum(xd, 0, S) / S
         bank = eng.download(0, S)
+        # numpy, not torch tensors: tensors cross the queue as file descriptors served by this process and the parent
+        # may fetch them only after it has exited
+        npy = lambda t: t.detach().cpu().numpy()  # noqa: E731
         q.put((rank, rel_err(probs.cpu(), p1.cpu()), rel_err(grads.cpu(), g1.cpu()),
-               grads.cpu(), probs.cpu(), adv.cpu(), bank if rank == 0 else None))
+               npy(grads), npy(probs), npy(adv), npy(bank) if rank == 0 else None))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -98,6 +101,8 @@ def test_two_rank_nccl_sharding_equals_single_device_and_oracle(case):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    tt = lambda a: None if a is None else torch.from_numpy(a)  # noqa: E731
+    res = [(r[0], r[1], r[2], tt(r[3]), tt(r[4]), tt(r[5]), tt(r[6])) for r in res]
     for (_, e_p, e_g, _, _, _, _) in res:
         assert e_p < 1e-5 and e_g < 1e-5          # only the summation order over samples differs
     # every rank holds the same reduced tensors

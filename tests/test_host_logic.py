@@ -269,7 +269,11 @@ def _rank_main(rank, world, port, q):
         bnn.attack_sharding = "samples"                                   # the all-reduce-per-iteration variant
         att_s = aa.attack(net=bnn, x_test=c.x, y_test=c.y, dataset_name="mnist", device="cpu", method="fgsm",
                           filename="a", savedir="a", hyperparams=hyper, n_samples=S)
-        q.put((rank, probs, grads, adv, sp, fr, pgd, ev[:2], ev[2], att, att_s))
+        # numpy, not torch tensors: tensors travel through the queue as file descriptors served by THIS process, and
+        # the parent may fetch them only after it has exited (FileNotFoundError in rebuild_storage_fd)
+        npy = lambda t: t.detach().cpu().numpy()  # noqa: E731
+        q.put((rank, npy(probs), npy(grads), npy(adv), npy(sp), npy(fr), npy(pgd), ev[:2], npy(ev[2]),
+               [npy(a) for a in att], npy(att_s)))
         dist.barrier()                      # nobody tears the group down while a peer is still inside a collective
     finally:
         dist.destroy_process_group()
@@ -289,6 +293,9 @@ def test_two_rank_gloo_sharding_equals_single_process():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    tt = torch.from_numpy
+    res = [(r[0], tt(r[1]), tt(r[2]), tt(r[3]), tt(r[4]), tt(r[5]), tt(r[6]), r[7], tt(r[8]), [tt(a) for a in r[9]], tt(r[10]))
+           for r in res]
     c = Case("hmc_fc16_fmnist")
     S = c.bank.shape[0]
     sched = lambda call: range(S)  # noqa: E731
