@@ -101,8 +101,8 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_units_per_s(n_img, n_samp, threads=None):
-    """The reference's CPU algorithm (loop order R1, weights re-drawn per unit, full backward)."""
+def reference_port_units_per_s(n_img, n_samp, threads=None):
+    """The reference's CPU algorithm (loop order R1, weights re-drawn per unit, full backward) as restated by the oracle."""
     import torch
     from oracle import oracle as orc
     if threads:
@@ -117,24 +117,91 @@ def reference_units_per_s(n_img, n_samp, threads=None):
     return n_img * n_samp / dt, dt
 
 
+_REF = {}
+
+
+def reference_real_units_per_s(n_img, n_samp):
+    """The reference's OWN modules (oracle/_ref: byte-for-byte copies made by oracle/build_ref.py, run against
+    oracle/pyro_shim because Pyro is not installed in this image): lossGradients.loss_gradients(net=BNN, data_loader, ...)
+    -- lossGradients.py:52-68 -> :20-50 -> model_bnn.py:198-258 -- on the host cores.  Returns None when oracle/_ref is
+    absent."""
+    import tempfile
+    import numpy as np
+    import torch
+    from oracle import build_ref
+    from oracle import oracle as orc
+    if "mods" not in _REF:
+        _REF["mods"] = build_ref.import_reference()
+    if _REF["mods"] is None:
+        return None
+    pyro, model_bnn, loss_gradients_mod, _ = _REF["mods"]
+    if "bnn" not in _REF:
+        bnn = model_bnn.BNN("mnist", HIDDEN, "leaky", ARCH, "svi", 1, 0.01, None, None, SHAPE, NCLS)
+        bnn.device = "cpu"
+        bnn.basenet.device = "cpu"
+        layout = [(k, tuple(v.shape)) for k, v in bnn.basenet.state_dict().items()]
+        loc, rho = orc.scaled_guide_params(layout, seed=1)
+        pyro.clear_param_store()
+        off = 0
+        for key, shp in layout:                     # the guide's parameters, as BNN.load leaves them (model_bnn.py:177-182)
+            n = int(np.prod(shp))
+            pyro.param(f"{key}_loc", loc[off:off + n].reshape(shp).clone())
+            pyro.param(f"{key}_scale", rho[off:off + n].reshape(shp).clone())
+            off += n
+        _REF["bnn"] = bnn
+    bnn = _REF["bnn"]
+    x, y = orc.synthetic_inputs(n_img, SHAPE, NCLS, seed=0)
+    loader = torch.utils.data.DataLoader(dataset=list(zip(x, y)), batch_size=128, shuffle=False)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)                               # loss_gradients pickles its result under ./data (lossGradients.py:67)
+        try:
+            with open(os.devnull, "w") as devnull:
+                so, sys.stdout = sys.stdout, devnull          # tqdm / prints of the reference
+                try:
+                    t0 = time.perf_counter()
+                    g = loss_gradients_mod.loss_gradients(net=bnn, data_loader=loader, device="cpu", filename="g",
+                                                          savedir="g/", n_samples=n_samp)
+                    dt = time.perf_counter() - t0
+                finally:
+                    sys.stdout = so
+        finally:
+            os.chdir(cwd)
+    assert g.shape[0] == n_img
+    return n_img * n_samp / dt, dt
+
+
+def reference_units_per_s(n_img, n_samp):
+    """(units/s, seconds, kind): the real reference when oracle/_ref travelled with the tree, else the oracle's port."""
+    r = reference_real_units_per_s(n_img, n_samp)
+    if r is not None:
+        return r[0], r[1], "reference"
+    v, dt = reference_port_units_per_s(n_img, n_samp)
+    return v, dt, "port"
+
+
 def run_reference(args, rank, world):
     import torch
     if rank != 0:
         return
     n_img, n_samp = 16, 32
+    kind = "port"
     for _ in range(args.warmup):
         reference_units_per_s(2, 2)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        reference_units_per_s(n_img, n_samp)
+        _, _, kind = reference_units_per_s(n_img, n_samp)
     dt = time.perf_counter() - t0
     value = args.steps * n_img * n_samp / dt
-    sample = "%d inputs x %d posterior samples per step (of 10000 x 1000), reference loop order" % (n_img, n_samp)
+    how = ("the reference's own modules (oracle/_ref, unmodified; Pyro calls answered by oracle/pyro_shim): "
+           "lossGradients.loss_gradients on a BNN" if kind == "reference" else "oracle port of the reference loop order")
+    sample = "%d inputs x %d posterior samples per step (of %d x %d), %s" % (n_img, n_samp, args.inputs, args.samples, how)
+    args.prec = "f16x3" if args.prec == "auto" else args.prec     # the arm it is compared with (config must match)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -175,6 +242,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from robustbnns_b200 import dist as rdist
     from robustbnns_b200 import lossGradients as lg
     from robustbnns_b200.model_bnn import BNN
     from robustbnns_b200._lib import HEAD_MEAN_OF_GRADS
@@ -204,7 +272,7 @@ def main():
     bnn.set_guide(torch.cat(locs), torch.cat(rhos))
     gx = torch.Generator().manual_seed(0)
     x_host = torch.rand((B, *SHAPE), generator=gx).pin_memory()
-    y_host = torch.randint(0, NCLS, (B,), generator=gx).pin_memory()
+    y_host = torch.randint(0, NCLS, (B,), generator=gx).to(torch.int32).pin_memory()
     out_host = torch.empty((B, *SHAPE)).pin_memory()
     eng = bnn.engine()
     prec = args.prec
@@ -236,10 +304,16 @@ def main():
         gsum *= 1.0 / S
         return gsum
 
+    io_lo, io_hi, _ = rdist.row_block(B, rank, world)
+
     def step_e2e():
+        # public API, host buffers in / host buffers out.  One rank: H2D of all inputs, D2H of all gradients.  N ranks: every
+        # rank copies ITS block of input rows over PCIe (the blocks are all-gathered over NVLink), the [B, 784] partial
+        # sums are reduce-scattered and every rank reads back its block of the result -- the job as a whole moves the
+        # same bytes as one rank does, instead of N times as many (round 1: 0.65 efficiency at 8 GPUs)
         bnn._reset_rows()                                            # no cached posterior samples: re-drawn every step
-        gr = lg.expected_loss_gradients(bnn, x_host, y_host, S)     # public API: H2D inside
-        out_host.copy_(gr, non_blocking=True)                        # D2H read of the result
+        blk, (lo, hi) = lg.expected_loss_gradients_block(bnn, x_host, y_host, S)
+        out_host[lo:hi].copy_(blk, non_blocking=True)                # D2H read of this rank's rows of the result
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -315,8 +389,38 @@ def main():
                                       "MAC, so the ceiling of this fp32-accurate mode is 1/3 of the bf16/fp16 peak (0.333)"
                              }.get(prec)}
 
-    # ---- secondary numbers (not the headline): bf16 throughput mode + its deviation, PGD images/s ------------
+    # ---- secondary numbers (not the headline) ---------------------------------------------------------------------
     extra = {}
+    import contextlib
+    import io
+    from robustbnns_b200 import adversarialAttacks as aa
+
+    def attack_ms(method, n_img, n_s, iters, hyper=None, reps=1):
+        """Wall time (device events, max over ranks) of attack_all on the first n_img inputs: every rank attacks its
+        block of the images with all n_s fresh posterior samples per gradient evaluation, blocks all-gathered at the end."""
+        xa, ya = x_dev[:n_img].contiguous(), y_dev[:n_img].to(torch.int64)
+        bnn.reseed(0)
+        aa.attack_all(bnn, xa, ya, method, hyperparams=hyper, n_samples=n_s, iters=2)          # warm-up (allocations)
+        bnn.reseed(0)
+        t, _ = timed(lambda: aa.attack_all(bnn, xa, ya, method, hyperparams=hyper, n_samples=n_s, iters=iters), reps)
+        return t / reps
+
+    if not args.no_extra and prec in ("tf32x3", "f16x3"):
+        try:
+            # BASELINE configs[2] shape: 1000 inputs, 20-step PGD, 100 posterior samples -- at EVERY world size
+            n_img, n_s, iters = 1000, 100, 20
+            pms = attack_ms("pgd", n_img, n_s, iters)
+            fms = attack_ms("fgsm", n_img, n_s, 1, hyper={"epsilon": 0.3}, reps=3)
+            extra["pgd"] = {"value": n_img / (pms * 1e-3), "unit": "imgs/s", "images": n_img, "posterior_samples": n_s,
+                            "iters": iters, "ms": pms, "n_gpus": world,
+                            "sharding": "inputs (every rank draws the same Philox samples and attacks its block of the "
+                                        "images; one all-gather at the end)" if world > 1 else "single GPU",
+                            "note": "Bayesian PGD (eps 0.5, alpha 2/225), fresh SVI samples per iteration as upstream, "
+                                    "no host round-trip between iterations"}
+            extra["fgsm"] = {"value": n_img / (fms * 1e-3), "unit": "imgs/s", "images": n_img, "posterior_samples": n_s,
+                             "ms": fms, "n_gpus": world, "note": "Bayesian FGSM, eps 0.3 (plot_baseline_attacks.py:65-66)"}
+        except Exception as e:
+            log("PGD / FGSM measurement failed:", e)
     if rank == 0 and world == 1 and not args.no_extra and prec in ("tf32x3", "f16x3"):
         ref_g = step_resident().clone()
         for other in [m for m in ("f16x3", "tf32x3", "bf16") if m != prec]:
@@ -339,6 +443,54 @@ def main():
         eng.set_precision(prec)
         step_resident()
         try:
+            # Library GPU baseline (SURVEY 8d / BASELINE.md 3.3): the same step in stock PyTorch eager on this B200 --
+            # torch.randn samples, bmm over a chunk of samples, autograd for the input gradient, fp32 (TF32 off) and
+            # TF32 (cuBLAS tensor cores, NOT parity grade).  The hand-written path is compared with cuBLAS-backed
+            # PyTorch here, not only with the CPU.
+            import torch.nn.functional as F
+            P, Hh, Dd, Cc = eng.P, HIDDEN, 784, NCLS
+            xf = x_dev.reshape(B, Dd)
+            yl = y_dev.to(torch.int64)
+            sig = F.softplus(bnn._rho)
+
+            def lib_step(n_s, chunk=20):
+                xg = xf.clone().requires_grad_(True)
+                for s0 in range(0, n_s, chunk):
+                    z = min(chunk, n_s - s0)
+                    w = bnn._loc + sig * torch.randn((z, P), device=dev)
+                    w1 = w[:, :Hh * Dd].view(z, Hh, Dd)
+                    b1 = w[:, Hh * Dd:Hh * Dd + Hh]
+                    wo = w[:, Hh * Dd + Hh:Hh * Dd + Hh + Cc * Hh].view(z, Cc, Hh)
+                    bo = w[:, Hh * Dd + Hh + Cc * Hh:]
+                    h = F.leaky_relu(torch.baddbmm(b1[:, None, :], xg.expand(z, B, Dd), w1.transpose(1, 2)))
+                    probs = torch.softmax(torch.baddbmm(bo[:, None, :], h, wo.transpose(1, 2)), -1)
+                    loss = F.cross_entropy(probs.reshape(z * B, Cc), yl.repeat(z), reduction="sum")   # CE of the probabilities
+                    loss.backward()
+                return xg.grad / n_s
+            lib = {}
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                n_lib = 200 if not tf32 else 1000
+                lib_step(40)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                lib_step(n_lib)
+                e1.record()
+                torch.cuda.synchronize()
+                lms = e0.elapsed_time(e1) * (S / n_lib)
+                lib[name] = {"ms_per_step": lms, "value": float(B) * S / (lms * 1e-3), "unit": UNIT,
+                             "posterior_samples_timed": n_lib,
+                             "speedup_of_this_repo": (float(B) * S / (lms * 1e-3)) and value / (float(B) * S / (lms * 1e-3))}
+            torch.backends.cuda.matmul.allow_tf32 = False
+            lib["note"] = ("stock PyTorch %s eager on the same GPU and workload: torch.randn posterior samples, baddbmm over "
+                           "chunks of 20 samples, autograd input gradient; fp32 = cuBLAS SGEMM (the parity-class library "
+                           "path), tf32 = cuBLAS tensor cores with 10-bit mantissas (not parity grade); timed on a subset "
+                           "of the samples and scaled (cost is linear in samples)" % torch.__version__)
+            extra["library_gpu_baseline"] = lib
+        except Exception as e:
+            log("library GPU baseline failed:", e)
+        try:
             # K-sample alone (HBM-bound side of the path): this rank's samples -> bank rows (+ the fp16 operand copies
             # when the engine writes them in the same pass), achieved bytes/s against the measured HBM copy rate
             torch.cuda.synchronize()
@@ -360,80 +512,110 @@ def main():
         except Exception as e:
             log("sampler measurement failed:", e)
         try:
-            from robustbnns_b200 import adversarialAttacks as aa
-            n_img, n_s, iters = 1000, 100, 20          # BASELINE configs[2] shape: 1000 inputs, 20-step PGD
+            # BASELINE configs[2]: FGSM + 20-step PGD + evaluation over 1 / 10 / 100 / 1000 posterior samples on 1000 inputs
+            # (plot_baseline_attacks.py:65-66, :206)
+            sweep = []
+            n_img = 1000
             xa, ya = x_dev[:n_img].contiguous(), y_dev[:n_img].to(torch.int64)
-            bnn.reseed(0)
-            aa.pgd_attack(bnn, xa, ya, hyperparams=None, n_samples=n_s, iters=2)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            aa.pgd_attack(bnn, xa, ya, hyperparams=None, n_samples=n_s, iters=iters)
-            e1.record()
-            torch.cuda.synchronize()
-            pms = e0.elapsed_time(e1)
-            extra["pgd"] = {"value": n_img / (pms * 1e-3), "unit": "imgs/s", "images": n_img, "posterior_samples": n_s,
-                            "iters": iters, "ms": pms, "note": "Bayesian PGD (eps 0.5, alpha 2/225), fresh SVI samples "
-                            "per iteration as upstream, no host round-trip between iterations"}
+            y1h = torch.nn.functional.one_hot(ya, NCLS).float()
+            for n_s in (1, 10, 100, 1000):
+                fms = attack_ms("fgsm", n_img, n_s, 1, hyper={"epsilon": 0.3}, reps=3)
+                pms = attack_ms("pgd", n_img, n_s, 20)
+                bnn.reseed(0)
+                adv = aa.attack_all(bnn, xa, ya, "fgsm", hyperparams={"epsilon": 0.3}, n_samples=n_s)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    aa.attack_evaluation(bnn, xa, adv, y1h, dev, n_samples=n_s)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    oa, ad, rob = aa.attack_evaluation(bnn, xa, adv, y1h, dev, n_samples=n_s)
+                    torch.cuda.synchronize()
+                    ems = 1e3 * (time.perf_counter() - t0)
+                sweep.append({"posterior_samples": n_s, "fgsm_ms": fms, "fgsm_imgs_per_s": n_img / (fms * 1e-3),
+                              "pgd20_ms": pms, "pgd20_imgs_per_s": n_img / (pms * 1e-3), "evaluation_ms": ems,
+                              "softmax_robustness_mean": float(rob.mean())})
+            extra["attack_sweep"] = {"images": n_img, "rows": sweep,
+                                     "note": "Bayesian FGSM (eps 0.3), 20-step PGD (eps 0.5, alpha 2/225) and "
+                                             "attack_evaluation (clean + adversarial forward in batches of 128, counts, "
+                                             "softmax robustness; wall clock with its host reads) per number of samples"}
         except Exception as e:
-            log("PGD measurement failed:", e)
+            log("attack sweep failed:", e)
         try:
-            # BASELINE configs[3] shape: conv-512 BNN, 100 F-MNIST-shaped inputs, 50 stored (HMC-like) posterior samples
-            from robustbnns_b200 import adversarialAttacks as aa
-            n_img, n_s, hid = 100, 50, 512
-            cb = BNN("fashion_mnist", hid, "leaky", "conv", "hmc", None, None, n_s, 5, SHAPE, NCLS)
-            gc = torch.Generator().manual_seed(2)
-            cols = []
-            for key, shp in cb.basenet.layout:
-                n = 1
-                for v in shp:
-                    n *= v
-                fan_c = n // shp[0] if len(shp) > 1 else 25
-                cols.append(torch.randn((n_s, n), generator=gc) / math.sqrt(fan_c))
-            cb.set_posterior_samples(torch.cat(cols, dim=1))
-            cb.set_precision("f16x3")
-            xc, yc = x_dev[:n_img].contiguous(), y_dev[:n_img].to(torch.int64)
-            lg.expected_loss_gradients(cb, xc, yc, n_s)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
+            # BASELINE configs[3] shape: conv BNN, 100 F-MNIST-shaped inputs, 50 stored (HMC-like) posterior samples,
+            # hidden 512 and 1024 (model_bnn.py:41-49), PGD over the eps list of plot_eps_attacks.py:89-90
+            rows_c = []
+            for hid in (512, 1024):
+                n_img, n_s = 100, 50
+                cb = BNN("fashion_mnist", hid, "leaky", "conv", "hmc", None, None, n_s, 5, SHAPE, NCLS)
+                gc = torch.Generator().manual_seed(2)
+                cols = []
+                for key, shp in cb.basenet.layout:
+                    n = 1
+                    for v in shp:
+                        n *= v
+                    fan_c = n // shp[0] if len(shp) > 1 else 25
+                    cols.append(torch.randn((n_s, n), generator=gc) / math.sqrt(fan_c))
+                cb.set_posterior_samples(torch.cat(cols, dim=1))
+                cb.set_precision("f16x3")
+                xc, yc = x_dev[:n_img].contiguous(), y_dev[:n_img].to(torch.int64)
                 lg.expected_loss_gradients(cb, xc, yc, n_s)
-            e1.record()
-            torch.cuda.synchronize()
-            gms = e0.elapsed_time(e1) / 5
-            aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=1)
-            torch.cuda.synchronize()
-            e0.record()
-            aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=4)
-            e1.record()
-            torch.cuda.synchronize()
-            pit = e0.elapsed_time(e1) / 4
-            extra["conv_cfg4"] = {"grads_per_s": n_img * n_s / (gms * 1e-3), "grad_ms": gms,
-                                  "tflops_algorithmic": n_img * n_s * 107704320 / (gms * 1e-3) / 1e12,
-                                  "pgd_ms_per_iter": pit, "pgd40_imgs_per_s": n_img / (pit * 40e-3), "engine": "f16x3",
-                                  "note": "conv-512 BNN (107.7 MFLOP per sample x input), 100 inputs x 50 stored samples: "
-                                          "conv2 as a tcgen05 implicit GEMM over 5-D TMA boxes, dgrad as a tcgen05 GEMM"}
-            del cb
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    lg.expected_loss_gradients(cb, xc, yc, n_s)
+                e1.record()
+                torch.cuda.synchronize()
+                gms = e0.elapsed_time(e1) / 5
+                flop_unit = 107704320 if hid == 512 else 213565440
+                per_eps = {}
+                for eps in (0.1, 0.15, 0.2, 0.25, 0.3):
+                    aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": eps}, n_samples=n_s, iters=1)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": eps}, n_samples=n_s, iters=4)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    per_eps[str(eps)] = e0.elapsed_time(e1) / 4
+                pit = sum(per_eps.values()) / len(per_eps)
+                rows_c.append({"hidden": hid, "grads_per_s": n_img * n_s / (gms * 1e-3), "grad_ms": gms,
+                               "tflops_algorithmic": n_img * n_s * flop_unit / (gms * 1e-3) / 1e12,
+                               "pgd_ms_per_iter": pit, "pgd_ms_per_iter_by_eps": per_eps,
+                               "pgd40_imgs_per_s": n_img / (pit * 40e-3)})
+                del cb
+            extra["conv_cfg4"] = dict(rows_c[0], engine="f16x3", hidden_1024=rows_c[1],
+                                      note="conv BNN (107.7 / 213.6 MFLOP per sample x input at hidden 512 / 1024), 100 "
+                                           "inputs x 50 stored samples: conv2 as a tcgen05 implicit GEMM over 5-D TMA "
+                                           "boxes, dgrad as a tcgen05 GEMM; PGD per-iteration time over the reference's "
+                                           "eps list")
         except Exception as e:
             log("conv measurement failed:", e)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_img, n_samp = 32, 96
-        v, dt = reference_units_per_s(n_img, n_samp)
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d inputs x %d samples of the same workload in the reference's loop order "
-                         "(%.1f s; cost is linear in inputs x samples)" % (n_img, n_samp, dt)}
+        n_img, n_samp = 32, 64
+        v, dt, kind = reference_units_per_s(n_img, n_samp)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": "%d inputs x %d samples of the same workload, %s (%.1f s; cost is linear in inputs x samples)"
+                         % (n_img, n_samp, "the reference's own lossGradients.loss_gradients (oracle/_ref + pyro shim)"
+                            if kind == "reference" else "oracle port of the reference's loop order", dt)}
 
     if rank == 0:
+        if roofline is not None:
+            roofline["gap_to_target"] = {
+                "target_frac_of_bf16_peak": 0.60, "whole_step_frac": value * FLOP_PER_UNIT / world / 1e12 / pk["bf16_tflops_sustained"],
+                "note": "the north star asks for >= 0.60 of the dense bf16 peak AND rel <= 1e-4; the parity-grade engine "
+                        "issues 3 tensor-core MACs per algorithmic MAC, so its ceiling is 0.333 -- the 0.60 target is out "
+                        "of reach for any fp32-accurate mode on this hardware; the single-pass bf16 mode (bf16_mode) shows "
+                        "what the same kernels reach without the accuracy"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32" if prec != "bf16" else "bf16",
                 "data": "synthetic", "config": config_dict(args, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                        "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
-                        "d2h_bytes_per_step": int(out_host.numel() * 4)},
+                        "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
+                        "d2h_bytes_per_step": int(out_host.numel() * 4),
+                        "io": "whole-job bytes; with N ranks each rank moves 1/N of them over its own PCIe link (input "
+                              "rows all-gathered over NVLink, gradient sums reduce-scattered)"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "engine": prec}
         line.update(extra)

@@ -95,6 +95,23 @@ RBNN_API int rbnn_bank_upload(rbnn_net* net, const float* weights, int s0, int c
  * `seed` (independent of how samples are sharded over GPUs). d_loc/d_rho: [P] device fp32. */
 RBNN_API int rbnn_bank_sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed,
                           int64_t sample_index0, int64_t sample_index_stride, int s0, int count, void* stream);
+/* The same draw with a DEVICE-resident addend: row s0+i uses global sample index sample_index0 + *d_index_offset +
+ * i*sample_index_stride, *d_index_offset being read when the kernel runs (NULL = 0).  This is what lets one captured
+ * CUDA graph of a PGD iteration draw FRESH posterior samples on every replay, as the reference's attacks do
+ * (adversarialAttacks.py:95-105 calls net.forward, i.e. a new guide draw, model_bnn.py:230-232, in every iteration): the
+ * caller advances the device counter between replays. */
+RBNN_API int rbnn_bank_sample_diag_at(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed,
+                             int64_t sample_index0, int64_t sample_index_stride, int s0, int count,
+                             const int64_t* d_index_offset, void* stream);
+/* A NEW posterior is about to be installed in this handle (other guide parameters / another stored bank; BNN.load,
+ * model_bnn.py:167-196): forget what was derived from the old weights -- the frozen power-of-two operand scale of the
+ * F16X3 engine, the kernel-ready copies, the kept forward.  Synchronous.  Uploads and draws that follow fix a new scale
+ * from the rows they touch (a range overflow under a frozen scale is otherwise caught and repaired inside the call that
+ * re-lays the rows). */
+RBNN_API int rbnn_bank_invalidate(rbnn_net* net);
+/* Counter bumped whenever a device buffer owned by the handle is (re)allocated.  A CUDA graph captured over calls on
+ * this handle must be re-captured when the value has changed (its nodes hold the old addresses). */
+RBNN_API int64_t rbnn_net_alloc_epoch(const rbnn_net* net);
 /* Copy rows [s0, s0+count) back to host (synchronous; test support). */
 RBNN_API int rbnn_bank_download(rbnn_net* net, float* h_out, int s0, int count);
 

@@ -36,6 +36,9 @@ SIGNATURES = {
     "rbnn_bank_capacity": (_i, [_p]),
     "rbnn_bank_upload": (_i, [_p, _p, _i, _i, _i, _p]),
     "rbnn_bank_sample_diag": (_i, [_p, _p, _p, _u64, _i64, _i64, _i, _i, _p]),
+    "rbnn_bank_sample_diag_at": (_i, [_p, _p, _p, _u64, _i64, _i64, _i, _i, _p, _p]),
+    "rbnn_bank_invalidate": (_i, [_p]),
+    "rbnn_net_alloc_epoch": (_i64, [_p]),
     "rbnn_bank_download": (_i, [_p, _p, _i, _i]),
     "rbnn_forward_probs_sum": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "rbnn_forward_probs_sum_keep": (_i, [_p, _p, _i, _i, _i, _p, _p]),

@@ -11,6 +11,7 @@ one batched device pass per gradient evaluation:
 with no host synchronisation between iterations of PGD.  Other network types
 (duck-typed `forward` returning logits) take the reference's generic autograd route.
 """
+import os
 import random
 
 import torch
@@ -169,27 +170,111 @@ def pgd_attack(net, image, label, hyperparams=None, n_samples=None, avg_posterio
     return _pgd_loop(net, x0, x0, y, alpha, epsilon, n_samples, avg_posterior, iters)
 
 
-def _pgd_loop(net, x, x0, y, alpha, epsilon, n_samples, avg_posterior, iters):
-    """`iters` PGD updates of `x` inside the eps-ball around `x0` (adversarialAttacks.py:95-105); all
-    launches are enqueued back to back, nothing is read back between iterations."""
+PGD_GRAPH = os.environ.get("RBNN_PGD_GRAPH", "1") != "0"    # replay PGD iterations as ONE captured CUDA graph
+PGD_GRAPH_MIN_ITERS = 4
+
+
+def _pgd_iteration(net, x, x0, y, alpha, epsilon, n_samples, avg_posterior):
     B = x0.shape[0]
+    g = _bnn_input_grad(net, x, y, n_samples, avg_posterior)
+    return net.engine().pgd_step(x.reshape(B, -1), x0.reshape(B, -1), g.reshape(B, -1), alpha, epsilon).reshape(x0.shape)
+
+
+def _pgd_loop(net, x, x0, y, alpha, epsilon, n_samples, avg_posterior, iters):
+    """`iters` PGD updates of `x` inside the eps-ball around `x0` (adversarialAttacks.py:95-105); nothing is read back
+    between iterations.  On one device (or inside `dist.replicated()`, where no collective is needed) an iteration --
+    K-sample of the fresh posterior draws, kept forward, loss head, input-gradient GEMM, sign / step / project / clip --
+    is captured ONCE as a CUDA graph and replayed: one launch per iteration instead of ~20, and the fresh draws of
+    every replay come from a device-resident sample counter, so the result is bit-identical to the eager loop."""
+    if _graph_eligible(net, x, iters, avg_posterior):
+        return _pgd_loop_graph(net, x, x0, y, alpha, epsilon, n_samples, iters)
     for _ in range(iters):
-        g = _bnn_input_grad(net, x, y, n_samples, avg_posterior)
-        x = net.engine().pgd_step(x.reshape(B, -1), x0.reshape(B, -1), g.reshape(B, -1), alpha, epsilon).reshape(x0.shape)
+        x = _pgd_iteration(net, x, x0, y, alpha, epsilon, n_samples, avg_posterior)
     return x
+
+
+def _graph_eligible(net, x, iters, avg_posterior):
+    if not PGD_GRAPH or iters < PGD_GRAPH_MIN_ITERS or avg_posterior or not x.is_cuda:
+        return False
+    eng = net.engine()
+    if not hasattr(eng, "alloc_epoch") or rdist.world()[1] != 1:       # sample sharding all-reduces inside an iteration
+        return False
+    if getattr(net, "_pgd_graph_disabled", False):
+        return False
+    return not torch.cuda.is_current_stream_capturing()
+
+
+class _PgdGraph(object):
+    __slots__ = ("graph", "x", "x0", "y", "alpha", "offset", "counter0", "epoch", "fresh")
+
+
+def _pgd_loop_graph(net, x, x0, y, alpha, epsilon, n_samples, iters):
+    eng = net.engine()
+    n = 10 if n_samples is None else int(n_samples)
+    fresh = net._bank_host is None                    # SVI: every iteration draws n new samples (model_bnn.py:230-232)
+    key = (tuple(x0.shape), n, float(epsilon), eng.precision, net._posterior_generation, net._fresh_key, net._pin_cap,
+           str(x0.device))
+    ent = net._pgd_graphs.get(key)
+    done = 0
+    if ent is None or ent.epoch != eng.alloc_epoch:
+        # one eager iteration first: it sizes every workspace of the engine (no allocation may happen during capture)
+        x = _pgd_iteration(net, x, x0, y, alpha, epsilon, n_samples, False)
+        done = 1
+        ent = _PgdGraph()
+        ent.x, ent.x0, ent.y, ent.alpha = x.clone(), x0.clone(), y.clone(), alpha.clone()
+        ent.offset = torch.zeros((1,), dtype=torch.int64, device=x0.device)
+        ent.fresh = fresh
+        ent.counter0 = net._fresh_counter
+        ent.graph = torch.cuda.CUDAGraph()
+        gen0 = net._scratch_generation
+        net._graph_offset = ent.offset if fresh else None
+        failed = None
+        try:
+            with torch.cuda.graph(ent.graph):
+                xn = _pgd_iteration(net, ent.x, ent.x0, ent.y, ent.alpha, epsilon, n_samples, False)
+                ent.x.copy_(xn)
+                if fresh:
+                    ent.offset.add_(n)
+        except Exception as e:                       # capture refused (driver / library state): stay on the eager loop
+            failed = e
+        finally:
+            net._graph_offset = None
+            net._fresh_counter = ent.counter0        # the captured iteration has not run
+            net._scratch_generation = gen0 + 1
+        if failed is not None:
+            import warnings
+            warnings.warn("robustbnns_b200: CUDA-graph capture of the PGD iteration failed (%s); using the eager loop" % failed)
+            net._pgd_graph_disabled = True
+            for _ in range(iters - done):
+                x = _pgd_iteration(net, x, x0, y, alpha, epsilon, n_samples, False)
+            return x
+        ent.epoch = eng.alloc_epoch
+        if len(net._pgd_graphs) >= 8:
+            net._pgd_graphs.clear()
+        net._pgd_graphs[key] = ent
+    ent.x.copy_(x)
+    ent.x0.copy_(x0)
+    ent.y.copy_(y)
+    ent.alpha.copy_(alpha)
+    if ent.fresh:
+        ent.offset.fill_(net._fresh_counter - ent.counter0)
+    for _ in range(iters - done):
+        ent.graph.replay()
+    if ent.fresh:
+        net._fresh_counter += n * (iters - done)
+    net._scratch_generation += 1
+    return ent.x.clone()
 
 
 ATTACK_BATCH = 8192     # images per device pass
 
 
-def attack(net, x_test, y_test, dataset_name, device, method, filename, savedir=None,
-           hyperparams=None, n_samples=None, avg_posterior=False):
-    """All test points at once (adversarialAttacks.py:111-143); returns [N, ch, h, w] on the device.
+def attack_all(net, x_test, labels, method, device=None, hyperparams=None, n_samples=None, avg_posterior=False,
+               iters=PGD_ITERS):
+    """The device part of `attack`: adversarial examples [N, ch, h, w] for all test points (`labels` are class indices).
     Multi-GPU (torch.distributed initialised, BNN with attack_sharding == "inputs", the default): every rank draws the
     same posterior samples (global Philox indices), attacks its own block of the test points without any collective,
     and the blocks are all-gathered at the end -- identical to the single-GPU result."""
-    print(f"\nProducing {method} attacks on {dataset_name}:")
-    labels = torch.as_tensor(y_test).argmax(-1)
     rank, world = rdist.real_world()
     shard_inputs = isinstance(net, BNN) and world > 1 and getattr(net, "attack_sharding", "inputs") == "inputs"
     n_total = len(x_test)
@@ -211,28 +296,57 @@ def attack(net, x_test, y_test, dataset_name, device, method, filename, savedir=
                                               n_samples=n_samples, avg_posterior=avg_posterior)
             elif method == "pgd":
                 perturbed_image = pgd_attack(net=net, image=image, label=label, hyperparams=hyperparams,
-                                             n_samples=n_samples, avg_posterior=avg_posterior)
+                                             n_samples=n_samples, avg_posterior=avg_posterior, iters=iters)
             out.append(perturbed_image)
         return out
 
-    if shard_inputs:
+    if not shard_inputs:
+        return torch.cat(run(0, n_total))
+    # The fresh-draw counter advances once per gradient evaluation of a device pass.  Ranks attack blocks of different
+    # sizes (possibly none), so afterwards every rank is put where ONE process attacking all N points would be:
+    # later sample-sharded calls then draw from the same global Philox indices on every rank.
+    counter0 = getattr(net, "_fresh_counter", 0)
+    try:
         with rdist.replicated():
             net._replace_rows()                      # every rank holds all the samples while it attacks its block
             parts = run(lo, hi)
-        net._replace_rows()                          # back to sample sharding
-        eng = net.engine()
-        shape = tuple(torch.as_tensor(x_test).shape[1:])
-        local = torch.cat(parts) if parts else torch.zeros((0,) + shape, dtype=torch.float32, device=eng.device)
-        adversarial_attack = rdist.all_gather_rows(local.reshape((-1,) + shape), per, n_total)
-    else:
-        adversarial_attack = torch.cat(run(0, n_total))
+            advance = (net._fresh_counter - counter0) if hi > lo else None
+    finally:
+        net._replace_rows()                          # back to sample sharding, also when the attack raised
+    if hasattr(net, "_fresh_counter"):
+        passes_local = max(1, -(-(hi - lo) // ATTACK_BATCH)) if hi > lo else 0
+        passes_all = -(-n_total // ATTACK_BATCH)
+        if advance is None:                          # this rank had no test points: learn the per-pass advance from rank 0
+            advance, passes_local = 0, 1
+        per_pass = torch.tensor([advance // max(1, passes_local)], dtype=torch.int64, device=net.engine().device)
+        if world > 1:
+            import torch.distributed as dist
+            dist.broadcast(per_pass, src=0)
+        net._fresh_counter = counter0 + int(per_pass.item()) * passes_all
+    eng = net.engine()
+    shape = tuple(torch.as_tensor(x_test).shape[1:])
+    local = torch.cat(parts) if parts else torch.zeros((0,) + shape, dtype=torch.float32, device=eng.device)
+    return rdist.all_gather_rows(local.reshape((-1,) + shape), per, n_total)
 
+
+def attack(net, x_test, y_test, dataset_name, device, method, filename, savedir=None,
+           hyperparams=None, n_samples=None, avg_posterior=False):
+    """All test points at once (adversarialAttacks.py:111-143); returns [N, ch, h, w] on the device (see `attack_all`
+    for the multi-GPU form).  The result pickle is written by rank 0 only."""
+    print(f"\nProducing {method} attacks on {dataset_name}:")
+    labels = torch.as_tensor(y_test).argmax(-1)
+    adversarial_attack = attack_all(net, x_test, labels, method, device=device, hyperparams=hyperparams,
+                                    n_samples=n_samples, avg_posterior=avg_posterior)
     path = TESTS + filename + "/" if savedir is None else TESTS + savedir + "/"
     name = filename + "_" + str(method)
     # (the reference also writes two PNG grids here through matplotlib, utils.py:276-290: plotting is out of scope)
     name = name + "_attackSamp=" + str(n_samples) + "_attack.pkl" if n_samples else name + "_attack.pkl"
-    if rank == 0 or not shard_inputs:
+    rank, world = rdist.real_world()
+    if rank == 0:
         save_to_pickle(data=adversarial_attack, path=path, filename=name)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()                               # nobody reads the file before rank 0 has written it
     return adversarial_attack
 
 

@@ -46,6 +46,7 @@ int ws_reserve(rbnn_net* net, size_t bytes) {
   }
   RBNN_CUDA(cudaMalloc(&net->ws, bytes));
   net->ws_bytes = bytes;
+  net->alloc_epoch++;
   return 0;
 }
 
@@ -451,6 +452,7 @@ int rbnn_bank_reserve(rbnn_net* n, int capacity) {
     n->woutp = nw;
   }
   n->capacity = capacity;
+  n->alloc_epoch++;
   return 0;
 }
 
@@ -476,6 +478,20 @@ int rbnn_bank_upload(rbnn_net* n, const float* weights, int s0, int count, int i
 
 int rbnn_bank_sample_diag(rbnn_net* n, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
                           int64_t sample_index_stride, int s0, int count, void* stream) {
+  return rbnn_bank_sample_diag_at(n, d_loc, d_rho, seed, sample_index0, sample_index_stride, s0, count, nullptr, stream);
+}
+
+int rbnn_bank_invalidate(rbnn_net* n) {
+  RBNN_CHECK(n != nullptr, "null net handle");
+  DeviceGuard dg(n->device);
+  return tc_bank_invalidate(n);
+}
+
+int64_t rbnn_net_alloc_epoch(const rbnn_net* n) { return n ? n->alloc_epoch : -1; }
+
+int rbnn_bank_sample_diag_at(rbnn_net* n, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
+                             int64_t sample_index_stride, int s0, int count, const int64_t* d_index_offset,
+                             void* stream) {
   RBNN_TRY(check_rows(n, s0, s0 + count));
   RBNN_CHECK(sample_index_stride >= 1, "sample_index_stride must be >= 1");
   RBNN_CHECK(sample_index0 >= 0 && sample_index0 + (int64_t)count * sample_index_stride <= 0xFFFFFFFFLL,
@@ -489,12 +505,12 @@ int rbnn_bank_sample_diag(rbnn_net* n, const float* d_loc, const float* d_rho, u
     const int r0 = s0 + c0;
     const int64_t idx0 = sample_index0 + (int64_t)c0 * sample_index_stride;
     int fused = 0;      // F16X3 / arch fc with a fixed weight scale: bank rows and operand copies in one pass
-    RBNN_TRY(tc_sample_relayout_f16(n, d_loc, d_rho, seed, idx0, sample_index_stride, r0, cnt, st, &fused));
+    RBNN_TRY(tc_sample_relayout_f16(n, d_loc, d_rho, seed, idx0, sample_index_stride, r0, cnt, st, &fused, d_index_offset));
     if (fused) {
       if (n->keep.valid && r0 < n->keep.s1 && r0 + cnt > n->keep.s0) n->keep.valid = 0;
       continue;
     }
-    RBNN_TRY(sample_diag(n, d_loc, d_rho, seed, idx0, sample_index_stride, r0, cnt, st));
+    RBNN_TRY(sample_diag(n, d_loc, d_rho, seed, idx0, sample_index_stride, r0, cnt, st, d_index_offset));
     RBNN_TRY(conv_permute_wout(n, r0, cnt, st));
     mark_dirty(n, r0, cnt);
   }

@@ -153,11 +153,31 @@ int add_inplace(rbnn_net* net, float* dst, const float* src, int64_t n, cudaStre
 
 using namespace rbnn;
 
+// The stateless entry points have no handle: they launch on the device that OWNS the buffers (the caller's current
+// device may be another one), restoring the caller's device afterwards.
+namespace {
+struct PtrDeviceGuard {
+  int prev = -1;
+  explicit PtrDeviceGuard(const void* p) {
+    cudaPointerAttributes a;
+    if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) {
+      int cur = -1;
+      cudaGetDevice(&cur);
+      if (cur != a.device) { prev = cur; cudaSetDevice(a.device); }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  ~PtrDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
 extern "C" int rbnn_fgsm_step(const float* d_x, const float* d_grad, float eps, float* d_out, int64_t n,
                               void* stream) {
   if (n <= 0) return 0;
   RBNN_CHECK(((uintptr_t)d_x | (uintptr_t)d_grad | (uintptr_t)d_out) % 16 == 0, "fgsm_step: buffers must be 16-byte aligned");
   const int64_t n4 = (n + 3) / 4;
+  PtrDeviceGuard dg(d_x);
   fgsm_step_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_grad, eps, d_out, n);
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -167,6 +187,7 @@ extern "C" int rbnn_pgd_step(const float* d_x, const float* d_x0, const float* d
                              float eps, float* d_out, int B, int D, void* stream) {
   const int64_t n = (int64_t)B * D;
   if (n <= 0) return 0;
+  PtrDeviceGuard dg(d_x);
   pgd_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_x0, d_grad, d_alpha, eps,
                                                                                 d_out, B, D);
   RBNN_CUDA(cudaGetLastError());
@@ -175,6 +196,7 @@ extern "C" int rbnn_pgd_step(const float* d_x, const float* d_x0, const float* d
 
 extern "C" int rbnn_pgd_alpha(const float* d_x, float* d_alpha, int B, int D, void* stream) {
   if (B <= 0) return 0;
+  PtrDeviceGuard dg(d_x);
   pgd_alpha_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(d_x, d_alpha, D);
   RBNN_CUDA(cudaGetLastError());
   return 0;
@@ -184,6 +206,7 @@ extern "C" int rbnn_softmax_robustness(const float* d_o0, const float* d_o1, int
                                        float* d_minmax, void* stream) {
   RBNN_CHECK(C >= 1 && C <= 32, "softmax_robustness: n_classes %d not in [1,32]", C);
   cudaStream_t st = (cudaStream_t)stream;
+  PtrDeviceGuard dg(d_minmax);
   minmax_init_kernel<<<1, 1, 0, st>>>(d_minmax);
   if (N > 0) {
     if (C <= 16)
@@ -200,6 +223,7 @@ extern "C" int rbnn_count_correct(const float* d_out, const int32_t* d_labels, i
   RBNN_CHECK(C >= 1 && C <= 32, "count_correct: n_classes %d not in [1,32]", C);
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  PtrDeviceGuard dg(d_out);
   if (C <= 16)
     count_correct_kernel<16><<<(N + 127) / 128, 128, 0, st>>>(d_out, d_labels, N, C, (unsigned long long*)d_count);
   else

@@ -115,6 +115,8 @@ struct rbnn_net {
   size_t ws_bytes = 0;
   size_t ws_budget = (size_t)12 << 30;   // upper bound of the activation workspace (HBM is 180 GB)
   int64_t launches = 0;
+  int64_t alloc_epoch = 0;    // bumped whenever a device buffer of this handle is (re)allocated: captured CUDA graphs of
+                              // earlier launches hold stale pointers afterwards (rbnn_net_alloc_epoch)
   int sm_count = 148;
   int cc_major = 0;           // compute capability major of `device` (10 = Blackwell: tcgen05 engine usable)
   TcBank tc;
@@ -173,11 +175,14 @@ int head_dlogits(rbnn_net* net, int head, const float* logits, const int32_t* la
                  int Z, int B, int C, float* dlogits, cudaStream_t st);
 
 // ---- sampler.cu -------------------------------------------------------------------------
+// d_index_offset (may be nullptr): device int64 added to every sample index when the kernel RUNS -- lets a captured
+// CUDA graph draw fresh samples on every replay (the caller advances the device counter between replays)
 int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
-                int64_t stride, int s0, int count, cudaStream_t st);
+                int64_t stride, int s0, int count, cudaStream_t st, const int64_t* d_index_offset = nullptr);
 int sample_sigma(rbnn_net* net, const float* d_rho, cudaStream_t st);      // net->sigma = softplus(rho)
 int sample_diag_from(rbnn_net* net, const float* d_loc, uint64_t seed, int64_t sample_index0, int64_t stride, int s0,
-                     int count, int64_t elem0, cudaStream_t st);            // elements [elem0, P) of the rows
+                     int count, int64_t elem0, cudaStream_t st,             // elements [elem0, P) of the rows
+                     const int64_t* d_index_offset = nullptr);
 int conv_permute_wout(rbnn_net* net, int s0, int count, cudaStream_t st);
 inline int conv_class_pitch(int C) { return C <= 4 ? 4 : (C <= 12 ? 12 : (C <= 16 ? 16 : 32)); }
 
@@ -228,7 +233,10 @@ int tc_bank_refresh(rbnn_net* net, int s0, int s1, cudaStream_t st);
 // writes the bank AND the fp16 hi/lo operand copies of W1 in one pass.  Returns 0 and sets *done = 1 when it ran;
 // *done = 0 means "not applicable, use sample_diag + the lazy refresh".
 int tc_sample_relayout_f16(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
-                           int64_t stride, int s0, int count, cudaStream_t st, int* done);
+                           int64_t stride, int s0, int count, cudaStream_t st, int* done,
+                           const int64_t* d_index_offset = nullptr);
+// a new posterior is being installed: forget the frozen F16X3 operand scale, mark every derived copy stale
+int tc_bank_invalidate(rbnn_net* net);
 
 // F16X3 operand ranges (device-resident): *bits = max(*bits, max|p|) as float bits; out[0..3] = s_x, 1/(s_x s_w),
 // s_d, 1/(s_d s_w) with s_d from the bound dh_factor * max|g| * max|Wo| (call_scales_kernel, tc_fc.cu)

@@ -23,11 +23,11 @@ __global__ void softplus_kernel(const float* __restrict__ rho, float* __restrict
 __global__ void __launch_bounds__(256)
 sample_diag_kernel(const float* __restrict__ loc, const float* __restrict__ sigma, float* __restrict__ bank,
                    int64_t P, uint32_t k0, uint32_t k1, int64_t sample_index0, int64_t stride, int s0, int vec,
-                   int64_t q0) {
+                   int64_t q0, const int64_t* __restrict__ index_offset) {
   const int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // q0: first quad (the tail of a row only)
   const int64_t i0 = q * 4;
   if (i0 >= P) return;
-  const int64_t g = sample_index0 + (int64_t)blockIdx.y * stride;
+  const int64_t g = sample_index0 + (index_offset ? *index_offset : 0) + (int64_t)blockIdx.y * stride;
   float z[4];
   philox_normals4((uint32_t)q, (uint32_t)g, k0, k1, z);
   float* __restrict__ row = bank + (int64_t)(s0 + blockIdx.y) * P;
@@ -46,7 +46,10 @@ sample_diag_kernel(const float* __restrict__ loc, const float* __restrict__ sigm
 
 int sample_sigma(rbnn_net* net, const float* d_rho, cudaStream_t st) {
   const int64_t P = net->L.P;
-  if (!net->sigma) RBNN_CUDA(cudaMalloc(&net->sigma, P * sizeof(float)));
+  if (!net->sigma) {
+    RBNN_CUDA(cudaMalloc(&net->sigma, P * sizeof(float)));
+    net->alloc_epoch++;
+  }
   softplus_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_rho, net->sigma, P);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
@@ -55,23 +58,24 @@ int sample_sigma(rbnn_net* net, const float* d_rho, cudaStream_t st) {
 
 // elements [elem0, P) of the rows (elem0 % 4 == 0; 0 = whole rows); net->sigma must hold softplus(rho) (sample_sigma)
 int sample_diag_from(rbnn_net* net, const float* d_loc, uint64_t seed, int64_t sample_index0, int64_t stride, int s0,
-                     int count, int64_t elem0, cudaStream_t st) {
+                     int count, int64_t elem0, cudaStream_t st, const int64_t* d_index_offset) {
   const int64_t P = net->L.P;
   const int64_t nq = (P + 3) / 4 - elem0 / 4;
   if (nq <= 0) return 0;
   dim3 grid((unsigned)((nq + 255) / 256), (unsigned)count);
   sample_diag_kernel<<<grid, 256, 0, st>>>(d_loc, net->sigma, net->bank, P, (uint32_t)(seed & 0xFFFFFFFFu),
                                            (uint32_t)(seed >> 32), sample_index0, stride, s0,
-                                           ((P & 1) == 0 && (reinterpret_cast<uintptr_t>(d_loc) & 15) == 0) ? 1 : 0, elem0 / 4);
+                                           ((P & 1) == 0 && (reinterpret_cast<uintptr_t>(d_loc) & 15) == 0) ? 1 : 0, elem0 / 4,
+                                           d_index_offset);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
   return 0;
 }
 
 int sample_diag(rbnn_net* net, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
-                int64_t stride, int s0, int count, cudaStream_t st) {
+                int64_t stride, int s0, int count, cudaStream_t st, const int64_t* d_index_offset) {
   RBNN_TRY(sample_sigma(net, d_rho, st));
-  return sample_diag_from(net, d_loc, seed, sample_index0, stride, s0, count, 0, st);
+  return sample_diag_from(net, d_loc, seed, sample_index0, stride, s0, count, 0, st, d_index_offset);
 }
 
 // conv: the output Linear consumes the pooled activations in (pos, h) order (HWC), the reference

@@ -264,6 +264,7 @@ int tc_conv_forward_keep(rbnn_net* n, const float* x, int B, int s0, int s1, flo
     cudaFree(k.conv_buf);
     k.conv_buf = nullptr; k.conv_cap = 0;
     RBNN_CUDA(cudaMalloc(&k.conv_buf, need));
+    n->alloc_epoch++;
     k.conv_cap = need;
   }
   const KeepView kv = keep_view(n, units);

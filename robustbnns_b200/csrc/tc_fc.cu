@@ -254,12 +254,12 @@ sample_relayout_f16_kernel(const float* __restrict__ loc, const float* __restric
                            int64_t P, int64_t off, int R, int C, int ld, int s0, int64_t sample_index0, int64_t stride,
                            uint32_t k0, uint32_t k1, TcScales* __restrict__ sc, __half* __restrict__ hi,
                            __half* __restrict__ lo, __half* __restrict__ thi, __half* __restrict__ tlo,
-                           float* __restrict__ wnorm) {
+                           float* __restrict__ wnorm, const int64_t* __restrict__ index_offset) {
   __shared__ float tile[32][33];
   __shared__ float red_n[8], red_m[8];
   const float sw = sc->s_w1;
   const int s = s0 + blockIdx.y;
-  const uint32_t g = (uint32_t)(sample_index0 + (int64_t)blockIdx.y * stride);
+  const uint32_t g = (uint32_t)(sample_index0 + (index_offset ? *index_offset : 0) + (int64_t)blockIdx.y * stride);
   const int r0 = blockIdx.x * 32;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int tr = tid >> 3, tg = tid & 7;              // row of the tile and 4-column group this thread draws
@@ -472,11 +472,35 @@ fc_head_kernel(int head, const float* __restrict__ Hact, const float* __restrict
 // One warp per (sample z, input b) row; H_hi (+ H_lo when the output is stored tf32-split) hold leaky(pre).
 // NCH = ceil(H / 128): the row (4 values per lane and 128-column chunk) stays in registers between the maximum pass
 // and the flag pass, so H is read once.
+// pre-activation of second-layer unit j of fc2 from the inputs, fp64 throughout (one warp; every lane returns it):
+// b2 + sum_i W2[j,i] leaky(b1[i] + <x, W1[i,:]>).  Slow path of the second worklist (it overflowed).
+__device__ float exact_unit2_warp(const float* __restrict__ xr, const float* __restrict__ wrow, int D, int H, int64_t w1_off,
+                                  int64_t b1_off, const float* __restrict__ w2row, float b2, int lane) {
+  double out = 0.0;
+  for (int i = 0; i < H; ++i) {
+    const float* __restrict__ wr = wrow + w1_off + (int64_t)i * D;
+    double s = 0.0;
+    for (int d = lane; d < D; d += 32) s = fma((double)__ldg(xr + d), (double)__ldg(wr + d), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s += (double)__ldg(wrow + b1_off + i);
+    out = fma(s > 0.0 ? s : s * (double)kLeakySlope, (double)__ldg(w2row + i), out);
+  }
+  return (float)(out + (double)b2);
+}
+
+//
+// Second layer of fc2 (wl2 != nullptr): the A operand of the re-evaluation is the FIRST-layer activation as the tensor
+// cores left it (~5e-6 of the layer maximum off, except for its own refined units), so the "exact" value still carries
+// that error times ||W2_j||: a second-layer unit within eps2 * (row max) of zero is therefore queued on a second
+// worklist as (z, b, j) and settled by refine2_kernel from EXACT first-layer values (fp64 all the way from x).
 template <int NCH>
 __global__ void __launch_bounds__(256)
 refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, int H, const float* __restrict__ a_hi,
               const float* __restrict__ a_lo, int64_t a_zstride, int K, const float* __restrict__ bank, int64_t P,
-              int64_t w_off, int64_t b_off, int z_row0, float eps) {
+              int64_t w_off, int64_t b_off, int z_row0, float eps, unsigned long long* __restrict__ wl2,
+              unsigned* __restrict__ wl2_count, unsigned wl2_cap, float eps2, const float* __restrict__ x0, int D0,
+              int64_t w1_off, int64_t b1_off) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < (int64_t)Z * B; row += nwarps) {
@@ -552,6 +576,17 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         s += (double)__ldg(wrow + b_off + jj);
         float val = (float)s;
+        if (wl2 && fabsf(val) < eps2 * m) {                     // warp-uniform: every lane holds the reduced sum
+          unsigned slot = 0;
+          if (lane == 0) slot = atomicAdd(wl2_count, 1u);       // order varies from run to run, the set of entries does not
+          slot = __shfl_sync(0xffffffffu, slot, 0);
+          if (slot < wl2_cap) {
+            if (lane == 0)
+              wl2[slot] = ((unsigned long long)z << 44) | ((unsigned long long)b << 20) | ((unsigned long long)jj << 4);
+          } else {                                              // worklist full (pathological inputs): settle it here
+            val = exact_unit2_warp(x0 + (int64_t)b * D0, wrow, D0, H, w1_off, b1_off, w + 0, __ldg(wrow + b_off + jj), lane);
+          }
+        }
         val = val > 0.f ? val : val * kLeakySlope;
         if (lane == src) {
 #pragma unroll
@@ -573,6 +608,84 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
           *reinterpret_cast<float4*>(hh + j) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
         }
       }
+    }
+  }
+}
+
+// Second-level refinement of fc2's second layer: every queued unit (z, b, j) is re-evaluated from the inputs in fp64,
+//   H1[i] = leaky(b1[i] + <x_b, W1_z[i,:]>) for ALL hidden i (kept in double), pre2 = b2[j] + <H1, W2_z[j,:]>,
+// and H2[z, b, j] = leaky(pre2) is rewritten.  Entries arrive roughly sorted by sample (refine_kernel walks rows
+// z-major), so a block takes kR2Group consecutive entries and re-uses every W1_z row it loads for all entries of the
+// same sample: W1_z (1.6 MB at fc2-512) is read once per group from L2 instead of once per entry.
+constexpr int kR2Group = 8;
+__global__ void __launch_bounds__(256)
+refine2_kernel(const unsigned long long* __restrict__ wl2, const unsigned* __restrict__ count_p, unsigned cap,
+               const float* __restrict__ x, int B, int D, int H, const float* __restrict__ bank, int64_t P, int64_t w1_off,
+               int64_t b1_off, int64_t w2_off, int64_t b2_off, int z_row0, float* __restrict__ H2) {
+  extern __shared__ double r2sm[];
+  double* h1 = r2sm;                                              // [kR2Group][H] exact first-layer activations
+  float* xs = reinterpret_cast<float*>(h1 + (size_t)kR2Group * H); // [kR2Group][D]
+  __shared__ unsigned long long ent[kR2Group];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned n = min(*count_p, cap);
+  for (unsigned g0 = blockIdx.x * kR2Group; g0 < n; g0 += gridDim.x * kR2Group) {
+    const int m_all = (int)min((unsigned)kR2Group, n - g0);
+    __syncthreads();
+    if (tid < m_all) ent[tid] = wl2[g0 + tid];
+    __syncthreads();
+    int k0 = 0;
+    while (k0 < m_all) {
+      const int z = (int)(ent[k0] >> 44);
+      int k1 = k0 + 1;
+      while (k1 < m_all && (int)(ent[k1] >> 44) == z) ++k1;
+      const int m = k1 - k0;
+      const float* __restrict__ wrow = bank + (int64_t)(z_row0 + z) * P;
+      for (int idx = tid; idx < m * D; idx += 256) {
+        const int r = idx / D, d = idx - r * D;
+        const int b = (int)((ent[k0 + r] >> 20) & 0xFFFFFF);
+        xs[r * D + d] = __ldg(x + (int64_t)b * D + d);
+      }
+      __syncthreads();
+      for (int i = warp; i < H; i += 8) {
+        const float* __restrict__ wr = wrow + w1_off + (int64_t)i * D;
+        double acc[kR2Group];
+#pragma unroll
+        for (int r = 0; r < kR2Group; ++r) acc[r] = 0.0;
+        for (int d = lane; d < D; d += 32) {
+          const double wv = (double)__ldg(wr + d);
+#pragma unroll
+          for (int r = 0; r < kR2Group; ++r)
+            if (r < m) acc[r] = fma((double)xs[r * D + d], wv, acc[r]);
+        }
+        const double bias = (double)__ldg(wrow + b1_off + i);
+#pragma unroll
+        for (int r = 0; r < kR2Group; ++r) {
+          if (r < m) {
+            double v = acc[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            v += bias;
+            if (lane == 0) h1[r * H + i] = v > 0.0 ? v : v * (double)kLeakySlope;
+          }
+        }
+      }
+      __syncthreads();
+      for (int r = warp; r < m; r += 8) {
+        const unsigned long long e = ent[k0 + r];
+        const int b = (int)((e >> 20) & 0xFFFFFF), j = (int)((e >> 4) & 0xFFFF);
+        const float* __restrict__ w2r = wrow + w2_off + (int64_t)j * H;
+        double sacc = 0.0;
+        for (int i = lane; i < H; i += 32) sacc = fma(h1[r * H + i], (double)__ldg(w2r + i), sacc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) {
+          const double pre = sacc + (double)__ldg(wrow + b2_off + j);
+          const float v = (float)pre;
+          H2[((int64_t)z * B + b) * H + j] = pre > 0.0 ? v : (float)(pre * (double)kLeakySlope);
+        }
+      }
+      __syncthreads();
+      k0 = k1;
     }
   }
 }
@@ -656,7 +769,7 @@ int tc_call_scales(rbnn_net* n, const unsigned* xmax_bits, const unsigned* gmax_
 }
 
 int tc_sample_relayout_f16(rbnn_net* n, const float* d_loc, const float* d_rho, uint64_t seed, int64_t sample_index0,
-                           int64_t stride, int s0, int count, cudaStream_t st, int* done) {
+                           int64_t stride, int s0, int count, cudaStream_t st, int* done, const int64_t* d_index_offset) {
   *done = 0;
   TcBank& tc = n->tc;
   const TcMat& m = tc.mat[0];
@@ -671,11 +784,11 @@ int tc_sample_relayout_f16(rbnn_net* n, const float* d_loc, const float* d_rho, 
   sample_relayout_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(
       d_loc, n->sigma, n->bank, n->L.P, m.off, m.R, m.C, m.ld, s0, sample_index0, stride, (uint32_t)(seed & 0xFFFFFFFFu),
       (uint32_t)(seed >> 32), tc.scales, reinterpret_cast<__half*>(m.h_hi), reinterpret_cast<__half*>(m.h_lo),
-      reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo), tc.wnorm);
+      reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo), tc.wnorm, d_index_offset);
   n->launches++;
   RBNN_CUDA(cudaGetLastError());
   // the rest of the rows (b1, Wo, bo) with the plain sampler, then the Wo range and the scale check
-  RBNN_TRY(sample_diag_from(n, d_loc, seed, sample_index0, stride, s0, count, (int64_t)m.R * m.C, st));
+  RBNN_TRY(sample_diag_from(n, d_loc, seed, sample_index0, stride, s0, count, (int64_t)m.R * m.C, st, d_index_offset));
   maxabs_kernel<<<n->sm_count, 256, 0, st>>>(n->bank + (int64_t)s0 * n->L.P + n->L.wo, n->L.P, (int64_t)n->C * n->H, count,
                                              &tc.scales->maxwo_bits);
   freeze_scales_kernel<<<1, 1, 0, st>>>(tc.scales, tc.overflow_dev);
@@ -725,20 +838,58 @@ void tc_bank_free(rbnn_net* n) {
   n->tc.frozen_host = 0;
 }
 
+// A new posterior is being installed (other guide parameters, another uploaded bank): the F16X3 weight scale that was
+// frozen for the old weights is forgotten and every derived copy is marked stale, so the next use fixes a scale from
+// the rows it actually touches.
+int tc_bank_invalidate(rbnn_net* n) {
+  TcBank& tc = n->tc;
+  n->keep.valid = 0;
+  if (tc.dirty) std::fill(tc.dirty, tc.dirty + tc.capacity, (uint8_t)1);
+  if (tc.scales) {
+    RBNN_CUDA(cudaDeviceSynchronize());
+    RBNN_CUDA(cudaMemset(tc.scales, 0, sizeof(TcScales)));
+    if (tc.overflow_host) *tc.overflow_host = 0;
+  }
+  tc.frozen_host = 0;
+  return 0;
+}
+
+static int tc_bank_refresh_once(rbnn_net* n, int s0, int s1, cudaStream_t st, bool* relaid);
+
 // Bring the derived copies of bank rows [s0, s1) up to date (all rows after a capacity / precision change).
+// F16X3: the power-of-two weight scale is frozen from the first rows it sees (2^6 of head room).  Whenever this call
+// re-lays rows it waits for the range check and, should a row exceed the fp16 range under the frozen scale, forgets
+// the scale and re-lays the rows of this call under a new one -- inside the same call, transparently.  (Rows drawn by
+// the fused sampler path between refreshes are covered by the sticky flag read at the start of the next call.)
 int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
   TcBank& tc = n->tc;
+  const bool f16 = n->prec == RBNN_PREC_F16X3;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    bool relaid = false;
+    RBNN_TRY(tc_bank_refresh_once(n, s0, s1, st, &relaid));
+    if (!f16 || !relaid || !tc.overflow_host) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return 0;          // no host reads inside a graph capture
+    RBNN_CUDA(cudaStreamSynchronize(st));
+    if (!*(volatile int*)tc.overflow_host) return 0;
+    RBNN_TRY(tc_bank_invalidate(n));                            // new scale from the rows of this call
+  }
+  set_error("F16X3: bank rows do not fit the fp16 operand range (non-finite weights?)");
+  return 1;
+}
+
+static int tc_bank_refresh_once(rbnn_net* n, int s0, int s1, cudaStream_t st, bool* relaid) {
+  TcBank& tc = n->tc;
   const bool bf = n->prec == RBNN_PREC_BF16, f16 = n->prec == RBNN_PREC_F16X3;
+  *relaid = false;
   if (f16 && tc.overflow_host && *(volatile int*)tc.overflow_host) {
-    // a row re-laid after s_w1 was frozen did not fit the fp16 range: results since then are invalid.  Start over
-    // (new scale from all rows) and tell the caller.
-    RBNN_CUDA(cudaDeviceSynchronize());
-    *tc.overflow_host = 0;
-    RBNN_CUDA(cudaMemset(tc.scales, 0, sizeof(TcScales)));
-    tc.frozen_host = 0;
-    std::fill(tc.dirty, tc.dirty + tc.capacity, (uint8_t)1);
-    set_error("F16X3: bank rows uploaded after the operand scale was fixed exceed the fp16 range (> 64x the earlier "
-              "maximum |w|); the results of calls since that upload are invalid.  The scale has been reset: repeat the call");
+    // rows drawn by the fused sampler path after s_w1 was frozen did not fit the fp16 range (the guide changed without
+    // rbnn_bank_invalidate): results since then are invalid.  Start over (new scale) and tell the caller.
+    RBNN_TRY(tc_bank_invalidate(n));
+    set_error("F16X3: posterior samples drawn after the operand scale was fixed exceed the fp16 range (> 64x the earlier "
+              "maximum |w|); the results of calls since then are invalid.  Call rbnn_bank_invalidate when the guide "
+              "parameters change.  The scale has been reset: repeat the call");
     return 1;
   }
   if (tc.capacity < n->capacity || tc.mode != n->prec) {
@@ -780,6 +931,7 @@ int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
     std::fill(tc.dirty, tc.dirty + n->capacity, (uint8_t)1);
     tc.capacity = n->capacity;
     tc.mode = n->prec;
+    n->alloc_epoch++;
   }
   if (f16) {
     // operand ranges of the dirty rows first (W1 fixes / checks the frozen scale, Wo bounds dH)
@@ -834,6 +986,7 @@ int tc_bank_refresh(rbnn_net* n, int s0, int s1, cudaStream_t st) {
       RBNN_CUDA(cudaGetLastError());
     }
     std::fill(tc.dirty + s, tc.dirty + e, (uint8_t)0);
+    *relaid = true;
     s = e;
   }
   return 0;
@@ -881,6 +1034,9 @@ struct FcWs {
   __nv_bfloat16 *dtop_bf = nullptr, *d1_bf = nullptr;
   float *logits = nullptr, *partial = nullptr, *xnorm = nullptr;
   unsigned long long* worklist = nullptr;
+  unsigned long long* wl2 = nullptr;       // fc2: second-layer units to settle from exact first-layer values
+  unsigned* wl2_count = nullptr;
+  unsigned wl2_cap = 0;
 };
 }  // namespace
 
@@ -899,6 +1055,7 @@ static size_t fc_per_z_bytes(const rbnn_net* n, int B, bool grad) {
   }
   size_t per = bh;                                   // h1 (fp32 or hi)
   if (two) per += (bf ? bh2 : bh) + bh;              // h1 lo / bf16 + h2
+  if (two && !bf) per += pad256((size_t)B * n->H / 8 + 64);   // second worklist: one 8-byte slot per 64 hidden units
   if (grad) {
     per += bf ? bh2 : 2 * bh;                        // dtop
     if (two) per += bf ? bh2 : 2 * bh;               // d1
@@ -920,12 +1077,20 @@ constexpr float kGuardEpsFused = 1.0f / 65536.0f;
 constexpr float kGuardEpsFusedF16 = 1.0f / 131072.0f;
 constexpr float kGuardEps = 1.0f / 4096.0f;   // ~50x the measured TF32x3 error bound (5e-6 of the output max)
 
+// Narrow band of fc2's second layer (fraction of the row maximum): bounds the first-layer tensor-core error (measured
+// <= 5e-6 of the layer maximum) propagated through one row of W2 -- ~6e-6 of the second layer's row maximum at 4 sigma for
+// well-scaled weights; 2^-14 = 6.1e-5 keeps 10x over that.  ~1.5e-4 of the units qualify.
+constexpr float kGuardEps2 = 1.0f / 16384.0f;
+
 static int refine(rbnn_net* n, float* h_hi, float* h_lo, int Z, int B, const float* a_hi, const float* a_lo,
-                  int64_t a_zstride, int K, int64_t w_off, int64_t b_off, int z0, cudaStream_t st) {
+                  int64_t a_zstride, int K, int64_t w_off, int64_t b_off, int z0, cudaStream_t st,
+                  unsigned long long* wl2 = nullptr, unsigned* wl2_count = nullptr, unsigned wl2_cap = 0,
+                  const float* x0 = nullptr) {
   const int64_t rows = (int64_t)Z * B;
   const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)n->sm_count * 8);
 #define RBNN_REFINE(NCH) refine_kernel<NCH><<<blocks, 256, 0, st>>>(h_hi, h_lo, Z, B, n->H, a_hi, a_lo, a_zstride, K, n->bank, \
-                                                                  n->L.P, w_off, b_off, z0, kGuardEps)
+                                                                  n->L.P, w_off, b_off, z0, kGuardEps, wl2, wl2_count,     \
+                                                                  wl2_cap, kGuardEps2, x0, n->D, n->L.w1, n->L.b1)
   const int nch = (n->H + 127) / 128;
   RBNN_CHECK(nch <= 16, "tcgen05 engine (unfused route): hidden sizes up to 2048");
   if (nch <= 1) RBNN_REFINE(1); else if (nch <= 2) RBNN_REFINE(2); else if (nch <= 4) RBNN_REFINE(4);
@@ -970,7 +1135,23 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
     q.bias = n->bank + (int64_t)z0 * P + n->L.b2; q.bias_zstride = P;
     q.out = w.h2; q.out_ld = H; q.out_zstride = (int64_t)B * H;
     RBNN_TRY(run_gemm(n, q, 0, st));
-    if (!bf) RBNN_TRY(refine(n, w.h2, nullptr, Z, B, w.h1, w.h1_lo, (int64_t)B * H, H, n->L.w2, n->L.b2, z0, st));
+    if (!bf) {
+      // guard band of the second layer: wide band from the stored first-layer activations, narrow band (their propagated
+      // tensor-core error) from exact first-layer values (refine2_kernel)
+      RBNN_CUDA(cudaMemsetAsync(w.wl2_count, 0, sizeof(unsigned), st));
+      RBNN_TRY(refine(n, w.h2, nullptr, Z, B, w.h1, w.h1_lo, (int64_t)B * H, H, n->L.w2, n->L.b2, z0, st, w.wl2,
+                      w.wl2_count, w.wl2_cap, x));
+      const int smem2 = kR2Group * (H * (int)sizeof(double) + D * (int)sizeof(float));
+      static int smem2_set = 0;
+      if (smem2 > 48 * 1024 && smem2_set < smem2) {
+        RBNN_CUDA(cudaFuncSetAttribute(refine2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        smem2_set = smem2;
+      }
+      refine2_kernel<<<n->sm_count * 2, 256, smem2, st>>>(w.wl2, w.wl2_count, w.wl2_cap, x, B, D, H, n->bank, P, n->L.w1,
+                                                           n->L.b1, n->L.w2, n->L.b2, z0, w.h2);
+      n->launches++;
+      RBNN_CUDA(cudaGetLastError());
+    }
     *top = w.h2;
   }
   return 0;
@@ -1117,7 +1298,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     return best;
   };
   int slots = slots_for(zc);
-  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots + pad256((size_t)B * 4) + 4096));
+  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots + pad256((size_t)B * 4) + 4096 + 65536));
   Arena ar(n);
   FcWs w;
   if (kept) { w.call_sc = n->keep.call_sc; w.max_bits = n->keep.max_bits; }
@@ -1145,6 +1326,11 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     else { w.d1_hi = ar.take<float>(zbh); w.d1_lo = ar.take<float>(zbh); }
   }
   if (fused && !bf && !kept) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc));
+  if (two && !bf && !kept) {
+    w.wl2_cap = (unsigned)std::max<size_t>(4096, zbh / 64);
+    w.wl2 = ar.take<unsigned long long>(w.wl2_cap);
+    w.wl2_count = ar.take<unsigned>(1);
+  }
   w.xnorm = ar.take<float>((size_t)B);
   w.partial = ar.take<float>((size_t)slots * B * D);
   if (kept) {
@@ -1274,7 +1460,7 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   size_t avail = n->ws_budget > x_bytes ? n->ws_budget - x_bytes : 0;
   int zc = (int)std::max<size_t>(1, std::min<size_t>(avail / per, (size_t)S));
   zc = (S + (S + zc - 1) / zc - 1) / ((S + zc - 1) / zc);      // equal chunks
-  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + pad256((size_t)B * 4)));
+  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + pad256((size_t)B * 4) + 65536));
   Arena ar(n);
   FcWs w;
   if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * ldx);
@@ -1295,6 +1481,11 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   }
   if (keep && fused) { if (!bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc)); }
   else w.logits = ar.take<float>((size_t)zc * B * C);
+  if (two && !bf) {
+    w.wl2_cap = (unsigned)std::max<size_t>(4096, zbh / 64);
+    w.wl2 = ar.take<unsigned long long>(w.wl2_cap);
+    w.wl2_count = ar.take<unsigned>(1);
+  }
   w.xnorm = ar.take<float>((size_t)B);
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, 2.f, st));
   if (fused) {
@@ -1363,6 +1554,7 @@ int tc_fc_forward_keep(rbnn_net* n, const float* x, int B, int s0, int s1, float
       k.fc_h = nullptr; k.fc_cap = 0;
       RBNN_CUDA(cudaMalloc(&k.fc_h, need * sizeof(float)));
       k.fc_cap = need;
+      n->alloc_epoch++;
     }
     RBNN_TRY(tc_forward_pass(n, x, B, s0, s1, out_sum, nullptr, st, true));
     k.valid = 1; k.B = B; k.s0 = s0; k.s1 = s1;
@@ -1377,10 +1569,12 @@ int tc_fc_forward_keep(rbnn_net* n, const float* x, int B, int s0, int s1, float
     RBNN_CUDA(cudaMalloc(&k.logits, need_l * sizeof(float)));
     RBNN_CUDA(cudaMalloc(&k.masks, need_m * sizeof(uint32_t)));
     k.logits_cap = need_l; k.masks_cap = need_m;
+    n->alloc_epoch++;
   }
   if (!k.call_sc) {
     RBNN_CUDA(cudaMalloc(&k.call_sc, 4 * sizeof(float)));
     RBNN_CUDA(cudaMalloc(&k.max_bits, 2 * sizeof(unsigned)));
+    n->alloc_epoch++;
   }
   RBNN_TRY(tc_forward_pass(n, x, B, s0, s1, out_sum, nullptr, st, true));
   k.valid = 1; k.B = B; k.s0 = s0; k.s1 = s1;

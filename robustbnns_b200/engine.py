@@ -12,8 +12,9 @@ from . import _lib
 from ._lib import ARCH, PREC, check, lib
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """torch's current stream ON `device` (the handle's / the tensors' device, not necessarily the current one)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class Net(object):
@@ -108,19 +109,33 @@ class Net(object):
         if on_dev:
             w = self._dev(w)
         check(lib().rbnn_bank_upload(self._h, C.c_void_p(w.data_ptr()), int(s0), int(w.shape[0]), int(on_dev),
-                                     _stream()))
+                                     _stream(self.device)))
         if not on_dev:
-            torch.cuda.current_stream().synchronize()   # pageable host source must outlive the copy
+            torch.cuda.current_stream(self.device).synchronize()   # pageable host source must outlive the copy
 
-    def sample_diag(self, loc, rho, seed, sample_index0, s0, count, stride=1):
-        """rows [s0, s0+count) <- loc + softplus(rho)*eps(seed, global index)  (BNN.guide, model_bnn.py:121-130)."""
+    def sample_diag(self, loc, rho, seed, sample_index0, s0, count, stride=1, index_offset=None):
+        """rows [s0, s0+count) <- loc + softplus(rho)*eps(seed, global index)  (BNN.guide, model_bnn.py:121-130).
+        index_offset: optional int64[1] DEVICE tensor added to the sample indices when the kernel runs (CUDA graphs)."""
         loc, rho = self._dev(loc).reshape(-1), self._dev(rho).reshape(-1)
         if loc.numel() != self.P or rho.numel() != self.P:
             raise ValueError("loc/rho must have %d elements" % self.P)
         self.reserve(max(self.capacity, s0 + count))
-        check(lib().rbnn_bank_sample_diag(self._h, C.c_void_p(loc.data_ptr()), C.c_void_p(rho.data_ptr()),
-                                          C.c_uint64(int(seed) & (2 ** 64 - 1)), int(sample_index0), int(stride),
-                                          int(s0), int(count), _stream()))
+        off = 0
+        if index_offset is not None:
+            if index_offset.dtype != torch.int64 or index_offset.device != self.device:
+                raise ValueError("index_offset must be an int64 tensor on %s" % self.device)
+            off = index_offset.data_ptr()
+        check(lib().rbnn_bank_sample_diag_at(self._h, C.c_void_p(loc.data_ptr()), C.c_void_p(rho.data_ptr()),
+                                             C.c_uint64(int(seed) & (2 ** 64 - 1)), int(sample_index0), int(stride),
+                                             int(s0), int(count), C.c_void_p(off), _stream(self.device)))
+
+    def invalidate(self):
+        """A new posterior is being installed: forget the derived operand scale / copies / kept forward."""
+        check(lib().rbnn_bank_invalidate(self._h))
+
+    @property
+    def alloc_epoch(self):
+        return int(lib().rbnn_net_alloc_epoch(self._h))
 
     def download(self, s0, count):
         out = torch.empty((count, self.P), dtype=torch.float32)
@@ -143,7 +158,7 @@ class Net(object):
         fn = lib().rbnn_forward_probs_sum_keep if keep else lib().rbnn_forward_probs_sum
         if keep:
             self.keep_serial = getattr(self, "keep_serial", 0) + 1      # identifies WHICH forward is kept
-        check(fn(self._h, C.c_void_p(x.data_ptr()), B, int(s0), int(s1), C.c_void_p(out.data_ptr()), _stream()))
+        check(fn(self._h, C.c_void_p(x.data_ptr()), B, int(s0), int(s1), C.c_void_p(out.data_ptr()), _stream(self.device)))
         return out
 
     @property
@@ -157,14 +172,14 @@ class Net(object):
         pb = self._dev(pbar) if pbar is not None else None
         check(lib().rbnn_input_grad_sum_kept(self._h, int(head), C.c_void_p(labels.data_ptr()),
                                              C.c_void_p(pb.data_ptr() if pb is not None else 0),
-                                             C.c_void_p(out.data_ptr()), _stream()))
+                                             C.c_void_p(out.data_ptr()), _stream(self.device)))
         return out
 
     def forward_logits(self, x, s):
         x, B = self._x(x)
         out = torch.empty((B, self.n_classes), dtype=torch.float32, device=self.device)
         check(lib().rbnn_forward_logits(self._h, C.c_void_p(x.data_ptr()), B, int(s), C.c_void_p(out.data_ptr()),
-                                        _stream()))
+                                        _stream(self.device)))
         return out
 
     def forward_logits_sum(self, x, s0, s1):
@@ -172,21 +187,25 @@ class Net(object):
         x, B = self._x(x)
         out = torch.empty((B, self.n_classes), dtype=torch.float32, device=self.device)
         check(lib().rbnn_forward_logits_sum(self._h, C.c_void_p(x.data_ptr()), B, int(s0), int(s1),
-                                            C.c_void_p(out.data_ptr()), _stream()))
+                                            C.c_void_p(out.data_ptr()), _stream(self.device)))
         return out
 
-    def input_grad_sum(self, head, x, labels, s0, s1, pbar=None):
+    def input_grad_sum(self, head, x, labels, s0, s1, pbar=None, out=None):
         x, B = self._x(x)
         labels = self._dev(labels, torch.int32).reshape(-1)
         if labels.numel() != B:
             raise ValueError("need one label per input")
-        out = torch.empty_like(x)
+        if out is None:
+            out = torch.empty_like(x)
+        elif (out.device != self.device or out.dtype != torch.float32 or not out.is_contiguous()
+              or out.numel() != x.numel()):
+            raise ValueError("out must be a contiguous fp32 tensor of %d elements on %s" % (x.numel(), self.device))
         pb = None
         if pbar is not None:
             pb = self._dev(pbar)
         check(lib().rbnn_input_grad_sum(self._h, int(head), C.c_void_p(x.data_ptr()), C.c_void_p(labels.data_ptr()),
                                         B, int(s0), int(s1), C.c_void_p(pb.data_ptr() if pb is not None else 0),
-                                        C.c_void_p(out.data_ptr()), _stream()))
+                                        C.c_void_p(out.data_ptr()), _stream(self.device)))
         return out
 
     def loss_gradients_host(self, x_host, labels_host, s0, s1, n_samples_global, out_host=None):
@@ -205,7 +224,7 @@ class Net(object):
 def fgsm_step(x, grad, eps):
     out = torch.empty_like(x)
     check(lib().rbnn_fgsm_step(C.c_void_p(x.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_float(eps),
-                               C.c_void_p(out.data_ptr()), x.numel(), _stream()))
+                               C.c_void_p(out.data_ptr()), x.numel(), _stream(x.device)))
     return out
 
 
@@ -213,7 +232,7 @@ def pgd_alpha(x):
     B = x.shape[0]
     alpha = torch.empty((B,), dtype=torch.float32, device=x.device)
     check(lib().rbnn_pgd_alpha(C.c_void_p(x.data_ptr()), C.c_void_p(alpha.data_ptr()), B, x.numel() // max(B, 1),
-                               _stream()))
+                               _stream(x.device)))
     return alpha
 
 
@@ -222,7 +241,7 @@ def pgd_step(x, x0, grad, alpha, eps):
     out = torch.empty_like(x)
     check(lib().rbnn_pgd_step(C.c_void_p(x.data_ptr()), C.c_void_p(x0.data_ptr()), C.c_void_p(grad.data_ptr()),
                               C.c_void_p(alpha.data_ptr()), C.c_float(eps), C.c_void_p(out.data_ptr()), B,
-                              x.numel() // max(B, 1), _stream()))
+                              x.numel() // max(B, 1), _stream(x.device)))
     return out
 
 
@@ -232,7 +251,7 @@ def softmax_robustness(o0, o1):
     rob = torch.empty((N,), dtype=torch.float32, device=o0.device)
     mm = torch.empty((2,), dtype=torch.float32, device=o0.device)
     check(lib().rbnn_softmax_robustness(C.c_void_p(o0.data_ptr()), C.c_void_p(o1.data_ptr()), N, Cc,
-                                        C.c_void_p(rob.data_ptr()), C.c_void_p(mm.data_ptr()), _stream()))
+                                        C.c_void_p(rob.data_ptr()), C.c_void_p(mm.data_ptr()), _stream(o0.device)))
     return rob, mm
 
 
@@ -240,7 +259,7 @@ def count_correct(out, labels_i32, counter):
     """counter (int64[1] on device) += #{argmax(out) == labels}."""
     N, Cc = out.shape
     check(lib().rbnn_count_correct(C.c_void_p(out.data_ptr()), C.c_void_p(labels_i32.data_ptr()), N, Cc,
-                                   C.c_void_p(counter.data_ptr()), _stream()))
+                                   C.c_void_p(counter.data_ptr()), _stream(out.device)))
 
 
 # the stateless kernels are also reachable through a Net (lets tests swap the whole engine)

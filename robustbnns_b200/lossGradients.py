@@ -18,12 +18,48 @@ DEBUG = False
 MAX_BATCH = 16384     # inputs per device pass
 
 
+def _to_device(eng, images, labels):
+    """Inputs and labels on the engine's device.  Host tensors under torch.distributed: every rank copies only its block
+    of rows over PCIe and the blocks are all-gathered over NVLink (dist.gather_rows_from_host)."""
+    images, labels = torch.as_tensor(images), torch.as_tensor(labels)
+    if images.device.type == "cpu" and rdist.world()[1] > 1:
+        images = rdist.gather_rows_from_host(images, eng.device, torch.float32)
+    else:
+        images = images.to(device=eng.device, dtype=torch.float32)
+    if labels.device.type == "cpu" and rdist.world()[1] > 1:
+        labels = rdist.gather_rows_from_host(labels.to(torch.int32), eng.device, torch.int32)
+    else:
+        labels = labels.to(device=eng.device, dtype=torch.int32)
+    return images, labels
+
+
+def expected_loss_gradients_block(net, images, labels, n_samples):
+    """Row-sharded result for multi-GPU callers: like `expected_loss_gradients`, but the [B, D] partial sums of the ranks
+    are reduce-SCATTERed, so every rank ends up with (and only has to read back) its own block of rows.
+    Returns (block [hi - lo, *input_shape] on the device, (lo, hi)); one process: the whole batch, (0, B)."""
+    eng = net.engine()
+    images, labels = _to_device(eng, images, labels)
+    B = images.shape[0]
+    rank, world = rdist.world()
+    if world == 1 or B > MAX_BATCH:
+        g = expected_loss_gradients(net, images, labels, n_samples)
+        lo, hi, _ = rdist.row_block(B, rank, world)
+        return g[lo:hi], (lo, hi)
+    lo, hi, per = rdist.row_block(B, rank, world)
+    rows, _ = net._rows(n_samples, list(range(n_samples)))
+    x = images.contiguous()
+    buf = torch.zeros((per * world, eng.D), dtype=torch.float32, device=eng.device) if per * world != B else \
+        torch.empty((B, eng.D), dtype=torch.float32, device=eng.device)
+    eng.input_grad_sum(HEAD_MEAN_OF_GRADS, x, labels.contiguous(), rows[0], rows[1], out=buf[:B])
+    blk = rdist.reduce_scatter_rows_(buf, per)[:hi - lo]
+    return (blk * (1.0 / float(n_samples))).reshape((hi - lo,) + tuple(x.shape[1:])), (lo, hi)
+
+
 def expected_loss_gradients(net, images, labels, n_samples):
     """[B, *input_shape] tensor on the device: (1/S) sum_{s<S} dL_s/dx for a batch
     (`labels` are class indices).  Sample s is seed s (lossGradients.py:33)."""
     eng = net.engine()
-    images = torch.as_tensor(images).to(device=eng.device, dtype=torch.float32)
-    labels = torch.as_tensor(labels).to(device=eng.device, dtype=torch.int32)
+    images, labels = _to_device(eng, images, labels)
     outs = []
     rows, _ = net._rows(n_samples, list(range(n_samples)))
     for b0 in range(0, images.shape[0], MAX_BATCH):
@@ -56,7 +92,12 @@ def loss_gradients(net, data_loader, device, filename, savedir, n_samples=None):
     grads = expected_loss_gradients(net, images, labels, n_samples)
     print(f"\nmin = {grads.min():.4f} \t max = {grads.max():.4f}")
     grads = grads.cpu().detach().numpy().squeeze()
-    save_loss_gradients(grads, n_samples, filename, savedir)
+    rank, world = rdist.real_world()
+    if rank == 0:                                   # one writer: concurrent open(..., "wb") by every rank truncates the file
+        save_loss_gradients(grads, n_samples, filename, savedir)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     return grads
 
 

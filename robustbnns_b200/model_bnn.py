@@ -127,6 +127,9 @@ class BNN(object):
         self.attack_sharding = "inputs"       # multi-GPU `attack`: shard the inputs (no collectives) or the "samples"
         self._loc = self._rho = None          # SVI guide parameters, flattened [P]
         self._bank_host = None                # explicit / HMC bank [S, P] (CPU tensor)
+        self._graph_offset = None             # int64[1] device tensor while a CUDA graph of a PGD iteration is captured
+        self._posterior_generation = 0        # bumped when another posterior is installed (cached CUDA graphs die with it)
+        self._pgd_graphs = {}
         self._reset_rows()
         self.reseed(0)
 
@@ -160,11 +163,20 @@ class BNN(object):
         self._pin_cap = 0             # local rows reserved for the pinned region; scratch starts here
         self._scratch_generation = 0
 
+    def _new_posterior(self):
+        """Other weights are about to live in the engine's bank: what the engine derived from the old ones (the frozen
+        F16X3 operand scale, kernel-ready copies, the kept forward) and every captured CUDA graph are dropped."""
+        self._posterior_generation += 1
+        self._pgd_graphs = {}
+        if self._engine is not None and hasattr(self._engine, "invalidate"):
+            self._engine.invalidate()
+
     def set_precision(self, name):
         """'auto' (default: the fastest parity-grade engine the network has -- 'f16x3' for arch fc / conv, 'tf32x3'
         for fc2, 'fp32' otherwise), 'fp32' (CUDA-core FFMA), 'f16x3' / 'tf32x3' (tcgen05, fp32-class accuracy) or
         'bf16' (tcgen05 single pass, throughput mode, not parity grade); see DESIGN.md section 4.1."""
         self._precision = name
+        self._pgd_graphs = {}
         if name == "auto":
             self.engine().set_best_precision()
         else:
@@ -193,6 +205,7 @@ class BNN(object):
         if self._engine is not None or torch.cuda.is_available():
             dev = self.engine().device
             self._loc, self._rho = self._loc.to(dev), self._rho.to(dev)
+        self._new_posterior()
         self._reset_rows()
 
     def set_posterior_samples(self, bank):
@@ -205,7 +218,10 @@ class BNN(object):
         bank = bank.detach().float().cpu().contiguous()
         if bank.dim() != 2 or bank.shape[1] != self.basenet.n_params:
             raise ValueError("bank must be [S, %d]" % self.basenet.n_params)
+        same = self._bank_host is not None and self._bank_host.shape == bank.shape and torch.equal(self._bank_host, bank)
         self._bank_host = bank
+        if not same:                          # (_replace_rows re-installs the SAME bank under another sharding)
+            self._new_posterior()
         self._reset_rows()
         rank, world = rdist.world()
         mine = bank[rank::world]
@@ -331,7 +347,11 @@ class BNN(object):
             first = FRESH_BASE + self._fresh_counter
             self._fresh_counter += n
             if nloc:
-                eng.sample_diag(self._loc, self._rho, self._fresh_key, first + rank, base, nloc, stride=world)
+                if self._graph_offset is not None:      # CUDA-graph capture: the draw index advances on the device
+                    eng.sample_diag(self._loc, self._rho, self._fresh_key, first + rank, base, nloc, stride=world,
+                                    index_offset=self._graph_offset)
+                else:
+                    eng.sample_diag(self._loc, self._rho, self._fresh_key, first + rank, base, nloc, stride=world)
         return (base, base + nloc), self._scratch_generation
 
     def _probs_mean(self, inputs, rows, n_total):

@@ -95,13 +95,18 @@ class OracleEngine(object):
     def set_best_precision(self):
         return "oracle"
 
-    def input_grad_sum(self, head, x, labels, s0, s1, pbar=None):
+    def input_grad_sum(self, head, x, labels, s0, s1, pbar=None, out=None):
         x = self._x(x)
         if s1 == s0:
-            return torch.zeros_like(x)
-        labels = torch.as_tensor(labels).long()
-        with torch.enable_grad():
-            return self._grad(head, x, labels, s0, s1, pbar)
+            g = torch.zeros_like(x)
+        else:
+            labels = torch.as_tensor(labels).long()
+            with torch.enable_grad():
+                g = self._grad(head, x, labels, s0, s1, pbar)
+        if out is not None:
+            out.copy_(g.reshape(out.shape))
+            return out
+        return g
 
     def _grad(self, head, x, labels, s0, s1, pbar):
         if head == 0:

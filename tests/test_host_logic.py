@@ -249,6 +249,10 @@ def _rank_main(rank, world, port, q):
         assert bnn.engine().bank.shape[0] >= 1 and bnn._pin_rows == len(range(rank, S, world))
         probs = bnn.forward(c.x, n_samples=S)
         grads = lg.expected_loss_gradients(bnn, c.x, c.labels, S)
+        # row-sharded I/O: every rank uploads / reads back only its block of rows (9 images -> 5 + 4)
+        blk, (lo, hi) = lg.expected_loss_gradients_block(bnn, c.x, c.labels, S)
+        assert (lo, hi) == ((0, 5) if rank == 0 else (5, 9)) and blk.shape[0] == hi - lo
+        assert rel_err(blk, grads[lo:hi]) < 1e-6
         adv = aa.fgsm_attack(bnn, c.x, c.labels, hyperparams={"epsilon": float(c.z["eps"])}, n_samples=S)
         s = Case("svi_fc2_32_moons")
         sb = _bnn(s)
