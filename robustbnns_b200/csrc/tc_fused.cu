@@ -17,8 +17,13 @@
 //                instruction, Wo_z as fp32 in shared memory, broadcast 16-byte loads).
 //                Head: the four column quarters of a row add their partial logits through shared memory (fixed order),
 //                one thread per row evaluates the loss head (softmax -> g -> dlogits).
-//                Pass 2: dH = (dlogits . Wo) * leaky'(H) from the mask bits, again packed fp32 FMAs, written pre-split
-//                (fp16 hi/lo, tf32 hi/lo or bf16) with 32-byte stores (one full sector per lane and instruction).
+//                Pass 2: dH = (dlogits . Wo) * leaky'(H), row-cooperative: a warp walks the 32 input rows of its TMEM lane
+//                quadrant and, for one row, lane l owns 4 consecutive hidden columns (n-tile l / 16, columns
+//                64 cq + 4 (l % 16) ..) whose Wo entries it keeps in registers for the whole item; the row's dlogits are a
+//                broadcast shared-memory load, its mask words come from the owner lane by shuffle.  16 lanes write one
+//                full 128-byte line of the pre-split output (fp16 hi/lo, tf32 hi/lo or bf16) per store instruction.
+//                (With thread = row in pass 2 a store instruction touched 32 different lines: 64 L1 wavefronts per KB
+//                written, and the dH stores alone cost 2.7 ms of a 10.2 ms chunk.)
 //   (Round 1 ran both small GEMMs of the head as mma.sync on fp16 hi/lo fragments: on sm_100 a legacy HMMA issues every
 //   ~32 cycles per sub-core, 24.5 k cycles per item for them alone against 38 k cycles of tcgen05 MMAs; the packed
 //   fp32 FMAs need ~10 k and no fragment shuffling, staging conversions or operand scaling.)
@@ -53,13 +58,14 @@ constexpr int kHMax = 512;                        // hidden units the staged par
 constexpr int kMaskWords = 4;                     // 32-column chunks per thread: n_tiles * ceil(BN / 128) <= 4
 constexpr int kMaskWordsItem = kHMax / 32;        // mask words per input row of an item (keep mode): word = j / 32
 constexpr int kXStride = kCMax + 1;               // floats per row of the exchange buffers (odd: conflict-free)
-// shared memory after the ring and the barriers: Wo [C][H] fp32 | b1 [kHMax] | bo [16] | xa [128][11] | xb [128][11]
-constexpr int kFusedSmem = kRingF + 1024 + 256 + (kCMax * kHMax + kHMax + 16 + 2 * kBM * kXStride) * 4 + 16;
+constexpr int kDStride = 12;                      // floats per row of the dlogits buffer pass 2 reads (16-byte aligned rows)
+// shared memory after the ring and the barriers: Wo [C][H] fp32 | b1 [kHMax] | bo [16] | xa [128][11] | xb [128][12]
+constexpr int kFusedSmem = kRingF + 1024 + 256 + (kCMax * kHMax + kHMax + 16 + kBM * kXStride + kBM * kDStride) * 4 + 16;
 static_assert(kFusedSmem <= 232448, "fused kernel exceeds the 227 KB shared memory of an sm_100 CTA");
 constexpr unsigned long long kSentinel = ~0ull;
 
 struct FParams {
-  int B, D, H, C, Z, BN, n_tiles, m_tiles, num_items, num_kb;
+  int B, D, H, C, Z, BN, n_tiles, m_tiles, m_units, num_items, num_kb;   // m_units = m_tiles, or ceil(m_tiles / 2) for CTA pairs
   int head;
   const float* bank; long long P, b1_off, wo_off, bo_off; int z_row0;
   const int32_t* labels; const float* pbar;
@@ -196,76 +202,99 @@ __device__ __forceinline__ void head_row(int head, float (&l)[kCMax], int C, int
   for (int c = 0; c < kCMax; ++c) l[c] = c < C ? l[c] * (g[c] - dot) : 0.f;
 }
 
-// Pass 2 on one chunk of 32 hidden columns j0 .. j0+31 of this thread's input row:
-//   dH[j] = (sum_c dl[c] Wo[c][j]) * leaky'(H[j])     (dl already carries the F16X3 range scale)
-// written as fp16 hi/lo (F16X3), tf32 hi/lo (TF32X3) or bf16.  bits: bit q = LeakyReLU mask of column j0 + q.
-// out: element offset of (row, j0) in the [Z][B][H] arrays.
-template <int MODE>
-__device__ __forceinline__ void pass2_chunk(const float (&dl)[kCMax], int C, const float* __restrict__ wo_s, int H, int j0,
-                                            uint32_t bits, bool rok, long long out, void* dh_hi, void* dh_lo,
-                                            __nv_bfloat16* dh_bf, bool no_store) {
-#pragma unroll 1
-  for (int hf = 0; hf < 2; ++hf) {                        // 16 columns at a time (register budget)
-    const int jh = j0 + 16 * hf;
-    const uint32_t hb = bits >> (16 * hf);
-    const long long o = out + 16 * hf;
-    uint64_t d2[8];
+// ---- pass 2, row-cooperative -------------------------------------------------------------------------------------
+// For one input row, lane l of epilogue warp (quad, cq) owns the 4 hidden columns j .. j+3 with
+//   n-tile n = l / 16, column inside the n-tile c = 64 cq + 4 (l % 16)      (the two 32-column chunks 2 cq, 2 cq + 1
+// of each n-tile that the warp also owns in pass 1), so 16 lanes cover one 128-byte line of fp16 output.
+struct P2Lane {
+  int j;          // first hidden unit of this lane
+  int word;       // which of the owner thread's mask words holds its bits: n * 2 + chunk parity
+  int shift;      // bit of column j inside that word
+  bool valid;     // inside the hidden layer
+};
+__device__ __forceinline__ P2Lane p2_lane(int lane, int cq, int BN, int n_tiles) {
+  P2Lane g;
+  const int n = lane >> 4, c = cq * 64 + 4 * (lane & 15);
+  g.valid = n < n_tiles && c < BN;
+  g.j = n * BN + c;
+  g.word = n * 2 + ((lane & 15) >> 3);
+  g.shift = 4 * (lane & 7);
+  return g;
+}
+// The lane's slice of Wo_z as column pairs, exactly as they lie in shared memory (so they stay in aligned register pairs):
+// wq[c][0] = (Wo[c][j], Wo[c][j+1]), wq[c][1] = (Wo[c][j+2], Wo[c][j+3]); classes >= C are zero.
+__device__ __forceinline__ void p2_load_wo(uint64_t (&wq)[kCMax][2], const float* __restrict__ wo_s, int H, int C,
+                                           const P2Lane& g) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d2[i] = 0ull;
+  for (int c = 0; c < kCMax; ++c) {
+    ulonglong2 t = make_ulonglong2(0ull, 0ull);
+    if (g.valid && c < C) t = *reinterpret_cast<const ulonglong2*>(wo_s + c * H + g.j);
+    wq[c][0] = t.x;
+    wq[c][1] = t.y;
+  }
+}
+__device__ __forceinline__ void st_cs_u2(void* ptr, uint32_t a, uint32_t b) {
+  asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(ptr), "r"(a), "r"(b) : "memory");
+}
+// dH[row][j .. j+3] = (sum_c dl[row][c] Wo[c][j ..]) * leaky'(H) for the 32 rows of TMEM lane quadrant `quad`, written as
+// fp16 hi/lo (F16X3), tf32 hi/lo (TF32X3) or bf16.  xd: [128][kDStride] dlogits (already carrying the F16X3 range scale,
+// slots >= C zero); mbits: this THREAD's mask words (thread = row `lane` of the quadrant), fetched by shuffle.
+// b0: input index of the quadrant's first row; zrow: z * B.  Two columns per FFMA2 (fma.rn.f32x2 with the row's dlogit
+// broadcast), 10-deep chains, two rows in flight.
+template <int MODE>
+__device__ __forceinline__ void pass2_rows(const uint64_t (&wq)[kCMax][2], const P2Lane& g, const float* xd,
+                                           const uint32_t (&mbits)[kMaskWords], int quad, int b0, int B, int H,
+                                           long long zrow, void* dh_hi, void* dh_lo, __nv_bfloat16* dh_bf, bool no_store) {
+  // byte pointers of (first row of the quadrant, column j) in the output arrays, advanced one row per iteration
+  constexpr int ES = MODE == MODE_TF32X3 ? 4 : 2;
+  const long long o0 = ((zrow + b0) * H + g.j) * ES;
+  char* ph = reinterpret_cast<char*>(MODE == MODE_BF16 ? (void*)dh_bf : dh_hi) + o0;
+  char* pl = MODE == MODE_BF16 ? nullptr : reinterpret_cast<char*>(dh_lo) + o0;
+  const int row_bytes = H * ES;
+  const int rows_ok = (g.valid && !no_store) ? min(32, B - b0) : 0;
+#pragma unroll 2
+  for (int rr = 0; rr < 32; ++rr, ph += row_bytes, pl += row_bytes) {
+    uint32_t w = 0u;
+#pragma unroll
+    for (int k = 0; k < kMaskWords; ++k) {
+      const uint32_t t = __shfl_sync(0xffffffffu, mbits[k], rr);
+      if (k == g.word) w = t;
+    }
+    const uint32_t bits = w >> g.shift;
+    const float* d = xd + (quad * 32 + rr) * kDStride;
+    const float4 d0 = *reinterpret_cast<const float4*>(d);
+    const float4 d1 = *reinterpret_cast<const float4*>(d + 4);
+    const float2 d2 = *reinterpret_cast<const float2*>(d + 8);
+    const float dl[kCMax] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y};
+    uint64_t a0 = 0ull, a1 = 0ull;
 #pragma unroll
     for (int c = 0; c < kCMax; ++c) {
-      if (c < C) {
-        const uint64_t dd = pack2(dl[c], dl[c]);
-        const float4* __restrict__ wr = reinterpret_cast<const float4*>(wo_s + c * H + jh);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 w = wr[q];
-          d2[2 * q] = ffma2(dd, pack2(w.x, w.y), d2[2 * q]);
-          d2[2 * q + 1] = ffma2(dd, pack2(w.z, w.w), d2[2 * q + 1]);
-        }
-      }
+      const uint64_t dd = pack2(dl[c], dl[c]);
+      a0 = ffma2(dd, wq[c][0], a0);
+      a1 = ffma2(dd, wq[c][1], a1);
     }
-    if (MODE == MODE_TF32X3) {
-      float* ph = reinterpret_cast<float*>(dh_hi) + o;
-      float* pl = reinterpret_cast<float*>(dh_lo) + o;
+    float v[4];
+    unpack2(a0, v[0], v[1]);
+    unpack2(a1, v[2], v[3]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[4];
-        unpack2(d2[2 * q], v[0], v[1]);
-        unpack2(d2[2 * q + 1], v[2], v[3]);
+    for (int q = 0; q < 4; ++q)
+      if (!((bits >> q) & 1u)) v[q] *= kSlopeF;
+    if (rr < rows_ok) {
+      if (MODE == MODE_TF32X3) {
         float4 hi4, lo4;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (!((hb >> (4 * q + e)) & 1u)) v[e] *= kSlopeF;
         hi4.x = to_tf32_rn(v[0]); hi4.y = to_tf32_rn(v[1]); hi4.z = to_tf32_rn(v[2]); hi4.w = to_tf32_rn(v[3]);
         lo4.x = v[0] - hi4.x; lo4.y = v[1] - hi4.y; lo4.z = v[2] - hi4.z; lo4.w = v[3] - hi4.w;
-        if (rok && !no_store) {
-          __stcs(reinterpret_cast<float4*>(ph) + q, hi4);     // streaming: do not displace X / W1 in L2
-          __stcs(reinterpret_cast<float4*>(pl) + q, lo4);
-        }
-      }
-    } else {
-      uint32_t whi[8], wlo[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float a, b;
-        unpack2(d2[i], a, b);
-        if (!((hb >> (2 * i)) & 1u)) a *= kSlopeF;
-        if (!((hb >> (2 * i + 1)) & 1u)) b *= kSlopeF;
-        if (MODE == MODE_BF16) {
-          const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-          whi[i] = *reinterpret_cast<const uint32_t*>(&t);
-        } else {
-          split_pair(a, b, whi[i], wlo[i]);
-        }
-      }
-      if (rok && !no_store) {
-        if (MODE == MODE_BF16) {
-          st_cs_u8(dh_bf + o, whi);
-        } else {
-          st_cs_u8(reinterpret_cast<__half*>(dh_hi) + o, whi);
-          st_cs_u8(reinterpret_cast<__half*>(dh_lo) + o, wlo);
-        }
+        __stcs(reinterpret_cast<float4*>(ph), hi4);   // streaming: keep X / W1 in L2
+        __stcs(reinterpret_cast<float4*>(pl), lo4);
+      } else if (MODE == MODE_BF16) {
+        const __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+        st_cs_u2(ph, *reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1));
+      } else {
+        uint32_t h0, l0, h1, l1;
+        split_pair(v[0], v[1], h0, l0);
+        split_pair(v[2], v[3], h1, l1);
+        st_cs_u2(ph, h0, h1);
+        st_cs_u2(pl, l0, l1);
       }
     }
   }
@@ -289,7 +318,15 @@ __device__ __forceinline__ void stage_head_params(const float* __restrict__ wrow
   if (bo_s && t < C) bo_s[t] = __ldg(wrow + bo_off + t);
 }
 
-template <int MODE, int KBB>
+// CT: class count known at compile time (0 = use p.C): the headline net has 10 classes, and with runtime bounds every
+// FFMA2 of pass 1 was predicated and shadowed by two MOVs.
+// PAIR: two CTAs of a cluster (the SM pair of a TPC) work on one sample and two adjacent 128-input tiles with
+// tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own inputs and HALF of the W1 n-tile, the leader issues the
+// MMAs for both, each CTA's TMEM receives its own 128 accumulator rows and each CTA runs its own epilogue.  Per SM this
+// removes a third of the operand bytes fetched from L2 and a third of the tensor cores' shared-memory operand reads --
+// the shared-memory data pipe (MMA operand reads + the epilogue's loads) is what bounds the single-CTA kernel.  The
+// barrier protocol is tc_gemm.cu's relay variant.
+template <int MODE, int KBB, int CT, bool PAIR>
 __global__ void __launch_bounds__(kThreadsF, 1)
 fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -297,7 +334,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   constexpr bool BF16 = MODE == MODE_BF16;
   constexpr bool F16K = MODE != MODE_TF32X3;            // kind::f16 MMAs on 2-byte operands
   constexpr int NARR = BF16 ? 1 : 2;
-  constexpr int kATileF = kBM * KBB, kBTileF = kBNMax * KBB;
+  constexpr int kATileF = kBM * KBB, kBTileF = (PAIR ? kBNMax / 2 : kBNMax) * KBB;
+  constexpr int NCTA = PAIR ? 2 : 1;
   constexpr int STAGE = NARR * (kATileF + kBTileF);
   constexpr int NSTAGE = kRingF / STAGE;
   constexpr int KBE = KBB / (F16K ? 2 : 4);
@@ -313,6 +351,11 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   uint8_t* gen = smem_raw + (bars - raw);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 16 * NSTAGE + 32);
   uint32_t* wl_count = reinterpret_cast<uint32_t*>(gen + 16 * NSTAGE + 40);
+  const uint32_t pfull0 = bars + 16 * NSTAGE + 48;         // pair protocol: "the peer's stage is full" (leader's copy)
+  static_assert(16 * NSTAGE + 48 + 8 * NSTAGE <= 256, "barrier block");
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // scheduling unit: CTA or CTA pair
+  const int num_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   float* wo_s = reinterpret_cast<float*>(gen + 256);       // [C][H] fp32
   float* b1_s = wo_s + kCMax * kHMax;                       // [H]
   float* bo_s = b1_s + kHMax;                               // [16]
@@ -325,10 +368,11 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
+      if (PAIR) mbar_init(pfull0 + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, kEpiWarps);
+      mbar_init(tempty0 + 8 * s, kEpiWarps * NCTA);           // one arrival per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
@@ -338,17 +382,15 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
     }
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  static_assert(kTmemCols == 512, "tmem_alloc allocates 512 columns");
+  if (warp == 1) tmem_alloc<PAIR>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                            // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t stage_tx = (uint32_t)NARR * (uint32_t)(kATileF + p.BN * KBB);
+  const int bn_cta = PAIR ? p.BN / 2 : p.BN;               // W1 rows (hidden units) staged by this CTA per n-tile
+  const uint32_t stage_tx = (uint32_t)NARR * (uint32_t)(kATileF + bn_cta * KBB);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -359,8 +401,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int z = item / p.m_tiles, m_idx = item % p.m_tiles;
+      for (int item = unit; item < p.num_items; item += num_units) {
+        const int z = item / p.m_units, m_idx = PAIR ? 2 * (item % p.m_units) + (int)rank : item % p.m_units;
         for (int n = 0; n < p.n_tiles; ++n) {
           for (int kb = 0; kb < p.num_kb; ++kb) {
             const long long t0 = clock64();
@@ -372,11 +414,11 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
             const uint32_t sb = sa + NARR * kATileF;
             if (hint) tma_load_3d_hint(sa, &tmAh, fb, kb * KBE, m_idx * kBM, 0, pol_x);
             else tma_load_3d(sa, &tmAh, fb, kb * KBE, m_idx * kBM, 0);
-            tma_load_3d(sb, &tmBh, fb, kb * KBE, n * p.BN, z);
+            tma_load_3d(sb, &tmBh, fb, kb * KBE, n * p.BN + (int)rank * bn_cta, z);
             if (!BF16) {
               if (hint) tma_load_3d_hint(sa + kATileF, &tmAl, fb, kb * KBE, m_idx * kBM, 0, pol_x);
               else tma_load_3d(sa + kATileF, &tmAl, fb, kb * KBE, m_idx * kBM, 0);
-              tma_load_3d(sb + kBTileF, &tmBl, fb, kb * KBE, n * p.BN, z);
+              tma_load_3d(sb + kBTileF, &tmBl, fb, kb * KBE, n * p.BN + (int)rank * bn_cta, z);
             }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
           }
@@ -386,14 +428,27 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         printf("[fused cta0] TMA producer: total %lld cyc, waiting for an empty stage %lld\n", clock64() - t_begin, w_empty);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (PAIR && lane == 0 && rank == 1) {
+      // ===================== peer relay: own stage full -> tell the leader =====================
+      const uint32_t pf = mapa_u32(pfull0, 0u);
+      uint32_t stage = 0, phase = 0;
+      for (int item = unit; item < p.num_items; item += num_units) {
+        const int total_kb = p.n_tiles * p.num_kb;
+        for (int i = 0; i < total_kb; ++i) {
+          mbar_wait(full0 + 8 * stage, phase);
+          mbar_arrive_cluster(pf + 8 * stage);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA of a pair) =====================
       const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                             ((uint32_t)(kBM >> 4) << 24);
+                             ((uint32_t)((kBM * NCTA) >> 4) << 24);
       uint32_t stage = 0, phase = 0, it = 0;
       long long w_tempty = 0, w_full = 0;
       const long long t_begin = clock64();
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = unit; item < p.num_items; item += num_units) {
         for (int n = 0; n < p.n_tiles; ++n, ++it) {
           const uint32_t as = it & 1u;
           long long t0 = clock64();
@@ -405,6 +460,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           for (int kb = 0; kb < p.num_kb; ++kb) {
             t0 = clock64();
             mbar_wait(full0 + 8 * stage, phase);
+            if (PAIR) mbar_wait(pfull0 + 8 * stage, phase);
             w_full += clock64() - t0;
             tc_fence_after();
             const uint32_t sa = ring + stage * STAGE;
@@ -413,23 +469,32 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
             if (BF16) {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                tc_mma<true>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                if (PAIR) tc_mma_pair<true>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                else tc_mma<true>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
                 accumulate = 1;
               }
             } else {
               const uint64_t a_lo = smem_desc<KBB>(sa + kATileF), b_lo = smem_desc<KBB>(sb + kBTileF);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
-                tc_mma<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
-                tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                if (PAIR) {
+                  tc_mma_pair<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                  tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                  tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                } else {
+                  tc_mma<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                  tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                  tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                }
                 accumulate = 1;
               }
             }
-            tc_commit(empty0 + 8 * stage);
+            if (PAIR) tc_commit_pair(empty0 + 8 * stage, (uint16_t)3);   // stage reusable in both CTAs once these MMAs retire
+            else tc_commit(empty0 + 8 * stage);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(tfull0 + 8 * as);
+          if (PAIR) tc_commit_pair(tfull0 + 8 * as, (uint16_t)3);        // accumulator complete (both CTAs' epilogues)
+          else tc_commit(tfull0 + 8 * as);
         }
       }
       if ((p.debug & 8) && blockIdx.x == 0)
@@ -438,17 +503,18 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     }
   } else {
     // ===================== epilogue: warps 2..17 =====================
-    // warp = (TMEM lane quadrant `quad` = warp % 4, column quarter `cq`); thread = input row quad*32 + lane.
-    // Of an n-tile's BN / 32 chunks of 32 columns this warp takes chunks cq and cq + 4.
+    // warp = (TMEM lane quadrant `quad` = warp % 4, column quarter `cq`); in pass 1 thread = input row quad*32 + lane.
+    // Of an n-tile's BN / 32 chunks of 32 columns this warp takes chunks 2 cq and 2 cq + 1 (64 contiguous columns).
     const int ew = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int cq = ew >> 2;                    // column quarter
     const int et = threadIdx.x - 64;           // 0..511
-    const int C = p.C, H = p.H;
+    const int C = CT ? CT : p.C, H = p.H;
     const int nchunks = p.BN / 32;             // chunks per n-tile (1..8)
     const int row = quad * 32 + lane;          // row inside the 128-input tile
     const float unscale = (MODE == MODE_F16X3) ? __ldg(p.unscale) : 1.f;     // 1 / (s_X s_W1)
     const float dh_scale = (MODE == MODE_F16X3) ? __ldg(p.dh_scale) : 1.f;   // dH -> fp16 range
+    const P2Lane g2 = p2_lane(lane, cq, p.BN, p.n_tiles);
     uint32_t it = 0;
 #ifdef RBNN_FUSED_TIMERS
     long long w_tfull = 0, c_stage = 0, c_p1 = 0, c_head = 0, c_p2 = 0, t_mark = clock64();
@@ -457,8 +523,11 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #else
 #define RBNN_TMARK(acc)
 #endif
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const int z = item / p.m_tiles, m_idx = item % p.m_tiles;
+    const uint32_t tempty_leader = PAIR ? mapa_u32(tempty0, 0u) : tempty0;
+    for (int item = unit; item < p.num_items; item += num_units) {
+      const int z = item / p.m_units, m_idx = PAIR ? 2 * (item % p.m_units) + (int)rank : item % p.m_units;
+      const bool tile_ok = m_idx < p.m_tiles;             // a pair's second tile may lie entirely past the last input
+      const long long item_w = (long long)z * p.m_tiles + m_idx;   // this tile's slot in the worklist / mask buffer
       const float* __restrict__ wrow = p.bank + (long long)(p.z_row0 + z) * p.P;
       RBNN_TMARK(c_p2)
       // ---------------- stage Wo_z, b1_z, bo_z (fp32) ----------------
@@ -469,17 +538,19 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       const int b = m_idx * kBM + row;
       const bool rok = b < p.B;
       const float guard = (rok && p.eps > 0.f) ? p.eps * __ldg(p.wnorm + p.z_row0 + z) * __ldg(p.xnorm + b) : 0.f;
-      unsigned long long* wl = p.worklist ? p.worklist + (long long)item * kWorkPerItem : nullptr;
+      unsigned long long* wl = (p.worklist && tile_ok) ? p.worklist + item_w * kWorkPerItem : nullptr;
       uint64_t acc2[kCMax];                     // partial logits: (even hidden units, odd hidden units) of this thread's chunks
 #pragma unroll
       for (int c = 0; c < kCMax; ++c) acc2[c] = 0ull;
-      uint32_t mbits[kMaskWords];               // word n * 2 + i: chunk cq + 4 i of n-tile n
+      uint32_t mbits[kMaskWords];               // word n * 2 + i: chunk 2 cq + i of n-tile n
 #pragma unroll
       for (int i = 0; i < kMaskWords; ++i) mbits[i] = 0u;
 
       RBNN_TMARK(c_stage)
       // ---------------- pass 1 ----------------
-      for (int n = 0; n < p.n_tiles; ++n, ++it) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        if (n >= p.n_tiles) break;
         const uint32_t as = it & 1u;
 #ifdef RBNN_FUSED_TIMERS
         { const long long t0 = clock64(); mbar_wait(tfull0 + 8 * as, (it >> 1) & 1u); w_tfull += clock64() - t0; }
@@ -488,83 +559,86 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 #endif
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)kBNMax;
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int ch = cq + 4 * i;
-          if (ch >= nchunks) break;
-          const int c0 = ch * 32;                                 // column inside the n-tile
-          const int j0 = n * p.BN + c0;
+          const int ch = 2 * cq + i;
           uint32_t bits = 0u;
+          if (ch < nchunks) {
+            const int c0 = ch * 32;                                 // column inside the n-tile
+            const int j0 = n * p.BN + c0;
 #pragma unroll 1
-          for (int hf = 0; hf < 2; ++hf) {                        // 16 columns at a time (register budget: 96 per thread)
-            uint32_t v[16];
-            tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16 * hf), v);
-            const int jh = j0 + 16 * hf;
-            tmem_ld_wait();
-            if (p.debug & 4) continue;
-            uint32_t hb = 0u;
-            float amin = INFINITY;
+            for (int hf = 0; hf < 2; ++hf) {                        // 16 columns at a time (register budget: 96 per thread)
+              uint32_t v[16];
+              tmem_ld16_nowait(taddr + (uint32_t)(c0 + 16 * hf), v);
+              const int jh = j0 + 16 * hf;
+              tmem_ld_wait();
+              if (p.debug & 4) continue;
+              uint32_t hb = 0u;
+              float amin = INFINITY;
 #pragma unroll
-            for (int q = 0; q < 16; q += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(b1_s + jh + q);
-              float h[4];
-              if (MODE == MODE_F16X3) {
-                h[0] = fmaf(__uint_as_float(v[q]), unscale, bb.x);
-                h[1] = fmaf(__uint_as_float(v[q + 1]), unscale, bb.y);
-                h[2] = fmaf(__uint_as_float(v[q + 2]), unscale, bb.z);
-                h[3] = fmaf(__uint_as_float(v[q + 3]), unscale, bb.w);
-              } else {
-                h[0] = __uint_as_float(v[q]) + bb.x;
-                h[1] = __uint_as_float(v[q + 1]) + bb.y;
-                h[2] = __uint_as_float(v[q + 2]) + bb.z;
-                h[3] = __uint_as_float(v[q + 3]) + bb.w;
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                amin = fminf(amin, fabsf(h[e]));
-                if (h[e] > 0.f) hb |= 1u << (q + e);
-                v[q + e] = __float_as_uint(h[e]);                 // keep the pre-activation for the guard-band path
-                h[e] = fmaxf(h[e], h[e] * kSlopeF);               // LeakyReLU (slope < 1)
-              }
-              const uint64_t a01 = pack2(h[0], h[1]), a23 = pack2(h[2], h[3]);
-#pragma unroll
-              for (int c = 0; c < kCMax; ++c)
-                if (c < C) {
-                  const float4 w = *reinterpret_cast<const float4*>(wo_s + c * H + jh + q);
-                  acc2[c] = ffma2(a01, pack2(w.x, w.y), acc2[c]);
-                  acc2[c] = ffma2(a23, pack2(w.z, w.w), acc2[c]);
+              for (int q = 0; q < 16; q += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(b1_s + jh + q);
+                float h[4];
+                if (MODE == MODE_F16X3) {
+                  h[0] = fmaf(__uint_as_float(v[q]), unscale, bb.x);
+                  h[1] = fmaf(__uint_as_float(v[q + 1]), unscale, bb.y);
+                  h[2] = fmaf(__uint_as_float(v[q + 2]), unscale, bb.z);
+                  h[3] = fmaf(__uint_as_float(v[q + 3]), unscale, bb.w);
+                } else {
+                  h[0] = __uint_as_float(v[q]) + bb.x;
+                  h[1] = __uint_as_float(v[q + 1]) + bb.y;
+                  h[2] = __uint_as_float(v[q + 2]) + bb.z;
+                  h[3] = __uint_as_float(v[q + 3]) + bb.w;
                 }
-            }
-            if (amin < guard) {
-              // rare: some pre-activation of these 16 columns lies inside the guard band
-#pragma unroll 1
-              for (int q = 0; q < 16; ++q) {
-                float hq = 0.f;
 #pragma unroll
-                for (int u = 0; u < 16; ++u)
-                  if (u == q) hq = __uint_as_float(v[u]);
-                if (!(fabsf(hq) < guard)) continue;
-                const bool pos = hq > 0.f;
-                const uint32_t slot = atomicAdd(wl_count, 1u);
-                if (slot < (uint32_t)kWorkPerItem) {
-                  wl[slot] = pack_entry(z, b, jh + q, pos);
-                } else {                                          // item budget exhausted: settle it here
-                  const bool ex = exact_positive_serial(p.x + (long long)b * p.D, wrow + (long long)(jh + q) * p.D,
-                                                        b1_s[jh + q], p.D);
-                  if (ex != pos) hb ^= 1u << q;
+                for (int e = 0; e < 4; ++e) {
+                  amin = fminf(amin, fabsf(h[e]));
+                  if (h[e] > 0.f) hb |= 1u << (q + e);
+                  v[q + e] = __float_as_uint(h[e]);                 // keep the pre-activation for the guard-band path
+                  h[e] = fmaxf(h[e], h[e] * kSlopeF);               // LeakyReLU (slope < 1)
+                }
+                const uint64_t a01 = pack2(h[0], h[1]), a23 = pack2(h[2], h[3]);
+#pragma unroll
+                for (int c = 0; c < kCMax; ++c)
+                  if (c < C) {
+                    const float4 w = *reinterpret_cast<const float4*>(wo_s + c * H + jh + q);
+                    acc2[c] = ffma2(a01, pack2(w.x, w.y), acc2[c]);
+                    acc2[c] = ffma2(a23, pack2(w.z, w.w), acc2[c]);
+                  }
+              }
+              if (amin < guard) {
+                // rare (one 16-column group in ten): some pre-activation lies inside the guard band.  Kept short on
+                // purpose -- the warps of an item meet at a barrier after pass 1, so a slow rare path stalls all of them.
+                uint32_t inband = 0u;
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                  if (fabsf(__uint_as_float(v[q])) < guard) inband |= 1u << q;
+                while (inband) {
+                  const int q = __ffs(inband) - 1;
+                  inband &= inband - 1u;
+                  const bool pos = (hb >> q) & 1u;
+                  const uint32_t slot = atomicAdd(wl_count, 1u);
+                  if (slot < (uint32_t)kWorkPerItem) {
+                    wl[slot] = pack_entry(z, b, jh + q, pos);
+                  } else {                                          // item budget exhausted: settle it here
+                    const bool ex = exact_positive_serial(p.x + (long long)b * p.D, wrow + (long long)(jh + q) * p.D,
+                                                          b1_s[jh + q], p.D);
+                    if (ex != pos) hb ^= 1u << q;
+                  }
                 }
               }
+              bits |= hb << (16 * hf);
             }
-            bits |= hb << (16 * hf);
           }
-          const int word = n * 2 + i;
-#pragma unroll
-          for (int k = 0; k < kMaskWords; ++k)
-            if (k == word) mbits[k] = bits;
+          mbits[n * 2 + i] = bits;
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(tempty_leader + 8 * as);
+          else mbar_arrive(tempty0 + 8 * as);
+        }
+        ++it;
       }
 
       RBNN_TMARK(c_p1)
@@ -605,8 +679,11 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           }
         } else {
           head_row(p.head, dl, C, rok ? p.labels[b] : 0, (rok && p.pbar) ? p.pbar + (long long)b * C : nullptr);
-#pragma unroll
-          for (int c = 0; c < kCMax; ++c) xb[row * kXStride + c] = dl[c] * dh_scale;   // power of two: exact
+          // dlogits (x the F16X3 range scale, a power of two: exact) for pass 2: rows of kDStride floats, slots >= C zero
+          float4* dst = reinterpret_cast<float4*>(xb + row * kDStride);
+          dst[0] = make_float4(dl[0] * dh_scale, dl[1] * dh_scale, dl[2] * dh_scale, dl[3] * dh_scale);
+          dst[1] = make_float4(dl[4] * dh_scale, dl[5] * dh_scale, dl[6] * dh_scale, dl[7] * dh_scale);
+          dst[2] = make_float4(dl[8] * dh_scale, dl[9] * dh_scale, 0.f, 0.f);
         }
       }
       epi_bar();
@@ -615,36 +692,23 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         const uint32_t used = min(*wl_count, (uint32_t)kWorkPerItem);
         for (uint32_t i = used + et; i < (uint32_t)kWorkPerItem; i += kEpiThreads) wl[i] = kSentinel;
       }
-      if (p.head == -2) {                       // keep mode: the LeakyReLU masks of this item for the gradient pass
-        uint32_t* mb = p.maskbuf + (long long)item * (kMaskWordsItem * kBM) + row;
+      if (p.head == -2 && tile_ok) {            // keep mode: the LeakyReLU masks of this item for the gradient pass
+        uint32_t* mb = p.maskbuf + item_w * (kMaskWordsItem * kBM) + row;
 #pragma unroll
         for (int k = 0; k < kMaskWords; ++k) {
-          const int n = k >> 1, ch = cq + 4 * (k & 1);
+          const int n = k >> 1, ch = 2 * cq + (k & 1);
           if (n < p.n_tiles && ch < nchunks) mb[(n * nchunks + ch) * kBM] = mbits[k];
         }
       }
       if (p.head < 0) continue;
-#pragma unroll
-      for (int c = 0; c < kCMax; ++c) dl[c] = xb[row * kXStride + c];
 
       RBNN_TMARK(c_head)
-      // ---------------- pass 2: dH = (dlogits . Wo) * leaky'(H) for this thread's chunks ----------------
+      // ---------------- pass 2: dH = (dlogits . Wo) * leaky'(H), row-cooperative ----------------
       if (!(p.debug & 2)) {
-        const long long orow = ((long long)z * p.B + b) * H;
-        for (int n = 0; n < p.n_tiles; ++n) {
-#pragma unroll 1
-          for (int i = 0; i < 2; ++i) {
-            const int ch = cq + 4 * i;
-            if (ch >= nchunks) break;
-            const int j0 = n * p.BN + ch * 32;
-            const int word = n * 2 + i;
-            uint32_t bits = 0u;
-#pragma unroll
-            for (int k = 0; k < kMaskWords; ++k)
-              if (k == word) bits = mbits[k];
-            pass2_chunk<MODE>(dl, C, wo_s, H, j0, bits, rok, orow + j0, p.dh_hi, p.dh_lo, p.dh_bf, (p.debug & 1) != 0);
-          }
-        }
+        uint64_t wq[kCMax][2];                  // the lane's slice of Wo (wo_s is stable until the next item's staging)
+        p2_load_wo(wq, wo_s, H, C, g2);
+        pass2_rows<MODE>(wq, g2, xb, mbits, quad, m_idx * kBM + quad * 32, p.B, H, (long long)z * p.B, p.dh_hi, p.dh_lo,
+                         p.dh_bf, (p.debug & 1) != 0);
       }
     }
 #ifdef RBNN_FUSED_TIMERS
@@ -657,9 +721,10 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                            // no CTA leaves while its peer may still signal / read it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    tmem_dealloc<PAIR>(tmem_base);
   }
 }
 
@@ -736,17 +801,19 @@ fixup_kernel(const unsigned long long* __restrict__ wl, int num_items, const flo
 // kernel without its GEMM.  One CTA of 512 threads per work item at a time: thread = (input row, column quarter) as in
 // the fused epilogue.
 template <int MODE>
-__global__ void __launch_bounds__(kEpiThreads, 2)
+__global__ void __launch_bounds__(kEpiThreads)
 dh_from_kept_kernel(int B, int H, int C, int num_items, int m_tiles, int head, const float* __restrict__ bank, long long P,
                     long long wo_off, int z_row0, const int32_t* __restrict__ labels, const float* __restrict__ pbar,
                     const float* __restrict__ logits, const uint32_t* __restrict__ masks, void* dh_hi, void* dh_lo,
                     __nv_bfloat16* dh_bf, const float* __restrict__ dh_scale_p) {
   extern __shared__ float ksm[];
   float* wo_s = ksm;                            // [C][H]
-  float* xd = ksm + kCMax * kHMax;              // [128][kXStride] dlogits
-  const int et = threadIdx.x;
-  const int row = et & (kBM - 1), cq = et >> 7;
-  const int nwords = H / 32;
+  float* xd = ksm + kCMax * kHMax;              // [128][kDStride] dlogits
+  const int et = threadIdx.x, warp = et >> 5, lane = et & 31;
+  const int quad = warp & 3, cq = warp >> 2;    // as in the fused epilogue: warp = (32-row group, column quarter)
+  const int row = quad * 32 + lane;
+  const int BN = H <= 256 ? H : 256, n_tiles = H <= 256 ? 1 : H / 256, nchunks = BN / 32;
+  const P2Lane g2 = p2_lane(lane, cq, BN, n_tiles);
   const float dh_scale = (MODE == MODE_F16X3) ? __ldg(dh_scale_p) : 1.f;
   for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
     const int z = item / m_tiles, m_idx = item % m_tiles;
@@ -761,19 +828,23 @@ dh_from_kept_kernel(int B, int H, int C, int num_items, int m_tiles, int head, c
 #pragma unroll
       for (int c = 0; c < kCMax; ++c) dl[c] = (c < C && rok) ? __ldg(lrow + c) : 0.f;
       head_row(head, dl, C, rok ? labels[b] : 0, (rok && pbar) ? pbar + (long long)b * C : nullptr);
+      float4* dst = reinterpret_cast<float4*>(xd + row * kDStride);
+      dst[0] = make_float4(dl[0] * dh_scale, dl[1] * dh_scale, dl[2] * dh_scale, dl[3] * dh_scale);
+      dst[1] = make_float4(dl[4] * dh_scale, dl[5] * dh_scale, dl[6] * dh_scale, dl[7] * dh_scale);
+      dst[2] = make_float4(dl[8] * dh_scale, dl[9] * dh_scale, 0.f, 0.f);
+    }
+    // this thread's mask words (thread = row): chunks 2 cq, 2 cq + 1 of every n-tile, the fused kernel's keep-mode layout
+    uint32_t mbits[kMaskWords];
+    const uint32_t* __restrict__ mb = masks + (long long)item * (kMaskWordsItem * kBM) + row;
 #pragma unroll
-      for (int c = 0; c < kCMax; ++c) xd[row * kXStride + c] = dl[c] * dh_scale;
+    for (int k = 0; k < kMaskWords; ++k) {
+      const int n = k >> 1, ch = 2 * cq + (k & 1);
+      mbits[k] = (n < n_tiles && ch < nchunks) ? __ldg(mb + (n * nchunks + ch) * kBM) : 0u;
     }
     __syncthreads();
-    float dl[kCMax];
-#pragma unroll
-    for (int c = 0; c < kCMax; ++c) dl[c] = xd[row * kXStride + c];
-    const long long orow = ((long long)z * B + b) * H;
-    const uint32_t* __restrict__ mb = masks + (long long)item * (kMaskWordsItem * kBM) + row;
-    for (int w = cq; w < nwords; w += 4) {
-      const uint32_t bits = __ldg(mb + w * kBM);
-      pass2_chunk<MODE>(dl, C, wo_s, H, w * 32, bits, rok, orow + w * 32, dh_hi, dh_lo, dh_bf, false);
-    }
+    uint64_t wq[kCMax][2];
+    p2_load_wo(wq, wo_s, H, C, g2);
+    pass2_rows<MODE>(wq, g2, xd, mbits, quad, m_idx * kBM + quad * 32, B, H, (long long)z * B, dh_hi, dh_lo, dh_bf, false);
   }
 }
 
@@ -796,24 +867,38 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   if (!fused_supported(d.H, d.C)) { *err = "fused_forward_head: unsupported hidden / class size"; return 1; }
   if (d.mode < 0 || d.mode > MODE_F16X3) { *err = "fused_forward_head: unknown mode"; return 1; }
   if (f16x3 && (!d.unscale || !d.dh_scale)) { *err = "fused_forward_head: F16X3 needs the scale scalars"; return 1; }
-  const int kbb = d.kblock_bytes == 128 ? 128 : 64;
+  static const int env_kbb = getenv("RBNN_FUSED_KBB") ? atoi(getenv("RBNN_FUSED_KBB")) : 0;   // experiments
+  const int kbb = env_kbb == 64 ? 64 : (env_kbb == 128 ? 128 : (d.kblock_bytes == 128 ? 128 : 64));
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FParams);
-  static const kern_t kerns[3][2] = {{fc_fused_kernel<MODE_TF32X3, 64>, fc_fused_kernel<MODE_TF32X3, 128>},
-                                     {fc_fused_kernel<MODE_BF16, 64>, fc_fused_kernel<MODE_BF16, 128>},
-                                     {fc_fused_kernel<MODE_F16X3, 64>, fc_fused_kernel<MODE_F16X3, 128>}};
-  kern_t kern = kerns[d.mode][kbb == 128];
-  static bool attr_done[3][2] = {};
-  if (!attr_done[d.mode][kbb == 128]) {
+  // [mode][runtime class count / 10 classes at compile time][variant: 64-byte K-blocks, 128-byte K-blocks, CTA pairs]
+  static const kern_t kerns[3][2][3] = {
+      {{fc_fused_kernel<MODE_TF32X3, 64, 0, false>, fc_fused_kernel<MODE_TF32X3, 128, 0, false>, fc_fused_kernel<MODE_TF32X3, 128, 0, true>},
+       {fc_fused_kernel<MODE_TF32X3, 64, 10, false>, fc_fused_kernel<MODE_TF32X3, 128, 10, false>, fc_fused_kernel<MODE_TF32X3, 128, 10, true>}},
+      {{fc_fused_kernel<MODE_BF16, 64, 0, false>, fc_fused_kernel<MODE_BF16, 128, 0, false>, fc_fused_kernel<MODE_BF16, 128, 0, true>},
+       {fc_fused_kernel<MODE_BF16, 64, 10, false>, fc_fused_kernel<MODE_BF16, 128, 10, false>, fc_fused_kernel<MODE_BF16, 128, 10, true>}},
+      {{fc_fused_kernel<MODE_F16X3, 64, 0, false>, fc_fused_kernel<MODE_F16X3, 128, 0, false>, fc_fused_kernel<MODE_F16X3, 128, 0, true>},
+       {fc_fused_kernel<MODE_F16X3, 64, 10, false>, fc_fused_kernel<MODE_F16X3, 128, 10, false>, fc_fused_kernel<MODE_F16X3, 128, 10, true>}}};
+  const int m_tiles = (d.B + kBM - 1) / kBM;
+  // CTA pairs pay off once every SM pair has several work items; small problems keep one CTA per tile
+  static const int env_pair = getenv("RBNN_FUSED_PAIR") ? atoi(getenv("RBNN_FUSED_PAIR")) : -1;   // experiments
+  bool pair = kbb == 128 && m_tiles >= 2 && d.sm_count >= 2 && (long long)m_tiles * d.Z >= 4LL * d.sm_count;
+  if (env_pair == 0) pair = false;
+  if (env_pair == 1 && kbb == 128 && m_tiles >= 2 && d.sm_count >= 2) pair = true;
+  const int ct = d.C == 10, variant = pair ? 2 : (kbb == 128 ? 1 : 0);
+  kern_t kern = kerns[d.mode][ct][variant];
+  static bool attr_done[3][2][3] = {};
+  if (!attr_done[d.mode][ct][variant]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem);
     if (e != cudaSuccess) { *err = std::string("fused_forward_head: cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
-    attr_done[d.mode][kbb == 128] = true;
+    attr_done[d.mode][ct][variant] = true;
   }
   FParams p{};
   p.B = d.B; p.D = d.D; p.H = d.H; p.C = d.C; p.Z = d.Z;
   p.BN = d.H <= 256 ? d.H : 256;
   p.n_tiles = d.H <= 256 ? 1 : d.H / 256;
-  p.m_tiles = (d.B + kBM - 1) / kBM;
-  p.num_items = p.m_tiles * d.Z;
+  p.m_tiles = m_tiles;
+  p.m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
+  p.num_items = p.m_units * d.Z;
   const int kbe = kbb / (dt == DT_F32 ? 4 : 2);
   p.num_kb = (d.D + kbe - 1) / kbe;
   p.head = d.head;
@@ -838,16 +923,32 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   }
   CUtensorMap mAh, mAl, mBh, mBl;
   if (make_map(&mAh, d.X.hi, dt, d.D, d.B, 1, d.X.ld, 0, kBM, kbb, err)) return 1;
-  if (make_map(&mBh, d.W1.hi, dt, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, p.BN, kbb, err)) return 1;
+  if (make_map(&mBh, d.W1.hi, dt, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, pair ? p.BN / 2 : p.BN, kbb, err)) return 1;
   if (!bf16) {
     if (make_map(&mAl, d.X.lo, dt, d.D, d.B, 1, d.X.ld, 0, kBM, kbb, err)) return 1;
-    if (make_map(&mBl, d.W1.lo, dt, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, p.BN, kbb, err)) return 1;
+    if (make_map(&mBl, d.W1.lo, dt, d.D, d.H, d.Z, d.W1.ld, d.W1.zstride, pair ? p.BN / 2 : p.BN, kbb, err)) return 1;
   } else {
     mAl = mAh;
     mBl = mBh;
   }
-  const int grid = p.num_items < d.sm_count ? p.num_items : d.sm_count;
-  kern<<<grid, kThreadsF, kFusedSmem, st>>>(mAh, mAl, mBh, mBl, p);
+  const int units = pair ? d.sm_count / 2 : d.sm_count;
+  const int grid_units = p.num_items < units ? p.num_items : units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pair ? 2 * grid_units : grid_units);
+  cfg.blockDim = dim3(kThreadsF);
+  cfg.dynamicSmemBytes = kFusedSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  {
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mAh, mAl, mBh, mBl, p);
+    if (le != cudaSuccess) { *err = std::string("fused_forward_head launch: ") + cudaGetErrorString(le); return 1; }
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("fused_forward_head launch: ") + cudaGetErrorString(e); return 1; }
   return 0;
@@ -896,7 +997,7 @@ int dh_from_kept(const KeptDesc& d, cudaStream_t st, std::string* err) {
   if (d.mode == MODE_F16X3 && !d.dh_scale) { *err = "dh_from_kept: F16X3 needs the dH scale"; return 1; }
   const int m_tiles = (d.B + kBM - 1) / kBM, items = m_tiles * d.Z;
   const int grid = std::min(items, d.sm_count * 2);
-  const int smem = (kCMax * kHMax + kBM * kXStride) * 4;
+  const int smem = (kCMax * kHMax + kBM * kDStride) * 4;
   __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(d.dh_bf);
 #define RBNN_KEPT_LAUNCH(M)                                                                                          \
   do {                                                                                                               \
