@@ -400,7 +400,9 @@ def main():
         block of the images with all n_s fresh posterior samples per gradient evaluation, blocks all-gathered at the end."""
         xa, ya = x_dev[:n_img].contiguous(), y_dev[:n_img].to(torch.int64)
         bnn.reseed(0)
-        aa.attack_all(bnn, xa, ya, method, hyperparams=hyper, n_samples=n_s, iters=2)          # warm-up (allocations)
+        # warm-up with the same iteration count: sizes the workspaces and, for PGD, captures the CUDA graph of one
+        # iteration (adversarialAttacks._pgd_loop_graph) so that the timed call replays it
+        aa.attack_all(bnn, xa, ya, method, hyperparams=hyper, n_samples=n_s, iters=iters)
         bnn.reseed(0)
         t, _ = timed(lambda: aa.attack_all(bnn, xa, ya, method, hyperparams=hyper, n_samples=n_s, iters=iters), reps)
         return t / reps

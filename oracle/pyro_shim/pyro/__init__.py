@@ -59,7 +59,7 @@ class _ParamStore(object):
 
     def save(self, filename):
         _torch.save({"params": {k: v.detach().clone() for k, v in _PARAM_STORE.items()},
-                     "constraints": {k: "real" for k in _PARAM_STORE}}, filename)
+                     "constraints": {k: _torch.distributions.constraints.real for k in _PARAM_STORE}}, filename)
 
     def load(self, filename, map_location=None):
         state = _torch.load(filename, map_location=map_location)

@@ -70,6 +70,37 @@ def expected_loss_gradients(net, images, labels, n_samples):
     return torch.cat(outs) if len(outs) != 1 else outs[0]
 
 
+def expected_loss_gradients_prefix(net, images, labels, n_samples_list):
+    """The expected loss gradients for EVERY sample count of `n_samples_list` from one pass over max(n_samples_list)
+    posterior samples.  Sample s is seed s (lossGradients.py:33), so the run with n samples uses a prefix of the run with
+    m > n samples: the reference's main() (lossGradients.py:132-151) and plot_gradients_components._get_gradients
+    (:125-142) evaluate [1, 10, 50, 100] one after the other -- 161 sample evaluations per image for 100 distinct ones.
+    Here the sample range is cut at the list's sizes, each piece is evaluated once and the running sum is divided by the
+    prefix length.  Returns a list of [B, *input_shape] device tensors in the order of `n_samples_list`."""
+    sizes = [int(n) for n in n_samples_list]
+    if not sizes or min(sizes) < 1:
+        raise ValueError("n_samples_list must hold positive sample counts")
+    order = sorted(set(sizes))
+    eng = net.engine()
+    images, labels = _to_device(eng, images, labels)
+    rows, _ = net._rows(order[-1], list(range(order[-1])))       # every sample placed (drawn / uploaded) exactly once
+    rank, world = rdist.world()
+    # rank r holds samples r, r + W, ... in consecutive rows: the prefix of n samples is its first local_count(n) rows
+    cuts = [rows[0] + rdist.local_count(n, rank, world) for n in order]
+    outs = dict((n, []) for n in order)
+    for b0 in range(0, images.shape[0], MAX_BATCH):
+        x = images[b0:b0 + MAX_BATCH].contiguous()
+        y = labels[b0:b0 + MAX_BATCH].contiguous()
+        acc, lo = None, rows[0]
+        for n, hi in zip(order, cuts):
+            g = eng.input_grad_sum(HEAD_MEAN_OF_GRADS, x, y, lo, hi)
+            rdist.allreduce_sum_(g)
+            acc = g.clone() if acc is None else acc + g
+            outs[n].append((acc * (1.0 / float(n))).reshape(x.shape))
+            lo = hi
+    return [torch.cat(outs[n]) if len(outs[n]) != 1 else outs[n][0] for n in sizes]
+
+
 def loss_gradient(net, image, label, n_samples=None):
     """One image [ch,h,w] + one-hot label -> expected loss gradient [ch,h,w] (lossGradients.py:20-50)."""
     if not n_samples:
@@ -99,6 +130,32 @@ def loss_gradients(net, data_loader, device, filename, savedir, n_samples=None):
         import torch.distributed as dist
         dist.barrier()
     return grads
+
+
+def loss_gradients_list(net, data_loader, device, filename, savedir, n_samples_list):
+    """`loss_gradients` for every entry of `n_samples_list` in ONE pass over the posterior samples
+    (`expected_loss_gradients_prefix`): the same prints, the same pickle per sample count
+    (`<filename>_samp=<n>_lossGrads.pkl`) and the same numpy arrays the reference's loop over
+    `posterior_samples_list` produces (lossGradients.py:148-151, plot_gradients_components.py:129-140)."""
+    images, labels = [], []
+    for x_batch, y_batch in data_loader:
+        images.append(torch.as_tensor(x_batch))
+        labels.append(torch.as_tensor(y_batch).argmax(-1))
+    images, labels = torch.cat(images), torch.cat(labels)
+    grads_list = expected_loss_gradients_prefix(net, images, labels, n_samples_list)
+    rank, world = rdist.real_world()
+    out = []
+    for n_samples, grads in zip(n_samples_list, grads_list):
+        print(f"\n === Loss gradients on {len(data_loader.dataset)} input images:")
+        print(f"\nmin = {grads.min():.4f} \t max = {grads.max():.4f}")
+        grads = grads.cpu().detach().numpy().squeeze()
+        if rank == 0:
+            save_loss_gradients(grads, n_samples, filename, savedir)
+        out.append(grads)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    return out
 
 
 def save_loss_gradients(loss_gradients, n_samples, filename, savedir, relpath=DATA):

@@ -246,7 +246,9 @@ class BNN(object):
                 params[key + "_loc"] = self._loc[off:off + n].reshape(shp).cpu().clone()
                 params[key + "_scale"] = self._rho[off:off + n].reshape(shp).cpu().clone()
                 off += n
-            torch.save({"params": params, "constraints": {k: "real" for k in params}}, path + filename + ".pt")
+            # pyro.get_param_store().get_state(): unconstrained values + the constraint OBJECT of every parameter
+            from torch.distributions import constraints
+            torch.save({"params": params, "constraints": {k: constraints.real for k in params}}, path + filename + ".pt")
         elif self.inference == "hmc":
             for idx in range(self._bank_host.shape[0]):
                 sd, off = {}, 0
