@@ -171,6 +171,60 @@ def reference_real_units_per_s(n_img, n_samp):
     return n_img * n_samp / dt, dt
 
 
+def reference_halfmoons_units_per_s(hidden, n_pts, n_samp):
+    """One model of the half-moons sweep the reference's way: grid_search_halfMoons._compute_grads -> loss_gradients on an
+    fc2 (2-H-H-2) HMC BNN with `n_samp` stored posterior networks, `n_pts` test points, on the host cores (the reference
+    fans the grid out over 10 such processes, grid_search_halfMoons.py:80-89).  Real reference modules when oracle/_ref
+    is here, else the oracle's restatement of the same loop order.  Returns (units/s, seconds, kind)."""
+    import copy
+    import tempfile
+    import torch
+    from oracle import build_ref
+    from oracle import oracle as orc
+    shape = (1, 2, 1)
+    net = orc.build_net("fc2", shape, hidden, 2, dataset_name="half_moons")
+    layout = orc.param_layout(net)
+    loc, rho = orc.scaled_guide_params(layout, seed=hidden, rho_mean=-2.0)
+    bank = loc + orc.softplus(rho) * torch.randn((n_samp, loc.numel()), generator=torch.Generator().manual_seed(hidden))
+    x, y = orc.synthetic_inputs(n_pts, shape, 2, seed=0)
+    if "mods" not in _REF:
+        _REF["mods"] = build_ref.import_reference()
+    if _REF["mods"] is None:
+        t0 = time.perf_counter()
+        for i in range(n_pts):                        # per image -> per stored network, batch 1 (lossGradients.py:29-38)
+            for sidx in range(n_samp):
+                orc.expected_loss_gradients(net, layout, bank, x[i:i + 1], y[i:i + 1].argmax(-1), [sidx])
+        dt = time.perf_counter() - t0
+        return n_pts * n_samp / dt, dt, "port"
+    _, model_bnn, loss_gradients_mod, _ = _REF["mods"]
+    bnn = model_bnn.BNN("half_moons", hidden, "leaky", "fc2", "hmc", None, None, n_samp, 5, shape, 2)
+    bnn.device = "cpu"
+    bnn.basenet.device = "cpu"
+    bnn.posterior_predictive = {}
+    for i in range(n_samp):                           # BNN.load's HMC branch (model_bnn.py:184-190), in memory
+        net_copy = copy.deepcopy(bnn.basenet)
+        net_copy.load_state_dict(orc.unpack(bank[i], layout))
+        net_copy.device = "cpu"
+        bnn.posterior_predictive.update({i: net_copy})
+    loader = torch.utils.data.DataLoader(dataset=list(zip(x, y)), batch_size=32, shuffle=False)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            with open(os.devnull, "w") as devnull:
+                so, sys.stdout = sys.stdout, devnull
+                try:
+                    t0 = time.perf_counter()
+                    loss_gradients_mod.loss_gradients(net=bnn, data_loader=loader, device="cpu", filename="g", savedir="g/",
+                                                      n_samples=n_samp)
+                    dt = time.perf_counter() - t0
+                finally:
+                    sys.stdout = so
+        finally:
+            os.chdir(cwd)
+    return n_pts * n_samp / dt, dt, "reference"
+
+
 def reference_units_per_s(n_img, n_samp):
     """(units/s, seconds, kind): the real reference when oracle/_ref travelled with the tree, else the oracle's port."""
     r = reference_real_units_per_s(n_img, n_samp)
@@ -423,6 +477,69 @@ def main():
                              "ms": fms, "n_gpus": world, "note": "Bayesian FGSM, eps 0.3 (plot_baseline_attacks.py:65-66)"}
         except Exception as e:
             log("PGD / FGSM measurement failed:", e)
+    if not args.no_extra:
+        try:
+            # BASELINE configs[0] / [4]: the half-moons over-parametrisation sweep (grid_search_halfMoons.py:155-176):
+            # fc2 2-H-H-2 BNNs, H in {32, 128, 256, 512} x 3 warm-ups x 3 training-set sizes = 36 models, 250 stored (HMC)
+            # posterior samples each, expected loss gradients on 100 test points.  The MODELS are dealt out to the ranks
+            # (model m -> rank m % N, no data-path collective); one rank runs all of them back to back, one sync at the end.
+            from robustbnns_b200.grid_search_halfMoons import MoonsBNN, sweep_expected_loss_gradients
+            widths, warmups, sizes, n_s, n_pts = [32, 128, 256, 512], [100, 200, 500], [5000, 10000, 15000], 250, 100
+            grid = [(h, w, n) for h in widths for w in warmups for n in sizes]
+            mine = grid[rank::world]
+            ghm = torch.Generator().manual_seed(5)
+            banks_h = {}
+            xs_hm = torch.rand((n_pts, 1, 2, 1), generator=ghm).to(dev)
+            ys_hm = torch.randint(0, 2, (n_pts,), generator=ghm).to(dev)
+            nets_hm = []
+            with rdist.replicated():
+                for (h, w, n) in mine:
+                    mb = MoonsBNN(h, "leaky", "fc2", "hmc", None, None, n_s, w, n, (1, 2, 1), 2)
+                    if h not in banks_h:                   # synthetic stored posterior, one host copy per width
+                        P_h = mb.basenet.n_params
+                        banks_h[h] = (torch.randn((n_s, P_h), generator=ghm) / math.sqrt(h)).pin_memory()
+                    mb.set_posterior_samples(banks_h[h])
+                    nets_hm.append(mb)
+                n_models = len(nets_hm)
+                args_hm = (nets_hm, [xs_hm] * n_models, [ys_hm] * n_models, [n_s] * n_models)
+                sweep_expected_loss_gradients(*args_hm)
+                l_hm = sum(m.engine().launch_count for m in nets_hm)
+                hm_ms, _ = timed(lambda: sweep_expected_loss_gradients(*args_hm), 3)
+                l_hm = (sum(m.engine().launch_count for m in nets_hm) - l_hm) // 3
+
+                def hm_e2e():                              # stored posteriors from pinned HOST memory every time (H2D)
+                    for m in nets_hm:
+                        m.set_posterior_samples(banks_h[m.basenet.hidden_size])
+                    sweep_expected_loss_gradients(*args_hm)
+                hm_e2e()
+                hm_e2e_ms, _ = timed(hm_e2e, 2)
+            hm_units = float(len(grid)) * n_pts * n_s
+            hm = {"value": hm_units / (hm_ms / 3 * 1e-3), "unit": UNIT, "ms": hm_ms / 3, "models": len(grid),
+                  "test_points": n_pts, "posterior_samples": n_s, "n_gpus": world, "engine": nets_hm[0].engine().precision if nets_hm else None,
+                  "gpu_launches": int(l_hm),
+                  "e2e": {"value": hm_units / (hm_e2e_ms / 2 * 1e-3), "unit": UNIT, "ms": hm_e2e_ms / 2,
+                          "h2d_bytes": int(sum(banks_h[m.basenet.hidden_size].numel() * 4 for m in nets_hm)),
+                          "note": "every model's 250 stored posterior samples re-uploaded from pinned host memory, then the sweep"},
+                  "sharding": "models dealt out to the ranks (model m -> rank m %% %d), no data-path collective" % world,
+                  "note": "BASELINE configs[0]/[4] shape: 36 fc2 2-H-H-2 BNNs (H = 32/128/256/512), 100 test points x 250 "
+                          "stored samples each; all models enqueued back to back, results copied to pinned host memory, one "
+                          "synchronisation (grid_search_halfMoons.sweep_expected_loss_gradients)"}
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                # the reference's per-model loop on the host (grid_search_halfMoons.py:66-78), bounded sample per width
+                tot_s, kinds, rows_cpu = 0.0, set(), {}
+                for h in widths:
+                    v, dt_, kind_ = reference_halfmoons_units_per_s(h, 8, 16)
+                    rows_cpu[str(h)] = v
+                    kinds.add(kind_)
+                    tot_s += 9 * n_pts * n_s / v              # 9 models of this width in the grid
+                hm["cpu_baseline"] = {"value": hm_units / tot_s, "unit": UNIT, "cores": torch.get_num_threads(),
+                                      "kind": "reference" if kinds == {"reference"} else "port",
+                                      "units_per_s_by_width": rows_cpu,
+                                      "sample": "8 test points x 16 stored samples per width, one process (upstream fans the "
+                                                "grid out over 10 processes with joblib), scaled to the 36-model sweep"}
+            extra["halfmoons"] = hm
+        except Exception as e:
+            log("half-moons sweep measurement failed:", e)
     if rank == 0 and world == 1 and not args.no_extra and prec in ("tf32x3", "f16x3"):
         ref_g = step_resident().clone()
         for other in [m for m in ("f16x3", "tf32x3", "bf16") if m != prec]:

@@ -218,7 +218,8 @@ class BNN(object):
         bank = bank.detach().float().cpu().contiguous()
         if bank.dim() != 2 or bank.shape[1] != self.basenet.n_params:
             raise ValueError("bank must be [S, %d]" % self.basenet.n_params)
-        same = self._bank_host is not None and self._bank_host.shape == bank.shape and torch.equal(self._bank_host, bank)
+        same = self._bank_host is not None and self._bank_host.shape == bank.shape and (
+            self._bank_host.data_ptr() == bank.data_ptr() or torch.equal(self._bank_host, bank))
         self._bank_host = bank
         if not same:                          # (_replace_rows re-installs the SAME bank under another sharding)
             self._new_posterior()

@@ -584,6 +584,23 @@ def test_half_moons_grid_sweep(tmp_path, monkeypatch):
         ref_adv = orc.fgsm_attack(net, layout, bank, xt, labels, lambda call: range(S), None, dtype=torch.float64)
         g64 = orc.attack_gradient(net, layout, bank, xt, labels, range(S), dtype=torch.float64)
         _assert_adv_equal_where_determined(adv, ref_adv, g64, what=("moons fgsm", hidden))
+    # the batched form (all models enqueued back to back, one synchronisation): same files, same numbers
+    serial = {name: load_loss_gradients(n_samples=S, filename=name, savedir=name + "/") for (_, _, _, name) in banks.values()}
+    import shutil
+    shutil.rmtree("data")
+    out = gs.parallel_compute_grads(list(widths), ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                                    rel_path="w/", test_points=pts)
+    gs.parallel_grid_attack("fgsm", list(widths), ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                            rel_path="w/", test_points=pts)
+    assert len(out) == len(widths)
+    order = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]  # noqa: E731
+    for hidden, (net, layout, bank, name) in banks.items():
+        got = load_loss_gradients(n_samples=S, filename=name, savedir=name + "/")
+        assert np.abs(order(got) - order(serial[name])).max() <= 1e-6 * np.abs(serial[name]).max()
+        adv = load_attack("fgsm", name, n_samples=S)
+        ref_adv = orc.fgsm_attack(net, layout, bank, xt, labels, lambda call: range(S), None, dtype=torch.float64)
+        g64 = orc.attack_gradient(net, layout, bank, xt, labels, range(S), dtype=torch.float64)
+        _assert_adv_equal_where_determined(adv, ref_adv, g64, what=("moons fgsm batched", hidden))
 
 
 def test_default_engine_is_the_fastest_parity_grade():

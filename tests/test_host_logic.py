@@ -232,6 +232,87 @@ def test_half_moons_grid_driver(tmp_path, monkeypatch):
         adv = load_attack("fgsm", name, n_samples=S)
         ref_adv = orc.fgsm_attack(net, layout, bank, xt, labels, lambda call: range(S), None)
         assert float((adv.cpu() - ref_adv).abs().max()) <= 1e-6
+    # the batched form (upstream: joblib fan-out over CPU processes): same files, same numbers, one synchronisation
+    serial = {name: (load_loss_gradients(n_samples=S, filename=name, savedir=name + "/"), load_attack("fgsm", name, n_samples=S))
+              for (_, _, _, name) in banks.values()}
+    import shutil
+    shutil.rmtree("data")
+    out = gs.parallel_compute_grads([16, 32], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                                    rel_path="w/", test_points=pts, device="cpu")
+    advs = gs.parallel_grid_attack("fgsm", [16, 32], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                                   rel_path="w/", test_points=pts, device="cpu")
+    assert len(out) == 2 and len(advs) == 2
+    for name, (g_ser, a_ser) in serial.items():
+        g_par = load_loss_gradients(n_samples=S, filename=name, savedir=name + "/")
+        order = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]  # noqa: E731
+        assert np.abs(order(g_par) - order(g_ser)).max() <= 1e-6 * np.abs(g_ser).max()
+        assert torch.equal(load_attack("fgsm", name, n_samples=S).cpu(), a_ser.cpu())
+
+
+def _grid_rank_main(rank, world, port, workdir, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import robustbnns_b200.engine as engine_mod
+        from robustbnns_b200 import grid_search_halfMoons as gs
+        torch.set_num_threads(1)
+        os.chdir(workdir)
+        engine_mod.Net = lambda arch, shape, hidden, C: OracleEngine(arch, shape, hidden, C, dataset="half_moons")
+        S, pts = 3, 8
+        out = gs.parallel_compute_grads([16, 32, 64], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                                        rel_path="w/", test_points=pts, device="cpu")
+        advs = gs.parallel_grid_attack("fgsm", [16, 32, 64], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100],
+                                       [S], rel_path="w/", test_points=pts, device="cpu")
+        q.put((rank, len(out), len(advs)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_model_sharded_grid(tmp_path, monkeypatch):
+    """parallel_compute_grads / parallel_grid_attack under torch.distributed: model m of the grid goes to rank m % 2, no
+    collective on the data path, every model's pickles are written by its owner and equal the single-process sweep."""
+    import socket
+    from robustbnns_b200 import grid_search_halfMoons as gs
+    from robustbnns_b200.adversarialAttacks import load_attack
+    from robustbnns_b200.lossGradients import load_loss_gradients
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr("robustbnns_b200.engine.Net",
+                        lambda arch, shape, hidden, C: OracleEngine(arch, shape, hidden, C, dataset="half_moons"))
+    S, pts, names = 3, 8, []
+    for hidden in (16, 32, 64):
+        bnn = gs.MoonsBNN(hidden, "leaky", "fc2", "hmc", None, None, S, 5, 100, (1, 2, 1), 2)
+        net = orc.build_net("fc2", (1, 2, 1), hidden, 2, dataset_name="half_moons")
+        loc, rho = orc.scaled_guide_params(orc.param_layout(net), seed=hidden, rho_mean=-2.0)
+        bnn.set_posterior_samples(loc + orc.softplus(rho) * torch.randn((S, loc.numel()), generator=torch.Generator().manual_seed(hidden)))
+        bnn.save(rel_path="w/")
+        names.append(bnn.name)
+    gs.parallel_compute_grads([16, 32, 64], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                              rel_path="w/", test_points=pts, device="cpu")
+    gs.parallel_grid_attack("fgsm", [16, 32, 64], ["leaky"], ["fc2"], ["hmc"], [None], [None], [S], [5], [100], [S],
+                            rel_path="w/", test_points=pts, device="cpu")
+    single = {n: (load_loss_gradients(n_samples=S, filename=n, savedir=n + "/"), load_attack("fgsm", n, n_samples=S)) for n in names}
+    import shutil
+    shutil.rmtree("data")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [ctx.Process(target=_grid_rank_main, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == [(0, 2, 2), (1, 1, 1)]                      # models 0, 2 -> rank 0; model 1 -> rank 1
+    order = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]  # noqa: E731
+    for n, (g, a) in single.items():
+        g2 = load_loss_gradients(n_samples=S, filename=n, savedir=n + "/")
+        assert np.abs(order(g2) - order(g)).max() <= 1e-6 * np.abs(g).max()
+        assert torch.equal(load_attack("fgsm", n, n_samples=S).cpu(), a.cpu())
 
 
 def _rank_main(rank, world, port, q):
