@@ -283,10 +283,18 @@ def attack_all(net, x_test, labels, method, device=None, hyperparams=None, n_sam
         per = (n_total + world - 1) // world
         lo, hi = min(n_total, rank * per), min(n_total, (rank + 1) * per)
 
+    # Unseeded SVI: the reference attacks one image per call, so every image sees its OWN fresh weight draws
+    # (adversarialAttacks.py:118-131 + model_bnn.py:230-232); one device pass shares the draws of an evaluation among its
+    # images (equal per-image marginals, correlated images).  `net.fresh_draws = "per_image"` restores the reference's
+    # independence at its price: one device pass -- and n_samples new weight draws per gradient evaluation -- per image.
+    per_image = (isinstance(net, BNN) and getattr(net, "fresh_draws", "per_pass") == "per_image"
+                 and getattr(net, "_bank_host", None) is None and not avg_posterior)
+    batch = 1 if per_image else ATTACK_BATCH
+
     def run(lo, hi):
         out = []
-        for b0 in range(lo, hi, ATTACK_BATCH):
-            b1 = min(hi, b0 + ATTACK_BATCH)
+        for b0 in range(lo, hi, batch):
+            b1 = min(hi, b0 + batch)
             image = torch.as_tensor(x_test[b0:b1])
             label = labels[b0:b1]
             if not isinstance(net, BNN):
@@ -314,8 +322,8 @@ def attack_all(net, x_test, labels, method, device=None, hyperparams=None, n_sam
     finally:
         net._replace_rows()                          # back to sample sharding, also when the attack raised
     if hasattr(net, "_fresh_counter"):
-        passes_local = max(1, -(-(hi - lo) // ATTACK_BATCH)) if hi > lo else 0
-        passes_all = -(-n_total // ATTACK_BATCH)
+        passes_local = max(1, -(-(hi - lo) // batch)) if hi > lo else 0
+        passes_all = -(-n_total // batch)
         if advance is None:                          # this rank had no test points: learn the per-pass advance from rank 0
             advance, passes_local = 0, 1
         per_pass = torch.tensor([advance // max(1, passes_local)], dtype=torch.int64, device=net.engine().device)

@@ -244,79 +244,106 @@ __global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, i
   }
 }
 
-// K-sample + re-layout in one pass (F16X3, scale already frozen): block = 32 rows of W1 x all C columns, looped in 32-column
-// tiles.  Per tile every thread draws the 4 normals of one Philox call (4 consecutive columns of one row: the bank's
-// element order), writes w = loc + sigma * eps to the bank row and s_w1 * w into the shared-memory tile, from which
-// the forward and transposed fp16 hi/lo copies are written as in relayout_f16_kernel.  Row norms (guard band) and
-// max|W1| (range check) come from the same registers.  grid: (ceil(R/32), count), block (32, 8); C % 4 == 0.
+// K-sample + re-layout in one pass (F16X3, scale already frozen): block = 32 rows of W1 x all C columns, looped in
+// 64-column tiles.  Per tile a thread draws the 8 normals of two Philox calls (8 consecutive columns of one row: the
+// bank's element order), writes w = loc + sigma * eps to the bank row, splits s_w1 * w into fp16 hi/lo and stores the 8
+// values of the forward copy with ONE 16-byte store per array straight from registers; the (hi | lo) pairs go through a
+// shared-memory tile from which every thread takes 8 consecutive ROWS of one column for the transposed copy (16-byte
+// stores again, 4 lanes = the 64 contiguous bytes of a column's 32 rows).  Row norms (guard band) and max|W1| (range
+// check) come from the same registers.  (The first version moved one value per store through 2-byte stores: 123
+// instructions per weight, issue-bound at 2.7 TB/s; this one needs ~45.)  grid: (ceil(R/32), count), block 256; C % 8 == 0,
+// R % 8 == 0, ld % 8 == 0.
+// Thread maps: draw phase  -- warp w, lane l: row (w/2)*8 + l/4, column group (w%2)*4 + l%4  (conflict-free tile writes);
+//              transposed  -- warp w, lane l: column w*8 + l/4, rows (l%4)*8 .. +7           (conflict-free tile reads).
 __global__ void __launch_bounds__(256)
 sample_relayout_f16_kernel(const float* __restrict__ loc, const float* __restrict__ sigma, float* __restrict__ bank,
                            int64_t P, int64_t off, int R, int C, int ld, int s0, int64_t sample_index0, int64_t stride,
                            uint32_t k0, uint32_t k1, TcScales* __restrict__ sc, __half* __restrict__ hi,
                            __half* __restrict__ lo, __half* __restrict__ thi, __half* __restrict__ tlo,
                            float* __restrict__ wnorm, const int64_t* __restrict__ index_offset) {
-  __shared__ float tile[32][33];
-  __shared__ float red_n[8], red_m[8];
+  __shared__ uint32_t tile[64][33];                      // [column][row]: fp16 hi | lo << 16
+  __shared__ float red_n[32][2], red_m[8];
   const float sw = sc->s_w1;
   const int s = s0 + blockIdx.y;
   const uint32_t g = (uint32_t)(sample_index0 + (index_offset ? *index_offset : 0) + (int64_t)blockIdx.y * stride);
   const int r0 = blockIdx.x * 32;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const int tr = tid >> 3, tg = tid & 7;              // row of the tile and 4-column group this thread draws
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tr = (warp >> 1) * 8 + (lane >> 2), tg = (warp & 1) * 4 + (lane & 3);
+  const int tc = warp * 8 + (lane >> 2), trg = (lane & 3) * 8;       // transposed phase: column of the tile, first row
   const int r = r0 + tr;
   float* __restrict__ brow = bank + (int64_t)s * P;
   float racc = 0.f, mabs = 0.f;
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    const int c = c0 + tg * 4;
-    float w[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    const int c = c0 + tg * 8;
+    uint32_t hp[4] = {0u, 0u, 0u, 0u}, lp[4] = {0u, 0u, 0u, 0u};     // packed fp16 pairs of s_w1 * w: hi and residual
     if (r < R && c < C) {
-      const int64_t i = off + (int64_t)r * C + c;      // multiple of 4
-      float z[4];
-      philox_normals4((uint32_t)(i >> 2), g, k0, k1, z);
-      const float4 sg = __ldg(reinterpret_cast<const float4*>(sigma + i));
-      const float4 lc = __ldg(reinterpret_cast<const float4*>(loc + i));
-      w[0] = fmaf(sg.x, z[0], lc.x); w[1] = fmaf(sg.y, z[1], lc.y);
-      w[2] = fmaf(sg.z, z[2], lc.z); w[3] = fmaf(sg.w, z[3], lc.w);
-      float2* out = reinterpret_cast<float2*>(brow + i);          // bank rows are 8-byte aligned (P even)
-      out[0] = make_float2(w[0], w[1]);
-      out[1] = make_float2(w[2], w[3]);
+      const int64_t i = off + (int64_t)r * C + c;        // multiple of 8
+      // the guide's parameters first: their L2 latency hides behind the ~300 instructions of the two Philox calls
+      float4 sg0, sg1, lc0, lc1;
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sg0.x), "=f"(sg0.y), "=f"(sg0.z), "=f"(sg0.w) : "l"(sigma + i));
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sg1.x), "=f"(sg1.y), "=f"(sg1.z), "=f"(sg1.w) : "l"(sigma + i + 4));
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(lc0.x), "=f"(lc0.y), "=f"(lc0.z), "=f"(lc0.w) : "l"(loc + i));
+      asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(lc1.x), "=f"(lc1.y), "=f"(lc1.z), "=f"(lc1.w) : "l"(loc + i + 4));
+      float z[8];
+      philox_normals4((uint32_t)(i >> 2), g, k0, k1, *reinterpret_cast<float(*)[4]>(&z[0]));
+      philox_normals4((uint32_t)(i >> 2) + 1u, g, k0, k1, *reinterpret_cast<float(*)[4]>(&z[4]));
+      float w[8];
+      w[0] = fmaf(sg0.x, z[0], lc0.x); w[1] = fmaf(sg0.y, z[1], lc0.y);
+      w[2] = fmaf(sg0.z, z[2], lc0.z); w[3] = fmaf(sg0.w, z[3], lc0.w);
+      w[4] = fmaf(sg1.x, z[4], lc1.x); w[5] = fmaf(sg1.y, z[5], lc1.y);
+      w[6] = fmaf(sg1.z, z[6], lc1.z); w[7] = fmaf(sg1.w, z[7], lc1.w);
+      float2* out = reinterpret_cast<float2*>(brow + i);             // bank rows are 8-byte aligned (P even)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { racc = fmaf(w[j], w[j], racc); mabs = fmaxf(mabs, fabsf(w[j])); }
+      for (int j = 0; j < 4; ++j) out[j] = make_float2(w[2 * j], w[2 * j + 1]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { racc = fmaf(w[j], w[j], racc); mabs = fmaxf(mabs, fabsf(w[j])); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = w[2 * j] * sw, b = w[2 * j + 1] * sw;
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+        hp[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lp[j] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      const int64_t o = ((int64_t)s * R + r) * ld + c;               // 16-byte aligned: ld % 8 == 0, c % 8 == 0
+      *reinterpret_cast<uint4*>(hi + o) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(lo + o) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) tile[tr][tg * 4 + j] = w[j] * sw;
+    for (int j = 0; j < 4; ++j) {                                    // (hi | lo << 16) of columns tg*8 + 2j, + 2j + 1
+      tile[tg * 8 + 2 * j][tr] = __byte_perm(hp[j], lp[j], 0x5410);
+      tile[tg * 8 + 2 * j + 1][tr] = __byte_perm(hp[j], lp[j], 0x7632);
+    }
     __syncthreads();
-    const int cc = c0 + threadIdx.x;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int rr = r0 + i;
-      if (rr < R && cc < C) {
-        const int64_t o = ((int64_t)s * R + rr) * ld + cc;
-        split_f16(tile[i][threadIdx.x], hi[o], lo[o]);
-      }
-    }
-    const int r2 = r0 + threadIdx.x;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int c2 = c0 + i;
-      if (r2 < R && c2 < C) {
-        const int64_t o = ((int64_t)s * C + c2) * R + r2;
-        split_f16(tile[threadIdx.x][i], thi[o], tlo[o]);
-      }
+    const int c2 = c0 + tc, r2 = r0 + trg;
+    if (c2 < C && r2 < R) {
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = tile[tc][trg + k];
+      uint4 th, tl;
+      th.x = __byte_perm(v[0], v[1], 0x5410); tl.x = __byte_perm(v[0], v[1], 0x7632);
+      th.y = __byte_perm(v[2], v[3], 0x5410); tl.y = __byte_perm(v[2], v[3], 0x7632);
+      th.z = __byte_perm(v[4], v[5], 0x5410); tl.z = __byte_perm(v[4], v[5], 0x7632);
+      th.w = __byte_perm(v[6], v[7], 0x5410); tl.w = __byte_perm(v[6], v[7], 0x7632);
+      const int64_t o = ((int64_t)s * C + c2) * R + r2;              // 16-byte aligned: R % 8 == 0, r2 % 8 == 0
+      *reinterpret_cast<uint4*>(thi + o) = th;
+      *reinterpret_cast<uint4*>(tlo + o) = tl;
     }
     __syncthreads();
   }
-  // row norm: the 8 threads of a row are consecutive lanes; then the maximum over the block's 32 rows
+  // row norm: a row's 8 column groups sit in 4 lanes of two neighbouring warps; then the maximum over the block's 32 rows
   racc += __shfl_xor_sync(0xffffffffu, racc, 1);
   racc += __shfl_xor_sync(0xffffffffu, racc, 2);
-  racc += __shfl_xor_sync(0xffffffffu, racc, 4);
-#pragma unroll
-  for (int o = 8; o < 32; o <<= 1) racc = fmaxf(racc, __shfl_xor_sync(0xffffffffu, racc, o));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, o));
-  if (threadIdx.x == 0) { red_n[threadIdx.y] = racc; red_m[threadIdx.y] = mabs; }
+  if ((lane & 3) == 0) red_n[tr][warp & 1] = racc;
+  if (lane == 0) red_m[warp] = mabs;
   __syncthreads();
   if (tid == 0) {
     float m = 0.f, a = 0.f;
-    for (int i = 0; i < 8; ++i) { m = fmaxf(m, red_n[i]); a = fmaxf(a, red_m[i]); }
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, red_n[i][0] + red_n[i][1]);
+    for (int i = 0; i < 8; ++i) a = fmaxf(a, red_m[i]);
     const bool bad = !(m == m) || !(a == a);
     atomicMax(reinterpret_cast<unsigned*>(wnorm + s), __float_as_uint(bad ? __int_as_float(0x7f800000) : sqrtf(m)));
     atomicMax(&sc->maxw1_bits, __float_as_uint(bad ? __int_as_float(0x7f800000) : a));
@@ -774,14 +801,14 @@ int tc_sample_relayout_f16(rbnn_net* n, const float* d_loc, const float* d_rho, 
   TcBank& tc = n->tc;
   const TcMat& m = tc.mat[0];
   if (n->prec != RBNN_PREC_F16X3 || n->arch != RBNN_ARCH_FC || tc.mode != n->prec || tc.capacity < s0 + count ||
-      tc.capacity != n->capacity || !tc.frozen_host || tc.nmat != 1 || m.off != 0 || (m.C & 3) || (n->L.P & 1) ||
+      tc.capacity != n->capacity || !tc.frozen_host || tc.nmat != 1 || m.off != 0 || (m.C & 7) || (m.R & 7) || (m.ld & 7) || (n->L.P & 1) ||
       (reinterpret_cast<uintptr_t>(d_loc) & 15) || count <= 0)
     return 0;
   if (tc.overflow_host && *(volatile int*)tc.overflow_host) return 0;      // let tc_bank_refresh report / reset it
   RBNN_TRY(sample_sigma(n, d_rho, st));
   RBNN_CUDA(cudaMemsetAsync(tc.wnorm + s0, 0, (size_t)count * sizeof(float), st));
   dim3 grid((m.R + 31) / 32, count);
-  sample_relayout_f16_kernel<<<grid, dim3(32, 8), 0, st>>>(
+  sample_relayout_f16_kernel<<<grid, 256, 0, st>>>(
       d_loc, n->sigma, n->bank, n->L.P, m.off, m.R, m.C, m.ld, s0, sample_index0, stride, (uint32_t)(seed & 0xFFFFFFFFu),
       (uint32_t)(seed >> 32), tc.scales, reinterpret_cast<__half*>(m.h_hi), reinterpret_cast<__half*>(m.h_lo),
       reinterpret_cast<__half*>(m.th_hi), reinterpret_cast<__half*>(m.th_lo), tc.wnorm, d_index_offset);

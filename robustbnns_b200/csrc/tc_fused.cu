@@ -800,26 +800,30 @@ fixup_kernel(const unsigned long long* __restrict__ wl, int num_items, const flo
 // dH of every (sample, input) from the stored logits and LeakyReLU masks -- the loss head and pass 2 of the fused
 // kernel without its GEMM.  One CTA of 512 threads per work item at a time: thread = (input row, column quarter) as in
 // the fused epilogue.
+// Work item = (sample, 128-input tile, half of the tile): CTAs of 256 threads, two resident per SM, so that one CTA's
+// staging of Wo_z overlaps the other's row loop.
+constexpr int kKeptThreads = 256;
 template <int MODE>
-__global__ void __launch_bounds__(kEpiThreads)
+__global__ void __launch_bounds__(kKeptThreads, 2)
 dh_from_kept_kernel(int B, int H, int C, int num_items, int m_tiles, int head, const float* __restrict__ bank, long long P,
                     long long wo_off, int z_row0, const int32_t* __restrict__ labels, const float* __restrict__ pbar,
                     const float* __restrict__ logits, const uint32_t* __restrict__ masks, void* dh_hi, void* dh_lo,
                     __nv_bfloat16* dh_bf, const float* __restrict__ dh_scale_p) {
   extern __shared__ float ksm[];
   float* wo_s = ksm;                            // [C][H]
-  float* xd = ksm + kCMax * kHMax;              // [128][kDStride] dlogits
+  float* xd = ksm + kCMax * kHMax;              // [128][kDStride] dlogits (only this half's 64 rows are used)
   const int et = threadIdx.x, warp = et >> 5, lane = et & 31;
-  const int quad = warp & 3, cq = warp >> 2;    // as in the fused epilogue: warp = (32-row group, column quarter)
-  const int row = quad * 32 + lane;
+  const int cq = warp >> 1;                     // as in the fused epilogue: warp = (32-row group, column quarter)
   const int BN = H <= 256 ? H : 256, n_tiles = H <= 256 ? 1 : H / 256, nchunks = BN / 32;
   const P2Lane g2 = p2_lane(lane, cq, BN, n_tiles);
   const float dh_scale = (MODE == MODE_F16X3) ? __ldg(dh_scale_p) : 1.f;
-  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+  for (int item2 = blockIdx.x; item2 < 2 * num_items; item2 += gridDim.x) {
+    const int item = item2 >> 1, quad = (item2 & 1) * 2 + (warp & 1);
+    const int row = quad * 32 + lane;
     const int z = item / m_tiles, m_idx = item % m_tiles;
     const float* __restrict__ wrow = bank + (long long)(z_row0 + z) * P;
     __syncthreads();                            // everyone is done with the previous item's Wo / dlogits
-    stage_head_params(wrow, wo_off, 0, 0, C, H, wo_s, nullptr, nullptr, et, kEpiThreads);
+    stage_head_params(wrow, wo_off, 0, 0, C, H, wo_s, nullptr, nullptr, et, kKeptThreads);
     const int b = m_idx * kBM + row;
     const bool rok = b < B;
     if (cq == 0) {
@@ -996,7 +1000,7 @@ int dh_from_kept(const KeptDesc& d, cudaStream_t st, std::string* err) {
   if (d.head < 0 || !d.logits || !d.masks) { *err = "dh_from_kept: missing kept forward"; return 1; }
   if (d.mode == MODE_F16X3 && !d.dh_scale) { *err = "dh_from_kept: F16X3 needs the dH scale"; return 1; }
   const int m_tiles = (d.B + kBM - 1) / kBM, items = m_tiles * d.Z;
-  const int grid = std::min(items, d.sm_count * 2);
+  const int grid = std::min(2 * items, d.sm_count * 2);
   const int smem = (kCMax * kHMax + kBM * kDStride) * 4;
   __nv_bfloat16* bf = reinterpret_cast<__nv_bfloat16*>(d.dh_bf);
 #define RBNN_KEPT_LAUNCH(M)                                                                                          \
@@ -1007,7 +1011,7 @@ int dh_from_kept(const KeptDesc& d, cudaStream_t st, std::string* err) {
       if (ea != cudaSuccess) { *err = std::string("dh_from_kept: cudaFuncSetAttribute: ") + cudaGetErrorString(ea); return 1; } \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    dh_from_kept_kernel<M><<<grid, kEpiThreads, smem, st>>>(d.B, d.H, d.C, items, m_tiles, d.head, d.bank, d.P, d.wo_off, \
+    dh_from_kept_kernel<M><<<grid, kKeptThreads, smem, st>>>(d.B, d.H, d.C, items, m_tiles, d.head, d.bank, d.P, d.wo_off, \
                                                             d.z_row0, d.labels, d.pbar, d.logits, d.masks, d.dh_hi,   \
                                                             d.dh_lo, bf, d.dh_scale);                                 \
   } while (0)

@@ -15,7 +15,9 @@ Posterior samples
   pin an explicit bank with `set_posterior_samples` for exact parity.
 * SVI, no seeds: fresh draws on every forward call (model_bnn.py:230-232); the
   draws of one call are shared by the inputs of that call.  `reseed(s)` plays the
-  part of `pyro.set_rng_seed(s)`.
+  part of `pyro.set_rng_seed(s)`.  `attack()` calls the reference's per-image
+  attack once per image, i.e. with fresh weights per image: set
+  `bnn.fresh_draws = "per_image"` for that (one device pass per image).
 * HMC / explicit bank: row i is `posterior_predictive[i]` (model_bnn.py:184-190,
   :248-255); no seeds means the first `n_samples` rows.
 * With torch.distributed initialised, position j of a call's sample list lives
@@ -125,6 +127,7 @@ class BNN(object):
         self._engine = engine
         self._precision = "auto"              # engine choice for an engine this object creates (set_precision)
         self.attack_sharding = "inputs"       # multi-GPU `attack`: shard the inputs (no collectives) or the "samples"
+        self.fresh_draws = "per_pass"         # unseeded SVI attacks: "per_image" = own fresh weights per image, as upstream
         self._loc = self._rho = None          # SVI guide parameters, flattened [P]
         self._bank_host = None                # explicit / HMC bank [S, P] (CPU tensor)
         self._graph_offset = None             # int64[1] device tensor while a CUDA graph of a PGD iteration is captured

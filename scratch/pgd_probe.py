@@ -23,7 +23,7 @@ bnn.set_guide(torch.cat(locs), torch.cat(rhos))
 bnn.set_precision(os.environ.get("PREC", "f16x3"))
 x = torch.rand((n_img, 1, 28, 28), generator=g).cuda()
 y = torch.randint(0, 10, (n_img,), generator=g).cuda()
-aa.pgd_attack(bnn, x, y, hyperparams=None, n_samples=n_s, iters=2)
+aa.pgd_attack(bnn, x, y, hyperparams=None, n_samples=n_s, iters=iters)   # same count: the CUDA graph is captured here
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -63,6 +63,33 @@ def test_svi_philox_prefix_and_fresh_draws():
     assert torch.equal(a, a2)
 
 
+def test_unseeded_svi_attack_fresh_draws_per_image():
+    """attack_all on an unseeded SVI BNN: one device pass shares the fresh draws of a gradient evaluation among its images;
+    `fresh_draws = "per_image"` gives every image its own draws, as the reference's per-image loop does
+    (adversarialAttacks.py:118-131 + model_bnn.py:230-232), and equals attacking the images one call at a time."""
+    from robustbnns_b200 import adversarialAttacks as aa
+    c = Case("svi_fc2_32_moons")
+    S, N = 3, len(c.x)
+    bnn = _bnn(c)
+    bnn.set_guide(c.t("loc"), c.t("rho"))
+    eng = bnn.engine()
+    hyper = {"epsilon": 0.2}
+    bnn.reseed(0)
+    n0 = len(eng.sampled)
+    aa.attack_all(bnn, c.x, c.labels, "fgsm", hyperparams=hyper, n_samples=S)
+    assert len(eng.sampled) - n0 == S                                      # one evaluation, S draws, shared by the N images
+    bnn.fresh_draws = "per_image"
+    bnn.reseed(0)
+    n0 = len(eng.sampled)
+    adv = aa.attack_all(bnn, c.x, c.labels, "fgsm", hyperparams=hyper, n_samples=S)
+    drawn = [g for (_, g, _) in eng.sampled[n0:]]
+    assert len(drawn) == N * S and len(set(drawn)) == N * S                 # every image its own S draws
+    bnn.reseed(0)
+    one_by_one = torch.cat([aa.fgsm_attack(bnn, c.x[i:i + 1], c.labels[i:i + 1], hyperparams=hyper, n_samples=S)
+                            for i in range(N)])
+    assert torch.equal(adv, one_by_one)
+
+
 def test_loss_gradients_and_attacks_through_the_drop_in(tmp_path, monkeypatch):
     from robustbnns_b200 import adversarialAttacks as aa
     from robustbnns_b200 import lossGradients as lg
