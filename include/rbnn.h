@@ -76,6 +76,12 @@ RBNN_API int rbnn_net_set_precision(rbnn_net* net, int prec);
 RBNN_API int rbnn_net_get_precision(const rbnn_net* net);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 RBNN_API int64_t rbnn_net_launch_count(const rbnn_net* net);
+/* Inputs on the 8-bit pixel grid.  Every image set the reference loads is uint8 / 255 (utils.py:102-103, 129-130,
+ * 190-191); scaled by 255 * 2^j such inputs are exact in fp16, the low half of their F16X3 split is zero and the fused
+ * forward of arch fc issues two tensor-core passes instead of three (detected on the device per call, bit-level test, no
+ * tolerance on the data; RBNN_XGRID=0 in the environment disables it).  Returns 1 when the last F16X3 forward of this
+ * handle took that route, 0 when not, -1 on error.  Synchronises the device (a test / bench query, not for the hot path). */
+RBNN_API int rbnn_net_input_grid(rbnn_net* net);
 /* Device timing of the two dominant kernel classes with CUDA events recorded on the launch
  * stream (1 = first-layer forward GEMM, 2 = input-gradient GEMM).  read() synchronises the
  * device, returns the summed kernel time and launch count since the last read, and resets. */

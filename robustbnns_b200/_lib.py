@@ -30,6 +30,7 @@ SIGNATURES = {
     "rbnn_net_set_precision": (_i, [_p, _i]),
     "rbnn_net_get_precision": (_i, [_p]),
     "rbnn_net_launch_count": (_i64, [_p]),
+    "rbnn_net_input_grid": (_i, [_p]),
     "rbnn_net_timing_enable": (_i, [_p, _i]),
     "rbnn_net_timing_read": (_i, [_p, _i, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "rbnn_bank_reserve": (_i, [_p, _i]),

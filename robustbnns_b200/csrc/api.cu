@@ -402,6 +402,15 @@ int rbnn_net_get_precision(const rbnn_net* n) { return n ? n->prec : -1; }
 
 int64_t rbnn_net_launch_count(const rbnn_net* n) { return n ? n->launches : -1; }
 
+int rbnn_net_input_grid(rbnn_net* n) {
+  if (!n) return -1;
+  if (!n->tc.xgrid_last) return 0;
+  unsigned v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, n->tc.xgrid_last, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v ? 1 : 0;
+}
+
 int rbnn_net_timing_enable(rbnn_net* n, int on) {
   RBNN_CHECK(n != nullptr, "null net handle");
   n->timing = on ? 1 : 0;

@@ -79,6 +79,7 @@ struct TcBank {
   TcMat mat[2];
   float* wnorm = nullptr;   // [capacity] max_j ||W1_s[j,:]||_2 (guard band of the fused forward kernel)
   TcScales* scales = nullptr;     // device (F16X3)
+  unsigned* xgrid_last = nullptr; // device (F16X3): 1 = the last forward found its inputs on the pixel grid (two-pass forward)
   int* overflow_host = nullptr;   // mapped pinned flag: a later row exceeded the fp16 range under the frozen s_w1
   int* overflow_dev = nullptr;    // device alias of overflow_host
   uint8_t* dirty = nullptr; // host flags per row (derived copies stale)
@@ -188,14 +189,16 @@ inline int conv_class_pitch(int C) { return C <= 4 ? 4 : (C <= 12 ? 12 : (C <= 1
 
 // ---- conv.cu ----------------------------------------------------------------------------
 int conv1_pool_fwd(rbnn_net* net, const float* x, const float* bank, int s0, int Z, int B, float* p1,
-                   uint8_t* idx1, cudaStream_t st);
+                   uint8_t* idx1, cudaStream_t st, float* p1lo = nullptr, unsigned* max_bits = nullptr);
 int im2col_conv2(rbnn_net* net, const float* p1, int ZB, float* col, cudaStream_t st);
 int pool2_fwd(rbnn_net* net, const float* a2, int ZB, int H, float* p2, cudaStream_t st);
 int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, float* dz2, cudaStream_t st,
               float* dz2_lo = nullptr);
 // f16_scale != nullptr: hi / lo are fp16 arrays holding the split of *f16_scale * P1 (F16X3), else tf32-split fp32
 int p1_split_hwc(rbnn_net* net, const float* p1, int ZB, void* hi, void* lo, const float* f16_scale, cudaStream_t st);
-int conv2_refine(rbnn_net* net, float* a2, const float* p1, int s0, int Z, int B, float eps, cudaStream_t st);
+// unit_max: [Z * B] float bits, max |conv2 pre-activation| of every (sample, image) unit (tc::GemmDesc::group_max)
+int conv2_refine(rbnn_net* net, float* a2, const float* p1, int s0, int Z, int B, float eps, cudaStream_t st,
+                 const float* p1lo, const unsigned* unit_max);
 int col2im_conv2(rbnn_net* net, const float* dcol, const float* p1, int ZB, float* g1, cudaStream_t st);
 // partial != nullptr && parts > 1: the sample range is cut into `parts` slices (partial: [parts][B][784] floats)
 int conv1_bwd_sum(rbnn_net* net, const float* g1, const uint8_t* idx1, const float* bank, int s0, int Z, int B,

@@ -31,11 +31,12 @@ int tc_conv_supported(const rbnn_net* n) {
 namespace {
 
 struct ConvTcBufs {
-  float *p1 = nullptr, *a2 = nullptr, *logits = nullptr, *lpart = nullptr;
+  float *p1 = nullptr, *p1lo = nullptr, *a2 = nullptr, *logits = nullptr, *lpart = nullptr;   // p1lo: fp32 residual of P1 (forward only)
   void *p1h = nullptr, *p1l = nullptr, *dzh = nullptr, *dzl = nullptr;     // tf32 split (fp32 arrays) or fp16 hi / lo
   float *dlogits = nullptr, *dcol = nullptr, *g1 = nullptr, *partial = nullptr;
   float* call_sc = nullptr;        // F16X3: [0] s_p, [1] 1/(s_p s_w), [2] s_d, [3] 1/(s_d s_w)
   unsigned* max_bits = nullptr;    // F16X3: [0] max|P1| of the chunk, [1] max|d_pbar|
+  unsigned* unit_max = nullptr;    // [ZB] max |conv2 pre-activation| per unit (float bits), from the GEMM epilogue
   uint8_t* idx1 = nullptr;
   int parts = 1;
 };
@@ -64,7 +65,7 @@ constexpr size_t kConvKeepBudget = (size_t)16 << 30;      // kept forward: at mo
 
 size_t bytes_per_zb(const rbnn_net* n, bool grad) {
   const size_t H = n->H, C = n->C;
-  size_t per = 3 * 4608 * 4 + 4608 + 64 * H * 4 + C * 4 + (H / 128 + 1) * C * 4;
+  size_t per = 4 * 4608 * 4 + 4608 + 64 * H * 4 + C * 4 + (H / 128 + 1) * C * 4 + 8;
   if (grad) per += C * 4 + 2 * 64 * H * 4 + 64 * 800 * 4 + 4608 * 4;
   return per + 64;
 }
@@ -88,7 +89,9 @@ void carve(rbnn_net* n, Arena& ar, int Z, int B, bool fwd, bool grad, ConvTcBufs
   if (fwd) {
     c.p1h = ar.take<float>((size_t)ZB * 4608);      // sized for fp32; the fp16 variant uses half of it
     c.p1l = ar.take<float>((size_t)ZB * 4608);
+    c.p1lo = ar.take<float>((size_t)ZB * 4608);
     c.lpart = ar.take<float>((size_t)pool2_logits_chunks(n) * ZB * C);
+    c.unit_max = ar.take<unsigned>(ZB);
   }
   if (grad) {
     c.dlogits = ar.take<float>((size_t)ZB * C);
@@ -124,10 +127,11 @@ int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs&
   const float* rows = n->bank + (int64_t)z0 * P;
   const TcMat& m = n->tc.mat[0];
   const bool f16 = n->prec == RBNN_PREC_F16X3;
-  RBNN_TRY(conv1_pool_fwd(n, x, n->bank, z0, Z, B, c.p1, c.idx1, st));
-  if (f16) {        // operand ranges of this chunk -> the call's power-of-two scales (device-resident, no read-back)
-    RBNN_CUDA(cudaMemsetAsync(c.max_bits, 0, 2 * sizeof(unsigned), st));
-    RBNN_TRY(tc_maxabs(n, c.p1, (int64_t)Z * B * 4608, c.max_bits, st));
+  // F16X3: operand ranges of this chunk -> the call's power-of-two scales (device-resident, no read-back); max|P1| is
+  // reduced by the conv1 kernel itself
+  if (f16) RBNN_CUDA(cudaMemsetAsync(c.max_bits, 0, 2 * sizeof(unsigned), st));
+  RBNN_TRY(conv1_pool_fwd(n, x, n->bank, z0, Z, B, c.p1, c.idx1, st, c.p1lo, f16 ? c.max_bits : nullptr));
+  if (f16) {
     if (gmax) RBNN_TRY(tc_maxabs(n, gmax, (int64_t)B * n->C, c.max_bits + 1, st));
     RBNN_TRY(tc_call_scales(n, c.max_bits, gmax ? c.max_bits + 1 : nullptr, dh_factor, c.call_sc, st));
   }
@@ -148,9 +152,11 @@ int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs&
   g.epi = tc::EPI_BIAS_LEAKY;
   g.bias = rows + n->L.cb2; g.bias_zstride = P;
   g.out = c.a2; g.out_ld = H; g.out_zstride = (int64_t)B * 64 * H;
+  RBNN_CUDA(cudaMemsetAsync(c.unit_max, 0, (size_t)Z * B * sizeof(unsigned), st));
+  g.group_max = c.unit_max;                          // GEMM rows of an image are one group of 64
   RBNN_TRY(run_tc(n, g, 1, st));
   static const float guard_eps = getenv("RBNN_CONV_GUARD_LOG2") ? ldexpf(1.f, -atoi(getenv("RBNN_CONV_GUARD_LOG2"))) : kConvGuardEps;   // experiments
-  RBNN_TRY(conv2_refine(n, c.a2, c.p1, z0, Z, B, guard_eps, st));
+  RBNN_TRY(conv2_refine(n, c.a2, c.p1, z0, Z, B, guard_eps, st, c.p1lo, c.unit_max));
   RBNN_TRY(pool2_logits(n, c.a2, z0, Z, B, logits, c.lpart, st));
   return 0;
 }

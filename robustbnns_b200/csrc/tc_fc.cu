@@ -164,6 +164,52 @@ maxabs_flat_kernel(const float* __restrict__ p, int64_t n, unsigned* __restrict_
   }
 }
 
+// Inputs on the 8-bit pixel grid.  Every image data set the reference loads is uint8 / 255 (utils.py:102-103, 129-130,
+// 190-191), i.e. x = fl(q / 255) with an integer |q| <= 2047.  Scaled by 255 * 2^j such an input IS its fp16 hi part and
+// the lo part of the F16X3 split is zero, so the forward GEMM needs two passes (X_hi W_hi + X_hi W_lo) instead of three.
+// Detection is exact, not a tolerance on the data: an element qualifies only when fl(255 x) is within two fp32 roundings
+// (2^-22 relative) of an integer, so reading it as q / 255 moves it by less than the rounding of the division that
+// produced it; anything else (PGD iterates, synthetic floats) keeps the three-pass split.
+// bits[0] = max|x| (as maxabs_flat_kernel), bits[2] |= 1 when some element is off the grid.
+constexpr float kGridDen = 255.f;
+constexpr float kGridRelTol = 2.4e-7f;       // 2^-22
+constexpr float kGridMaxQ = 2047.f;          // 11 significant bits: exact in fp16
+__device__ __forceinline__ bool off_grid(float v) {
+  const float t = v * kGridDen, q = rintf(t);
+  return !(fabsf(t - q) <= fabsf(q) * kGridRelTol && fabsf(q) <= kGridMaxQ);
+}
+__global__ void __launch_bounds__(256)
+maxabs_grid_kernel(const float* __restrict__ p, int64_t n, unsigned* __restrict__ bits) {
+  __shared__ float red[8];
+  __shared__ int red_off[8];
+  float m = 0.f;
+  bool off = false;
+  const int64_t n4 = (reinterpret_cast<uintptr_t>(p) & 15) ? 0 : n / 4;
+  const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(p4 + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    off = off || off_grid(v.x) || off_grid(v.y) || off_grid(v.z) || off_grid(v.w);
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(p + i);
+    m = fmaxf(m, fabsf(v));
+    off = off || off_grid(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const unsigned any_off = __ballot_sync(0xffffffffu, off);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; red_off[threadIdx.x >> 5] = any_off != 0u; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int o = red_off[0];
+    for (int i = 1; i < 8; ++i) { m = fmaxf(m, red[i]); o |= red_off[i]; }
+    if (!(m == m)) { m = __int_as_float(0x7f800000); o = 1; }
+    atomicMax(bits, __float_as_uint(m));
+    if (o) atomicOr(bits + 2, 1u);
+  }
+}
+
 // after the maxima of the dirty rows are in: fix s_w1 on first use, afterwards only check that the frozen scale
 // still keeps every |W1| inside the fp16 range (2^6 head room); otherwise raise the sticky host-visible flag
 __global__ void freeze_scales_kernel(TcScales* sc, int* overflow) {
@@ -182,9 +228,18 @@ __global__ void freeze_scales_kernel(TcScales* sc, int* overflow) {
 // |dH| <= 2 max|g| max|Wo| with max|g| <= 1 for the built-in heads (g = softmax(.) - e_y) and max|d_pbar| for UPSTREAM
 // dh_factor: the bound of the hidden-layer gradient is dh_factor * max|g| * max|Wo| (2 for the FC nets; the conv net
 // passes 8: a position collects up to 4 pooling windows)
+// xgrid != nullptr (the 4 words of an FC call: [0] max|x|, [1] max|g|, [2] off-grid flag of maxabs_grid_kernel): the
+// inputs' scale becomes 255 * 2^j when they lie on the pixel grid, and xgrid[3] = 1 tells split_f16_kernel and the fused
+// kernel that the lo part of the inputs is zero (two-pass forward).
 __global__ void call_scales_kernel(const TcScales* sc, const unsigned* xmax_bits, const unsigned* gmax_bits,
-                                   float* out, float dh_factor) {
-  const float sx = pow2_scale_for(__uint_as_float(*xmax_bits), kF16TargetExpExact);
+                                   float* out, float dh_factor, unsigned* xgrid = nullptr) {
+  float sx = pow2_scale_for(__uint_as_float(*xmax_bits), kF16TargetExpExact);
+  if (xgrid) {
+    const float xmax = __uint_as_float(*xmax_bits);
+    const bool on = xgrid[2] == 0u && xmax > 0.f && isfinite(xmax);
+    if (on) sx = kGridDen * pow2_scale_for(rintf(xmax * kGridDen), kF16TargetExpExact);   // q_max 2^j in [2^14, 2^15)
+    xgrid[3] = on ? 1u : 0u;
+  }
   const float gmax = gmax_bits ? __uint_as_float(*gmax_bits) : 1.f;
   const float sd = pow2_scale_for(dh_factor * gmax * __uint_as_float(sc->maxwo_bits), kF16TargetExpExact);
   out[0] = sx;
@@ -199,15 +254,25 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 }
 
 // x[n] -> fp16 hi/lo of s_x * x
+// xgrid[3] != 0 (inputs on the pixel grid, s = 255 * 2^j): hi = q 2^j exactly, lo = 0
 __global__ void split_f16_kernel(const float* __restrict__ x, const float* __restrict__ call_sc,
-                                 __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4, int d4, int ld4) {
+                                 __half* __restrict__ hi, __half* __restrict__ lo, int64_t n4, int d4, int ld4,
+                                 const unsigned* __restrict__ xgrid) {
   const float s = __ldg(call_sc);
+  const bool grid = xgrid && __ldg(xgrid + 3) != 0u;
+  const float s2 = s / kGridDen;                      // 2^j (exact)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     const int64_t row = i / d4, o = row * ld4 + (i - row * d4);
     __half h[4], l[4];
-    split_f16(v.x * s, h[0], l[0]); split_f16(v.y * s, h[1], l[1]);
-    split_f16(v.z * s, h[2], l[2]); split_f16(v.w * s, h[3], l[3]);
+    if (grid) {
+      h[0] = __float2half_rn(rintf(v.x * kGridDen) * s2); h[1] = __float2half_rn(rintf(v.y * kGridDen) * s2);
+      h[2] = __float2half_rn(rintf(v.z * kGridDen) * s2); h[3] = __float2half_rn(rintf(v.w * kGridDen) * s2);
+      l[0] = l[1] = l[2] = l[3] = __float2half_rn(0.f);
+    } else {
+      split_f16(v.x * s, h[0], l[0]); split_f16(v.y * s, h[1], l[1]);
+      split_f16(v.z * s, h[2], l[2]); split_f16(v.w * s, h[3], l[3]);
+    }
     reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(h);
     reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(l);
   }
@@ -856,6 +921,8 @@ void tc_bank_free(rbnn_net* n) {
   n->tc.wnorm = nullptr;
   cudaFree(n->tc.scales);
   n->tc.scales = nullptr;
+  cudaFree(n->tc.xgrid_last);
+  n->tc.xgrid_last = nullptr;
   if (n->tc.overflow_host) cudaFreeHost(n->tc.overflow_host);
   n->tc.overflow_host = n->tc.overflow_dev = nullptr;
   delete[] n->tc.dirty;
@@ -950,6 +1017,8 @@ static int tc_bank_refresh_once(rbnn_net* n, int s0, int s1, cudaStream_t st, bo
     if (f16) {
       RBNN_CUDA(cudaMalloc(&tc.scales, sizeof(TcScales)));
       RBNN_CUDA(cudaMemset(tc.scales, 0, sizeof(TcScales)));
+      RBNN_CUDA(cudaMalloc(&tc.xgrid_last, sizeof(unsigned)));
+      RBNN_CUDA(cudaMemset(tc.xgrid_last, 0, sizeof(unsigned)));
       RBNN_CUDA(cudaHostAlloc(&tc.overflow_host, sizeof(int), cudaHostAllocMapped));
       *tc.overflow_host = 0;
       RBNN_CUDA(cudaHostGetDevicePointer(&tc.overflow_dev, tc.overflow_host, 0));
@@ -1202,6 +1271,7 @@ static int fused_chunk(rbnn_net* n, const FcWs& w, int head, const float* x, con
     f.W1.hi = reinterpret_cast<const __half*>(m1.h_hi) + (int64_t)z0 * H * m1.ld;
     f.W1.lo = reinterpret_cast<const __half*>(m1.h_lo) + (int64_t)z0 * H * m1.ld;
     f.unscale = w.call_sc + 1; f.dh_scale = w.call_sc + 2;
+    f.xlo_zero = w.max_bits + 3;
   } else {
     f.X.hi = w.x_hi; f.X.lo = w.x_lo;
     f.W1.hi = m1.hi + (int64_t)z0 * H * m1.ld; f.W1.lo = m1.lo + (int64_t)z0 * H * m1.ld;
@@ -1266,15 +1336,20 @@ static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const fl
   const int d4 = n->D / 4, ld4 = n->tc.mat[0].ld / 4;      // the copies take the row pitch of the W1 copies
   const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
   if (n->prec == RBNN_PREC_F16X3) {
-    RBNN_CUDA(cudaMemsetAsync(w.max_bits, 0, 2 * sizeof(unsigned), st));
-    maxabs_flat_kernel<<<n->sm_count * 4, 256, 0, st>>>(x, count, w.max_bits);
+    // RBNN_XGRID=0: never take the two-pass route for inputs on the pixel grid (A/B measurements)
+    static const bool xgrid_on = !(getenv("RBNN_XGRID") && atoi(getenv("RBNN_XGRID")) == 0);
+    RBNN_CUDA(cudaMemsetAsync(w.max_bits, 0, 4 * sizeof(unsigned), st));
+    if (xgrid_on && use_fused(n)) maxabs_grid_kernel<<<n->sm_count * 4, 256, 0, st>>>(x, count, w.max_bits);
+    else maxabs_flat_kernel<<<n->sm_count * 4, 256, 0, st>>>(x, count, w.max_bits);
     if (pbar_for_scale) {
       maxabs_kernel<<<n->sm_count, 256, 0, st>>>(pbar_for_scale, 0, pbar_count, 1, w.max_bits + 1);
       n->launches++;
     }
     call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, pbar_for_scale ? w.max_bits + 1 : nullptr, w.call_sc,
-                                        dh_factor);
-    split_f16_kernel<<<blocks, 256, 0, st>>>(x, w.call_sc, w.x_h16, w.x_l16, n4, d4, ld4);
+                                        dh_factor, (xgrid_on && use_fused(n)) ? w.max_bits : nullptr);
+    split_f16_kernel<<<blocks, 256, 0, st>>>(x, w.call_sc, w.x_h16, w.x_l16, n4, d4, ld4, w.max_bits);
+    if (n->tc.xgrid_last)      // for rbnn_net_input_grid()
+      RBNN_CUDA(cudaMemcpyAsync(n->tc.xgrid_last, w.max_bits + 3, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     n->launches += 3;
     RBNN_CUDA(cudaGetLastError());
     return 0;
@@ -1332,7 +1407,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   else if (bf) w.x_bf = ar.take<__nv_bfloat16>((size_t)B * ldx);
   else if (f16) {
     w.x_h16 = ar.take<__half>((size_t)B * ldx); w.x_l16 = ar.take<__half>((size_t)B * ldx);
-    w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2);
+    w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(4);
   } else { w.x_hi = ar.take<float>((size_t)B * ldx); w.x_lo = ar.take<float>((size_t)B * ldx); }
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
@@ -1369,7 +1444,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
         n->launches++;
       }
       call_scales_kernel<<<1, 1, 0, st>>>(n->tc.scales, w.max_bits, up ? w.max_bits + 1 : nullptr, w.call_sc,
-                                          head == RBNN_HEAD_LOGITS_UPSTREAM ? (float)n->C : 2.f);
+                                          head == RBNN_HEAD_LOGITS_UPSTREAM ? (float)n->C : 2.f, w.max_bits);
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }
@@ -1494,7 +1569,7 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   else if (f16) {
     w.x_h16 = ar.take<__half>((size_t)B * ldx); w.x_l16 = ar.take<__half>((size_t)B * ldx);
     if (keep) { w.call_sc = n->keep.call_sc; w.max_bits = n->keep.max_bits; }
-    else { w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(2); }
+    else { w.call_sc = ar.take<float>(4); w.max_bits = ar.take<unsigned>(4); }
   } else { w.x_hi = ar.take<float>((size_t)B * ldx); w.x_lo = ar.take<float>((size_t)B * ldx); }
   const size_t zbh = (size_t)zc * B * H;
   const bool fused = use_fused(n);
@@ -1600,7 +1675,7 @@ int tc_fc_forward_keep(rbnn_net* n, const float* x, int B, int s0, int s1, float
   }
   if (!k.call_sc) {
     RBNN_CUDA(cudaMalloc(&k.call_sc, 4 * sizeof(float)));
-    RBNN_CUDA(cudaMalloc(&k.max_bits, 2 * sizeof(unsigned)));
+    RBNN_CUDA(cudaMalloc(&k.max_bits, 4 * sizeof(unsigned)));
     n->alloc_epoch++;
   }
   RBNN_TRY(tc_forward_pass(n, x, B, s0, s1, out_sum, nullptr, st, true));

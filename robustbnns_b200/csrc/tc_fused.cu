@@ -72,6 +72,7 @@ struct FParams {
   const float* x; const float* xnorm; const float* wnorm; float eps;
   void* dh_hi; void* dh_lo; __nv_bfloat16* dh_bf; float* logits;
   const float* unscale; const float* dh_scale;      // F16X3 device scalars (see FusedDesc)
+  const unsigned* xlo_zero;                          // F16X3 device flag: the lo part of the inputs is zero -> two passes
   uint32_t* maskbuf;                                 // head == -2 (keep mode): [item][kMaskWordsItem][128] LeakyReLU mask words
   int debug;                                         // timing experiments (RBNN_FUSED_DEBUG): 1 no dH stores, 2 no pass 2, 4 no pass-1 math, 8 phase timers, 16 no L2 hint
   unsigned long long* worklist;
@@ -338,6 +339,10 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   constexpr int NCTA = PAIR ? 2 : 1;
   constexpr int STAGE = NARR * (kATileF + kBTileF);
   constexpr int NSTAGE = kRingF / STAGE;
+  // two-pass forward (F16X3, inputs on the pixel grid: X.lo is zero and never loaded): a stage shrinks by the X.lo tile
+  // and the ring holds more of them (CTA pairs: 4 x 48 KB instead of 3 x 64 KB)
+  constexpr int STAGE2 = MODE == MODE_F16X3 ? STAGE - kATileF : STAGE;
+  constexpr int NBAR = kRingF / STAGE2;                   // barriers are laid out for the larger stage count
   constexpr int KBE = KBB / (F16K ? 2 : 4);
   constexpr int KSTEPS = KBB / 32;
   constexpr uint32_t FMT = MODE == MODE_BF16 ? 1u : (MODE == MODE_F16X3 ? 0u : 2u);
@@ -346,13 +351,13 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t ring = (raw + 1023u) & ~1023u;
   const uint32_t bars = ring + kRingF;
-  const uint32_t full0 = bars, empty0 = bars + 8 * NSTAGE;
-  const uint32_t tfull0 = bars + 16 * NSTAGE, tempty0 = tfull0 + 16;
+  const uint32_t full0 = bars, empty0 = bars + 8 * NBAR;
+  const uint32_t tfull0 = bars + 16 * NBAR, tempty0 = tfull0 + 16;
   uint8_t* gen = smem_raw + (bars - raw);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 16 * NSTAGE + 32);
-  uint32_t* wl_count = reinterpret_cast<uint32_t*>(gen + 16 * NSTAGE + 40);
-  const uint32_t pfull0 = bars + 16 * NSTAGE + 48;         // pair protocol: "the peer's stage is full" (leader's copy)
-  static_assert(16 * NSTAGE + 48 + 8 * NSTAGE <= 256, "barrier block");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 16 * NBAR + 32);
+  uint32_t* wl_count = reinterpret_cast<uint32_t*>(gen + 16 * NBAR + 40);
+  const uint32_t pfull0 = bars + 16 * NBAR + 48;         // pair protocol: "the peer's stage is full" (leader's copy)
+  static_assert(16 * NBAR + 48 + 8 * NBAR <= 256, "barrier block");
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
   const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // scheduling unit: CTA or CTA pair
   const int num_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -365,7 +370,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NBAR; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
       if (PAIR) mbar_init(pfull0 + 8 * s, 1);
@@ -391,6 +396,10 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const int bn_cta = PAIR ? p.BN / 2 : p.BN;               // W1 rows (hidden units) staged by this CTA per n-tile
   const uint32_t stage_tx = (uint32_t)NARR * (uint32_t)(kATileF + bn_cta * KBB);
+  const bool two_pass = MODE == MODE_F16X3 && p.xlo_zero && __ldg(p.xlo_zero) != 0u;   // same word for every role / CTA
+  const int nst = two_pass ? NBAR : NSTAGE;
+  const uint32_t stage_bytes = two_pass ? (uint32_t)STAGE2 : (uint32_t)STAGE;
+  const uint32_t b_off = (two_pass ? 1u : (uint32_t)NARR) * (uint32_t)kATileF;            // B tiles follow the A tile(s)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -398,6 +407,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       uint64_t pol_x;      // the inputs are re-read for every posterior sample: keep them in L2 while dH streams through
       asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
       const bool hint = !(p.debug & 16);
+      const bool a_lo = !BF16 && !two_pass;              // X.lo needed
+      const uint32_t tx = a_lo || BF16 ? stage_tx : stage_tx - (uint32_t)kATileF;
       uint32_t stage = 0, phase = 0;
       long long w_empty = 0;
       const long long t_begin = clock64();
@@ -409,18 +420,20 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
             mbar_wait(empty0 + 8 * stage, phase ^ 1u);
             w_empty += clock64() - t0;
             const uint32_t fb = full0 + 8 * stage;
-            mbar_expect_tx(fb, stage_tx);
-            const uint32_t sa = ring + stage * STAGE;
-            const uint32_t sb = sa + NARR * kATileF;
+            mbar_expect_tx(fb, tx);
+            const uint32_t sa = ring + stage * stage_bytes;
+            const uint32_t sb = sa + b_off;
             if (hint) tma_load_3d_hint(sa, &tmAh, fb, kb * KBE, m_idx * kBM, 0, pol_x);
             else tma_load_3d(sa, &tmAh, fb, kb * KBE, m_idx * kBM, 0);
             tma_load_3d(sb, &tmBh, fb, kb * KBE, n * p.BN + (int)rank * bn_cta, z);
             if (!BF16) {
-              if (hint) tma_load_3d_hint(sa + kATileF, &tmAl, fb, kb * KBE, m_idx * kBM, 0, pol_x);
-              else tma_load_3d(sa + kATileF, &tmAl, fb, kb * KBE, m_idx * kBM, 0);
+              if (a_lo) {
+                if (hint) tma_load_3d_hint(sa + kATileF, &tmAl, fb, kb * KBE, m_idx * kBM, 0, pol_x);
+                else tma_load_3d(sa + kATileF, &tmAl, fb, kb * KBE, m_idx * kBM, 0);
+              }
               tma_load_3d(sb + kBTileF, &tmBl, fb, kb * KBE, n * p.BN + (int)rank * bn_cta, z);
             }
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -437,7 +450,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         for (int i = 0; i < total_kb; ++i) {
           mbar_wait(full0 + 8 * stage, phase);
           mbar_arrive_cluster(pf + 8 * stage);
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+          if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -445,6 +458,7 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       // ===================== MMA issuer (leader CTA of a pair) =====================
       const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)((kBM * NCTA) >> 4) << 24);
+      const bool a_lo_used = !two_pass;
       uint32_t stage = 0, phase = 0, it = 0;
       long long w_tempty = 0, w_full = 0;
       const long long t_begin = clock64();
@@ -463,8 +477,8 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
             if (PAIR) mbar_wait(pfull0 + 8 * stage, phase);
             w_full += clock64() - t0;
             tc_fence_after();
-            const uint32_t sa = ring + stage * STAGE;
-            const uint32_t sb = sa + NARR * kATileF;
+            const uint32_t sa = ring + stage * stage_bytes;
+            const uint32_t sb = sa + b_off;
             const uint64_t a_hi = smem_desc<KBB>(sa), b_hi = smem_desc<KBB>(sb);
             if (BF16) {
 #pragma unroll
@@ -475,23 +489,37 @@ fc_fused_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
               }
             } else {
               const uint64_t a_lo = smem_desc<KBB>(sa + kATileF), b_lo = smem_desc<KBB>(sb + kBTileF);
+              if (a_lo_used) {
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                if (PAIR) {
-                  tc_mma_pair<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
-                  tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                  tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
-                } else {
-                  tc_mma<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
-                  tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                  tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  if (PAIR) {
+                    tc_mma_pair<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                    tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  } else {
+                    tc_mma<F16K>(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                    tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  }
+                  accumulate = 1;
                 }
-                accumulate = 1;
+              } else {          // inputs on the pixel grid: X_lo == 0, the X_lo . W1_hi pass drops out
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  if (PAIR) {
+                    tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate);
+                    tc_mma_pair<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  } else {
+                    tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, accumulate);
+                    tc_mma<F16K>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                  }
+                  accumulate = 1;
+                }
               }
             }
             if (PAIR) tc_commit_pair(empty0 + 8 * stage, (uint16_t)3);   // stage reusable in both CTAs once these MMAs retire
             else tc_commit(empty0 + 8 * stage);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+            if (++stage == (uint32_t)nst) { stage = 0; phase ^= 1u; }
           }
           if (PAIR) tc_commit_pair(tfull0 + 8 * as, (uint16_t)3);        // accumulator complete (both CTAs' epilogues)
           else tc_commit(tfull0 + 8 * as);
@@ -913,7 +941,7 @@ int fused_forward_head(const FusedDesc& d, cudaStream_t st, std::string* err) {
   p.maskbuf = d.maskbuf;
   p.dh_hi = d.dh_hi; p.dh_lo = d.dh_lo; p.dh_bf = reinterpret_cast<__nv_bfloat16*>(d.dh_bf); p.logits = d.logits;
   p.worklist = p.eps > 0.f ? d.worklist : nullptr;
-  p.unscale = d.unscale; p.dh_scale = d.dh_scale;
+  p.unscale = d.unscale; p.dh_scale = d.dh_scale; p.xlo_zero = d.xlo_zero;
   {
     static const int dbg = getenv("RBNN_FUSED_DEBUG") ? atoi(getenv("RBNN_FUSED_DEBUG")) : 0;
     p.debug = dbg;

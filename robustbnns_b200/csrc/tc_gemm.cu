@@ -44,6 +44,7 @@ struct KParams {
   const float* act; long long act_zstride, act_ld;
   float* out; float* out_lo; __nv_bfloat16* out_bf;
   long long out_ld, out_zstride;
+  unsigned* group_max;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -266,6 +267,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const long long arow = (long long)zz * p.act_zstride + (long long)m * p.act_ld;
       const float* bias = p.bias ? p.bias + (long long)zz * p.bias_zstride : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)kBNMax;
+      float gmx = 0.f;                                   // max |pre-activation| of this row (p.group_max)
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
@@ -282,6 +284,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             // scalar loads: bank rows are P floats apart, so bias_z is only 4-byte aligned
             v[0] += __ldg(bias + n); v[1] += __ldg(bias + n + 1); v[2] += __ldg(bias + n + 2); v[3] += __ldg(bias + n + 3);
             if (p.epi == EPI_BIAS_LEAKY) {
+              gmx = fmaxf(fmaxf(gmx, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
 #pragma unroll
               for (int q = 0; q < 4; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * kSlope;
             }
@@ -316,6 +319,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       if (lane == 0) {
         if (PAIR) mbar_arrive_cluster(tempty_leader + 8 * as);
         else mbar_arrive(tempty0 + 8 * as);
+      }
+      if (p.group_max) {           // the 32 rows of a warp lie in one group of 64 (tile rows start at multiples of 128)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmx = fmaxf(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+        const int m0 = m_idx * kBM + quad * 32;
+        if (lane == 0 && m0 < p.M && gmx == gmx)
+          atomicMax(p.group_max + (long long)zz * ((p.M + 63) / 64) + (m0 >> 6), __float_as_uint(gmx));
       }
     }
   }
@@ -478,6 +488,7 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   p.act = d.act; p.act_zstride = d.act_zstride; p.act_ld = d.act_ld;
   p.out = d.out; p.out_lo = d.out_lo; p.out_bf = reinterpret_cast<__nv_bfloat16*>(d.out_bf);
   p.out_ld = d.out_ld; p.out_zstride = d.out_zstride;
+  p.group_max = d.epi == EPI_BIAS_LEAKY ? d.group_max : nullptr;
   if ((d.epi == EPI_BIAS_LEAKY || d.epi == EPI_BIAS) && !d.bias) { *err = "tc::gemm: bias epilogue without bias"; return 1; }
   if (d.epi == EPI_MASK && !d.act) { *err = "tc::gemm: mask epilogue without activations"; return 1; }
   if ((d.out_ld & 3) || (d.epi == EPI_MASK && (d.act_ld & 3))) { *err = "tc::gemm: leading dimensions must be multiples of 4"; return 1; }

@@ -63,6 +63,10 @@ struct GemmDesc {
   float* out_lo = nullptr;    // optional: tf32 residual -> the result is written pre-split for the next GEMM
   void* out_bf = nullptr;     // optional: bf16 copy of the result
   int64_t out_ld = 0, out_zstride = 0;
+  // EPI_BIAS_LEAKY, optional: group_max[z * ceil(M / 64) + m / 64] = max(.., |pre-activation|) as float bits (atomicMax;
+  // zero it first) -- the per-image maximum the guard band of the conv net scales with, taken where the accumulator
+  // is in registers anyway instead of in a separate pass over the output
+  unsigned* group_max = nullptr;
   int sm_count = 148;
   int pair_relay = 1;      // pair mode: 1 = own-barrier TMA + relayed full signal, 0 = cta_group::2 TMA onto the leader's barrier
   int spin_wait = 0;       // 1: poll mbarriers with test_wait instead of the suspending try_wait
@@ -107,6 +111,8 @@ struct FusedDesc {
   void* dh_hi = nullptr; void* dh_lo = nullptr; void* dh_bf = nullptr;   // [Z][B][H]; hi/lo: fp32 (TF32X3) or fp16 (F16X3)
   const float* unscale = nullptr;   // F16X3: device scalar 1 / (s_X s_W1) applied to the forward accumulator
   const float* dh_scale = nullptr;  // F16X3: device scalar dH is multiplied by before the fp16 hi/lo split
+  const unsigned* xlo_zero = nullptr;   // F16X3: device flag, != 0 = X.lo is all zero (inputs on the pixel grid): X.lo is not
+                                        // loaded and the X_lo . W1_hi MMAs are not issued (two passes instead of three)
   float* logits = nullptr;        // [Z][B][C] (head == -1)
   unsigned long long* worklist = nullptr;   // num_items * kWorkPerItem slots
   int kblock_bytes = 128;

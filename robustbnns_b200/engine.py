@@ -79,6 +79,12 @@ class Net(object):
     def launch_count(self):
         return int(lib().rbnn_net_launch_count(self._h))
 
+    @property
+    def input_grid(self):
+        """True when the last F16X3 forward found its inputs on the 8-bit pixel grid (uint8 / 255, what the reference's
+        image loaders produce) and ran the two-pass forward; synchronises the device."""
+        return int(lib().rbnn_net_input_grid(self._h)) == 1
+
     def timing_enable(self, on=True):
         check(lib().rbnn_net_timing_enable(self._h, int(bool(on))))
 

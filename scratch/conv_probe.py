@@ -49,7 +49,7 @@ for prec in precs:
     else:
         r["max_rel_deviation_from_" + precs[0]] = float((gr - ref).abs().max() / ref.abs().max())
     iters = 4
-    aa.pgd_attack(bnn, x, y, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=1)
+    aa.pgd_attack(bnn, x, y, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=iters)   # also captures the graph
     torch.cuda.synchronize()
     e0.record()
     aa.pgd_attack(bnn, x, y, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=iters)

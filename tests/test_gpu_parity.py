@@ -758,10 +758,13 @@ def test_full_size_properties_fc_headline():
     eng.close()
 
 
-def test_headline_engine_at_headline_size_against_fp64_oracle():
+@pytest.mark.parametrize("inputs", ["pixel", "float"])
+def test_headline_engine_at_headline_size_against_fp64_oracle(inputs):
     """BASELINE configs[1] at FULL size on the engine bench.py times: 10 000 inputs x 1000 posterior samples drawn on the
     device from bench.py's guide (loc ~ N(0, 1/fan_in), rho ~ N(-5, 1)), fc 784-512-10, F16X3.  32 random rows of the
-    expected loss gradient are held to the fp64 oracle evaluated on the very weights the device drew (downloaded bank)."""
+    expected loss gradient are held to the fp64 oracle evaluated on the very weights the device drew (downloaded bank).
+    "pixel": inputs on the 8-bit grid uint8 / 255 as the reference's loaders produce them (utils.py:102-103) and as
+    bench.py draws them -- the two-pass forward; "float": arbitrary fp32 inputs -- the three-pass forward."""
     import math
     from robustbnns_b200 import lossGradients as lg
     from robustbnns_b200.model_bnn import BNN
@@ -780,18 +783,77 @@ def test_headline_engine_at_headline_size_against_fp64_oracle():
     bnn.set_guide(torch.cat(locs), torch.cat(rhos))
     bnn.set_precision("f16x3")
     gx = torch.Generator().manual_seed(0)
-    x = torch.rand((B, 1, 28, 28), generator=gx)
+    if inputs == "pixel":
+        x = torch.randint(0, 256, (B, 1, 28, 28), generator=gx).to(torch.float32) / 255
+    else:
+        x = torch.rand((B, 1, 28, 28), generator=gx)
     y = torch.randint(0, 10, (B,), generator=gx)
     grads = lg.expected_loss_gradients(bnn, x.cuda(), y.cuda(), S).cpu()
+    assert bnn.engine().input_grid == (inputs == "pixel")
     idx = torch.randperm(B, generator=torch.Generator().manual_seed(3))[:32]
     bank = bnn.engine().download(0, S)              # the 1000 weight vectors the Philox kernel drew (1.6 GB)
     ref = orc.expected_loss_gradients(net, layout, bank, x[idx], y[idx], range(S), dtype=torch.float64)
     err = rel_err(grads[idx], ref)
-    print(f"headline size, f16x3: 32 rows vs fp64 oracle: {err:.2e}")
+    print(f"headline size, f16x3, {inputs} inputs: 32 rows vs fp64 oracle: {err:.2e}")
     assert err < REL
     # the posterior-mean gradient is a heavily cancelling sum: per-row errors relative to that row's own maximum
     row_err = (grads[idx].double() - ref).abs().flatten(1).max(1)[0] / ref.abs().flatten(1).max(1)[0]
     assert float(row_err.max()) < 10 * REL, row_err
+
+
+@pytest.mark.parametrize("S", [1, 10, 1000])
+def test_two_pass_forward_for_inputs_on_the_pixel_grid(S):
+    """F16X3, arch fc: inputs that are uint8 / 255 (every image set the reference loads, utils.py:102-103, 129-130,
+    190-191) have a zero low half once scaled by 255 * 2^j, so the fused forward issues TWO tensor-core passes instead of
+    three.  That route must be parity grade on its own: expected loss gradients, the attack gradient and the mean
+    prediction against the fp64 oracle at 1, 10 and 1000 posterior samples (tolerance 1e-4, the north-star one), the
+    detection must be bit-exact (inputs a hair off the grid, or with more than 11 significant bits, take three passes),
+    and a PGD iterate, which leaves the grid, must switch back by itself."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200.engine import Net
+    hidden, B = (512, 130) if S <= 10 else (256, 96)
+    net, layout, loc, rho, bank, x, labels = _problem("fc", (1, 28, 28), hidden, 10, B, S, seed=11)
+    g = torch.Generator().manual_seed(4)
+    q = torch.randint(0, 256, x.shape, generator=g)
+    q[:, :, :6, :] = 0                                      # a blank border, as MNIST has
+    x = q.to(torch.float32) / 255                           # exactly what `x_test /= 255` yields
+    eng = Net("fc", (1, 28, 28), hidden, 10)
+    eng.set_precision("f16x3")
+    eng.upload(bank, 0)
+    xd, ld = x.cuda(), labels.cuda().to(torch.int32)
+    gm = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, 0, S).cpu().reshape(x.shape) / S
+    assert eng.input_grid, "inputs on the pixel grid were not recognised"
+    ref = orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    e_mean = rel_err(gm, ref)
+    probs = eng.forward_probs_sum(xd, 0, S) / S
+    e_p = rel_err(probs.cpu(), orc.bnn_forward(net, layout, bank, x, range(S)).detach())
+    ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, xd, ld, 0, S, pbar=probs).cpu().reshape(x.shape) / S
+    e_att = rel_err(ga, orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64))
+    pk = eng.forward_probs_sum(xd, 0, S, keep=True)        # two-phase form of the attacks
+    gk = eng.input_grad_sum_kept(_lib.HEAD_GRAD_OF_MEAN, ld, pbar=pk / S).cpu().reshape(x.shape) / S
+    assert rel_err(gk, ga) < 1e-6
+    print(f"two-pass forward, fc-{hidden} B={B} S={S}: mean-of-grads {e_mean:.2e} grad-of-mean {e_att:.2e} probs {e_p:.2e}")
+    assert max(e_mean, e_att, e_p) < REL
+    # the three-pass route on the same inputs (RBNN_XGRID cannot be flipped inside a process: perturb ONE pixel instead)
+    x3 = x.clone()
+    x3[0, 0, 10, 10] = x3[0, 0, 10, 10] * (1 + 1e-6) if float(x3[0, 0, 10, 10]) > 0 else 1e-9
+    g3 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, x3.cuda(), ld, 0, S).cpu().reshape(x.shape) / S
+    assert not eng.input_grid, "one input off the grid by 1e-6 (relative) must send the call down the three-pass route"
+    assert rel_err(g3[1:], gm[1:]) < 2e-5                  # rows 1.. did not change: both routes agree far below 1e-4
+    # 12 significant bits (q up to 4095) do not fit the fp16 hi part
+    x12 = torch.randint(0, 4096, x.shape, generator=g).to(torch.float32) / 255
+    eng.forward_probs_sum(x12.cuda(), 0, S)
+    assert not eng.input_grid
+    # all-zero inputs: no scale to derive, three-pass route, finite result
+    z0 = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, torch.zeros_like(xd), ld, 0, S)
+    assert not eng.input_grid and bool(torch.isfinite(z0).all())
+    # a PGD iterate x + alpha * sign(g) leaves the grid: back to three passes without being told
+    xi = (xd + (2.0 / 225) * torch.sign(torch.randn(xd.shape, device=xd.device))).clamp(0, 1)
+    gi = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xi, ld, 0, S).cpu().reshape(x.shape) / S
+    assert not eng.input_grid
+    refi = orc.expected_loss_gradients(net, layout, bank, xi.cpu(), labels, range(S), dtype=torch.float64)
+    assert rel_err(gi, refi) < REL
+    eng.close()
 
 
 def test_full_size_properties_conv_cfg4():
