@@ -619,8 +619,11 @@ int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0
 }
 
 // ---- tcgen05 route (tc_conv.cu): operand preparation and guard-band refinement of conv2 ---------------------
-// P1[zb][c][y][x] (fp32, CHW) -> channels-last tf32-split copies hi/lo[zb][y][x][c]: a pixel's 32 channels are the
-// 128-byte K-block row of the implicit GEMM.  One block per image, transposed through shared memory.
+// P1[zb][c][y][x] (fp32, CHW) -> channels-last split copies, one block per image, transposed through shared memory.
+//   TF32X3: hi/lo[zb][y][x][32] fp32 -- a pixel's 32 channels are the 128-byte K-block row of the implicit GEMM.
+//   F16X3 : hi/lo[zb][y][x][64] fp16 -- the channels of pixel (y, x) FOLLOWED BY those of pixel (y, x + 1) (zeros past
+//           the row end), so that one 128-byte row carries two horizontally adjacent filter taps: K-blocks of 64 bytes
+//           (one tap) left the tensor pipe 46 % busy (twice the TMA requests and barrier round trips per byte).
 __global__ void __launch_bounds__(256)
 p1_split_hwc_kernel(const float* __restrict__ p1, void* __restrict__ hi, void* __restrict__ lo,
                     const float* __restrict__ f16_scale) {
@@ -629,16 +632,27 @@ p1_split_hwc_kernel(const float* __restrict__ p1, void* __restrict__ hi, void* _
   for (int i = threadIdx.x; i < 4608; i += blockDim.x) t[(i / 144) * 145 + i % 144] = __ldg(p1 + zb * 4608 + i);
   __syncthreads();
   const float sc = f16_scale ? __ldg(f16_scale) : 1.f;
+  if (f16_scale) {
+    __half* h16 = reinterpret_cast<__half*>(hi) + zb * 9216;
+    __half* l16 = reinterpret_cast<__half*>(lo) + zb * 9216;
+    for (int o = threadIdx.x; o < 4608; o += blockDim.x) {      // pairs of output elements: 4-byte stores
+      const int e = (o & 31) * 2, px = o >> 5;                   // element pair e, e + 1 of the 64-element row of pixel px
+      const int c = e & 31, src = px + (e >> 5);                 // second half: the next pixel of the same image row
+      const bool in = (e < 32) || (px % 12) != 11;
+      __half2 hh, ll;
+      split_f16(in ? t[c * 145 + src] * sc : 0.f, hh.x, ll.x);
+      split_f16(in ? t[(c + 1) * 145 + src] * sc : 0.f, hh.y, ll.y);
+      reinterpret_cast<__half2*>(h16)[px * 32 + (e >> 1)] = hh;
+      reinterpret_cast<__half2*>(l16)[px * 32 + (e >> 1)] = ll;
+    }
+    return;
+  }
   for (int o = threadIdx.x; o < 4608; o += blockDim.x) {
     const int c = o & 31, px = o >> 5;
     const float v = t[c * 145 + px];
-    if (f16_scale) {
-      split_f16(v * sc, reinterpret_cast<__half*>(hi)[zb * 4608 + o], reinterpret_cast<__half*>(lo)[zb * 4608 + o]);
-    } else {
-      const float h = tf32_rn(v);
-      reinterpret_cast<float*>(hi)[zb * 4608 + o] = h;
-      reinterpret_cast<float*>(lo)[zb * 4608 + o] = v - h;
-    }
+    const float h = tf32_rn(v);
+    reinterpret_cast<float*>(hi)[zb * 4608 + o] = h;
+    reinterpret_cast<float*>(lo)[zb * 4608 + o] = v - h;
   }
 }
 

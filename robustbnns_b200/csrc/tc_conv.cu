@@ -137,11 +137,14 @@ int forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, ConvTcBufs&
   }
   RBNN_TRY(p1_split_hwc(n, c.p1, Z * B, c.p1h, c.p1l, f16 ? c.call_sc : nullptr, st));
   tc::GemmDesc g;
-  g.M = B * 64; g.N = H; g.K = 800; g.Z = Z; g.BN = std::min(H, 256);
+  g.M = B * 64; g.N = H; g.K = f16 ? 960 : 800; g.Z = Z; g.BN = std::min(H, 256);
   g.conv_images = B;
-  g.A.hi = c.p1h; g.A.lo = c.p1l; g.A.rows = g.M; g.A.ld = 800; g.A.zstride = (int64_t)B * 4608;
+  g.A.hi = c.p1h; g.A.lo = c.p1l; g.A.rows = g.M; g.A.ld = g.K; g.A.zstride = (int64_t)B * 4608;
+  // CTA pairs (each CTA stages half of the filter tile): the single-CTA tile needs ~62 bytes per clock and SM from L2
+  static const int conv_pair = getenv("RBNN_CONV_PAIR") ? atoi(getenv("RBNN_CONV_PAIR")) : 3;   // bit 0: conv2, bit 1: dgrad
   if (f16) {
-    g.kblock_bytes = 64;                            // 32 fp16 channels per filter tap
+    g.kblock_bytes = 128;                           // two filter taps (2 x 32 fp16 channels) per K-block
+    g.pair = (conv_pair & 1) && (B % 4 == 0) && (g.BN % 32 == 0);
     g.B.hi = reinterpret_cast<const uint16_t*>(m.h_hi) + (int64_t)z0 * H * m.ld;
     g.B.lo = reinterpret_cast<const uint16_t*>(m.h_lo) + (int64_t)z0 * H * m.ld;
     g.unscale = c.call_sc + 1;
@@ -172,6 +175,8 @@ int backward_chunk(rbnn_net* n, int head, const int32_t* labels, const float* pb
   // dcol[z][b * 64 + pos][c * 25 + ky * 5 + kx] = sum_h dZ2[z][b * 64 + pos][h] W2_z[h][c][ky][kx]
   tc::GemmDesc d;
   d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = 160;
+  static const int conv_pair = getenv("RBNN_CONV_PAIR") ? atoi(getenv("RBNN_CONV_PAIR")) : 3;
+  d.pair = (conv_pair & 2) ? 1 : 0;
   d.A.hi = c.dzh; d.A.lo = c.dzl; d.A.rows = d.M; d.A.ld = H; d.A.zstride = (int64_t)B * 64 * H;
   if (f16) {
     d.B.hi = reinterpret_cast<const uint16_t*>(m.th_hi) + (int64_t)z0 * 800 * H;

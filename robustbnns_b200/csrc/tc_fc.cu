@@ -292,7 +292,10 @@ __global__ void relayout_f16_kernel(const float* __restrict__ bank, int64_t P, i
     float v = 0.f;
     if (r < R && c < C) {
       v = __ldg(src + (int64_t)r * C + c) * sw;
-      const int cf = perm25 ? (c % 25) * 32 + c / 25 : c;     // conv2 filters: tap-major forward copy (TcMat::perm25)
+      // conv2 filters: tap-major forward copy (TcMat::perm25); 2 = rows of 5 x 6 taps, the 6th a zero padding tap
+      // (K = 960: 128-byte K-blocks of two taps; the padding slots were zeroed when the copies were allocated)
+      const int tap = c % 25;
+      const int cf = perm25 == 2 ? ((tap / 5) * 6 + tap % 5) * 32 + c / 25 : (perm25 ? tap * 32 + c / 25 : c);
       const int64_t o = ((int64_t)s * R + r) * ld + cf;
       split_f16(v, hi[o], lo[o]);
     }
@@ -993,6 +996,7 @@ static int tc_bank_refresh_once(rbnn_net* n, int s0, int s1, cudaStream_t st, bo
     tc.mat[0].off = n->L.w1; tc.mat[0].R = n->H; tc.mat[0].C = n->D; tc.mat[0].ld = k_pitch(n, n->D);
     if (n->arch == RBNN_ARCH_CONV) {      // the conv2 filters [H][32*5*5]; conv1 and the output layer stay on CUDA cores
       tc.mat[0].off = n->L.cw2; tc.mat[0].C = 800; tc.mat[0].ld = k_pitch(n, 800); tc.mat[0].perm25 = 1;
+      if (f16) { tc.mat[0].ld = 960; tc.mat[0].perm25 = 2; }       // two taps per 128-byte K-block, 5 x 6 taps per filter
     }
     if (tc.nmat == 2) { tc.mat[1].off = n->L.w2; tc.mat[1].R = n->H; tc.mat[1].C = n->H; tc.mat[1].ld = n->H; }
     for (int i = 0; i < tc.nmat; ++i) {
@@ -1004,6 +1008,10 @@ static int tc_bank_refresh_once(rbnn_net* n, int s0, int s1, cudaStream_t st, bo
       } else if (f16) {
         RBNN_CUDA(cudaMalloc(&m.h_hi, elems * 2));
         RBNN_CUDA(cudaMalloc(&m.h_lo, elems * 2));
+        if (m.perm25 == 2) {                                          // zero padding taps
+          RBNN_CUDA(cudaMemset(m.h_hi, 0, elems * 2));
+          RBNN_CUDA(cudaMemset(m.h_lo, 0, elems * 2));
+        }
         RBNN_CUDA(cudaMalloc(&m.th_hi, telems * 2));
         RBNN_CUDA(cudaMalloc(&m.th_lo, telems * 2));
       } else {

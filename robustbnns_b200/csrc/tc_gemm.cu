@@ -30,7 +30,8 @@ constexpr float kSlope = 0.01f;            // nn.LeakyReLU() default (model_nn.p
 // The MMAs of a stage and its TMA refill cannot overlap, so with S stages the K-block period is
 // max(T_mma, (T_mma + T_tma) / S): narrower tiles with a third stage beat wide tiles with two.
 constexpr int kRingBytes = 221184;
-constexpr int kSmemBytes = kRingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = kRingBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 2048 /*epilogue staging tiles*/;
+static_assert(kSmemBytes <= 232448, "tc_gemm_kernel exceeds the 227 KB shared memory of an sm_100 CTA");
 
 size_t smem_bytes() { return kSmemBytes; }
 
@@ -134,12 +135,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               // forwards "full" to the leader with one remote arrive per stage
               const uint32_t fb = full0 + 8 * stage;
               mbar_expect_tx(fb, stage_tx);
-              tma_load_3d(sa, &tmAh, fb, kb * KBE, m_idx * kBM, za);
-              tma_load_3d(sb, &tmBh, fb, kb * KBE, n_idx * p.BN + (int)rank * bn_cta, z);
-              if (!BF16) {
-                tma_load_3d(sa + kATile, &tmAl, fb, kb * KBE, m_idx * kBM, za);
-                tma_load_3d(sb + kBTile, &tmBl, fb, kb * KBE, n_idx * p.BN + (int)rank * bn_cta, z);
+              if (!BF16 && KBB == 128 && p.conv_a) {       // implicit GEMM (see the single-CTA branch): this CTA's two images
+                int cx, cy;
+                if (MODE == MODE_F16X3) { cy = kb / 3; cx = 2 * (kb - 3 * cy); }
+                else { cy = kb / 5; cx = kb - 5 * cy; }
+                tma_load_5d(sa, &tmAh, fb, 0, cx, cy, 2 * m_idx, z);
+                tma_load_5d(sa + kATile, &tmAl, fb, 0, cx, cy, 2 * m_idx, z);
+              } else {
+                tma_load_3d(sa, &tmAh, fb, kb * KBE, m_idx * kBM, za);
+                if (!BF16) tma_load_3d(sa + kATile, &tmAl, fb, kb * KBE, m_idx * kBM, za);
               }
+              tma_load_3d(sb, &tmBh, fb, kb * KBE, n_idx * p.BN + (int)rank * bn_cta, z);
+              if (!BF16) tma_load_3d(sb + kBTile, &tmBl, fb, kb * KBE, n_idx * p.BN + (int)rank * bn_cta, z);
             } else if (PAIR) {
               const uint32_t fb = mapa_u32(full0 + 8 * stage, 0u);          // the leader's barrier collects both CTAs' bytes
               if (rank == 0) mbar_expect_tx(full0 + 8 * stage, stage_tx);
@@ -150,12 +157,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 tma_load_3d_pair(sa + kATile, &tmAl, fb, kb * KBE, m_idx * kBM, za);
                 tma_load_3d_pair(sb + kBTile, &tmBl, fb, kb * KBE, n_idx * p.BN + (int)rank * bn_cta, z);
               }
-            } else if (((MODE == MODE_TF32X3 && KBB == 128) || (MODE == MODE_F16X3 && KBB == 64)) && p.conv_a) {
+            } else if ((MODE == MODE_TF32X3 && KBB == 128 || MODE == MODE_F16X3) && p.conv_a) {
               // implicit GEMM: K-block kb = filter tap (ky, kx); the 128 tile rows are the 8x8 output positions of two
               // images, i.e. the box {32 channels, x in [kx, kx+8), y in [ky, ky+8), images 2 m_idx .. +1} of the map
-              // (32 channels = 128 bytes of fp32 / tf32, 64 bytes of fp16)
+              // (32 channels = 128 bytes of fp32 / tf32, 64 bytes of fp16).  F16X3 with 128-byte K-blocks: kb = (ky, tap
+              // pair), the box is {64 elements = pixels x, x + 1} at x offset 0 / 2 / 4 of the pixel-pair layout.
               const uint32_t fb = full0 + 8 * stage;
-              const int ky = kb / 5, kx = kb - 5 * ky;
+              int ky, kx;
+              if (MODE == MODE_F16X3 && KBB == 128) { ky = kb / 3; kx = 2 * (kb - 3 * ky); }
+              else { ky = kb / 5; kx = kb - 5 * ky; }
               mbar_expect_tx(fb, stage_tx);
               tma_load_5d(sa, &tmAh, fb, 0, kx, ky, 2 * m_idx, z);
               tma_load_3d(sb, &tmBh, fb, kb * KBE, n_idx * p.BN, z);
@@ -254,6 +264,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int quad = warp & 3;
     const uint32_t tempty_leader = PAIR ? mapa_u32(tempty0, 0u) : tempty0;
     const float unscale = p.unscale ? __ldg(p.unscale) : 1.f;   // F16X3: 1 / (operand scales), a power of two
+    float* stg = reinterpret_cast<float*>(smem_raw + (bars - raw) + 256) + (warp - 2) * 512;   // 32 rows x 16 floats per warp
     uint32_t it = 0;
     for (int t = unit; t < p.num_tiles; t += num_units, ++it) {
       const int n_idx = t % p.n_tiles, m_unit = (t / p.n_tiles) % p.m_units, zz = t / tiles_mn;
@@ -261,57 +272,88 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const uint32_t as = it & 1u;
       mbar_wait_mode(tfull0 + 8 * as, (it >> 1) & 1u, p.spin);
       tc_fence_after();
-      const int m = m_idx * kBM + quad * 32 + lane;
-      const bool row_ok = m < p.M;
-      const long long orow = (long long)zz * p.out_zstride + (long long)m * p.out_ld;
-      const long long arow = (long long)zz * p.act_zstride + (long long)m * p.act_ld;
-      const float* bias = p.bias ? p.bias + (long long)zz * p.bias_zstride : nullptr;
+      // The accumulator arrives with lane = tile row (tcgen05.ld 32x32b).  Stored that way a warp's 16-byte stores hit 32
+      // different lines per instruction and the bias loads sit between them, one dependent load per 4 columns (the
+      // conv2 epilogue took 41 k cycles per tile against 23 k of MMAs).  So 16 columns at a time go through a 2 KB
+      // per-warp staging tile (16-byte chunks XOR-swizzled: conflict-free both ways) and come back transposed: lane =
+      // (row srow + 8 i, columns 4 sk .. 4 sk + 3), i.e. 4 lanes write 64 contiguous bytes of a row, the bias of a lane's
+      // 4 columns is loaded once per 16-column group (and prefetched one group ahead), the mask operand of EPI_MASK is
+      // read with the same coalesced pattern.
+      const int m_base = m_idx * kBM + quad * 32;
+      const int srow = lane >> 2, sk = lane & 3;
+      const float* __restrict__ bias = p.bias ? p.bias + (long long)zz * p.bias_zstride : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)kBNMax;
-      float gmx = 0.f;                                   // max |pre-activation| of this row (p.group_max)
+      const bool has_bias = p.epi == EPI_BIAS_LEAKY || p.epi == EPI_BIAS;
+      float gmx = 0.f;                                   // max |pre-activation| seen by this lane (p.group_max)
+      float bnext[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const int n = n_idx * p.BN + 4 * sk;
+        if (has_bias && 4 * sk < p.BN && n < p.N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bnext[q] = __ldg(bias + n + q);   // scalar: bank rows are only 4-byte aligned
+        }
+      }
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
-        const int n0 = n_idx * p.BN + c0;
-        if (!row_ok) continue;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + j;
-          if (c0 + j >= p.BN || n >= p.N) break;           // BN % 16 == 0 and N % 4 == 0: groups of 4 are all-in or all-out
-          float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                        __uint_as_float(r[j + 3])};
-          if (MODE == MODE_F16X3) { v[0] *= unscale; v[1] *= unscale; v[2] *= unscale; v[3] *= unscale; }
-          if (p.epi == EPI_BIAS_LEAKY || p.epi == EPI_BIAS) {
-            // scalar loads: bank rows are P floats apart, so bias_z is only 4-byte aligned
-            v[0] += __ldg(bias + n); v[1] += __ldg(bias + n + 1); v[2] += __ldg(bias + n + 2); v[3] += __ldg(bias + n + 3);
-            if (p.epi == EPI_BIAS_LEAKY) {
-              gmx = fmaxf(fmaxf(gmx, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          const int cc = c0 + 16 * hlf + 4 * sk;           // this lane's first column inside the tile
+          const int n = n_idx * p.BN + cc;
+          const bool col_ok = cc < p.BN && n < p.N;        // BN % 16 == 0 and N % 4 == 0: groups of 4 are all-in or all-out
+          float bv[4] = {bnext[0], bnext[1], bnext[2], bnext[3]};
+          if (has_bias && cc + 16 < p.BN && n + 16 < p.N) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * kSlope;
+            for (int q = 0; q < 4; ++q) bnext[q] = __ldg(bias + n + 16 + q);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
+                make_uint4(r[16 * hlf + 4 * k], r[16 * hlf + 4 * k + 1], r[16 * hlf + 4 * k + 2], r[16 * hlf + 4 * k + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = srow + 8 * i;
+            const uint4 t = *reinterpret_cast<const uint4*>(stg + rr * 16 + ((sk ^ ((rr >> 1) & 3)) << 2));
+            const int m = m_base + rr;
+            if (!col_ok || m >= p.M) continue;
+            const long long orow = (long long)zz * p.out_zstride + (long long)m * p.out_ld;
+            float v[4] = {__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w)};
+            if (MODE == MODE_F16X3) { v[0] *= unscale; v[1] *= unscale; v[2] *= unscale; v[3] *= unscale; }
+            if (has_bias) {
+              v[0] += bv[0]; v[1] += bv[1]; v[2] += bv[2]; v[3] += bv[3];
+              if (p.epi == EPI_BIAS_LEAKY) {
+                gmx = fmaxf(fmaxf(gmx, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * kSlope;
+              }
+            } else if (p.epi == EPI_MASK) {
+              const long long arow = (long long)zz * p.act_zstride + (long long)m * p.act_ld;
+              const float4 h = __ldg(reinterpret_cast<const float4*>(p.act + arow + n));
+              v[0] = h.x > 0.f ? v[0] : v[0] * kSlope;
+              v[1] = h.y > 0.f ? v[1] : v[1] * kSlope;
+              v[2] = h.z > 0.f ? v[2] : v[2] * kSlope;
+              v[3] = h.w > 0.f ? v[3] : v[3] * kSlope;
             }
-          } else if (p.epi == EPI_MASK) {
-            const float4 h = __ldg(reinterpret_cast<const float4*>(p.act + arow + n));
-            v[0] = h.x > 0.f ? v[0] : v[0] * kSlope;
-            v[1] = h.y > 0.f ? v[1] : v[1] * kSlope;
-            v[2] = h.z > 0.f ? v[2] : v[2] * kSlope;
-            v[3] = h.w > 0.f ? v[3] : v[3] * kSlope;
-          }
-          if (p.out_lo) {
-            float hi[4], lo[4];
+            if (p.out_lo) {
+              float hi[4], lo[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { hi[q] = to_tf32_rn(v[q]); lo[q] = v[q] - hi[q]; }
-            *reinterpret_cast<float4*>(p.out + orow + n) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(p.out_lo + orow + n) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          } else if (p.out) {
-            *reinterpret_cast<float4*>(p.out + orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+              for (int q = 0; q < 4; ++q) { hi[q] = to_tf32_rn(v[q]); lo[q] = v[q] - hi[q]; }
+              *reinterpret_cast<float4*>(p.out + orow + n) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(p.out_lo + orow + n) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            } else if (p.out) {
+              *reinterpret_cast<float4*>(p.out + orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            if (p.out_bf) {
+              __nv_bfloat162 b01 = __floats2bfloat162_rn(v[0], v[1]);
+              __nv_bfloat162 b23 = __floats2bfloat162_rn(v[2], v[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&b01);
+              pk.y = *reinterpret_cast<uint32_t*>(&b23);
+              *reinterpret_cast<uint2*>(p.out_bf + orow + n) = pk;
+            }
           }
-          if (p.out_bf) {
-            __nv_bfloat162 b01 = __floats2bfloat162_rn(v[0], v[1]);
-            __nv_bfloat162 b23 = __floats2bfloat162_rn(v[2], v[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&b01);
-            pk.y = *reinterpret_cast<uint32_t*>(&b23);
-            *reinterpret_cast<uint2*>(p.out_bf + orow + n) = pk;
-          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -323,9 +365,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       if (p.group_max) {           // the 32 rows of a warp lie in one group of 64 (tile rows start at multiples of 128)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmx = fmaxf(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
-        const int m0 = m_idx * kBM + quad * 32;
-        if (lane == 0 && m0 < p.M && gmx == gmx)
-          atomicMax(p.group_max + (long long)zz * ((p.M + 63) / 64) + (m0 >> 6), __float_as_uint(gmx));
+        if (lane == 0 && m_base < p.M && gmx == gmx)
+          atomicMax(p.group_max + (long long)zz * ((p.M + 63) / 64) + (m_base >> 6), __float_as_uint(gmx));
       }
     }
   }
@@ -384,18 +425,21 @@ int make_map(CUtensorMap* map, const void* base, int dtype, int64_t K, int64_t r
 
 // 5-D map over channels-last activations [Z][images][12][12][32] fp32: box = {32 channels, 8, 8, 2 images, 1}, i.e. the
 // 128 rows x 128 bytes of one filter tap of the implicit GEMM (rows ordered image, oy, ox), SWIZZLE_128B.
-static int make_map_conv_a(CUtensorMap* map, const void* base, int dtype, int64_t images, int64_t Z, std::string* err) {
+static int make_map_conv_a(CUtensorMap* map, const void* base, int dtype, int kb_bytes, int64_t images, int64_t Z, std::string* err) {
   auto fn = encode_fn();
   if (!fn) { *err = "cuTensorMapEncodeTiled is not available from the driver"; return 1; }
-  const cuuint64_t px = dtype == DT_F32 ? 128u : 64u;      // bytes of one pixel's 32 channels
-  cuuint64_t dims[5] = {32u, 12u, 12u, (cuuint64_t)images, (cuuint64_t)Z};
+  // fp32: 32 channels = 128 bytes per pixel.  fp16, kb_bytes 64: 32 channels = 64 bytes per pixel (one tap per K-block);
+  // fp16, kb_bytes 128: the pixel-pair layout of p1_split_hwc_kernel, 64 elements = 128 bytes per pixel (two taps)
+  const bool pairs = dtype != DT_F32 && kb_bytes == 128;
+  const cuuint64_t px = (dtype == DT_F32 || pairs) ? 128u : 64u;      // bytes between pixels
+  cuuint64_t dims[5] = {pairs ? 64u : 32u, 12u, 12u, (cuuint64_t)images, (cuuint64_t)Z};
   cuuint64_t strides[4] = {px, 12u * px, 144u * px, (cuuint64_t)images * 144u * px};
-  cuuint32_t box[5] = {32u, 8u, 8u, 2u, 1u};
+  cuuint32_t box[5] = {pairs ? 64u : 32u, 8u, 8u, 2u, 1u};
   cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
   if (reinterpret_cast<uintptr_t>(base) & 127) { *err = "tc::gemm: conv activations must be 128-byte aligned"; return 1; }
   CUresult r = fn(map, dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  dtype == DT_F32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  px == 128u ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     *err = "cuTensorMapEncodeTiled (conv activations) failed with CUresult " + std::to_string((int)r);
@@ -419,10 +463,15 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
   if (d.reduce_z && (d.slots < 1 || d.slots > d.Z)) { *err = "tc::gemm: slots must be in [1, Z]"; return 1; }
 
   const int kbb = d.kblock_bytes == 128 ? 128 : 64;
-  if (d.conv_images > 0 && (!((d.mode == MODE_TF32X3 && kbb == 128) || (d.mode == MODE_F16X3 && kbb == 64)) || d.pair ||
-                            d.K != 800 || d.reduce_z || d.M != d.conv_images * 64)) {
-    *err = "tc::gemm: the implicit-GEMM conv operand needs TF32X3 with 128-byte or F16X3 with 64-byte K-blocks (32 channels), "
-           "single CTAs, K = 800, M = 64 * images";
+  // implicit-GEMM conv operand: TF32X3 / 128-byte K-blocks and F16X3 / 64-byte K-blocks walk the 25 taps (K = 800);
+  // F16X3 / 128-byte K-blocks walk 15 tap PAIRS (ky, {0,1} {2,3} {4,pad}) of the pixel-pair layout: K = 960, the B rows
+  // carry zeros for the padding tap
+  const bool conv_pairs = d.conv_images > 0 && d.mode == MODE_F16X3 && kbb == 128;
+  if (d.conv_images > 0 && (!((d.mode == MODE_TF32X3 && kbb == 128) || d.mode == MODE_F16X3) ||
+                            d.K != (conv_pairs ? 960 : 800) || d.reduce_z || d.M != d.conv_images * 64 ||
+                            (d.pair && ((d.conv_images & 3) || !d.pair_relay)))) {
+    *err = "tc::gemm: the implicit-GEMM conv operand needs TF32X3 with 128-byte K-blocks or F16X3 (K = 800; K = 960 with "
+           "128-byte K-blocks of two taps), M = 64 * images, CTA pairs only with images % 4 == 0 and the relay protocol";
     return 1;
   }
   const bool pair = d.pair && (d.BN % 32 == 0 || d.BN % 16 == 0) && ((d.BN / 2) % 8 == 0) && d.sm_count >= 2;
@@ -454,12 +503,12 @@ int gemm(const GemmDesc& d, cudaStream_t st, std::string* err) {
 
   CUtensorMap mAh, mAl, mBh, mBl;
   if (d.conv_images > 0) {
-    if (make_map_conv_a(&mAh, d.A.hi, dt, d.conv_images, d.Z, err)) return 1;
+    if (make_map_conv_a(&mAh, d.A.hi, dt, kbb, d.conv_images, d.Z, err)) return 1;
   } else if (make_map(&mAh, d.A.hi, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
   if (make_map(&mBh, d.B.hi, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   if (!bf16) {
     if (d.conv_images > 0) {
-      if (make_map_conv_a(&mAl, d.A.lo, dt, d.conv_images, d.Z, err)) return 1;
+      if (make_map_conv_a(&mAl, d.A.lo, dt, kbb, d.conv_images, d.Z, err)) return 1;
     } else if (make_map(&mAl, d.A.lo, dt, d.K, d.A.rows, d.Z, d.A.ld, d.A.zstride, kBM, kbb, err)) return 1;
     if (make_map(&mBl, d.B.lo, dt, d.K, d.B.rows, d.Z, d.B.ld, d.B.zstride, pair ? d.BN / 2 : d.BN, kbb, err)) return 1;
   } else {

@@ -43,6 +43,14 @@ for prec in precs:
         ref = gr.clone()
     else:
         r["max_rel_deviation_from_" + precs[0]] = float((gr - ref).abs().max() / ref.abs().max())
+    if os.environ.get("ORACLE", "1") != "0":          # 64 rows against the fp64 oracle (the north-star tolerance is 1e-4)
+        from oracle import oracle as orc
+        net = orc.build_net("fc2", (1, 28, 28), hidden, 10)
+        layout = orc.param_layout(net)
+        idx = torch.arange(0, n_img, max(1, n_img // 64))[:64]
+        bank = bnn.engine().download(0, n_s)
+        r64 = orc.expected_loss_gradients(net, layout, bank, x.cpu()[idx], y.cpu()[idx], range(n_s), dtype=torch.float64)
+        r["max_rel_err_vs_fp64_oracle_64_rows"] = float((gr.cpu()[idx].double() - r64).abs().max() / r64.abs().max())
     aa.pgd_attack(bnn, x, y, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=1)
     torch.cuda.synchronize()
     e0.record()

@@ -856,9 +856,10 @@ def test_two_pass_forward_for_inputs_on_the_pixel_grid(S):
     eng.close()
 
 
-def test_full_size_properties_conv_cfg4():
+@pytest.mark.parametrize("prec", ["f16x3", "tf32x3"])
+def test_full_size_properties_conv_cfg4(prec):
     """BASELINE configs[3] shape (100 F-MNIST-shaped inputs, conv-512, 50 stored posterior samples) on the tensor-core
-    conv engine: size-independent properties plus an oracle check on a subset of the rows."""
+    conv engine: size-independent properties, and EVERY one of the 5000 (sample, image) units against the fp64 oracle."""
     import math
     from robustbnns_b200 import _lib
     from robustbnns_b200.engine import Net
@@ -875,7 +876,7 @@ def test_full_size_properties_conv_cfg4():
     x = torch.rand((B, 1, 28, 28), generator=g)
     labels = torch.randint(0, 10, (B,), generator=g)
     eng = Net("conv", (1, 28, 28), H, 10)
-    eng.set_precision("tf32x3")
+    eng.set_precision(prec)
     eng.upload(bank, 0)
     xd, ld = x.cuda(), labels.cuda().to(torch.int32)
     full = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, 0, S)
@@ -888,20 +889,20 @@ def test_full_size_properties_conv_cfg4():
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).cuda()
     gp = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd[perm].contiguous(), ld[perm].contiguous(), 0, S)
     assert rel_err(gp.cpu(), full[perm].cpu()) < 1e-5
-    # (4) 16 (sample, image) units against the fp64 oracle.  At this size a unit holds 32 768 second-layer activations
-    # competing in pooling windows, and the pooled conv1 map is stored in fp32: roughly one unit in a hundred has a
-    # window arg-max that fp32 storage decides differently from fp64 (measured with scratch/conv_dbg.py: FP32 engine
-    # 3 of 192 units, tensor-core engine 1 of 192 -- the unit (sample 4, image 63) below).  Such a unit moves by ~1e-3;
-    # all others must meet the north-star tolerance.
-    idx = torch.tensor([0, 17, 63, 99])
-    xs, ls = xd[idx.cuda()].contiguous(), ld[idx.cuda()].contiguous()
-    errs = []
-    for smp in range(3, 7):
-        got = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xs, ls, smp, smp + 1).cpu().reshape(4, 1, 28, 28).double()
-        ref = orc.expected_loss_gradients(net, layout, bank, x[idx], labels[idx], [smp], dtype=torch.float64)
-        errs.append((got - ref).abs().flatten(1).max(-1)[0] / ref.abs().flatten(1).max(-1)[0])
-    errs = torch.stack(errs)
-    assert int((errs > REL).sum()) <= 1 and float(errs.max()) < 5e-2, errs
+    # (4) the FULL workload against the fp64 oracle, unit by unit.  A unit holds 4608 first-layer and 32 768 second-layer
+    # activations, each deciding a LeakyReLU sign and competing in a pooling window, and the gradient jumps by 1e-3..5e-2
+    # of its size whenever one of those decisions flips: the reference's own fp32 arithmetic disagrees with fp64 on 70 of
+    # these 5000 units (profiles/r2_conv_cfg4_oracle.json).  The tensor-core engine takes every decision as exact
+    # arithmetic does (first layer accumulated in fp64, guard-band re-evaluation of the second, fp32 ties of the pooling
+    # settled from the exact values), so ALL units must meet the north-star tolerance.
+    ref = torch.stack([orc.expected_loss_gradients(net, layout, bank, x, labels, [smp], dtype=torch.float64)
+                       for smp in range(S)])                                                  # [S, B, 1, 28, 28]
+    got = torch.stack([eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, smp, smp + 1).cpu().reshape(x.shape)
+                       for smp in range(S)]).double()
+    errs = (got - ref).abs().flatten(2).max(-1)[0] / ref.abs().flatten(2).max(-1)[0]           # [S, B]
+    print(f"conv cfg4 {prec}: worst of {errs.numel()} units {float(errs.max()):.2e}, units above 1e-4: {int((errs > REL).sum())}")
+    assert int((errs > REL).sum()) == 0, errs.max()
+    assert rel_err(full.cpu().reshape(x.shape).double() / S, ref.mean(0)) < REL                # the expected gradient itself
     # (5) probabilities: rows sum to one; mean logits of the bank == sum of single rows
     p = eng.forward_probs_sum(xd, 0, S) / S
     assert float((p.sum(-1) - 1).abs().max()) < 1e-5
