@@ -673,11 +673,12 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
         float val = (float)s;
         if (wl2 && fabsf(val) < eps2 * m) {                     // warp-uniform: every lane holds the reduced sum
           unsigned slot = 0;
-          if (lane == 0) slot = atomicAdd(wl2_count, 1u);       // order varies from run to run, the set of entries does not
+          if (lane == 0) slot = atomicAdd(wl2_count + z, 1u);   // list of sample z; order varies from run to run, the set of entries does not
           slot = __shfl_sync(0xffffffffu, slot, 0);
           if (slot < wl2_cap) {
             if (lane == 0)
-              wl2[slot] = ((unsigned long long)z << 44) | ((unsigned long long)b << 20) | ((unsigned long long)jj << 4);
+              wl2[(size_t)z * wl2_cap + slot] =
+                  ((unsigned long long)z << 44) | ((unsigned long long)b << 20) | ((unsigned long long)jj << 4);
           } else {                                              // worklist full (pathological inputs): settle it here
             val = exact_unit2_warp(x0 + (int64_t)b * D0, wrow, D0, H, w1_off, b1_off, w + 0, __ldg(wrow + b_off + jj), lane);
           }
@@ -709,78 +710,91 @@ refine_kernel(float* __restrict__ Hhi, float* __restrict__ Hlo, int Z, int B, in
 
 // Second-level refinement of fc2's second layer: every queued unit (z, b, j) is re-evaluated from the inputs in fp64,
 //   H1[i] = leaky(b1[i] + <x_b, W1_z[i,:]>) for ALL hidden i (kept in double), pre2 = b2[j] + <H1, W2_z[j,:]>,
-// and H2[z, b, j] = leaky(pre2) is rewritten.  Entries arrive roughly sorted by sample (refine_kernel walks rows
-// z-major), so a block takes kR2Group consecutive entries and re-uses every W1_z row it loads for all entries of the
-// same sample: W1_z (1.6 MB at fc2-512) is read once per group from L2 instead of once per entry.
-constexpr int kR2Group = 8;
+// and H2[z, b, j] = leaky(pre2) is rewritten.  The worklist is kept PER SAMPLE (refine_kernel appends to list z), so a
+// block takes kR2Group entries of one sample and every W1_z row it loads serves all of them -- with one global list
+// the entries of ~10 samples interleaved, almost every entry paid for its own pass over W1_z (1.6 MB at fc2-512) and the
+// kernel took 21.6 ms of a 24 ms gradient evaluation (fc2-512, 1000 inputs x 100 samples).  The first-layer part is a
+// small fp64 GEMM [entries x D] . [D x H]: a warp takes 4 rows of W1_z at a time, so a shared-memory load of an input
+// feeds 4 DFMAs (one per row left the shared-memory pipe 4x oversubscribed), and the 32 partial sums of a lane are
+// reduced over the warp by halving (31 exchanges instead of 160).
+constexpr int kR2Group = 8, kR2Rows = 4;
 __global__ void __launch_bounds__(256)
-refine2_kernel(const unsigned long long* __restrict__ wl2, const unsigned* __restrict__ count_p, unsigned cap,
+refine2_kernel(const unsigned long long* __restrict__ wl2, const unsigned* __restrict__ counts, unsigned cap,
                const float* __restrict__ x, int B, int D, int H, const float* __restrict__ bank, int64_t P, int64_t w1_off,
                int64_t b1_off, int64_t w2_off, int64_t b2_off, int z_row0, float* __restrict__ H2) {
   extern __shared__ double r2sm[];
-  double* h1 = r2sm;                                              // [kR2Group][H] exact first-layer activations
-  float* xs = reinterpret_cast<float*>(h1 + (size_t)kR2Group * H); // [kR2Group][D]
+  double* h1 = r2sm;                                  // [kR2Group][H] exact first-layer activations
+  double* xs = h1 + (size_t)kR2Group * H;             // [kR2Group / 2][D] pairs: inputs of entries (2 r2, 2 r2 + 1), zeros past m
   __shared__ unsigned long long ent[kR2Group];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned n = min(*count_p, cap);
+  const int z = blockIdx.y;
+  const unsigned n = min(counts[z], cap);
+  const unsigned long long* __restrict__ list = wl2 + (size_t)z * cap;
+  const float* __restrict__ wrow = bank + (int64_t)(z_row0 + z) * P;
   for (unsigned g0 = blockIdx.x * kR2Group; g0 < n; g0 += gridDim.x * kR2Group) {
-    const int m_all = (int)min((unsigned)kR2Group, n - g0);
+    const int m = (int)min((unsigned)kR2Group, n - g0);
     __syncthreads();
-    if (tid < m_all) ent[tid] = wl2[g0 + tid];
+    if (tid < kR2Group) ent[tid] = tid < m ? list[g0 + tid] : 0ull;
     __syncthreads();
-    int k0 = 0;
-    while (k0 < m_all) {
-      const int z = (int)(ent[k0] >> 44);
-      int k1 = k0 + 1;
-      while (k1 < m_all && (int)(ent[k1] >> 44) == z) ++k1;
-      const int m = k1 - k0;
-      const float* __restrict__ wrow = bank + (int64_t)(z_row0 + z) * P;
-      for (int idx = tid; idx < m * D; idx += 256) {
-        const int r = idx / D, d = idx - r * D;
-        const int b = (int)((ent[k0 + r] >> 20) & 0xFFFFFF);
-        xs[r * D + d] = __ldg(x + (int64_t)b * D + d);
-      }
-      __syncthreads();
-      for (int i = warp; i < H; i += 8) {
-        const float* __restrict__ wr = wrow + w1_off + (int64_t)i * D;
-        double acc[kR2Group];
+    for (int idx = tid; idx < kR2Group * D; idx += 256) {
+      const int r = idx / D, d = idx - r * D;
+      const int b = (int)((ent[r] >> 20) & 0xFFFFFF);
+      xs[((size_t)(r >> 1) * D + d) * 2 + (r & 1)] = r < m ? (double)__ldg(x + (int64_t)b * D + d) : 0.0;
+    }
+    __syncthreads();
+    for (int i0 = warp * kR2Rows; i0 < H; i0 += 8 * kR2Rows) {
+      double acc[kR2Rows * kR2Group];
 #pragma unroll
-        for (int r = 0; r < kR2Group; ++r) acc[r] = 0.0;
-        for (int d = lane; d < D; d += 32) {
-          const double wv = (double)__ldg(wr + d);
+      for (int q = 0; q < kR2Rows * kR2Group; ++q) acc[q] = 0.0;
+      const float* __restrict__ wr = wrow + w1_off + (int64_t)i0 * D;
+#pragma unroll 2
+      for (int d = lane; d < D; d += 32) {
+        double wv[kR2Rows];
 #pragma unroll
-          for (int r = 0; r < kR2Group; ++r)
-            if (r < m) acc[r] = fma((double)xs[r * D + d], wv, acc[r]);
-        }
-        const double bias = (double)__ldg(wrow + b1_off + i);
+        for (int rr = 0; rr < kR2Rows; ++rr) wv[rr] = i0 + rr < H ? (double)__ldg(wr + (int64_t)rr * D + d) : 0.0;
+        const double2* xp = reinterpret_cast<const double2*>(xs) + d;      // entry pair r2 of input element d: xp[r2 * D]
 #pragma unroll
-        for (int r = 0; r < kR2Group; ++r) {
-          if (r < m) {
-            double v = acc[r];
+        for (int r2 = 0; r2 < kR2Group / 2; ++r2) {
+          const double2 xv = xp[(size_t)r2 * D];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            v += bias;
-            if (lane == 0) h1[r * H + i] = v > 0.0 ? v : v * (double)kLeakySlope;
+          for (int rr = 0; rr < kR2Rows; ++rr) {
+            acc[rr * kR2Group + 2 * r2] = fma(xv.x, wv[rr], acc[rr * kR2Group + 2 * r2]);
+            acc[rr * kR2Group + 2 * r2 + 1] = fma(xv.y, wv[rr], acc[rr * kR2Group + 2 * r2 + 1]);
           }
         }
       }
-      __syncthreads();
-      for (int r = warp; r < m; r += 8) {
-        const unsigned long long e = ent[k0 + r];
-        const int b = (int)((e >> 20) & 0xFFFFFF), j = (int)((e >> 4) & 0xFFFF);
-        const float* __restrict__ w2r = wrow + w2_off + (int64_t)j * H;
-        double sacc = 0.0;
-        for (int i = lane; i < H; i += 32) sacc = fma(h1[r * H + i], (double)__ldg(w2r + i), sacc);
+      // reduction by halving: after the round with stride s a lane keeps the half of its values selected by (lane & s);
+      // lane l ends up with the warp-wide sum of value l = (row l / 8, entry l % 8)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-        if (lane == 0) {
-          const double pre = sacc + (double)__ldg(wrow + b2_off + j);
-          const float v = (float)pre;
-          H2[((int64_t)z * B + b) * H + j] = pre > 0.0 ? v : (float)(pre * (double)kLeakySlope);
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        const bool up = (lane & sft) != 0;
+#pragma unroll
+        for (int q = 0; q < sft; ++q) {
+          const double keep = up ? acc[q + sft] : acc[q];
+          const double send = up ? acc[q] : acc[q + sft];
+          acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
         }
       }
-      __syncthreads();
-      k0 = k1;
+      const int rr = lane >> 3, r = lane & 7, i = i0 + rr;
+      if (i < H && r < m) {
+        const double v = acc[0] + (double)__ldg(wrow + b1_off + i);
+        h1[r * H + i] = v > 0.0 ? v : v * (double)kLeakySlope;
+      }
+    }
+    __syncthreads();
+    for (int r = warp; r < m; r += 8) {
+      const unsigned long long e = ent[r];
+      const int b = (int)((e >> 20) & 0xFFFFFF), j = (int)((e >> 4) & 0xFFFF);
+      const float* __restrict__ w2r = wrow + w2_off + (int64_t)j * H;
+      double sacc = 0.0;
+      for (int i = lane; i < H; i += 32) sacc = fma(h1[r * H + i], (double)__ldg(w2r + i), sacc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (lane == 0) {
+        const double pre = sacc + (double)__ldg(wrow + b2_off + j);
+        const float v = (float)pre;
+        H2[((int64_t)z * B + b) * H + j] = pre > 0.0 ? v : (float)(pre * (double)kLeakySlope);
+      }
     }
   }
 }
@@ -1159,7 +1173,7 @@ static size_t fc_per_z_bytes(const rbnn_net* n, int B, bool grad) {
   }
   size_t per = bh;                                   // h1 (fp32 or hi)
   if (two) per += (bf ? bh2 : bh) + bh;              // h1 lo / bf16 + h2
-  if (two && !bf) per += pad256((size_t)B * n->H / 8 + 64);   // second worklist: one 8-byte slot per 64 hidden units
+  if (two && !bf) per += pad256(std::max<size_t>((size_t)B * n->H / 8, 2048) + 64);   // second worklist: one 8-byte slot per 64 hidden units (>= 256 slots) + its counter
   if (grad) {
     per += bf ? bh2 : 2 * bh;                        // dtop
     if (two) per += bf ? bh2 : 2 * bh;               // d1
@@ -1242,17 +1256,18 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
     if (!bf) {
       // guard band of the second layer: wide band from the stored first-layer activations, narrow band (their propagated
       // tensor-core error) from exact first-layer values (refine2_kernel)
-      RBNN_CUDA(cudaMemsetAsync(w.wl2_count, 0, sizeof(unsigned), st));
+      RBNN_CUDA(cudaMemsetAsync(w.wl2_count, 0, (size_t)Z * sizeof(unsigned), st));
       RBNN_TRY(refine(n, w.h2, nullptr, Z, B, w.h1, w.h1_lo, (int64_t)B * H, H, n->L.w2, n->L.b2, z0, st, w.wl2,
                       w.wl2_count, w.wl2_cap, x));
-      const int smem2 = kR2Group * (H * (int)sizeof(double) + D * (int)sizeof(float));
+      const int smem2 = kR2Group * (H + D) * (int)sizeof(double);
       static int smem2_set = 0;
       if (smem2 > 48 * 1024 && smem2_set < smem2) {
         RBNN_CUDA(cudaFuncSetAttribute(refine2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
         smem2_set = smem2;
       }
-      refine2_kernel<<<n->sm_count * 2, 256, smem2, st>>>(w.wl2, w.wl2_count, w.wl2_cap, x, B, D, H, n->bank, P, n->L.w1,
-                                                           n->L.b1, n->L.w2, n->L.b2, z0, w.h2);
+      const int gx = std::max(1, std::min(16, (2 * n->sm_count + Z - 1) / Z));      // blocks per sample
+      refine2_kernel<<<dim3(gx, Z), 256, smem2, st>>>(w.wl2, w.wl2_count, w.wl2_cap, x, B, D, H, n->bank, P, n->L.w1,
+                                                       n->L.b1, n->L.w2, n->L.b2, z0, w.h2);
       n->launches++;
       RBNN_CUDA(cudaGetLastError());
     }
@@ -1437,9 +1452,9 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   }
   if (fused && !bf && !kept) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc));
   if (two && !bf && !kept) {
-    w.wl2_cap = (unsigned)std::max<size_t>(4096, zbh / 64);
-    w.wl2 = ar.take<unsigned long long>(w.wl2_cap);
-    w.wl2_count = ar.take<unsigned>(1);
+    w.wl2_cap = (unsigned)std::max<size_t>(256, (size_t)B * H / 64);      // per sample of the chunk
+    w.wl2 = ar.take<unsigned long long>((size_t)w.wl2_cap * zc);
+    w.wl2_count = ar.take<unsigned>((size_t)zc);
   }
   w.xnorm = ar.take<float>((size_t)B);
   w.partial = ar.take<float>((size_t)slots * B * D);
@@ -1592,9 +1607,9 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
   if (keep && fused) { if (!bf) w.worklist = ar.take<unsigned long long>(tc::fused_worklist_slots(B, zc)); }
   else w.logits = ar.take<float>((size_t)zc * B * C);
   if (two && !bf) {
-    w.wl2_cap = (unsigned)std::max<size_t>(4096, zbh / 64);
-    w.wl2 = ar.take<unsigned long long>(w.wl2_cap);
-    w.wl2_count = ar.take<unsigned>(1);
+    w.wl2_cap = (unsigned)std::max<size_t>(256, (size_t)B * H / 64);      // per sample of the chunk
+    w.wl2 = ar.take<unsigned long long>((size_t)w.wl2_cap * zc);
+    w.wl2_count = ar.take<unsigned>((size_t)zc);
   }
   w.xnorm = ar.take<float>((size_t)B);
   RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, 2.f, st));
