@@ -439,7 +439,8 @@ def main():
         if os.path.exists(tp):
             # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, stored per
             # (sample x input) unit; scaled to the units one launch of this run processes
-            per_unit = json.load(open(tp)).get(prec, {}).get(kkey)
+            tr = json.load(open(tp)).get(prec, {})
+            per_unit = tr.get("fwd3" if (kkey == "fwd" and prec == "f16x3" and not two_pass and "fwd3" in tr) else kkey)
             if per_unit:
                 traffic = per_unit * local_units / max(kn, 1)
         roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
