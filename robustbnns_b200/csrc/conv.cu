@@ -227,12 +227,14 @@ int pool2_bwd(rbnn_net* net, const float* a2, const float* dp2, int ZB, int H, f
 // coalesced 400-byte runs, then gathered (the direct gather strides 3200 bytes between neighbouring threads).
 __global__ void __launch_bounds__(256)
 col2im_conv2_kernel(const float* __restrict__ dcol, const float* __restrict__ p1, float* __restrict__ g1) {
-  __shared__ float t[64 * 100];
+  __shared__ __align__(16) float t[64 * 100];
   const int64_t zb = blockIdx.x;
   const int cg = blockIdx.y;
-  for (int i = threadIdx.x; i < 6400; i += blockDim.x) {
-    const int pos = i / 100, j = i - pos * 100;
-    t[i] = __ldg(dcol + (zb * 64 + pos) * 800 + cg * 100 + j);
+  // 16-byte loads: a position's 100 floats of this channel group start at a multiple of 400 bytes (the kernel was
+  // instruction-bound on scalar loads and their index arithmetic at half the HBM rate)
+  for (int i = threadIdx.x; i < 1600; i += blockDim.x) {
+    const int pos = i / 25, j = i - pos * 25;
+    reinterpret_cast<float4*>(t)[i] = __ldg(reinterpret_cast<const float4*>(dcol + (zb * 64 + pos) * 800 + cg * 100) + j);
   }
   __syncthreads();
   for (int o = threadIdx.x; o < 4 * 144; o += blockDim.x) {
@@ -688,23 +690,29 @@ conv2_refine_kernel(float* __restrict__ a2, const float* __restrict__ p1, const 
   extern __shared__ __align__(16) unsigned char rsm[];
   const int hw = (H + 31) >> 5;                 // 32-channel words per position
   double* tie_v = reinterpret_cast<double*>(rsm);                        // [kTieCap] exact post-LeakyReLU values
-  float* ps = reinterpret_cast<float*>(tie_v + kTieCap);                 // [4608] P1
-  float* pl = ps + 4608;                                                 // [4608] fp32 residual of P1 (zeros without p1lo)
-  unsigned* fl = reinterpret_cast<unsigned*>(pl + 4608);                 // [64 * hw] recompute flags, bit = channel
+  double* pd = tie_v + kTieCap;                                          // [4608] P1 = hi + lo as fp64 (converted once)
+  unsigned* fl = reinterpret_cast<unsigned*>(pd + 4608);                 // [64 * hw] recompute flags, bit = channel
   int* tie_at = reinterpret_cast<int*>(fl + 64 * hw);                    // [kTieCap] position * H + channel
-  short* tab = reinterpret_cast<short*>(tie_at + kTieCap);               // [800] filter element -> offset inside the map
-  int* ctr = reinterpret_cast<int*>(tab + 800);                          // [0] tie count, [1] next chunk of phase 2
+  int* ctr = reinterpret_cast<int*>(tie_at + kTieCap);                   // [0] tie count, [1] next chunk of phase 2
   const int zb = blockIdx.x, z = zb / B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* A = a2 + (int64_t)zb * 64 * H;
   for (int i = threadIdx.x; i < 1152; i += blockDim.x) {
-    reinterpret_cast<float4*>(ps)[i] = __ldg(reinterpret_cast<const float4*>(p1 + (int64_t)zb * 4608) + i);
-    reinterpret_cast<float4*>(pl)[i] = p1lo ? __ldg(reinterpret_cast<const float4*>(p1lo + (int64_t)zb * 4608) + i)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 h = __ldg(reinterpret_cast<const float4*>(p1 + (int64_t)zb * 4608) + i);
+    const float4 l = p1lo ? __ldg(reinterpret_cast<const float4*>(p1lo + (int64_t)zb * 4608) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<double2*>(pd)[2 * i] = make_double2((double)h.x + (double)l.x, (double)h.y + (double)l.y);
+    reinterpret_cast<double2*>(pd)[2 * i + 1] = make_double2((double)h.z + (double)l.z, (double)h.w + (double)l.w);
   }
-  for (int k = threadIdx.x; k < 800; k += blockDim.x) {
-    const int c = k / 25, r = k - 25 * c, ky = r / 5, kx = r - 5 * ky;
-    tab[k] = (short)(c * 144 + ky * 12 + kx);
+  // this lane's 25 filter elements k = lane + 32 i are the same for every entry: their offsets inside the 32x12x12 map,
+  // two per register (the fp64 conversions of P1 and the table lookups were 40 % of the instructions of phase 2)
+  unsigned toff[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) {
+    const int k0 = lane + 64 * i, k1 = lane + 64 * i + 32;
+    const int c0 = k0 / 25, r0 = k0 - 25 * c0, c1 = k1 / 25, r1 = k1 - 25 * c1;
+    const unsigned o0 = (unsigned)(c0 * 144 + (r0 / 5) * 12 + r0 % 5);
+    const unsigned o1 = k1 < 800 ? (unsigned)(c1 * 144 + (r1 / 5) * 12 + r1 % 5) : 0u;
+    toff[i] = o0 | (o1 << 16);
   }
   if (threadIdx.x < 2) ctr[threadIdx.x] = 0;
   const float guard = eps * __uint_as_float(__ldg(unit_max + zb));
@@ -786,8 +794,8 @@ conv2_refine_kernel(float* __restrict__ a2, const float* __restrict__ p1, const 
         double s = 0.0;
 #pragma unroll
         for (int i = 0; i < 25; ++i) {
-          const int t = poff + tab[lane + 32 * i];
-          s = fma((double)ps[t] + (double)pl[t], (double)wv[i], s);
+          const int t = poff + (int)((i & 1) ? (toff[i >> 1] >> 16) : (toff[i >> 1] & 0xffffu));
+          s = fma(pd[t], (double)wv[i], s);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
