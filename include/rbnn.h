@@ -49,6 +49,9 @@ enum { RBNN_ARCH_FC = 0, RBNN_ARCH_FC2 = 1, RBNN_ARCH_CONV = 2 };
  * F16X3 = tcgen05 kind::f16 with a 3-term split of power-of-two-scaled fp16 hi/lo
  *         operands (fp32-class accuracy at twice the TF32X3 rate; arch fc and arch conv). */
 enum { RBNN_PREC_FP32 = 0, RBNN_PREC_TF32X3 = 1, RBNN_PREC_BF16 = 2, RBNN_PREC_F16X3 = 3 };
+/* Hidden-layer activation, NN.set_model model_nn.py:66-75 ("leaky" = nn.LeakyReLU(), the only one the saved models use,
+ * model_bnn.py:36-66, and the default). */
+enum { RBNN_ACT_LEAKY = 0, RBNN_ACT_RELU = 1, RBNN_ACT_SIGM = 2, RBNN_ACT_TANH = 3 };
 
 /* Which scalar loss the input gradient is taken of. */
 enum {
@@ -74,6 +77,10 @@ RBNN_API int rbnn_net_destroy(rbnn_net* net);
 RBNN_API int64_t rbnn_net_param_count(const rbnn_net* net);
 RBNN_API int rbnn_net_set_precision(rbnn_net* net, int prec);
 RBNN_API int rbnn_net_get_precision(const rbnn_net* net);
+/* relu / sigm / tanh (model_nn.py:66-73) run on the FP32 CUDA-core engine for arch fc / fc2: every tensor-core kernel
+ * and the conv kernels fuse LeakyReLU(0.01) and its guard band.  Selecting another activation switches the handle to
+ * RBNN_PREC_FP32; rbnn_net_set_precision then refuses the tensor-core modes, and arch conv is refused here. */
+RBNN_API int rbnn_net_set_activation(rbnn_net* net, int act);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 RBNN_API int64_t rbnn_net_launch_count(const rbnn_net* net);
 /* Inputs on the 8-bit pixel grid.  Every image set the reference loads is uint8 / 255 (utils.py:102-103, 129-130,

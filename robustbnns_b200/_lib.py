@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "librbnn.so")
 
 ARCH = {"fc": 0, "fc2": 1, "conv": 2}
 PREC = {"fp32": 0, "tf32x3": 1, "bf16": 2, "f16x3": 3}
+ACT = {"leaky": 0, "relu": 1, "sigm": 2, "tanh": 3}      # RBNN_ACT_* (model_nn.py:66-75)
 HEAD_MEAN_OF_GRADS, HEAD_GRAD_OF_MEAN, HEAD_LOGITS_CE, HEAD_UPSTREAM, HEAD_LOGITS_UPSTREAM = 0, 1, 2, 3, 4
 
 _p = C.c_void_p
@@ -31,6 +32,7 @@ SIGNATURES = {
     "rbnn_net_get_precision": (_i, [_p]),
     "rbnn_net_launch_count": (_i64, [_p]),
     "rbnn_net_input_grid": (_i, [_p]),
+    "rbnn_net_set_activation": (_i, [_p, _i]),
     "rbnn_net_timing_enable": (_i, [_p, _i]),
     "rbnn_net_timing_read": (_i, [_p, _i, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "rbnn_bank_reserve": (_i, [_p, _i]),

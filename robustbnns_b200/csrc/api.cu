@@ -116,7 +116,7 @@ static int fc_forward_chunk(rbnn_net* n, const float* x, int B, int z0, int Z, F
   g.B = rows + n->L.w1; g.ldb = D; g.sBz = P;
   g.bias = rows + n->L.b1; g.sbz = P;
   g.C = f.h1; g.ldc = H; g.sCz = (int64_t)B * H;
-  g.M = B; g.N = H; g.K = D; g.Z = Z; g.epi = EPI_BIAS_LEAKY;
+  g.M = B; g.N = H; g.K = D; g.Z = Z; g.epi = EPI_BIAS_LEAKY; g.act = n->act;
   g.tag = 1;
   RBNN_TRY(gemm_simt(n, g, st));
   g.tag = 0;
@@ -166,7 +166,7 @@ static int fc_grad_simt(rbnn_net* n, int head, const float* x, const int32_t* la
     g.B = rows + n->L.wo; g.ldb = H; g.sBz = P;
     g.C = f.dtop; g.ldc = H; g.sCz = (int64_t)B * H;
     g.mask = two ? f.h2 : f.h1; g.ldm = H; g.sMz = (int64_t)B * H;
-    g.M = B; g.N = H; g.K = C; g.Z = Z; g.epi = EPI_MASK;
+    g.M = B; g.N = H; g.K = C; g.Z = Z; g.epi = EPI_MASK; g.act = n->act;
     RBNN_TRY(gemm_simt(n, g, st));
     const float* dfirst = f.dtop;
     if (two) {
@@ -393,8 +393,22 @@ int rbnn_net_set_precision(rbnn_net* n, int prec) {
     RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%8==0 and H>=32 on sm_100 only");
   if (prec == RBNN_PREC_F16X3 && n->arch != RBNN_ARCH_CONV)
     RBNN_CHECK(tc_f16x3_supported(n), "F16X3 covers arch fc with hidden sizes the fused forward+head kernel supports");
+  RBNN_CHECK(prec == RBNN_PREC_FP32 || n->act == RBNN_ACT_LEAKY,
+             "the tensor-core engines fuse LeakyReLU: activation %d runs on RBNN_PREC_FP32 only", n->act);
   if (n->prec != prec) n->keep.valid = 0;
   n->prec = prec;
+  return 0;
+}
+
+int rbnn_net_set_activation(rbnn_net* n, int act) {
+  RBNN_CHECK(n != nullptr, "null net handle");
+  RBNN_CHECK(act == RBNN_ACT_LEAKY || act == RBNN_ACT_RELU || act == RBNN_ACT_SIGM || act == RBNN_ACT_TANH,
+             "unknown activation %d", act);
+  RBNN_CHECK(act == RBNN_ACT_LEAKY || n->arch != RBNN_ARCH_CONV,
+             "arch conv implements LeakyReLU only (its kernels fuse it with the pooling layers)");
+  if (act != n->act) n->keep.valid = 0;
+  n->act = act;
+  if (act != RBNN_ACT_LEAKY) n->prec = RBNN_PREC_FP32;
   return 0;
 }
 

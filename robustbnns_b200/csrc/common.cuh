@@ -104,6 +104,7 @@ struct rbnn_net {
   int arch = 0, in_ch = 1, in_h = 28, in_w = 28, D = 784, H = 512, C = 10;
   int device = 0;
   int prec = RBNN_PREC_FP32;
+  int act = RBNN_ACT_LEAKY;   // hidden-layer activation (model_nn.py:66-75); anything but LeakyReLU: FP32 engine, arch fc / fc2
   rbnn::ParamLayout L;
   // bank
   int capacity = 0;
@@ -160,6 +161,7 @@ struct GemmArgs {
   const float* mask; int64_t ldm, sMz;   // activation[z][m][n]    (EPI_MASK: acc *= act>0 ? 1 : slope)
   int M, N, K, Z;
   int epi;
+  int act;         // RBNN_ACT_*: EPI_BIAS_LEAKY applies it, EPI_MASK multiplies by its derivative (from the stored activation)
   int b_kn;        // 0 = NT, 1 = NN
   int reduce_z;    // 1: C[m][n] (+)= sum_z ...  (C is a single [M,N] matrix)
   int accumulate;  // reduce_z only: add to what C already holds

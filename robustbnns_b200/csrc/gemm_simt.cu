@@ -12,6 +12,25 @@
 
 namespace rbnn {
 
+// hidden-layer activation and its derivative expressed through the STORED activation value (model_nn.py:66-75)
+__device__ __forceinline__ float act_fwd(int act, float v) {
+  switch (act) {
+    case RBNN_ACT_RELU: return v > 0.f ? v : 0.f;
+    case RBNN_ACT_SIGM: return 1.f / (1.f + expf(-v));
+    case RBNN_ACT_TANH: return tanhf(v);
+    default: return v > 0.f ? v : v * kLeakySlope;
+  }
+}
+__device__ __forceinline__ float act_grad(int act, float a) {
+  switch (act) {
+    case RBNN_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case RBNN_ACT_SIGM: return a * (1.f - a);
+    case RBNN_ACT_TANH: return 1.f - a * a;
+    default: return a > 0.f ? 1.f : kLeakySlope;
+  }
+}
+
+
 template <int BM, int BN, int BK, int TM, int TN, bool BKN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(GemmArgs a, int z_per_block, float* __restrict__ partial) {
@@ -88,11 +107,8 @@ gemm_simt_kernel(GemmArgs a, int z_per_block, float* __restrict__ partial) {
           if (n >= a.N) continue;
           float v = acc[i][j];
           if (a.epi == EPI_BIAS || a.epi == EPI_BIAS_LEAKY) v += __ldg(a.bias + (int64_t)z * a.sbz + n);
-          if (a.epi == EPI_BIAS_LEAKY) v = v > 0.f ? v : v * kLeakySlope;
-          if (a.epi == EPI_MASK) {
-            const float h = __ldg(a.mask + (int64_t)z * a.sMz + (int64_t)m * a.ldm + n);
-            v = h > 0.f ? v : v * kLeakySlope;
-          }
+          if (a.epi == EPI_BIAS_LEAKY) v = act_fwd(a.act, v);
+          if (a.epi == EPI_MASK) v *= act_grad(a.act, __ldg(a.mask + (int64_t)z * a.sMz + (int64_t)m * a.ldm + n));
           C[(int64_t)m * a.ldc + n] = v;
           acc[i][j] = 0.f;
         }

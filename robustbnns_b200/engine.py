@@ -58,10 +58,16 @@ class Net(object):
     def set_precision(self, name):
         check(lib().rbnn_net_set_precision(self._h, PREC[name]))
 
+    def set_activation(self, name):
+        """Hidden-layer activation, model_nn.py:66-75: "leaky" (default; every engine), "relu" / "sigm" / "tanh" (arch fc /
+        fc2 on the FP32 CUDA-core engine: the handle is switched to it)."""
+        check(lib().rbnn_net_set_activation(self._h, _lib.ACT[name]))
+        self.activation = name
+
     def set_best_precision(self):
         """The fastest parity-grade engine this network has: F16X3 (arch fc with a fused hidden size, arch conv), else
         TF32X3 (fc / fc2 with D % 8 == 0 and H >= 32), else the FP32 CUDA-core engine.  Returns its name."""
-        for cand in ("f16x3", "tf32x3"):
+        for cand in (("f16x3", "tf32x3") if getattr(self, "activation", "leaky") == "leaky" else ()):
             try:
                 self.set_precision(cand)
                 return cand

@@ -155,6 +155,8 @@ class BNN(object):
             from .engine import Net
             self._engine = Net(self.basenet.architecture, self.input_shape, self.basenet.hidden_size,
                                self.output_size)
+            if self.basenet.activation != "leaky":          # relu / sigm / tanh: FP32 engine, arch fc / fc2
+                self._engine.set_activation(self.basenet.activation)
             if self._precision == "auto":
                 self._engine.set_best_precision()
             else:

@@ -67,9 +67,10 @@ class NN(object):
         self.input_shape = tuple(int(v) for v in input_shape)
         self.lr, self.epochs = lr, epochs
         self.layout = param_layout(architecture, self.input_shape, hidden_size, output_size)
-        if activation != "leaky":
-            # every saved model uses leaky (model_bnn.py:36-66); the CUDA path implements only it
-            raise NotImplementedError("the B200 path implements activation='leaky' only")
+        if activation != "leaky" and architecture == "conv":
+            # every saved model uses leaky (model_bnn.py:36-66); the conv kernels fuse LeakyReLU with the pooling layers.
+            # relu / sigm / tanh (model_nn.py:66-73) run for fc / fc2, on the FP32 CUDA-core engine
+            raise NotImplementedError("the B200 path implements arch conv with activation='leaky' only")
         self.name = self.get_name(dataset_name, hidden_size, activation, architecture, lr, epochs)
 
     def get_name(self, dataset_name, hidden_size, activation, architecture, lr, epochs):
@@ -106,6 +107,8 @@ class NN(object):
         if self._engine is None:
             from .engine import Net
             self._engine = Net(self.architecture, self.input_shape, self.hidden_size, self.output_size)
+            if self.activation != "leaky":
+                self._engine.set_activation(self.activation)
             self._engine.set_best_precision()        # tensor-core engines where the network has one
         return self._engine
 

@@ -801,6 +801,55 @@ def test_headline_engine_at_headline_size_against_fp64_oracle(inputs):
     assert float(row_err.max()) < 10 * REL, row_err
 
 
+@pytest.mark.parametrize("arch,shape,hidden,ds", [("fc", (1, 28, 28), 64, "mnist"), ("fc2", (1, 28, 28), 32, "mnist"),
+                                                  ("fc2", (1, 2, 1), 32, "half_moons")])
+@pytest.mark.parametrize("act", ["relu", "sigm", "tanh"])
+def test_other_activations_on_the_fp32_engine(act, arch, shape, hidden, ds):
+    """model_nn.py:66-75: relu / sigm / tanh hidden layers (no saved model uses them) run for arch fc / fc2 on the FP32
+    CUDA-core engine; the tensor-core modes and arch conv, which fuse LeakyReLU, refuse them."""
+    from robustbnns_b200 import _lib
+    from robustbnns_b200 import adversarialAttacks as aa
+    from robustbnns_b200 import lossGradients as lg
+    from robustbnns_b200.engine import Net
+    from robustbnns_b200.model_bnn import BNN
+    C, B, S = (10 if ds == "mnist" else 2), 37, 5
+    net = orc.build_net(arch, shape, hidden, C, activation=act, dataset_name=ds)
+    layout = orc.param_layout(net)
+    loc, rho = orc.scaled_guide_params(layout, seed=9, rho_mean=-4.0)
+    g = torch.Generator().manual_seed(10)
+    bank = loc + orc.softplus(rho) * torch.randn((S, loc.numel()), generator=g)
+    x, y = orc.synthetic_inputs(B, shape, C, seed=12)
+    labels = y.argmax(-1)
+    eng = Net(arch, shape, hidden, C)
+    eng.set_activation(act)
+    assert eng.precision == "fp32" and eng.set_best_precision() == "fp32"
+    for prec in ("tf32x3", "f16x3", "bf16"):
+        with pytest.raises(_lib.RbnnError):
+            eng.set_precision(prec)
+    eng.upload(bank, 0)
+    xd, ld = x.cuda(), labels.cuda().to(torch.int32)
+    probs = eng.forward_probs_sum(xd, 0, S) / S
+    assert rel_err(probs.cpu(), orc.bnn_forward(net, layout, bank, x, range(S)).detach()) < REL
+    gm = eng.input_grad_sum(_lib.HEAD_MEAN_OF_GRADS, xd, ld, 0, S).cpu().reshape(x.shape) / S
+    assert rel_err(gm, orc.expected_loss_gradients(net, layout, bank, x, labels, range(S), dtype=torch.float64)) < REL
+    ga = eng.input_grad_sum(_lib.HEAD_GRAD_OF_MEAN, xd, ld, 0, S, pbar=probs).cpu().reshape(x.shape) / S
+    assert rel_err(ga, orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)) < REL
+    eng.close()
+    # through the drop-in: the reference's constructor arguments
+    bnn = BNN(ds, hidden, act, arch, "hmc", None, None, S, 5, shape, C)
+    bnn.set_posterior_samples(bank)
+    assert bnn.engine().precision == "fp32"
+    gd = lg.expected_loss_gradients(bnn, x, labels, S).cpu()
+    assert rel_err(gd, gm) < 1e-6
+    adv = aa.fgsm_attack(bnn, x, labels, hyperparams={"epsilon": 0.1}, n_samples=S).cpu()
+    ref_adv = orc.fgsm_attack(net, layout, bank, x, labels, lambda call: range(S), {"epsilon": 0.1})
+    gref = orc.attack_gradient(net, layout, bank, x, labels, range(S), dtype=torch.float64)
+    decided = gref.abs() > REL * gref.abs().max()             # pixels whose gradient sign is above the tolerance
+    assert float((adv - ref_adv).abs()[decided].max()) < 1e-6
+    with pytest.raises(NotImplementedError):
+        BNN("mnist", 32, act, "conv", "hmc", None, None, S, 5, (1, 28, 28), 10)
+
+
 @pytest.mark.parametrize("S", [1, 10, 1000])
 def test_two_pass_forward_for_inputs_on_the_pixel_grid(S):
     """F16X3, arch fc: inputs that are uint8 / 255 (every image set the reference loads, utils.py:102-103, 129-130,
