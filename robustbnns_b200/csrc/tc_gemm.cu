@@ -359,8 +359,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(tempty_leader + 8 * as);
-        else mbar_arrive(tempty0 + 8 * as);
+        if (PAIR) mbar_arrive_relaxed_cluster(tempty_leader + 8 * as);
+        else mbar_arrive_relaxed(tempty0 + 8 * as);
       }
       if (p.group_max) {           // the 32 rows of a warp lie in one group of 64 (tile rows start at multiples of 128)
 #pragma unroll

@@ -90,6 +90,17 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// "This warp is done reading the TMEM accumulator stage": the hand-over is ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync, nothing this thread WROTE has to be visible to the MMA issuer.  With the default
+// .release semantics the arrive carries a memory barrier (cluster scope: MEMBAR.ALL.GPU) that waits for every global
+// store the warp still has in flight -- in the fused forward kernel the dH stores of the previous item, ~18 % of the
+// kernel (ncu: stall_membar on the arrive; the kernel ran 1.0 ms per chunk faster with the stores compiled out).
+__device__ __forceinline__ void mbar_arrive_relaxed_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // TMA load issued by either CTA of a pair; completion bytes are signalled on `bar` (a shared::cluster address,
 // normally the leader CTA's barrier)
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,

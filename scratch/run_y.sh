@@ -1,5 +1,5 @@
 T=${1:-s3l}
-for D in 0 4 2 6 1 7; do
+for D in 0 32 64 1; do
 RBNN_FUSED_DEBUG=$D timeout 300 python bench.py --no-cpu-baseline --no-extra --steps 2 --warmup 3 > gpurun_out/${T}_dbg$D.json 2> gpurun_out/${T}_dbg$D.err
 python - <<PY
 import json
