@@ -505,6 +505,13 @@ def main():
                                     "no host round-trip between iterations"}
             extra["fgsm"] = {"value": n_img / (fms * 1e-3), "unit": "imgs/s", "images": n_img, "posterior_samples": n_s,
                              "ms": fms, "n_gpus": world, "note": "Bayesian FGSM, eps 0.3 (plot_baseline_attacks.py:65-66)"}
+            # the same attack on all 10 000 bench inputs: 1000 images are one 128-row tile per rank at 8 GPUs (and every
+            # rank re-draws all samples), so the small case cannot scale; this one shows how the attack path scales with N
+            n_big = min(B, 10000)
+            bms = attack_ms("pgd", n_big, 100, 20)
+            extra["pgd_10k"] = {"value": n_big / (bms * 1e-3), "unit": "imgs/s", "images": n_big, "posterior_samples": 100,
+                                "iters": 20, "ms": bms, "n_gpus": world,
+                                "note": "20-step Bayesian PGD on all bench inputs (input sharding over the ranks)"}
         except Exception as e:
             log("PGD / FGSM measurement failed:", e)
     if not args.no_extra:
