@@ -174,7 +174,8 @@ int backward_chunk(rbnn_net* n, int head, const int32_t* labels, const float* pb
   RBNN_TRY(pool2_bwd_fused(n, c.a2, c.dlogits, z0, Z, B, c.dzh, c.dzl, f16 ? c.call_sc + 2 : nullptr, st));
   // dcol[z][b * 64 + pos][c * 25 + ky * 5 + kx] = sum_h dZ2[z][b * 64 + pos][h] W2_z[h][c][ky][kx]
   tc::GemmDesc d;
-  d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = 160;
+  static const int dgrad_bn = getenv("RBNN_CONV_DGRAD_BN") ? atoi(getenv("RBNN_CONV_DGRAD_BN")) : 160;   // experiments
+  d.M = B * 64; d.N = 800; d.K = H; d.Z = Z; d.BN = dgrad_bn;
   static const int conv_pair = getenv("RBNN_CONV_PAIR") ? atoi(getenv("RBNN_CONV_PAIR")) : 3;
   d.pair = (conv_pair & 2) ? 1 : 0;
   d.A.hi = c.dzh; d.A.lo = c.dzl; d.A.rows = d.M; d.A.ld = H; d.A.zstride = (int64_t)B * 64 * H;
