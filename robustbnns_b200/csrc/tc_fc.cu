@@ -1113,6 +1113,9 @@ static int tc_bank_refresh_once(rbnn_net* n, int s0, int s1, cudaStream_t st, bo
 static int run_gemm(rbnn_net* n, tc::GemmDesc& d, int tag, cudaStream_t st) {
   d.mode = n->prec == RBNN_PREC_BF16 ? tc::MODE_BF16 : (n->prec == RBNN_PREC_F16X3 ? tc::MODE_F16X3 : tc::MODE_TF32X3);
   d.sm_count = n->sm_count;
+  // RBNN_FC_PAIR (experiments): 1 = per-sample GEMMs on CTA pairs, 2 = the sample-reduced input-gradient GEMM too
+  static const int fc_pair = getenv("RBNN_FC_PAIR") ? atoi(getenv("RBNN_FC_PAIR")) : 0;
+  if (fc_pair && !d.pair && (!d.reduce_z || fc_pair >= 2) && d.BN % 32 == 0) d.pair = 1;
   std::string err;
   if (tag) RBNN_TRY(timing_begin(n, tag, st));
   if (tc::gemm(d, st, &err)) {

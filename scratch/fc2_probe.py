@@ -51,7 +51,7 @@ for prec in precs:
         bank = bnn.engine().download(0, n_s)
         r64 = orc.expected_loss_gradients(net, layout, bank, x.cpu()[idx], y.cpu()[idx], range(n_s), dtype=torch.float64)
         r["max_rel_err_vs_fp64_oracle_64_rows"] = float((gr.cpu()[idx].double() - r64).abs().max() / r64.abs().max())
-    aa.pgd_attack(bnn, x, y, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=1)
+    aa.pgd_attack(bnn, x, y, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=4)   # also captures the graph
     torch.cuda.synchronize()
     e0.record()
     aa.pgd_attack(bnn, x, y, hyperparams={"epsilon": 0.2}, n_samples=n_s, iters=4)
