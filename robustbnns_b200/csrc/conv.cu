@@ -513,16 +513,18 @@ int pool2_logits(rbnn_net* net, const float* a2, int s0, int Z, int B, float* lo
 constexpr int kBwdImgs = 2;
 
 template <int C_MAX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ dlogits, const float* __restrict__ woutp,
                        int s0, int B, int H, int C, void* __restrict__ dz2v, void* __restrict__ dz2_lov,
                        const float* __restrict__ f16_scale) {
   float* __restrict__ dz2 = reinterpret_cast<float*>(dz2v);
   float* __restrict__ dz2_lo = reinterpret_cast<float*>(dz2_lov);
   const float f16s = f16_scale ? __ldg(f16_scale) : 0.f;
+  // blockDim.y image pairs share a block: they read the same output weights at nearly the same time, so all but the
+  // first read of a line hit L1 (one pair per block re-read the block's 301 KB weight slice from L2 for every pair)
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
-  const int z = blockIdx.z, b0 = blockIdx.y * kBwdImgs;
+  const int z = blockIdx.z, b0 = (blockIdx.y * blockDim.y + threadIdx.y) * kBwdImgs;
+  if (h >= H || b0 >= B) return;
   const int nimg = min(kBwdImgs, B - b0);
   const int64_t F = (int64_t)49 * H;
   const float4* __restrict__ W = reinterpret_cast<const float4*>(woutp + ((int64_t)(s0 + z) * F + h) * C_MAX);
@@ -612,8 +614,12 @@ pool2_bwd_fused_kernel(const float* __restrict__ a2, const float* __restrict__ d
 int pool2_bwd_fused(rbnn_net* net, const float* a2, const float* dlogits, int s0, int Z, int B, void* dz2,
                     void* dz2_lo, const float* f16_scale, cudaStream_t st) {
   const int threads = std::min(128, (net->H + 31) / 32 * 32);
-  dim3 grid((net->H + threads - 1) / threads, (B + kBwdImgs - 1) / kBwdImgs, Z);
-  RBNN_CONV_C_DISPATCH(pool2_bwd_fused_kernel, grid, threads, a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo,
+  static const int pairs_env = getenv("RBNN_POOL_PAIRS") ? atoi(getenv("RBNN_POOL_PAIRS")) : 2;     // image pairs per block
+  const int pairs = std::max(1, std::min(pairs_env, 256 / threads));
+  const int per_block = kBwdImgs * pairs;
+  dim3 grid((net->H + threads - 1) / threads, (B + per_block - 1) / per_block, Z);
+  const dim3 block(threads, pairs);
+  RBNN_CONV_C_DISPATCH(pool2_bwd_fused_kernel, grid, block, a2, dlogits, net->woutp, s0, B, net->H, net->C, dz2, dz2_lo,
                        f16_scale);
   net->launches++;
   RBNN_CUDA(cudaGetLastError());
