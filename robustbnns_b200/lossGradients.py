@@ -18,6 +18,27 @@ DEBUG = False
 MAX_BATCH = 16384     # inputs per device pass
 
 
+_COPY_STREAMS = {}
+
+
+def _h2d(t, device, dtype):
+    """Host -> device.  A pinned host tensor of the right dtype is copied on a side stream, so that whatever the caller
+    already enqueued on the compute stream (the K-sample of the posterior draws) runs while the bytes cross PCIe; the
+    compute stream waits for the copy before it continues."""
+    if t.device.type != "cpu" or t.dtype != dtype or not t.is_pinned() or not torch.cuda.is_available():
+        return t.to(device=device, dtype=dtype)
+    device = torch.device(device)
+    cs = _COPY_STREAMS.get(device.index)
+    if cs is None:
+        cs = _COPY_STREAMS[device.index] = torch.cuda.Stream(device)
+    main = torch.cuda.current_stream(device)
+    with torch.cuda.stream(cs):
+        d = t.to(device, non_blocking=True)
+    main.wait_stream(cs)
+    d.record_stream(main)
+    return d
+
+
 def _to_device(eng, images, labels):
     """Inputs and labels on the engine's device.  Host tensors under torch.distributed: every rank copies only its block
     of rows over PCIe and the blocks are all-gathered over NVLink (dist.gather_rows_from_host)."""
@@ -25,11 +46,11 @@ def _to_device(eng, images, labels):
     if images.device.type == "cpu" and rdist.world()[1] > 1:
         images = rdist.gather_rows_from_host(images, eng.device, torch.float32)
     else:
-        images = images.to(device=eng.device, dtype=torch.float32)
+        images = _h2d(images, eng.device, torch.float32)
     if labels.device.type == "cpu" and rdist.world()[1] > 1:
         labels = rdist.gather_rows_from_host(labels.to(torch.int32), eng.device, torch.int32)
     else:
-        labels = labels.to(device=eng.device, dtype=torch.int32)
+        labels = _h2d(labels, eng.device, torch.int32)
     return images, labels
 
 
@@ -38,6 +59,7 @@ def expected_loss_gradients_block(net, images, labels, n_samples):
     are reduce-SCATTERed, so every rank ends up with (and only has to read back) its own block of rows.
     Returns (block [hi - lo, *input_shape] on the device, (lo, hi)); one process: the whole batch, (0, B)."""
     eng = net.engine()
+    net._rows(n_samples, list(range(n_samples)))                # K-sample first (cached afterwards): it runs while the inputs cross PCIe
     images, labels = _to_device(eng, images, labels)
     B = images.shape[0]
     rank, world = rdist.world()
@@ -59,9 +81,9 @@ def expected_loss_gradients(net, images, labels, n_samples):
     """[B, *input_shape] tensor on the device: (1/S) sum_{s<S} dL_s/dx for a batch
     (`labels` are class indices).  Sample s is seed s (lossGradients.py:33)."""
     eng = net.engine()
+    rows, _ = net._rows(n_samples, list(range(n_samples)))      # K-sample first: it runs while the inputs cross PCIe
     images, labels = _to_device(eng, images, labels)
     outs = []
-    rows, _ = net._rows(n_samples, list(range(n_samples)))
     for b0 in range(0, images.shape[0], MAX_BATCH):
         x = images[b0:b0 + MAX_BATCH].contiguous()
         g = eng.input_grad_sum(HEAD_MEAN_OF_GRADS, x, labels[b0:b0 + MAX_BATCH].contiguous(), rows[0], rows[1])
