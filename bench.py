@@ -725,7 +725,7 @@ def main():
                 flop_unit = 107704320 if hid == 512 else 213565440
                 per_eps = {}
                 for eps in (0.1, 0.15, 0.2, 0.25, 0.3):
-                    aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": eps}, n_samples=n_s, iters=1)
+                    aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": eps}, n_samples=n_s, iters=4)   # warm-up: also captures this eps' graph
                     torch.cuda.synchronize()
                     e0.record()
                     aa.pgd_attack(cb, xc, yc, hyperparams={"epsilon": eps}, n_samples=n_s, iters=4)
