@@ -495,7 +495,7 @@ def main():
         try:
             # BASELINE configs[2] shape: 1000 inputs, 20-step PGD, 100 posterior samples -- at EVERY world size
             n_img, n_s, iters = 1000, 100, 20
-            pms = attack_ms("pgd", n_img, n_s, iters)
+            pms = attack_ms("pgd", n_img, n_s, iters, reps=3)
             fms = attack_ms("fgsm", n_img, n_s, 1, hyper={"epsilon": 0.3}, reps=3)
             extra["pgd"] = {"value": n_img / (pms * 1e-3), "unit": "imgs/s", "images": n_img, "posterior_samples": n_s,
                             "iters": iters, "ms": pms, "n_gpus": world,
