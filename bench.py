@@ -552,7 +552,7 @@ def main():
                 hm_e2e_ms, _ = timed(hm_e2e, 2)
             hm_units = float(len(grid)) * n_pts * n_s
             hm = {"value": hm_units / (hm_ms / 3 * 1e-3), "unit": UNIT, "ms": hm_ms / 3, "models": len(grid),
-                  "test_points": n_pts, "posterior_samples": n_s, "n_gpus": world, "engine": nets_hm[0].engine().precision if nets_hm else None,
+                  "test_points": n_pts, "posterior_samples": n_s, "n_gpus": world, "engine": "/".join(sorted(set(m.engine().precision for m in nets_hm))) if nets_hm else None,
                   "gpu_launches": int(l_hm),
                   "e2e": {"value": hm_units / (hm_e2e_ms / 2 * 1e-3), "unit": UNIT, "ms": hm_e2e_ms / 2,
                           "h2d_bytes": int(sum(banks_h[m.basenet.hidden_size].numel() * 4 for m in nets_hm)),

@@ -393,6 +393,8 @@ int rbnn_net_set_precision(rbnn_net* n, int prec) {
     RBNN_CHECK(tc_supported(n), "the tcgen05 engine covers arch fc/fc2 with D%%8==0 and H>=32 on sm_100 only");
   if (prec == RBNN_PREC_F16X3 && n->arch != RBNN_ARCH_CONV)
     RBNN_CHECK(tc_f16x3_supported(n), "F16X3 covers arch fc with hidden sizes the fused forward+head kernel supports");
+  RBNN_CHECK(prec == RBNN_PREC_FP32 || prec == RBNN_PREC_TF32X3 || n->arch == RBNN_ARCH_CONV || (n->D & 7) == 0,
+             "networks with D %% 8 != 0 (half moons) run on RBNN_PREC_FP32 or, arch fc2, RBNN_PREC_TF32X3");
   RBNN_CHECK(prec == RBNN_PREC_FP32 || n->act == RBNN_ACT_LEAKY,
              "the tensor-core engines fuse LeakyReLU: activation %d runs on RBNN_PREC_FP32 only", n->act);
   if (n->prec != prec) n->keep.valid = 0;

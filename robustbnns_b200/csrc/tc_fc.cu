@@ -910,9 +910,15 @@ int tc_sample_relayout_f16(rbnn_net* n, const float* d_loc, const float* d_rho, 
 
 int tc_supported(const rbnn_net* n) {
   if (n->arch != RBNN_ARCH_FC && n->arch != RBNN_ARCH_FC2) return 0;
-  if ((n->D & 7) || n->H < 32 || n->H > 2048 || n->C > kMaxC) return 0;      // refine_kernel keeps a row of <= 2048 units in registers
+  if (n->H < 32 || n->H > 2048 || n->C > kMaxC) return 0;      // refine_kernel keeps a row of <= 2048 units in registers
+  // D % 8 != 0 (half moons: D = 2): only fc2, whose bulk is the H x H layer -- the first layer and its input gradient
+  // (K = D / N = D: a TMA row would be 8 bytes) run on the CUDA-core GEMM, the middle GEMMs on tcgen05 (TF32X3)
+  if ((n->D & 7) && !(n->arch == RBNN_ARCH_FC2 && (n->H & 7) == 0)) return 0;
   return n->cc_major == 10;
 }
+
+// D % 8 != 0: the first layer cannot be a TMA operand (see tc_supported)
+static bool small_d(const rbnn_net* n) { return (n->D & 7) != 0; }
 
 // Row pitch (elements) of a K-major operand copy with K elements per row: rows start on 128-byte lines, so that a
 // 128-byte TMA box row is one L2 line.  (784 fp16 = 1568 B rows straddle two lines per box row and halve the TMA
@@ -1228,6 +1234,22 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
   const int64_t P = n->L.P;
   const bool two = n->arch == RBNN_ARCH_FC2, bf = n->prec == RBNN_PREC_BF16;
   const TcMat& m1 = n->tc.mat[0];
+  if (small_d(n)) {
+    // first layer in fp32 on the CUDA cores (exactly the FP32 engine's), then H1 -> tf32 hi (in place) + residual for the
+    // tcgen05 GEMM of the second layer; no guard band needed for it
+    GemmArgs a{};
+    a.A = x; a.lda = D; a.sAz = 0;
+    a.B = n->bank + (int64_t)z0 * P + n->L.w1; a.ldb = D; a.sBz = P;
+    a.bias = n->bank + (int64_t)z0 * P + n->L.b1; a.sbz = P;
+    a.C = w.h1; a.ldc = H; a.sCz = (int64_t)B * H;
+    a.M = B; a.N = H; a.K = D; a.Z = Z; a.epi = EPI_BIAS_LEAKY; a.act = RBNN_ACT_LEAKY;
+    a.tag = 1;
+    RBNN_TRY(gemm_simt(n, a, st));
+    const int64_t n4 = (int64_t)Z * B * H / 4;
+    split_kernel<<<(unsigned)std::min<int64_t>((n4 + 255) / 256, 148 * 16), 256, 0, st>>>(w.h1, w.h1, w.h1_lo, nullptr, n4, H / 4, H / 4);
+    n->launches++;
+    RBNN_CUDA(cudaGetLastError());
+  }
   tc::GemmDesc g;
   g.M = B; g.N = H; g.K = D; g.Z = Z; g.BN = pick_bn(H);
   g.A.hi = bf ? (const void*)w.x_bf : (const void*)w.x_hi; g.A.lo = w.x_lo; g.A.rows = B; g.A.ld = m1.ld; g.A.zstride = 0;
@@ -1240,8 +1262,10 @@ static int fc_forward_chunk_tc(rbnn_net* n, const FcWs& w, const float* x, int B
   if (two) {
     if (bf) g.out_bf = w.h1_bf; else g.out_lo = w.h1_lo;
   }
-  RBNN_TRY(run_gemm(n, g, 1, st));
-  if (!bf) RBNN_TRY(refine(n, w.h1, two ? w.h1_lo : nullptr, Z, B, x, nullptr, 0, D, n->L.w1, n->L.b1, z0, st));
+  if (!small_d(n)) {
+    RBNN_TRY(run_gemm(n, g, 1, st));
+    if (!bf) RBNN_TRY(refine(n, w.h1, two ? w.h1_lo : nullptr, Z, B, x, nullptr, 0, D, n->L.w1, n->L.b1, z0, st));
+  }
   *top = w.h1;
   if (two) {
     const TcMat& m2 = n->tc.mat[1];
@@ -1476,9 +1500,10 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     }
   } else {
     // |dH| <= sum_c |dlogits_c| max|Wo|: <= 2 max|g| for the softmax heads, <= C max|g| when g goes to the logits as is
-    RBNN_TRY(split_x(n, x, (int64_t)B * D, w,
-                     (head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM) ? pbar : nullptr, (int64_t)B * n->C,
-                     head == RBNN_HEAD_LOGITS_UPSTREAM ? (float)n->C : 2.f, st));
+    if (!small_d(n))
+      RBNN_TRY(split_x(n, x, (int64_t)B * D, w,
+                       (head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM) ? pbar : nullptr, (int64_t)B * n->C,
+                       head == RBNN_HEAD_LOGITS_UPSTREAM ? (float)n->C : 2.f, st));
   }
   if (fused && !kept) {       // row norms: guard band (parity modes) and the activation range of the fused head
     xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
@@ -1532,11 +1557,25 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
       q.B.rows = H; q.B.ld = H; q.B.zstride = (int64_t)H * H;
       q.epi = tc::EPI_MASK;
       q.act = w.h1; q.act_zstride = (int64_t)B * H; q.act_ld = H;
-      if (bf) q.out_bf = w.d1_bf; else { q.out = w.d1_hi; q.out_lo = w.d1_lo; }
+      if (bf) q.out_bf = w.d1_bf; else { q.out = w.d1_hi; q.out_lo = small_d(n) ? nullptr : w.d1_lo; }   // small D: plain fp32 for the CUDA-core GEMM below
       q.out_ld = H; q.out_zstride = (int64_t)B * H;
       RBNN_TRY(run_gemm(n, q, 0, st));
       dfirst_hi = bf ? (const void*)w.d1_bf : (const void*)w.d1_hi;
       dfirst_lo = w.d1_lo;
+    }
+    if (small_d(n)) {
+      // dX (+)= sum_z dH1_z . W1_z with N = D < 8: the FP32 engine's CUDA-core GEMM, summed over the chunk's samples
+      GemmArgs a{};
+      a.b_kn = 1;
+      a.A = w.d1_hi; a.lda = H; a.sAz = (int64_t)B * H;
+      a.B = n->bank + (int64_t)z0 * n->L.P + n->L.w1; a.ldb = D; a.sBz = n->L.P;
+      a.C = out_sum; a.ldc = D;
+      a.M = B; a.N = D; a.K = H; a.Z = Z; a.epi = EPI_NONE;
+      a.reduce_z = 1; a.accumulate = first ? 0 : 1;
+      a.tag = 2;
+      RBNN_TRY(gemm_simt(n, a, st));
+      first = false;
+      continue;
     }
     // dX partial sums: K-concatenated over the samples of each slot
     const TcMat& m1 = n->tc.mat[0];
@@ -1615,7 +1654,7 @@ static int tc_forward_pass(rbnn_net* n, const float* x, int B, int s0, int s1, f
     w.wl2_count = ar.take<unsigned>((size_t)zc);
   }
   w.xnorm = ar.take<float>((size_t)B);
-  RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, 2.f, st));
+  if (!small_d(n)) RBNN_TRY(split_x(n, x, (int64_t)B * D, w, nullptr, 0, 2.f, st));
   if (fused) {
     xnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(x, B, D, w.xnorm);
     n->launches++;

@@ -283,6 +283,8 @@ TC_CONFIGS = [
     ("fc", (1, 28, 28), 32, 10, 130, 3),
     ("fc2", (1, 28, 28), 128, 10, 130, 5),
     ("fc2", (1, 28, 28), 512, 10, 257, 6),
+    ("fc2", (1, 2, 1), 512, 2, 100, 7),         # half moons (D = 2): first layer on the CUDA cores, H x H layer on tcgen05
+    ("fc2", (1, 2, 1), 32, 2, 130, 4),
 ]
 
 
@@ -297,6 +299,8 @@ def test_tcgen05_engine_vs_oracle(arch, shape, hidden, C, B, S, prec, tol, route
     from robustbnns_b200.engine import Net
     if prec == "f16x3" and (arch != "fc" or route == "unfused"):
         pytest.skip("F16X3 rides on the fused forward+head kernel (arch fc)")
+    if prec == "bf16" and (shape[0] * shape[1] * shape[2]) % 8:
+        pytest.skip("D % 8 != 0 (half moons): TF32X3 / FP32 only")
     if route == "unfused":
         if arch != "fc":
             pytest.skip("fc2 has a single (unfused) route")
@@ -562,7 +566,8 @@ def test_half_moons_grid_sweep(tmp_path, monkeypatch):
     banks = {}
     for hidden in widths:
         bnn = gs.MoonsBNN(hidden, "leaky", "fc2", "hmc", None, None, S, 5, 100, (1, 2, 1), 2)
-        assert bnn.engine().precision == "fp32"                       # D = 2: no tensor-core shape
+        # D = 2: the CUDA-core engine for the narrow nets; from H = 256 the H x H layer runs on tcgen05 (TF32X3)
+        assert bnn.engine().precision == ("tf32x3" if hidden >= 256 else "fp32")
         net = orc.build_net("fc2", (1, 2, 1), hidden, 2, dataset_name="half_moons")
         layout = orc.param_layout(net)
         loc, rho = orc.scaled_guide_params(layout, seed=hidden, rho_mean=-2.0)
@@ -604,13 +609,14 @@ def test_half_moons_grid_sweep(tmp_path, monkeypatch):
 
 
 def test_default_engine_is_the_fastest_parity_grade():
-    """A BNN that creates its own engine picks F16X3 (fc-512, conv), TF32X3 (fc2) or FP32 (half-moons: D = 2)."""
+    """A BNN that creates its own engine picks F16X3 (fc-512, conv), TF32X3 (fc2; half moons from H = 256) or FP32."""
     from robustbnns_b200.model_bnn import BNN
     from robustbnns_b200.model_nn import NN
     for arch, shape, hidden, C, ds, want in (("fc", (1, 28, 28), 512, 10, "mnist", "f16x3"),
                                              ("conv", (1, 28, 28), 64, 10, "mnist", "f16x3"),
                                              ("fc2", (1, 28, 28), 128, 10, "mnist", "tf32x3"),
                                              ("fc2", (1, 2, 1), 32, 2, "half_moons", "fp32"),
+                                             ("fc2", (1, 2, 1), 512, 2, "half_moons", "tf32x3"),   # H x H layer on tcgen05
                                              ("fc", (1, 28, 28), 16, 10, "mnist", "fp32")):
         bnn = BNN(ds, hidden, "leaky", arch, "hmc", None, None, 2, 5, shape, C)
         assert bnn.engine().precision == want, (arch, hidden)
