@@ -1163,6 +1163,7 @@ struct FcWs {
   unsigned long long* worklist = nullptr;
   unsigned long long* wl2 = nullptr;       // fc2: second-layer units to settle from exact first-layer values
   unsigned* wl2_count = nullptr;
+  float* dx_part = nullptr;                                   // D % 8 != 0: [Z][B][D] per-sample dX partials (dx_small_rows_kernel)
   unsigned wl2_cap = 0;
 };
 }  // namespace
@@ -1410,6 +1411,45 @@ static int split_x(rbnn_net* n, const float* x, int64_t count, FcWs& w, const fl
   return 0;
 }
 
+// dX of a net with D < 8 inputs (half moons): part[z][b][d] = sum_j dH1[z][b][j] W1_z[j][d], one warp per (z, b) row, then
+// a fixed-order sum over the samples.  (The CUDA-core GEMM pads N = D to a 64-column tile: 0.46 ms of a 1.1 ms evaluation
+// at H = 512; this pass reads dH1 once.)
+__global__ void __launch_bounds__(256)
+dx_small_rows_kernel(const float* __restrict__ dh, const float* __restrict__ bank, int64_t P, int64_t w1_off, int z_row0,
+                     int Z, int B, int H, int D, float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)Z * B, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps) {
+    const int z = (int)(row / B);
+    const float* __restrict__ d = dh + row * H;
+    const float* __restrict__ w = bank + (int64_t)(z_row0 + z) * P + w1_off;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int j = lane; j < H; j += 32) {
+      const float v = __ldg(d + j);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < D) acc[k] = fmaf(v, __ldg(w + (int64_t)j * D + k), acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k >= D) break;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      if (lane == 0) part[row * D + k] = acc[k];
+    }
+  }
+}
+// out[b][d] (+)= sum_z part[z][b][d], fixed order
+__global__ void dx_small_reduce_kernel(const float* __restrict__ part, int Z, int n, float* __restrict__ out, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = accumulate ? out[i] : 0.f;
+  for (int z = 0; z < Z; ++z) t += __ldg(part + (int64_t)z * n + i);
+  out[i] = t;
+}
+
 // rows of the batch per pass such that at least one sample fits the workspace budget
 static int tc_batch_rows(const rbnn_net* n, int B, bool grad) {
   const size_t per_row = fc_per_z_bytes(n, 1024, grad) / 1024 + (size_t)n->D * 12 + 64;
@@ -1450,7 +1490,8 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     return best;
   };
   int slots = slots_for(zc);
-  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots + pad256((size_t)B * 4) + 4096 + 65536));
+  RBNN_TRY(ws_reserve(n, x_bytes + per * zc + out_bytes * slots + pad256((size_t)B * 4) + 4096 + 65536 +
+                         (small_d(n) ? pad256((size_t)zc * B * D * 4) : 0)));
   Arena ar(n);
   FcWs w;
   if (kept) { w.call_sc = n->keep.call_sc; w.max_bits = n->keep.max_bits; }
@@ -1485,6 +1526,7 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
   }
   w.xnorm = ar.take<float>((size_t)B);
   w.partial = ar.take<float>((size_t)slots * B * D);
+  if (small_d(n)) w.dx_part = ar.take<float>((size_t)zc * B * D);
   if (kept) {
     if (f16) {       // the dH range of THIS head (max|x| is still in keep.max_bits[0] from the forward phase)
       const bool up = head == RBNN_HEAD_UPSTREAM || head == RBNN_HEAD_LOGITS_UPSTREAM;
@@ -1565,15 +1607,15 @@ static int tc_grad_pass(rbnn_net* n, int head, const float* x, const int32_t* la
     }
     if (small_d(n)) {
       // dX (+)= sum_z dH1_z . W1_z with N = D < 8: the FP32 engine's CUDA-core GEMM, summed over the chunk's samples
-      GemmArgs a{};
-      a.b_kn = 1;
-      a.A = w.d1_hi; a.lda = H; a.sAz = (int64_t)B * H;
-      a.B = n->bank + (int64_t)z0 * n->L.P + n->L.w1; a.ldb = D; a.sBz = n->L.P;
-      a.C = out_sum; a.ldc = D;
-      a.M = B; a.N = D; a.K = H; a.Z = Z; a.epi = EPI_NONE;
-      a.reduce_z = 1; a.accumulate = first ? 0 : 1;
-      a.tag = 2;
-      RBNN_TRY(gemm_simt(n, a, st));
+      // dX (+)= sum_z dH1_z . W1_z with N = D < 8: per-sample partials (w.dx_part), then a fixed-order sum over the samples
+      RBNN_TRY(timing_begin(n, 2, st));
+      const int64_t rows = (int64_t)Z * B;
+      dx_small_rows_kernel<<<(unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)n->sm_count * 8), 256, 0, st>>>(
+          w.d1_hi, n->bank, n->L.P, n->L.w1, z0, Z, B, H, D, w.dx_part);
+      dx_small_reduce_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(w.dx_part, Z, B * D, out_sum, first ? 0 : 1);
+      n->launches += 2;
+      RBNN_CUDA(cudaGetLastError());
+      RBNN_TRY(timing_end(n, 2, st));
       first = false;
       continue;
     }

@@ -66,10 +66,10 @@ class Net(object):
 
     def set_best_precision(self):
         """The fastest parity-grade engine this network has: F16X3 (arch fc with a fused hidden size, arch conv), else
-        TF32X3 (fc / fc2 with H >= 32; D % 8 != 0 -- half moons -- only fc2 from H = 128: its H x H layer runs on tcgen05,
+        TF32X3 (fc / fc2 with H >= 32; D % 8 != 0 -- half moons -- only fc2 from H = 64: its H x H layer runs on tcgen05,
         the D-wide first layer on the CUDA cores), else the FP32 CUDA-core engine.  Returns its name."""
         cands = ("f16x3", "tf32x3") if getattr(self, "activation", "leaky") == "leaky" else ()
-        if self.D % 8 and self.hidden < 128:
+        if self.D % 8 and self.hidden < 64:
             cands = ()        # half moons with narrow layers: launch-bound, the CUDA-core engine has fewer launches
         for cand in cands:
             try:

@@ -566,8 +566,8 @@ def test_half_moons_grid_sweep(tmp_path, monkeypatch):
     banks = {}
     for hidden in widths:
         bnn = gs.MoonsBNN(hidden, "leaky", "fc2", "hmc", None, None, S, 5, 100, (1, 2, 1), 2)
-        # D = 2: the CUDA-core engine for the narrow nets; from H = 128 the H x H layer runs on tcgen05 (TF32X3)
-        assert bnn.engine().precision == ("tf32x3" if hidden >= 128 else "fp32")
+        # D = 2: the CUDA-core engine for the narrow nets; from H = 64 the H x H layer runs on tcgen05 (TF32X3)
+        assert bnn.engine().precision == ("tf32x3" if hidden >= 64 else "fp32")
         net = orc.build_net("fc2", (1, 2, 1), hidden, 2, dataset_name="half_moons")
         layout = orc.param_layout(net)
         loc, rho = orc.scaled_guide_params(layout, seed=hidden, rho_mean=-2.0)
@@ -609,7 +609,7 @@ def test_half_moons_grid_sweep(tmp_path, monkeypatch):
 
 
 def test_default_engine_is_the_fastest_parity_grade():
-    """A BNN that creates its own engine picks F16X3 (fc-512, conv), TF32X3 (fc2; half moons from H = 128) or FP32."""
+    """A BNN that creates its own engine picks F16X3 (fc-512, conv), TF32X3 (fc2; half moons from H = 64) or FP32."""
     from robustbnns_b200.model_bnn import BNN
     from robustbnns_b200.model_nn import NN
     for arch, shape, hidden, C, ds, want in (("fc", (1, 28, 28), 512, 10, "mnist", "f16x3"),
