@@ -285,6 +285,7 @@ TC_CONFIGS = [
     ("fc2", (1, 28, 28), 512, 10, 257, 6),
     ("fc2", (1, 2, 1), 512, 2, 100, 7),         # half moons (D = 2): first layer on the CUDA cores, H x H layer on tcgen05
     ("fc2", (1, 2, 1), 32, 2, 130, 4),
+    ("fc2", (1, 5, 1), 64, 3, 50, 4),           # another D % 8 != 0 shape: the small-D kernels are not tied to D = 2
 ]
 
 
